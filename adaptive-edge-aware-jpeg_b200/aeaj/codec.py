@@ -1,0 +1,363 @@
+"""Device pipelines: torch owns device memory and streams, libaeaj.so does the work.
+
+``DeviceCodec`` caches one plan (geometry + q tables + workspace + output buffers) per
+(batch, H, W, colour space, block range) and exposes
+
+    encode(rgb_dev)  -> EncodedBatch      Jpeg.compress  minus _entropy_encode (jpeg.py:262-270)
+    decode(encoded)  -> rgb_dev           Jpeg.decompress minus _entropy_decode (jpeg.py:285-297)
+
+plus host-buffer variants used by the reference-facing ``Jpeg`` shim and by ``bench.py``'s e2e leg.
+Everything is asynchronous on the current torch CUDA stream; nothing falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import native, tables
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise native.AeajError("no CUDA device: the adaptive edge-aware JPEG B200 path has no CPU fallback")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+@dataclass
+class EncodedBatch:
+    """Device-resident result of one encode call (buffers are owned by the plan and reused)."""
+    coef: List[torch.Tensor]       # 3 x int32 [B, cap_coef_l]
+    leaves: List[torch.Tensor]     # 3 x int32 [B, cap_leaves_l, 4]  (x, y, size, coef offset)
+    states: List[torch.Tensor]     # 3 x uint8 [B, cap_states_l]
+    counts: torch.Tensor           # int32 [B, 3, 4]  n_leaves, n_states, n_coef, root
+    status: torch.Tensor           # int32 [2]        hysteresis rounds, converged
+    shape: Tuple[int, int, int]    # B, H, W
+    layers: Optional[List[torch.Tensor]] = None   # taps (float32 [B,h,w]) if requested
+    edges: Optional[List[torch.Tensor]] = None    # taps (uint8  [B,h,w]) if requested
+
+
+@dataclass
+class _Plan:
+    ptr: C.c_void_p
+    info: native.PlanInfo
+    workspace: torch.Tensor
+    out: EncodedBatch
+    rgb_out: torch.Tensor
+    qkey: Optional[tuple] = None
+    keep: list = field(default_factory=list)
+
+
+class DeviceCodec:
+    def __init__(self, device: int = 0):
+        _require_cuda()
+        self.device = device
+        self.lib = native.load()
+        self.handle = native.handle(device)
+        self._plans: Dict[tuple, _Plan] = {}
+        self.last_launches = 0
+
+    # ------------------------------------------------------------------------------------------
+    def _plan(self, B, H, W, space, brange, qrange) -> _Plan:
+        key = (B, H, W, space, tuple(brange))
+        p = self._plans.get(key)
+        dev = torch.device("cuda", self.device)
+        if p is None:
+            if space not in tables.CODEC_SPACES:
+                raise ValueError(f"Unsupported color space: {space}")
+            ptr = C.c_void_p()
+            native.check(self.lib.aeaj_plan_create(self.handle, B, H, W, tables.SPACE_ID[space], brange[0], brange[1], C.byref(ptr)),
+                         "aeaj_plan_create")
+            info = native.PlanInfo()
+            native.check(self.lib.aeaj_plan_get_info(ptr, C.byref(info)), "aeaj_plan_get_info")
+            ws = torch.empty(int(info.workspace_bytes), dtype=torch.uint8, device=dev)
+            out = EncodedBatch(
+                coef=[torch.empty((B, int(info.cap_coef[l])), dtype=torch.int32, device=dev) for l in range(3)],
+                leaves=[torch.empty((B, int(info.cap_leaves[l]), 4), dtype=torch.int32, device=dev) for l in range(3)],
+                states=[torch.empty((B, int(info.cap_states[l])), dtype=torch.uint8, device=dev) for l in range(3)],
+                counts=torch.zeros((B, 3, 4), dtype=torch.int32, device=dev),
+                status=torch.zeros(2, dtype=torch.int32, device=dev), shape=(B, H, W))
+            rgb_out = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
+            p = _Plan(ptr, info, ws, out, rgb_out)
+            self._plans[key] = p
+        qkey = tuple(qrange)
+        if p.qkey != qkey:
+            cache = tables.quantization_cache(qrange, brange)
+            sizes = tables.block_sizes(brange)
+            flat = np.concatenate([cache[t][s].ravel() for t in (0, 1) for s in sizes]).astype(np.int32)
+            native.check(self.lib.aeaj_plan_set_qtables(p.ptr, flat.ctypes.data, flat.size, _stream()), "aeaj_plan_set_qtables")
+            torch.cuda.current_stream().synchronize()     # `flat` is pageable host memory
+            p.qkey = qkey
+        return p
+
+    def plan_info(self, B, H, W, space, brange, qrange=(40, 80)) -> native.PlanInfo:
+        return self._plan(B, H, W, space, brange, qrange).info
+
+    # ------------------------------------------------------------------------------------------
+    def encode(self, rgb: torch.Tensor, space: str, qrange, brange, taps: bool = False) -> EncodedBatch:
+        """rgb: float32 CUDA tensor [B,H,W,3] (or [H,W,3]). Asynchronous on the current stream."""
+        if rgb.dim() == 3:
+            rgb = rgb.unsqueeze(0)
+        if rgb.dtype != torch.float32 or not rgb.is_cuda or rgb.dim() != 4 or rgb.shape[-1] != 3:
+            raise TypeError("encode expects a float32 CUDA tensor of shape [B,H,W,3]")
+        rgb = rgb.contiguous()
+        B, H, W, _ = rgb.shape
+        p = self._plan(B, H, W, space, brange, qrange)
+        o = p.out
+        io = native.EncodeIO()
+        io.rgb = rgb.data_ptr()
+        for l in range(3):
+            io.coef[l] = o.coef[l].data_ptr()
+            io.leaves[l] = o.leaves[l].data_ptr()
+            io.states[l] = o.states[l].data_ptr()
+        io.counts = o.counts.data_ptr()
+        io.status = o.status.data_ptr()
+        if taps:
+            dev = rgb.device
+            o.layers = [torch.empty((B, p.info.layer_h[l], p.info.layer_w[l]), dtype=torch.float32, device=dev) for l in range(3)]
+            o.edges = [torch.empty((B, p.info.layer_h[l], p.info.layer_w[l]), dtype=torch.uint8, device=dev) for l in range(3)]
+            for l in range(3):
+                io.tap_layers[l] = o.layers[l].data_ptr()
+                io.tap_edges[l] = o.edges[l].data_ptr()
+        native.check(self.lib.aeaj_encode(p.ptr, C.byref(io), p.workspace.data_ptr(), _stream()), "aeaj_encode")
+        self.last_launches = self.lib.aeaj_plan_last_launches(p.ptr)
+        return o
+
+    def decode(self, coef, leaves, counts, B, H, W, space: str, qrange, brange, taps: bool = False):
+        """coef/leaves: 3 device tensors laid out like EncodedBatch; counts int32 [B,3,4]. Returns rgb [B,H,W,3]."""
+        p = self._plan(B, H, W, space, brange, qrange)
+        io = native.DecodeIO()
+        for l in range(3):
+            if coef[l].shape[1] != p.info.cap_coef[l] or leaves[l].shape[1] != p.info.cap_leaves[l]:
+                raise ValueError("decode buffers must use the plan's capacities")
+            io.coef[l] = coef[l].data_ptr()
+            io.leaves[l] = leaves[l].data_ptr()
+        io.counts = counts.data_ptr()
+        io.rgb = p.rgb_out.data_ptr()
+        tl = None
+        if taps:
+            tl = [torch.empty((B, p.info.layer_h[l], p.info.layer_w[l]), dtype=torch.float32, device=p.rgb_out.device) for l in range(3)]
+            for l in range(3):
+                io.tap_layers[l] = tl[l].data_ptr()
+        native.check(self.lib.aeaj_decode(p.ptr, C.byref(io), p.workspace.data_ptr(), _stream()), "aeaj_decode")
+        self.last_launches = self.lib.aeaj_plan_last_launches(p.ptr)
+        return (p.rgb_out, tl) if taps else p.rgb_out
+
+    def decode_encoded(self, enc: EncodedBatch, space, qrange, brange):
+        B, H, W = enc.shape
+        return self.decode(enc.coef, enc.leaves, enc.counts, B, H, W, space, qrange, brange)
+
+    # ------------------------------------------------------------------------------------------
+    # host <-> device helpers for the reference-facing shim
+    # ------------------------------------------------------------------------------------------
+    def download(self, enc: EncodedBatch):
+        """D2H of exactly the used parts. Returns per image a list of 3 dicts(leaves, states, coef, root)."""
+        counts = enc.counts.cpu().numpy()                  # synchronises the stream
+        if int(enc.status[1].item()) != 1:
+            raise native.AeajError("hysteresis did not converge")
+        B = enc.shape[0]
+        out = []
+        for b in range(B):
+            layers = []
+            for l in range(3):
+                nl, ns, nc, root = (int(v) for v in counts[b, l])
+                layers.append(dict(leaves=enc.leaves[l][b, :nl].cpu().numpy(), states=enc.states[l][b, :ns].cpu().numpy(),
+                                   coef=enc.coef[l][b, :nc].cpu().numpy(), root=root))
+            out.append(layers)
+        return out
+
+    def upload_for_decode(self, per_image_layers, B, H, W, space, qrange, brange):
+        """per_image_layers[b][l] = dict(leaves (n,4) int32 incl. coef offsets, coef int32). Returns device buffers."""
+        p = self._plan(B, H, W, space, brange, qrange)
+        o = p.out
+        counts = np.zeros((B, 3, 4), dtype=np.int32)
+        for b in range(B):
+            for l in range(3):
+                d = per_image_layers[b][l]
+                nl, nc = len(d["leaves"]), len(d["coef"])
+                if nl > p.info.cap_leaves[l] or nc > p.info.cap_coef[l]:
+                    raise ValueError("stream does not fit the layer geometry (corrupt input?)")
+                counts[b, l, 0] = nl
+                counts[b, l, 2] = nc
+                o.leaves[l][b, :nl].copy_(torch.from_numpy(np.ascontiguousarray(d["leaves"], dtype=np.int32)), non_blocking=False)
+                o.coef[l][b, :nc].copy_(torch.from_numpy(np.ascontiguousarray(d["coef"], dtype=np.int32)), non_blocking=False)
+        o.counts.copy_(torch.from_numpy(counts))
+        return o.coef, o.leaves, o.counts
+
+
+_codecs: Dict[int, DeviceCodec] = {}
+
+
+def get_codec(device: Optional[int] = None) -> DeviceCodec:
+    _require_cuda()
+    if device is None:
+        device = torch.cuda.current_device()
+    if device not in _codecs:
+        _codecs[device] = DeviceCodec(device)
+    return _codecs[device]
+
+
+# ----------------------------------------------------------------------------------------------
+# single-plane stage calls (numpy in / numpy out) used by the color / jpeg drop-in modules and tests
+# ----------------------------------------------------------------------------------------------
+class Stages:
+    def __init__(self, device: Optional[int] = None):
+        _require_cuda()
+        self.device = torch.cuda.current_device() if device is None else device
+        self.lib = native.load()
+        self.handle = native.handle(self.device)
+        self.dev = torch.device("cuda", self.device)
+
+    def _ws(self, h, w, mn=0, mx=0):
+        n = self.lib.aeaj_stage_workspace_bytes(h, w, mn, mx)
+        return torch.empty(int(n), dtype=torch.uint8, device=self.dev)
+
+    def _to(self, a, dtype):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(self.dev)
+
+    def color(self, space: str, x: np.ndarray, inverse: bool) -> np.ndarray:
+        t = self._to(x, np.float32)
+        o = torch.empty_like(t)
+        fn = self.lib.aeaj_color_inverse if inverse else self.lib.aeaj_color_forward
+        native.check(fn(self.handle, tables.SPACE_ID[space], t.data_ptr(), o.data_ptr(), t.shape[0], _stream()), "aeaj_color")
+        return o.cpu().numpy()
+
+    def normalize(self, space: str, channel: int, x: np.ndarray, inverse: bool) -> np.ndarray:
+        t = self._to(x, np.float32)
+        o = torch.empty_like(t)
+        native.check(self.lib.aeaj_normalize(self.handle, tables.SPACE_ID[space], channel, int(inverse), t.data_ptr(), o.data_ptr(),
+                                             t.numel(), _stream()), "aeaj_normalize")
+        return o.cpu().numpy()
+
+    def downsample(self, layer: np.ndarray, h: int, w: int) -> np.ndarray:
+        t = self._to(layer, np.float32)
+        o = torch.empty((h, w), dtype=torch.float32, device=self.dev)
+        native.check(self.lib.aeaj_downsample_area(self.handle, t.data_ptr(), t.shape[0], t.shape[1], o.data_ptr(), h, w, _stream()),
+                     "aeaj_downsample_area")
+        return o.cpu().numpy()
+
+    def resize_linear(self, layer: np.ndarray, H: int, W: int) -> np.ndarray:
+        t = self._to(layer, np.float32)
+        o = torch.empty((H, W), dtype=torch.float32, device=self.dev)
+        native.check(self.lib.aeaj_resize_linear(self.handle, t.data_ptr(), t.shape[0], t.shape[1], o.data_ptr(), H, W, _stream()),
+                     "aeaj_resize_linear")
+        return o.cpu().numpy()
+
+    def cast_u8(self, layer: np.ndarray) -> np.ndarray:
+        t = self._to(layer, np.float32)
+        o = torch.empty(t.shape, dtype=torch.uint8, device=self.dev)
+        native.check(self.lib.aeaj_cast_u8(self.handle, t.data_ptr(), o.data_ptr(), t.numel(), _stream()), "aeaj_cast_u8")
+        return o.cpu().numpy()
+
+    def _u8_stage(self, fn, src: np.ndarray) -> np.ndarray:
+        t = self._to(src, np.uint8)
+        h, w = t.shape
+        o = torch.empty_like(t)
+        ws = self._ws(h, w)
+        native.check(fn(self.handle, t.data_ptr(), h, w, o.data_ptr(), ws.data_ptr(), _stream()), "u8 stage")
+        return o.cpu().numpy()
+
+    def clahe(self, src):
+        return self._u8_stage(self.lib.aeaj_clahe, src)
+
+    def gauss3(self, src):
+        return self._u8_stage(self.lib.aeaj_gauss3, src)
+
+    def bilateral5(self, src):
+        return self._u8_stage(self.lib.aeaj_bilateral5, src)
+
+    def percentile_thresholds(self, src: np.ndarray):
+        t = self._to(src, np.uint8)
+        h, w = t.shape
+        thr = torch.empty(2, dtype=torch.float64, device=self.dev)
+        ws = self._ws(h, w)
+        native.check(self.lib.aeaj_percentile_thresholds(self.handle, t.data_ptr(), h, w, thr.data_ptr(), ws.data_ptr(), _stream()),
+                     "aeaj_percentile_thresholds")
+        v = thr.cpu().numpy()
+        return float(v[0]), float(v[1])
+
+    def canny_u8(self, src: np.ndarray, lo: float, hi: float) -> np.ndarray:
+        t = self._to(src, np.uint8)
+        h, w = t.shape
+        thr = torch.tensor([lo, hi], dtype=torch.float64, device=self.dev)
+        o = torch.empty_like(t)
+        ws = self._ws(h, w)
+        native.check(self.lib.aeaj_canny_u8(self.handle, t.data_ptr(), h, w, thr.data_ptr(), o.data_ptr(), ws.data_ptr(), _stream()),
+                     "aeaj_canny_u8")
+        return o.cpu().numpy()
+
+    def canny(self, layer: np.ndarray) -> np.ndarray:
+        t = self._to(layer, np.float32)
+        h, w = t.shape
+        o = torch.empty((h, w), dtype=torch.uint8, device=self.dev)
+        ws = self._ws(h, w)
+        native.check(self.lib.aeaj_canny(self.handle, t.data_ptr(), h, w, o.data_ptr(), ws.data_ptr(), _stream()), "aeaj_canny")
+        return o.cpu().numpy()
+
+    def quadtree(self, edge: np.ndarray, max_size: int, min_size: int):
+        """-> (leaves (n,4) int32 x,y,size,coef_off ; states uint8 ; root)"""
+        e = np.ascontiguousarray(edge == 1).astype(np.uint8)
+        t = self._to(e, np.uint8)
+        h, w = t.shape
+        cl, cs, cc, root = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
+        native.check(self.lib.aeaj_quadtree_caps(h, w, min_size, max_size, C.byref(cl), C.byref(cs), C.byref(cc), C.byref(root)),
+                     "aeaj_quadtree_caps")
+        leaves = torch.empty((cl.value, 4), dtype=torch.int32, device=self.dev)
+        states = torch.empty(cs.value, dtype=torch.uint8, device=self.dev)
+        counts = torch.zeros(4, dtype=torch.int32, device=self.dev)
+        ws = self._ws(h, w, min_size, max_size)
+        native.check(self.lib.aeaj_quadtree(self.handle, t.data_ptr(), h, w, min_size, max_size, leaves.data_ptr(), states.data_ptr(),
+                                            counts.data_ptr(), ws.data_ptr(), _stream()), "aeaj_quadtree")
+        c = counts.cpu().numpy()
+        return leaves[: int(c[0])].cpu().numpy(), states[: int(c[1])].cpu().numpy(), int(c[3])
+
+    def _qtab_ptrs(self, tabs: dict):
+        arr = (C.c_void_p * 9)()
+        keep = []
+        for s, m in tabs.items():
+            t = self._to(m, np.int32)
+            keep.append(t)
+            arr[int(np.log2(s))] = t.data_ptr()
+        return arr, keep
+
+    def dct_quant(self, layer: np.ndarray, leaves: np.ndarray, tabs: dict, mid: float, scale: float, brange) -> np.ndarray:
+        t = self._to(layer, np.float32)
+        h, w = t.shape
+        lv = self._to(leaves, np.int32)
+        n_coef = int((leaves[:, 2].astype(np.int64) ** 2).sum())
+        counts = torch.tensor([len(leaves), 0, n_coef, 0], dtype=torch.int32, device=self.dev)
+        coef = torch.empty(max(n_coef, 1), dtype=torch.int32, device=self.dev)
+        arr, keep = self._qtab_ptrs(tabs)
+        ws = self._ws(h, w, brange[0], brange[1])
+        native.check(self.lib.aeaj_dct_quant(self.handle, t.data_ptr(), h, w, mid, scale, lv.data_ptr(), counts.data_ptr(), brange[0], brange[1],
+                                             arr, coef.data_ptr(), ws.data_ptr(), _stream()), "aeaj_dct_quant")
+        return coef[:n_coef].cpu().numpy()
+
+    def dequant_idct(self, coef: np.ndarray, leaves: np.ndarray, tabs: dict, h: int, w: int, mid: float, scale: float, brange) -> np.ndarray:
+        cf = self._to(coef, np.int32)
+        lv = self._to(leaves, np.int32)
+        counts = torch.tensor([len(leaves), 0, len(coef), 0], dtype=torch.int32, device=self.dev)
+        out = torch.zeros((h, w), dtype=torch.float32, device=self.dev)
+        arr, keep = self._qtab_ptrs(tabs)
+        ws = self._ws(h, w, brange[0], brange[1])
+        native.check(self.lib.aeaj_dequant_idct(self.handle, cf.data_ptr(), lv.data_ptr(), counts.data_ptr(), brange[0], brange[1], arr, h, w,
+                                                mid, scale, out.data_ptr(), ws.data_ptr(), _stream()), "aeaj_dequant_idct")
+        return out.cpu().numpy()
+
+
+_stages: Dict[int, Stages] = {}
+
+
+def get_stages(device: Optional[int] = None) -> Stages:
+    _require_cuda()
+    if device is None:
+        device = torch.cuda.current_device()
+    if device not in _stages:
+        _stages[device] = Stages(device)
+    return _stages[device]

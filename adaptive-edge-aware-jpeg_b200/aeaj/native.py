@@ -1,0 +1,141 @@
+"""ctypes binding of libaeaj.so (include/aeaj.h).  Fails loudly: a missing library, a missing
+symbol or a missing sm_100 device raises -- nothing here ever computes on the CPU."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+from . import tables
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "libaeaj.so")
+
+EXPORTS = [
+    "aeaj_last_error", "aeaj_version", "aeaj_create", "aeaj_destroy", "aeaj_set_color_tables", "aeaj_set_srgb_lut",
+    "aeaj_color_forward", "aeaj_color_inverse", "aeaj_normalize", "aeaj_downsample_area", "aeaj_resize_linear",
+    "aeaj_stage_workspace_bytes", "aeaj_cast_u8", "aeaj_clahe", "aeaj_gauss3", "aeaj_bilateral5",
+    "aeaj_percentile_thresholds", "aeaj_canny_u8", "aeaj_canny", "aeaj_quadtree_caps", "aeaj_quadtree",
+    "aeaj_dct_quant", "aeaj_dequant_idct", "aeaj_plan_create", "aeaj_plan_destroy", "aeaj_plan_get_info",
+    "aeaj_plan_set_qtables", "aeaj_encode", "aeaj_decode", "aeaj_plan_last_launches",
+    "aeaj_states_to_leaves_host", "aeaj_pack_states_host",
+]
+
+
+class AeajError(RuntimeError):
+    pass
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [("batch", C.c_int), ("height", C.c_int), ("width", C.c_int), ("space", C.c_int),
+                ("block_min", C.c_int), ("block_max", C.c_int),
+                ("layer_h", C.c_int * 3), ("layer_w", C.c_int * 3), ("root", C.c_int * 3),
+                ("cap_leaves", C.c_int64 * 3), ("cap_states", C.c_int64 * 3), ("cap_coef", C.c_int64 * 3),
+                ("workspace_bytes", C.c_int64)]
+
+
+class EncodeIO(C.Structure):
+    _fields_ = [("rgb", C.c_void_p), ("coef", C.c_void_p * 3), ("leaves", C.c_void_p * 3), ("states", C.c_void_p * 3),
+                ("counts", C.c_void_p), ("tap_layers", C.c_void_p * 3), ("tap_edges", C.c_void_p * 3), ("status", C.c_void_p)]
+
+
+class DecodeIO(C.Structure):
+    _fields_ = [("coef", C.c_void_p * 3), ("leaves", C.c_void_p * 3), ("counts", C.c_void_p), ("rgb", C.c_void_p),
+                ("tap_layers", C.c_void_p * 3)]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load libaeaj.so; raises ImportError if it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} not found: build it with `make -C {os.path.join(_PKG, 'csrc')}` "
+                              "(or __graft_entry__.build()); there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        missing = [s for s in EXPORTS if not hasattr(lib, s)]
+        if missing:
+            raise ImportError(f"libaeaj.so lacks symbols {missing}")
+        lib.aeaj_last_error.restype = C.c_char_p
+        lib.aeaj_stage_workspace_bytes.restype = C.c_size_t
+        lib.aeaj_stage_workspace_bytes.argtypes = [C.c_int] * 4
+        vp, i, sz, f = C.c_void_p, C.c_int, C.c_size_t, C.c_float
+        lib.aeaj_create.argtypes = [i, C.POINTER(vp)]
+        lib.aeaj_destroy.argtypes = [vp]
+        lib.aeaj_set_color_tables.argtypes = [vp, i] + [vp] * 6
+        lib.aeaj_set_srgb_lut.argtypes = [vp, vp]
+        lib.aeaj_color_forward.argtypes = [vp, i, vp, vp, sz, vp]
+        lib.aeaj_color_inverse.argtypes = [vp, i, vp, vp, sz, vp]
+        lib.aeaj_normalize.argtypes = [vp, i, i, i, vp, vp, sz, vp]
+        lib.aeaj_downsample_area.argtypes = [vp, vp, i, i, vp, i, i, vp]
+        lib.aeaj_resize_linear.argtypes = [vp, vp, i, i, vp, i, i, vp]
+        lib.aeaj_cast_u8.argtypes = [vp, vp, vp, sz, vp]
+        for name in ("aeaj_clahe", "aeaj_gauss3", "aeaj_bilateral5"):
+            getattr(lib, name).argtypes = [vp, vp, i, i, vp, vp, vp]
+        lib.aeaj_percentile_thresholds.argtypes = [vp, vp, i, i, vp, vp, vp]
+        lib.aeaj_canny_u8.argtypes = [vp, vp, i, i, vp, vp, vp, vp]
+        lib.aeaj_canny.argtypes = [vp, vp, i, i, vp, vp, vp]
+        lib.aeaj_quadtree_caps.argtypes = [i, i, i, i, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(i)]
+        lib.aeaj_quadtree.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp, vp]
+        lib.aeaj_dct_quant.argtypes = [vp, vp, i, i, f, f, vp, vp, i, i, C.POINTER(vp), vp, vp, vp]
+        lib.aeaj_dequant_idct.argtypes = [vp, vp, vp, vp, i, i, C.POINTER(vp), i, i, f, f, vp, vp, vp]
+        lib.aeaj_plan_create.argtypes = [vp, i, i, i, i, i, i, C.POINTER(vp)]
+        lib.aeaj_plan_destroy.argtypes = [vp]
+        lib.aeaj_plan_get_info.argtypes = [vp, C.POINTER(PlanInfo)]
+        lib.aeaj_plan_set_qtables.argtypes = [vp, vp, sz, vp]
+        lib.aeaj_encode.argtypes = [vp, C.POINTER(EncodeIO), vp, vp]
+        lib.aeaj_decode.argtypes = [vp, C.POINTER(DecodeIO), vp, vp]
+        lib.aeaj_plan_last_launches.argtypes = [vp]
+        lib.aeaj_states_to_leaves_host.argtypes = [vp, i, i, i, i, vp, C.POINTER(i), C.POINTER(C.c_int64)]
+        lib.aeaj_pack_states_host.argtypes = [vp, i, vp]
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str = "libaeaj call"):
+    if rc != 0:
+        msg = load().aeaj_last_error().decode("utf-8", "replace")
+        raise AeajError(f"{what} failed (code {rc}): {msg}")
+
+
+_handles = {}
+
+
+def handle(device: int = 0):
+    """The per-device handle, created on first use with the host-derived colour tables uploaded."""
+    lib = load()
+    with _lock:
+        if device in _handles:
+            return _handles[device]
+    h = C.c_void_p()
+    check(lib.aeaj_create(device, C.byref(h)), "aeaj_create")
+    keep = []
+    for name, sid in tables.SPACE_ID.items():
+        arrs = tables.color_tables(name)
+        keep.append(arrs)
+        check(lib.aeaj_set_color_tables(h, sid, *[a.ctypes.data for a in arrs]), "aeaj_set_color_tables")
+    lut = tables.srgb_to_linear_lut()
+    check(lib.aeaj_set_srgb_lut(h, lut.ctypes.data), "aeaj_set_srgb_lut")
+    with _lock:
+        _handles[device] = h
+    return h
+
+
+def states_to_leaves(states: np.ndarray, root: int, h: int, w: int):
+    """Host-side inverse of the state stream (jpeg.py:768-800 + 428-448): DFS pre-order 2-bit states
+    -> (x, y, size, coefficient offset) per leaf.  Part of the entropy-decode side, runs on the host."""
+    lib = load()
+    states = np.ascontiguousarray(states, dtype=np.uint8)
+    leaves = np.empty((max(len(states), 1), 4), dtype=np.int32)
+    n = C.c_int()
+    ncoef = C.c_int64()
+    check(lib.aeaj_states_to_leaves_host(states.ctypes.data, len(states), root, h, w, leaves.ctypes.data, C.byref(n), C.byref(ncoef)),
+          "aeaj_states_to_leaves_host")
+    return leaves[: n.value], int(ncoef.value)

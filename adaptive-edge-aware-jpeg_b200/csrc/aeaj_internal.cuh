@@ -1,0 +1,189 @@
+// aeaj_internal.cuh -- shared declarations for libaeaj.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <algorithm>
+#include <type_traits>
+#include "../../include/aeaj.h"
+
+#define AEAJ_MAX_PLANES_INLINE 0
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+void aeaj_set_error(const char* fmt, ...);
+#define AEAJ_CUDA(call)                                                                     \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            aeaj_set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,             \
+                           cudaGetErrorString(e_));                                         \
+            return (int)e_;                                                                 \
+        }                                                                                   \
+    } while (0)
+#define AEAJ_LAUNCH_CHECK()                                                                 \
+    do {                                                                                    \
+        cudaError_t e_ = cudaGetLastError();                                                \
+        if (e_ != cudaSuccess) {                                                            \
+            aeaj_set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,         \
+                           cudaGetErrorString(e_));                                         \
+            return (int)e_;                                                                 \
+        }                                                                                   \
+    } while (0)
+#define AEAJ_REQUIRE(cond, msg)                                                             \
+    do {                                                                                    \
+        if (!(cond)) { aeaj_set_error("%s (%s:%d)", msg, __FILE__, __LINE__); return AEAJ_EINVAL; } \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// geometry shared by host and device
+// ---------------------------------------------------------------------------------------------
+struct ColorConsts {          // per colour space, device-resident copy inside the handle
+    float fwd1[9], fwd2[9];   // forward: XYZ->LMS, LMS'->space   (linear spaces: fwd1 = the 3x3)
+    float inv1[9], inv2[9];   // inverse: space->LMS', LMS->XYZ   (linear spaces: inv1 = the 3x3)
+    float mid[3], scale[3];   // normalisation (MIDPOINTS / SCALE_FACTORS)
+};
+
+// one "plane" = one layer of one image
+struct PlaneGeom {
+    int h, w;          // layer size
+    int wpr;           // bitmap words per row = ceil(w/32)
+    int root;          // quadtree root size
+    int top;           // top block size T = min(max_block, root)
+    int ntx, nty;      // in-bounds top blocks per axis
+};
+
+static inline __host__ __device__ int aeaj_cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline __host__ __device__ int64_t aeaj_cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// BORDER_REFLECT_101 with OpenCV's loop (valid for any p, any len >= 1)
+static inline __host__ __device__ int reflect101(int p, int len) {
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) { if (p < 0) p = -p; else p = 2 * (len - 1) - p; }
+    return p;
+}
+static inline __host__ __device__ int clampi(int p, int lo, int hi) { return p < lo ? lo : (p > hi ? hi : p); }
+// np.pad(mode='reflect') index for position p >= 0 in a length-n axis (n==1 replicates)
+static inline __host__ __device__ int pad_reflect(int p, int n) {
+    if (n == 1) return 0;
+    int period = 2 * (n - 1);
+    p %= period;
+    return p < n ? p : period - p;
+}
+static inline __host__ __device__ int ilog2i(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
+
+// utils.py:24-41 + quadtree.py:89-90
+static inline __host__ __device__ int aeaj_root_size(int h, int w) {
+    int n = h > w ? h : w;
+    if (n <= 2) return n * 2;
+    int p = 1;
+    while (p * 2 < n) p *= 2;
+    return p * 2;
+}
+
+// Morton helpers: z = interleave(y,x), x in even bits (TL,TR,BL,BR child order)
+static inline __host__ __device__ uint32_t compact1by1(uint32_t v) {
+    v &= 0x55555555u;
+    v = (v | (v >> 1)) & 0x33333333u;
+    v = (v | (v >> 2)) & 0x0f0f0f0fu;
+    v = (v | (v >> 4)) & 0x00ff00ffu;
+    v = (v | (v >> 8)) & 0x0000ffffu;
+    return v;
+}
+static inline __host__ __device__ uint32_t part1by1(uint32_t v) {
+    v &= 0x0000ffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// handle / plan
+// ---------------------------------------------------------------------------------------------
+struct aeaj_handle {
+    int device;
+    int sm_count;
+    ColorConsts colors_host[8];
+    ColorConsts* colors_dev;      // [8]
+    float* srgb_lut_dev;          // 256 floats, 0 until aeaj_set_srgb_lut
+    int has_srgb_lut;
+    float* dct_dev[9];            // DCT-II matrices C (s x s, row-major) for s = 2^k, k = 1..8
+    float* dct_all_dev;
+    // device scratch for single-plane stage calls
+    struct PlaneDesc* stage_plane_dev;
+    long long* stage_class_off_dev;   // [9]
+    int* stage_tile_base_dev;         // [1]
+    uint8_t** stage_outs_dev;         // [1]
+};
+
+// device-side description of every plane of a batch; lives in the plan's device memory
+struct PlaneDesc {
+    int h, w, wpr, root, top, ntx, nty, layer;
+    float mid, scale;
+    float* layer_f32;        // downsampled un-normalised layer
+    uint8_t* u8a;            // cast / stage ping
+    uint8_t* u8b;            // stage pong (post-bilateral)
+    uint32_t* strong;        // bitmaps [h][wpr]
+    uint32_t* weak;
+    uint32_t* clahe_hist;    // [16][256]
+    uint8_t* clahe_lut;      // [16][256]
+    uint32_t* hist;          // [256] post-bilateral histogram
+    int* thr;                // low, high (ints, squared)
+    double* thr_d;           // percentile values (float64) for the stage API
+    int32_t* leaves;         // [cap][4]
+    uint8_t* states;
+    int32_t* coef;
+    int32_t* counts;         // n_leaves, n_states, n_coef, root
+    int2* tb_tot;            // per in-bounds top block: (n_states, n_leaves)
+    int* tb_coef;            // per in-bounds top block: n_coef
+    int4* tb_base;           // per in-bounds top block: state base, leaf base, coef base, -
+    const int32_t* qtab[9];  // per log2(size)
+    int64_t cap_leaves, cap_states, cap_coef;
+};
+
+struct ClassEntry { int x, y, plane, coef_off; };
+
+// kernels' host launchers (defined in the .cu files)
+int aeaj_canny_init_constants();
+int aeaj_dct_init(aeaj_handle* h);
+
+int launch_color_forward_planar(aeaj_handle* h, int space, const float* rgb, int B, int H, int W,
+                                const PlaneDesc* planes_dev, const PlaneDesc* planes_host,
+                                float* full_c1, float* full_c2, cudaStream_t st, int* launches);
+int launch_color_pixels(aeaj_handle* h, int space, int inverse, const float* in, float* out, size_t n, cudaStream_t st);
+int launch_normalize(const float* in, float* out, size_t n, float mid, float scale, int inverse, cudaStream_t st);
+int launch_area(const float* src, int H, int W, float* dst, int dh, int dw, uint8_t* u8_out, int planes,
+                size_t src_stride, size_t dst_stride, cudaStream_t st);
+int launch_resize_linear(const float* src, int sh, int sw, float* dst, int H, int W, cudaStream_t st);
+int launch_upsample_color_inverse(aeaj_handle* h, int space, const PlaneDesc* planes_host, int B, int H, int W,
+                                  float* rgb, cudaStream_t st);
+int launch_cast_u8(const float* in, uint8_t* out, size_t n, cudaStream_t st);
+
+int launch_clahe_hist(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, cudaStream_t st);
+int launch_clahe_lut(const PlaneDesc* planes_dev, int nplanes, cudaStream_t st);
+int launch_prefilter(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, int stages, int do_hist, cudaStream_t st);
+int launch_hist_u8(const uint8_t* src, size_t n, unsigned int* hist, cudaStream_t st);
+int launch_thresholds(const PlaneDesc* planes_dev, int nplanes, cudaStream_t st);
+int launch_thresholds_from_double(const double* thr_d, int* thr, cudaStream_t st);
+int launch_canny_nms(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, cudaStream_t st);
+int hysteresis_tiles(const PlaneDesc* planes_host, int nplanes, int* tile_base_host);
+int launch_hysteresis(aeaj_handle* h, const PlaneDesc* planes_dev, int nplanes, const int* tile_base_dev, int ntiles,
+                      int* flags, int* ctrl, int* status, cudaStream_t st);
+int launch_bitmap_to_u8(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes,
+                        uint8_t* const* outs_dev, cudaStream_t st);
+int launch_u8_to_bitmap(const uint8_t* edge, int h, int w, uint32_t* bits, cudaStream_t st);
+
+int launch_quadtree(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, int min_size, int max_size,
+                    ClassEntry* class_lists, int* class_counts, const long long* class_offsets_dev, cudaStream_t st,
+                    int* launches);
+int launch_bucket_leaves(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, ClassEntry* class_lists,
+                         int* class_counts, const long long* class_offsets_dev, cudaStream_t st);
+int launch_dct_quant(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,
+                     const int64_t* class_offsets_host, const int64_t* class_caps_host, int lg_min, int lg_max,
+                     cudaStream_t st, int* launches);
+int launch_dequant_idct(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,
+                        const int64_t* class_offsets_host, const int64_t* class_caps_host, int lg_min, int lg_max,
+                        cudaStream_t st, int* launches);

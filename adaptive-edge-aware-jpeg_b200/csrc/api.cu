@@ -1,0 +1,647 @@
+// api.cu -- the C ABI of libaeaj.so (include/aeaj.h): handles, plans, workspace carving, stage entry
+// points and the fused encode / decode pipelines.  No kernels here.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "aeaj_internal.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void aeaj_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* aeaj_last_error(void) { return g_err; }
+extern "C" int aeaj_version(void) { return AEAJ_VERSION; }
+
+// ---------------------------------------------------------------------------------------------
+// bump allocator over a caller-provided workspace
+// ---------------------------------------------------------------------------------------------
+struct Bump {
+    uint8_t* base; size_t off;
+    explicit Bump(void* p) : base((uint8_t*)p), off(0) {}
+    template <typename T> T* take(size_t n) {
+        off = (off + 255) & ~(size_t)255;
+        T* r = base ? (T*)(base + off) : (T*)nullptr;
+        off += n * sizeof(T);
+        return r;
+    }
+    size_t used() const { return (off + 255) & ~(size_t)255; }
+};
+
+static int64_t cap_leaves_of(int h, int w, int mn) { return (int64_t)aeaj_cdiv(h, mn) * aeaj_cdiv(w, mn); }
+static int64_t cap_states_of(int h, int w, int mn, int root) {
+    int64_t n = 1;
+    for (int64_t s = 2 * (int64_t)mn; s <= root; s *= 2) n += 4 * aeaj_cdiv64(h, s) * aeaj_cdiv64(w, s);
+    return n + 8;
+}
+static int64_t cap_coef_of(int h, int w, int top) { return (int64_t)aeaj_cdiv(h, top) * top * (int64_t)aeaj_cdiv(w, top) * top; }
+
+static void plane_geom(PlaneDesc& P, int h, int w, int mn, int mx) {
+    P.h = h; P.w = w; P.wpr = aeaj_cdiv(w, 32);
+    P.root = aeaj_root_size(h, w);
+    if (mx > 0) {
+        P.top = std::min(mx, P.root);
+        P.ntx = aeaj_cdiv(w, P.top); P.nty = aeaj_cdiv(h, P.top);
+        P.cap_leaves = cap_leaves_of(h, w, mn);
+        P.cap_states = cap_states_of(h, w, mn, P.root);
+        P.cap_coef = cap_coef_of(h, w, P.top);
+    } else { P.top = 0; P.ntx = P.nty = 0; P.cap_leaves = P.cap_states = P.cap_coef = 0; }
+}
+
+// scratch that belongs to one plane (carved per plane; pointers may be null when b.base is null)
+static void carve_plane_scratch(Bump& b, PlaneDesc& P, bool canny, bool qt) {
+    if (canny) {
+        P.strong = b.take<uint32_t>((size_t)P.h * P.wpr);
+        P.weak = b.take<uint32_t>((size_t)P.h * P.wpr);
+        P.clahe_hist = b.take<uint32_t>(16 * 256);
+        P.clahe_lut = b.take<uint8_t>(16 * 256);
+        P.hist = b.take<uint32_t>(256);
+        P.thr = b.take<int>(2);
+        P.thr_d = b.take<double>(2);
+    }
+    if (qt) {
+        size_t ntb = (size_t)P.ntx * P.nty;
+        P.tb_tot = b.take<int2>(ntb);
+        P.tb_coef = b.take<int>(ntb);
+        P.tb_base = b.take<int4>(ntb);
+    }
+}
+
+struct ClassGeom { int64_t off[9], cap[9], total; };
+static void class_geom(const PlaneDesc* P, int nplanes, int lg_min, int lg_max, ClassGeom& g) {
+    g.total = 0;
+    for (int k = 0; k < 9; k++) { g.off[k] = 0; g.cap[k] = 0; }
+    for (int k = lg_min; k <= lg_max; k++) {
+        int s = 1 << k;
+        int64_t c = 0;
+        for (int i = 0; i < nplanes; i++) c += (int64_t)aeaj_cdiv(P[i].h, s) * aeaj_cdiv(P[i].w, s);
+        g.off[k] = g.total; g.cap[k] = c; g.total += c;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+extern "C" int aeaj_create(int device, aeaj_handle** out) {
+    if (!out) { aeaj_set_error("aeaj_create: out is NULL"); return AEAJ_EINVAL; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        aeaj_set_error("no CUDA device available (%s); libaeaj has no CPU fallback", cudaGetErrorString(e));
+        return AEAJ_ENOCUDA;
+    }
+    AEAJ_REQUIRE(device >= 0 && device < ndev, "aeaj_create: bad device index");
+    AEAJ_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    AEAJ_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        aeaj_set_error("device %d is sm_%d%d; libaeaj is built for sm_100a only", device, prop.major, prop.minor);
+        return AEAJ_ENOCUDA;
+    }
+    aeaj_handle* h = (aeaj_handle*)calloc(1, sizeof(aeaj_handle));
+    if (!h) return AEAJ_ENOMEM;
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    int rc = aeaj_dct_init(h);
+    if (rc) { free(h); return rc; }
+    rc = aeaj_canny_init_constants();
+    if (rc) { free(h); return rc; }
+    AEAJ_CUDA(cudaMalloc(&h->srgb_lut_dev, 256 * sizeof(float)));
+    AEAJ_CUDA(cudaMalloc(&h->stage_plane_dev, sizeof(PlaneDesc)));
+    AEAJ_CUDA(cudaMalloc(&h->stage_class_off_dev, 9 * sizeof(long long)));
+    AEAJ_CUDA(cudaMalloc(&h->stage_tile_base_dev, sizeof(int)));
+    AEAJ_CUDA(cudaMalloc(&h->stage_outs_dev, sizeof(uint8_t*)));
+    AEAJ_CUDA(cudaMemset(h->stage_tile_base_dev, 0, sizeof(int)));
+    *out = h;
+    return 0;
+}
+
+extern "C" int aeaj_destroy(aeaj_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaFree(h->srgb_lut_dev); cudaFree(h->dct_all_dev); cudaFree(h->stage_plane_dev);
+    cudaFree(h->stage_class_off_dev); cudaFree(h->stage_tile_base_dev); cudaFree(h->stage_outs_dev);
+    free(h);
+    return 0;
+}
+
+extern "C" int aeaj_set_color_tables(aeaj_handle* h, int space, const float* f1, const float* f2, const float* i1,
+                                     const float* i2, const float* mid, const float* scale) {
+    AEAJ_REQUIRE(h && space >= 0 && space < 8, "aeaj_set_color_tables: bad arguments");
+    ColorConsts& C = h->colors_host[space];
+    if (f1) memcpy(C.fwd1, f1, sizeof C.fwd1);
+    if (f2) memcpy(C.fwd2, f2, sizeof C.fwd2);
+    if (i1) memcpy(C.inv1, i1, sizeof C.inv1);
+    if (i2) memcpy(C.inv2, i2, sizeof C.inv2);
+    if (mid) memcpy(C.mid, mid, sizeof C.mid);
+    if (scale) memcpy(C.scale, scale, sizeof C.scale);
+    return 0;
+}
+
+extern "C" int aeaj_set_srgb_lut(aeaj_handle* h, const float* lut) {
+    AEAJ_REQUIRE(h, "aeaj_set_srgb_lut: NULL handle");
+    if (!lut) { h->has_srgb_lut = 0; return 0; }
+    AEAJ_CUDA(cudaSetDevice(h->device));
+    AEAJ_CUDA(cudaMemcpy(h->srgb_lut_dev, lut, 256 * sizeof(float), cudaMemcpyHostToDevice));
+    h->has_srgb_lut = 1;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// simple stage entry points
+// ---------------------------------------------------------------------------------------------
+#define ST(stream) ((cudaStream_t)(stream))
+
+extern "C" int aeaj_color_forward(aeaj_handle* h, int space, const float* rgb, float* out, size_t n, void* stream) {
+    AEAJ_REQUIRE(h && rgb && out && space >= 0 && space < 8, "aeaj_color_forward: bad arguments");
+    return launch_color_pixels(h, space, 0, rgb, out, n, ST(stream));
+}
+extern "C" int aeaj_color_inverse(aeaj_handle* h, int space, const float* in, float* rgb, size_t n, void* stream) {
+    AEAJ_REQUIRE(h && rgb && in && space >= 0 && space < 8, "aeaj_color_inverse: bad arguments");
+    return launch_color_pixels(h, space, 1, in, rgb, n, ST(stream));
+}
+extern "C" int aeaj_normalize(aeaj_handle* h, int space, int channel, int inverse, const float* in, float* out, size_t n, void* stream) {
+    AEAJ_REQUIRE(h && in && out && space >= 0 && space < 8 && channel >= 0 && channel < 3, "aeaj_normalize: bad arguments");
+    return launch_normalize(in, out, n, h->colors_host[space].mid[channel], h->colors_host[space].scale[channel], inverse, ST(stream));
+}
+extern "C" int aeaj_downsample_area(aeaj_handle* h, const float* src, int H, int W, float* dst, int dh, int dw, void* stream) {
+    AEAJ_REQUIRE(h && src && dst && H > 0 && W > 0 && dh > 0 && dw > 0 && dh <= H && dw <= W, "aeaj_downsample_area: bad arguments");
+    if (dh == H && dw == W) { AEAJ_CUDA(cudaMemcpyAsync(dst, src, sizeof(float) * (size_t)H * W, cudaMemcpyDeviceToDevice, ST(stream))); return 0; }
+    return launch_area(src, H, W, dst, dh, dw, nullptr, 1, 0, 0, ST(stream));
+}
+extern "C" int aeaj_resize_linear(aeaj_handle* h, const float* src, int sh, int sw, float* dst, int H, int W, void* stream) {
+    AEAJ_REQUIRE(h && src && dst && H > 0 && W > 0 && sh > 0 && sw > 0, "aeaj_resize_linear: bad arguments");
+    return launch_resize_linear(src, sh, sw, dst, H, W, ST(stream));
+}
+extern "C" int aeaj_cast_u8(aeaj_handle* h, const float* layer, uint8_t* out, size_t n, void* stream) {
+    AEAJ_REQUIRE(h && layer && out, "aeaj_cast_u8: bad arguments");
+    return launch_cast_u8(layer, out, n, ST(stream));
+}
+
+// ---- single-plane stage workspace -------------------------------------------------------------
+struct StageWs {
+    PlaneDesc P;
+    uint8_t* u8a; uint8_t* u8b;
+    int* flags; int* ctrl; int* status;
+    ClassEntry* class_lists; int* class_counts;
+    ClassGeom cg;
+    int ntiles;
+    size_t bytes;
+};
+static void stage_ws(void* ws, int h, int w, int mn, int mx, StageWs& S) {
+    memset(&S, 0, sizeof S);
+    Bump b(ws);
+    plane_geom(S.P, h, w, mn, mx);
+    carve_plane_scratch(b, S.P, true, mx > 0);
+    S.u8a = b.take<uint8_t>((size_t)h * w);
+    S.u8b = b.take<uint8_t>((size_t)h * w);
+    int tb = 0;
+    S.ntiles = hysteresis_tiles(&S.P, 1, &tb);
+    S.flags = b.take<int>(2 * (size_t)S.ntiles);
+    S.ctrl = b.take<int>(4);
+    S.status = b.take<int>(2);
+    S.class_counts = b.take<int>(16);
+    if (mx > 0) {
+        class_geom(&S.P, 1, ilog2i(mn), ilog2i(mx), S.cg);
+        S.class_lists = b.take<ClassEntry>((size_t)S.cg.total);
+    }
+    S.bytes = b.used();
+}
+extern "C" size_t aeaj_stage_workspace_bytes(int h, int w, int min_size, int max_size) {
+    if (h <= 0 || w <= 0) return 0;
+    StageWs S;
+    stage_ws(nullptr, h, w, min_size, max_size, S);
+    return S.bytes + 256;
+}
+static int push_stage_plane(aeaj_handle* h, const PlaneDesc& P, cudaStream_t st) {
+    AEAJ_CUDA(cudaMemcpyAsync(h->stage_plane_dev, &P, sizeof(PlaneDesc), cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+static int run_clahe(aeaj_handle* hd, StageWs& S, cudaStream_t st) {
+    AEAJ_CUDA(cudaMemsetAsync(S.P.clahe_hist, 0, 16 * 256 * sizeof(uint32_t), st));
+    int rc = launch_clahe_hist(hd->stage_plane_dev, &S.P, 1, st); if (rc) return rc;
+    return launch_clahe_lut(hd->stage_plane_dev, 1, st);
+}
+
+extern "C" int aeaj_clahe(aeaj_handle* hd, const uint8_t* src, int h, int w, uint8_t* dst, void* ws, void* stream) {
+    AEAJ_REQUIRE(hd && src && dst && ws && h > 0 && w > 0, "aeaj_clahe: bad arguments");
+    StageWs S; stage_ws(ws, h, w, 0, 0, S);
+    S.P.u8a = (uint8_t*)src; S.P.u8b = dst;
+    int rc = push_stage_plane(hd, S.P, ST(stream)); if (rc) return rc;
+    rc = run_clahe(hd, S, ST(stream)); if (rc) return rc;
+    return launch_prefilter(hd->stage_plane_dev, &S.P, 1, 1, 0, ST(stream));
+}
+static int prefilter_only(aeaj_handle* hd, const uint8_t* src, int h, int w, uint8_t* dst, void* ws, void* stream, int stages) {
+    StageWs S; stage_ws(ws, h, w, 0, 0, S);
+    S.P.u8a = (uint8_t*)src; S.P.u8b = dst;
+    int rc = push_stage_plane(hd, S.P, ST(stream)); if (rc) return rc;
+    return launch_prefilter(hd->stage_plane_dev, &S.P, 1, stages, 0, ST(stream));
+}
+extern "C" int aeaj_gauss3(aeaj_handle* hd, const uint8_t* src, int h, int w, uint8_t* dst, void* ws, void* stream) {
+    AEAJ_REQUIRE(hd && src && dst && ws && h > 0 && w > 0, "aeaj_gauss3: bad arguments");
+    return prefilter_only(hd, src, h, w, dst, ws, stream, 2);
+}
+extern "C" int aeaj_bilateral5(aeaj_handle* hd, const uint8_t* src, int h, int w, uint8_t* dst, void* ws, void* stream) {
+    AEAJ_REQUIRE(hd && src && dst && ws && h > 0 && w > 0, "aeaj_bilateral5: bad arguments");
+    return prefilter_only(hd, src, h, w, dst, ws, stream, 4);
+}
+extern "C" int aeaj_percentile_thresholds(aeaj_handle* hd, const uint8_t* src, int h, int w, double* thr, void* ws, void* stream) {
+    AEAJ_REQUIRE(hd && src && thr && ws && h > 0 && w > 0, "aeaj_percentile_thresholds: bad arguments");
+    StageWs S; stage_ws(ws, h, w, 0, 0, S);
+    S.P.thr_d = thr;
+    cudaStream_t st = ST(stream);
+    AEAJ_CUDA(cudaMemsetAsync(S.P.hist, 0, 256 * sizeof(uint32_t), st));
+    int rc = push_stage_plane(hd, S.P, st); if (rc) return rc;
+    rc = launch_hist_u8(src, (size_t)h * w, S.P.hist, st); if (rc) return rc;
+    return launch_thresholds(hd->stage_plane_dev, 1, st);
+}
+
+static int run_nms_hysteresis(aeaj_handle* hd, StageWs& S, uint8_t* edge, cudaStream_t st) {
+    int rc = launch_canny_nms(hd->stage_plane_dev, &S.P, 1, st); if (rc) return rc;
+    rc = launch_hysteresis(hd, hd->stage_plane_dev, 1, hd->stage_tile_base_dev, S.ntiles, S.flags, S.ctrl, S.status, st);
+    if (rc) return rc;
+    if (edge) {
+        AEAJ_CUDA(cudaMemcpyAsync(hd->stage_outs_dev, &edge, sizeof(uint8_t*), cudaMemcpyHostToDevice, st));
+        rc = launch_bitmap_to_u8(hd->stage_plane_dev, &S.P, 1, hd->stage_outs_dev, st);
+    }
+    return rc;
+}
+extern "C" int aeaj_canny_u8(aeaj_handle* hd, const uint8_t* src, int h, int w, const double* thr, uint8_t* edge, void* ws, void* stream) {
+    AEAJ_REQUIRE(hd && src && thr && edge && ws && h > 0 && w > 0, "aeaj_canny_u8: bad arguments");
+    StageWs S; stage_ws(ws, h, w, 0, 0, S);
+    S.P.u8b = (uint8_t*)src;
+    cudaStream_t st = ST(stream);
+    int rc = push_stage_plane(hd, S.P, st); if (rc) return rc;
+    rc = launch_thresholds_from_double(thr, S.P.thr, st); if (rc) return rc;
+    return run_nms_hysteresis(hd, S, edge, st);
+}
+extern "C" int aeaj_canny(aeaj_handle* hd, const float* layer, int h, int w, uint8_t* edge, void* ws, void* stream) {
+    AEAJ_REQUIRE(hd && layer && edge && ws && h > 0 && w > 0, "aeaj_canny: bad arguments");
+    StageWs S; stage_ws(ws, h, w, 0, 0, S);
+    S.P.u8a = S.u8a; S.P.u8b = S.u8b;
+    cudaStream_t st = ST(stream);
+    int rc = push_stage_plane(hd, S.P, st); if (rc) return rc;
+    rc = launch_cast_u8(layer, S.u8a, (size_t)h * w, st); if (rc) return rc;
+    rc = run_clahe(hd, S, st); if (rc) return rc;
+    AEAJ_CUDA(cudaMemsetAsync(S.P.hist, 0, 256 * sizeof(uint32_t), st));
+    rc = launch_prefilter(hd->stage_plane_dev, &S.P, 1, 7, 1, st); if (rc) return rc;
+    rc = launch_thresholds(hd->stage_plane_dev, 1, st); if (rc) return rc;
+    return run_nms_hysteresis(hd, S, edge, st);
+}
+
+extern "C" int aeaj_quadtree_caps(int h, int w, int mn, int mx, int64_t* cl, int64_t* cs, int64_t* cc, int* root) {
+    if (h <= 0 || w <= 0 || mn < 2 || mx < mn || (mn & (mn - 1)) || (mx & (mx - 1))) { aeaj_set_error("aeaj_quadtree_caps: bad arguments"); return AEAJ_EINVAL; }
+    PlaneDesc P; plane_geom(P, h, w, mn, mx);
+    if (cl) *cl = P.cap_leaves; if (cs) *cs = P.cap_states; if (cc) *cc = P.cap_coef; if (root) *root = P.root;
+    return 0;
+}
+static int check_blocks(int h, int w, int mn, int mx) {
+    AEAJ_REQUIRE(mn >= 2 && mx >= mn && !(mn & (mn - 1)) && !(mx & (mx - 1)), "block sizes must be powers of two with 2 <= min <= max");
+    AEAJ_REQUIRE(mx <= 128, "block sizes above 128 are not supported by this build");
+    AEAJ_REQUIRE(aeaj_root_size(h, w) >= mn, "image smaller than the minimum block size");
+    AEAJ_REQUIRE(std::min(mx, aeaj_root_size(h, w)) / mn <= 128, "max/min block ratio above 128 is not supported");
+    return 0;
+}
+extern "C" int aeaj_quadtree(aeaj_handle* hd, const uint8_t* edge, int h, int w, int mn, int mx, int32_t* leaves, uint8_t* states,
+                             int32_t* counts, void* ws, void* stream) {
+    AEAJ_REQUIRE(hd && edge && leaves && states && counts && ws && h > 0 && w > 0, "aeaj_quadtree: bad arguments");
+    int rc = check_blocks(h, w, mn, mx); if (rc) return rc;
+    StageWs S; stage_ws(ws, h, w, mn, mx, S);
+    S.P.leaves = leaves; S.P.states = states; S.P.counts = counts;
+    cudaStream_t st = ST(stream);
+    rc = push_stage_plane(hd, S.P, st); if (rc) return rc;
+    long long off[9]; for (int k = 0; k < 9; k++) off[k] = S.cg.off[k];
+    AEAJ_CUDA(cudaMemcpyAsync(hd->stage_class_off_dev, off, sizeof off, cudaMemcpyHostToDevice, st));
+    AEAJ_CUDA(cudaMemsetAsync(S.class_counts, 0, 16 * sizeof(int), st));
+    rc = launch_u8_to_bitmap(edge, h, w, S.P.strong, st); if (rc) return rc;
+    return launch_quadtree(hd->stage_plane_dev, &S.P, 1, mn, mx, S.class_lists, S.class_counts, hd->stage_class_off_dev, st, nullptr);
+}
+
+static int stage_blocks(aeaj_handle* hd, bool inverse, float* layer, int h, int w, float mid, float scale, const int32_t* leaves,
+                        const int32_t* counts, int mn, int mx, const int32_t* const* qtab, int32_t* coef, void* ws, cudaStream_t st) {
+    int rc = check_blocks(h, w, mn, mx); if (rc) return rc;
+    StageWs S; stage_ws(ws, h, w, mn, mx, S);
+    S.P.layer_f32 = layer; S.P.mid = mid; S.P.scale = scale;
+    S.P.leaves = (int32_t*)leaves; S.P.counts = (int32_t*)counts; S.P.coef = coef;
+    for (int k = 0; k < 9; k++) S.P.qtab[k] = qtab[k];
+    rc = push_stage_plane(hd, S.P, st); if (rc) return rc;
+    long long off[9]; for (int k = 0; k < 9; k++) off[k] = S.cg.off[k];
+    AEAJ_CUDA(cudaMemcpyAsync(hd->stage_class_off_dev, off, sizeof off, cudaMemcpyHostToDevice, st));
+    AEAJ_CUDA(cudaMemsetAsync(S.class_counts, 0, 16 * sizeof(int), st));
+    rc = launch_bucket_leaves(hd->stage_plane_dev, &S.P, 1, S.class_lists, S.class_counts, hd->stage_class_off_dev, st); if (rc) return rc;
+    if (inverse) return launch_dequant_idct(hd, hd->stage_plane_dev, S.class_lists, S.class_counts, S.cg.off, S.cg.cap, ilog2i(mn), ilog2i(mx), st, nullptr);
+    return launch_dct_quant(hd, hd->stage_plane_dev, S.class_lists, S.class_counts, S.cg.off, S.cg.cap, ilog2i(mn), ilog2i(mx), st, nullptr);
+}
+extern "C" int aeaj_dct_quant(aeaj_handle* hd, const float* layer, int h, int w, float mid, float scale, const int32_t* leaves,
+                              const int32_t* counts, int mn, int mx, const int32_t* const* qtab, int32_t* coef, void* ws, void* stream) {
+    AEAJ_REQUIRE(hd && layer && leaves && counts && qtab && coef && ws && h > 0 && w > 0, "aeaj_dct_quant: bad arguments");
+    return stage_blocks(hd, false, (float*)layer, h, w, mid, scale, leaves, counts, mn, mx, qtab, coef, ws, ST(stream));
+}
+extern "C" int aeaj_dequant_idct(aeaj_handle* hd, const int32_t* coef, const int32_t* leaves, const int32_t* counts, int mn, int mx,
+                                 const int32_t* const* qtab, int h, int w, float mid, float scale, float* layer, void* ws, void* stream) {
+    AEAJ_REQUIRE(hd && layer && leaves && counts && qtab && coef && ws && h > 0 && w > 0, "aeaj_dequant_idct: bad arguments");
+    return stage_blocks(hd, true, layer, h, w, mid, scale, leaves, counts, mn, mx, qtab, (int32_t*)coef, ws, ST(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan: geometry of a batch of same-shape images + q tables
+// ---------------------------------------------------------------------------------------------
+struct aeaj_plan {
+    aeaj_handle* h;
+    aeaj_plan_info info;
+    int nplanes, lg_min, lg_max;
+    std::vector<PlaneDesc> planes;       // host copy, index b*3 + l
+    PlaneDesc* planes_dev;
+    int* tile_base_dev; int ntiles;
+    long long* class_off_dev;
+    ClassGeom cg;
+    int32_t* qtab_dev; size_t qtab_entries;
+    const int32_t* qtab_ptr[2][9];       // device pointers per table (0 luma, 1 chroma) and log2 size
+    uint8_t** outs_dev;                  // tap pointers [nplanes]
+    int last_launches;
+    bool need_full_chroma;
+};
+
+static int sub_ratio(int space, int& rh, int& rw) {
+    switch (space) {
+        case AEAJ_ICACB: case AEAJ_ICTCP: rh = 1; rw = 4; return 0;
+        case AEAJ_JZAZBZ: case AEAJ_OKLAB: case AEAJ_YCBCR: case AEAJ_YCOCG: case AEAJ_YCOCG_R: rh = 2; rw = 2; return 0;
+    }
+    aeaj_set_error("colour space %d has no compression settings (jpeg.py:62-147)", space);
+    return AEAJ_EINVAL;
+}
+
+// carve the plan workspace; with ws == nullptr only sizes are computed
+static size_t plan_carve(aeaj_plan* p, void* ws) {
+    Bump b(ws);
+    const int B = p->info.batch;
+    for (int l = 0; l < 3; l++) {
+        const size_t n = (size_t)p->info.layer_h[l] * p->info.layer_w[l];
+        float* lay = b.take<float>(n * B);
+        uint8_t* a = b.take<uint8_t>(n * B);
+        uint8_t* c = b.take<uint8_t>(n * B);
+        for (int i = 0; i < B; i++) {
+            PlaneDesc& P = p->planes[i * 3 + l];
+            P.layer_f32 = lay ? lay + n * i : nullptr; P.u8a = a ? a + n * i : nullptr; P.u8b = c ? c + n * i : nullptr;
+        }
+    }
+    // accumulators of all planes are contiguous so that one memset clears them
+    const int NP = p->nplanes;
+    uint32_t* ch = b.take<uint32_t>((size_t)NP * 16 * 256);
+    uint32_t* hi = b.take<uint32_t>((size_t)NP * 256);
+    uint8_t* lut = b.take<uint8_t>((size_t)NP * 16 * 256);
+    int* thr = b.take<int>((size_t)NP * 2);
+    double* thrd = b.take<double>((size_t)NP * 2);
+    for (int i = 0; i < NP; i++) {
+        PlaneDesc& P = p->planes[i];
+        P.clahe_hist = ch ? ch + (size_t)i * 16 * 256 : nullptr; P.hist = hi ? hi + (size_t)i * 256 : nullptr;
+        P.clahe_lut = lut ? lut + (size_t)i * 16 * 256 : nullptr; P.thr = thr ? thr + 2 * i : nullptr; P.thr_d = thrd ? thrd + 2 * i : nullptr;
+        P.strong = b.take<uint32_t>((size_t)P.h * P.wpr);
+        P.weak = b.take<uint32_t>((size_t)P.h * P.wpr);
+        size_t ntb = (size_t)P.ntx * P.nty;
+        P.tb_tot = b.take<int2>(ntb); P.tb_coef = b.take<int>(ntb); P.tb_base = b.take<int4>(ntb);
+    }
+    return b.off;
+}
+
+struct PlanAux { float* full_c1; float* full_c2; int* flags; int* ctrl; int* class_counts; ClassEntry* class_lists; };
+static size_t plan_carve_aux(aeaj_plan* p, void* ws, size_t start, PlanAux& A) {
+    Bump b(ws); b.off = start;
+    const size_t HW = (size_t)p->info.height * p->info.width;
+    if (p->need_full_chroma) { A.full_c1 = b.take<float>(HW * p->info.batch); A.full_c2 = b.take<float>(HW * p->info.batch); }
+    else { A.full_c1 = A.full_c2 = nullptr; }
+    A.flags = b.take<int>(2 * (size_t)p->ntiles);
+    A.ctrl = b.take<int>(4);
+    A.class_counts = b.take<int>(16);
+    A.class_lists = b.take<ClassEntry>((size_t)p->cg.total);
+    return b.used();
+}
+
+extern "C" int aeaj_plan_create(aeaj_handle* h, int batch, int height, int width, int space, int bmin, int bmax, aeaj_plan** out) {
+    AEAJ_REQUIRE(h && out && batch > 0 && height > 0 && width > 0, "aeaj_plan_create: bad arguments");
+    int rh, rw;
+    int rc = sub_ratio(space, rh, rw); if (rc) return rc;
+    AEAJ_REQUIRE(height / rh > 0 && width / rw > 0, "image too small for the chroma subsampling of this colour space");
+    AEAJ_CUDA(cudaSetDevice(h->device));
+    aeaj_plan* p = new aeaj_plan();
+    p->h = h;
+    memset(&p->info, 0, sizeof p->info);
+    p->info.batch = batch; p->info.height = height; p->info.width = width; p->info.space = space;
+    p->info.block_min = bmin; p->info.block_max = bmax;
+    p->nplanes = batch * 3;
+    p->planes.resize(p->nplanes);
+    for (int l = 0; l < 3; l++) {
+        int lh = l ? height / rh : height, lw = l ? width / rw : width;     // jpeg.py:676-686
+        rc = check_blocks(lh, lw, bmin, bmax);
+        if (rc) { delete p; return rc; }
+        p->info.layer_h[l] = lh; p->info.layer_w[l] = lw;
+        for (int i = 0; i < batch; i++) {
+            PlaneDesc& P = p->planes[i * 3 + l];
+            memset(&P, 0, sizeof P);
+            plane_geom(P, lh, lw, bmin, bmax);
+            P.layer = l;
+            P.mid = h->colors_host[space].mid[l]; P.scale = h->colors_host[space].scale[l];
+        }
+        const PlaneDesc& P0 = p->planes[l];
+        p->info.root[l] = P0.root; p->info.cap_leaves[l] = P0.cap_leaves; p->info.cap_states[l] = P0.cap_states; p->info.cap_coef[l] = P0.cap_coef;
+        AEAJ_REQUIRE(P0.cap_coef < (int64_t)1 << 31, "layer too large for int32 coefficient offsets");
+    }
+    p->lg_min = ilog2i(bmin); p->lg_max = ilog2i(bmax);
+    const int ch = p->info.layer_h[1], cw = p->info.layer_w[1];
+    p->need_full_chroma = !((ch * 2 == height && cw * 2 == width && (width % 4) == 0) || (ch == height && cw * 4 == width));
+    class_geom(p->planes.data(), p->nplanes, p->lg_min, p->lg_max, p->cg);
+    std::vector<int> tile_base(p->nplanes);
+    p->ntiles = hysteresis_tiles(p->planes.data(), p->nplanes, tile_base.data());
+    size_t s1 = plan_carve(p, nullptr);
+    PlanAux A;
+    p->info.workspace_bytes = (int64_t)plan_carve_aux(p, nullptr, s1, A) + 256;
+    AEAJ_CUDA(cudaMalloc(&p->planes_dev, sizeof(PlaneDesc) * p->nplanes));
+    AEAJ_CUDA(cudaMalloc(&p->tile_base_dev, sizeof(int) * p->nplanes));
+    AEAJ_CUDA(cudaMalloc(&p->class_off_dev, sizeof(long long) * 9));
+    AEAJ_CUDA(cudaMalloc(&p->outs_dev, sizeof(uint8_t*) * p->nplanes));
+    AEAJ_CUDA(cudaMemcpy(p->tile_base_dev, tile_base.data(), sizeof(int) * p->nplanes, cudaMemcpyHostToDevice));
+    long long off[9]; for (int k = 0; k < 9; k++) off[k] = p->cg.off[k];
+    AEAJ_CUDA(cudaMemcpy(p->class_off_dev, off, sizeof off, cudaMemcpyHostToDevice));
+    p->qtab_dev = nullptr; p->qtab_entries = 0;
+    memset(p->qtab_ptr, 0, sizeof p->qtab_ptr);
+    p->last_launches = 0;
+    *out = p;
+    return 0;
+}
+
+extern "C" int aeaj_plan_destroy(aeaj_plan* p) {
+    if (!p) return 0;
+    cudaSetDevice(p->h->device);
+    cudaFree(p->planes_dev); cudaFree(p->tile_base_dev); cudaFree(p->class_off_dev); cudaFree(p->outs_dev); cudaFree(p->qtab_dev);
+    delete p;
+    return 0;
+}
+extern "C" int aeaj_plan_get_info(const aeaj_plan* p, aeaj_plan_info* info) {
+    AEAJ_REQUIRE(p && info, "aeaj_plan_get_info: bad arguments");
+    *info = p->info;
+    return 0;
+}
+extern "C" int aeaj_plan_last_launches(const aeaj_plan* p) { return p ? p->last_launches : 0; }
+
+extern "C" int aeaj_plan_set_qtables(aeaj_plan* p, const int32_t* tables, size_t n_entries, void* stream) {
+    AEAJ_REQUIRE(p && tables, "aeaj_plan_set_qtables: bad arguments");
+    size_t per = 0;
+    for (int k = p->lg_min; k <= p->lg_max; k++) per += (size_t)1 << (2 * k);
+    AEAJ_REQUIRE(n_entries == 2 * per, "aeaj_plan_set_qtables: expected [luma sizes...][chroma sizes...] entries");
+    AEAJ_CUDA(cudaSetDevice(p->h->device));
+    if (!p->qtab_dev) AEAJ_CUDA(cudaMalloc(&p->qtab_dev, sizeof(int32_t) * n_entries));
+    p->qtab_entries = n_entries;
+    AEAJ_CUDA(cudaMemcpyAsync(p->qtab_dev, tables, sizeof(int32_t) * n_entries, cudaMemcpyHostToDevice, ST(stream)));
+    size_t o = 0;
+    for (int t = 0; t < 2; t++)
+        for (int k = p->lg_min; k <= p->lg_max; k++) { p->qtab_ptr[t][k] = p->qtab_dev + o; o += (size_t)1 << (2 * k); }
+    for (int i = 0; i < p->nplanes; i++)
+        for (int k = 0; k < 9; k++) p->planes[i].qtab[k] = p->qtab_ptr[p->planes[i].layer ? 1 : 0][k];
+    return 0;
+}
+
+static int plan_push_planes(aeaj_plan* p, cudaStream_t st) {
+    AEAJ_CUDA(cudaMemcpyAsync(p->planes_dev, p->planes.data(), sizeof(PlaneDesc) * p->nplanes, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+extern "C" int aeaj_encode(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, void* stream) {
+    AEAJ_REQUIRE(p && io && workspace && io->rgb && io->counts, "aeaj_encode: bad arguments");
+    AEAJ_REQUIRE(p->qtab_dev, "aeaj_encode: quantisation tables not set (aeaj_plan_set_qtables)");
+    aeaj_handle* h = p->h;
+    cudaStream_t st = ST(stream);
+    const int B = p->info.batch, NP = p->nplanes;
+    int launches = 0;
+    size_t s1 = plan_carve(p, workspace);
+    PlanAux A;
+    plan_carve_aux(p, workspace, s1, A);
+    std::vector<uint8_t*> outs(NP, nullptr);
+    bool any_tap_edge = false;
+    for (int l = 0; l < 3; l++) {
+        AEAJ_REQUIRE(io->coef[l] && io->leaves[l] && io->states[l], "aeaj_encode: NULL output buffer");
+        for (int i = 0; i < B; i++) {
+            PlaneDesc& P = p->planes[i * 3 + l];
+            P.coef = io->coef[l] + (size_t)i * p->info.cap_coef[l];
+            P.leaves = io->leaves[l] + (size_t)i * p->info.cap_leaves[l] * 4;
+            P.states = io->states[l] + (size_t)i * p->info.cap_states[l];
+            P.counts = io->counts + ((size_t)i * 3 + l) * 4;
+            if (io->tap_edges[l]) { outs[i * 3 + l] = io->tap_edges[l] + (size_t)i * P.h * P.w; any_tap_edge = true; }
+        }
+    }
+    int rc = plan_push_planes(p, st); if (rc) return rc;
+    // accumulators
+    AEAJ_CUDA(cudaMemsetAsync(p->planes[0].clahe_hist, 0, (size_t)NP * 16 * 256 * sizeof(uint32_t), st));
+    AEAJ_CUDA(cudaMemsetAsync(p->planes[0].hist, 0, (size_t)NP * 256 * sizeof(uint32_t), st));
+    AEAJ_CUDA(cudaMemsetAsync(A.class_counts, 0, 16 * sizeof(int), st));
+    // colour + chroma subsampling + u8 cast
+    rc = launch_color_forward_planar(h, p->info.space, io->rgb, B, p->info.height, p->info.width, p->planes_dev, p->planes.data(),
+                                     A.full_c1, A.full_c2, st, &launches);
+    if (rc) return rc;
+    // Canny pipeline on all planes of the batch at once
+    rc = launch_clahe_hist(p->planes_dev, p->planes.data(), NP, st); if (rc) return rc;
+    rc = launch_clahe_lut(p->planes_dev, NP, st); if (rc) return rc;
+    rc = launch_prefilter(p->planes_dev, p->planes.data(), NP, 7, 1, st); if (rc) return rc;
+    rc = launch_thresholds(p->planes_dev, NP, st); if (rc) return rc;
+    rc = launch_canny_nms(p->planes_dev, p->planes.data(), NP, st); if (rc) return rc;
+    rc = launch_hysteresis(h, p->planes_dev, NP, p->tile_base_dev, p->ntiles, A.flags, A.ctrl, io->status, st); if (rc) return rc;
+    launches += 6;
+    if (any_tap_edge) {
+        AEAJ_CUDA(cudaMemcpyAsync(p->outs_dev, outs.data(), sizeof(uint8_t*) * NP, cudaMemcpyHostToDevice, st));
+        rc = launch_bitmap_to_u8(p->planes_dev, p->planes.data(), NP, p->outs_dev, st); if (rc) return rc;
+        launches++;
+    }
+    for (int l = 0; l < 3; l++)
+        if (io->tap_layers[l])
+            AEAJ_CUDA(cudaMemcpyAsync(io->tap_layers[l], p->planes[l].layer_f32, sizeof(float) * (size_t)B * p->info.layer_h[l] * p->info.layer_w[l],
+                                      cudaMemcpyDeviceToDevice, st));
+    // quadtree + DCT/quantise
+    rc = launch_quadtree(p->planes_dev, p->planes.data(), NP, p->info.block_min, p->info.block_max, A.class_lists, A.class_counts,
+                         p->class_off_dev, st, &launches);
+    if (rc) return rc;
+    rc = launch_dct_quant(h, p->planes_dev, A.class_lists, A.class_counts, p->cg.off, p->cg.cap, p->lg_min, p->lg_max, st, &launches);
+    if (rc) return rc;
+    p->last_launches = launches;
+    return 0;
+}
+
+extern "C" int aeaj_decode(aeaj_plan* p, const aeaj_decode_io* io, void* workspace, void* stream) {
+    AEAJ_REQUIRE(p && io && workspace && io->rgb && io->counts, "aeaj_decode: bad arguments");
+    AEAJ_REQUIRE(p->qtab_dev, "aeaj_decode: quantisation tables not set (aeaj_plan_set_qtables)");
+    aeaj_handle* h = p->h;
+    cudaStream_t st = ST(stream);
+    const int B = p->info.batch, NP = p->nplanes;
+    int launches = 0;
+    size_t s1 = plan_carve(p, workspace);
+    PlanAux A;
+    plan_carve_aux(p, workspace, s1, A);
+    for (int l = 0; l < 3; l++) {
+        AEAJ_REQUIRE(io->coef[l] && io->leaves[l], "aeaj_decode: NULL input buffer");
+        for (int i = 0; i < B; i++) {
+            PlaneDesc& P = p->planes[i * 3 + l];
+            P.coef = (int32_t*)io->coef[l] + (size_t)i * p->info.cap_coef[l];
+            P.leaves = (int32_t*)io->leaves[l] + (size_t)i * p->info.cap_leaves[l] * 4;
+            P.counts = (int32_t*)io->counts + ((size_t)i * 3 + l) * 4;
+        }
+    }
+    int rc = plan_push_planes(p, st); if (rc) return rc;
+    AEAJ_CUDA(cudaMemsetAsync(A.class_counts, 0, 16 * sizeof(int), st));
+    rc = launch_bucket_leaves(p->planes_dev, p->planes.data(), NP, A.class_lists, A.class_counts, p->class_off_dev, st); if (rc) return rc;
+    launches++;
+    rc = launch_dequant_idct(h, p->planes_dev, A.class_lists, A.class_counts, p->cg.off, p->cg.cap, p->lg_min, p->lg_max, st, &launches);
+    if (rc) return rc;
+    for (int l = 0; l < 3; l++)
+        if (io->tap_layers[l])
+            AEAJ_CUDA(cudaMemcpyAsync(io->tap_layers[l], p->planes[l].layer_f32, sizeof(float) * (size_t)B * p->info.layer_h[l] * p->info.layer_w[l],
+                                      cudaMemcpyDeviceToDevice, st));
+    rc = launch_upsample_color_inverse(h, p->info.space, p->planes.data(), B, p->info.height, p->info.width, io->rgb, st); if (rc) return rc;
+    launches++;
+    p->last_launches = launches;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side helpers (entropy-coding side; CPU only)
+// ---------------------------------------------------------------------------------------------
+extern "C" int aeaj_states_to_leaves_host(const uint8_t* states, int n_states, int root, int h, int w, int32_t* leaves,
+                                          int* n_leaves, int64_t* n_coef) {
+    AEAJ_REQUIRE(states && leaves && n_leaves && n_states >= 0 && root > 0, "aeaj_states_to_leaves_host: bad arguments");
+    (void)h; (void)w;
+    struct Node { int x, y, s; };
+    std::vector<Node> st;
+    st.push_back({0, 0, root});
+    int nl = 0, si = 0;
+    int64_t off = 0;
+    while (!st.empty() && si < n_states) {
+        Node nd = st.back(); st.pop_back();
+        int s = states[si++];
+        if (s == 0) {
+            leaves[4 * nl] = nd.x; leaves[4 * nl + 1] = nd.y; leaves[4 * nl + 2] = nd.s; leaves[4 * nl + 3] = (int32_t)off;
+            off += (int64_t)nd.s * nd.s; nl++;
+        } else if (s == 1) {
+            int hs = nd.s / 2;
+            st.push_back({nd.x + hs, nd.y + hs, hs});
+            st.push_back({nd.x, nd.y + hs, hs});
+            st.push_back({nd.x + hs, nd.y, hs});
+            st.push_back({nd.x, nd.y, hs});
+        }
+    }
+    *n_leaves = nl;
+    if (n_coef) *n_coef = off;
+    return 0;
+}
+extern "C" int aeaj_pack_states_host(const uint8_t* states, int n, uint8_t* packed) {
+    AEAJ_REQUIRE(states && packed && n >= 0, "aeaj_pack_states_host: bad arguments");
+    for (int i = 0; i < (n + 3) / 4; i++) {
+        unsigned v = 0;
+        for (int k = 0; k < 4; k++) { int idx = 4 * i + k; v = (v << 2) | (idx < n ? (states[idx] & 3u) : 0u); }
+        packed[i] = (uint8_t)v;
+    }
+    return 0;
+}

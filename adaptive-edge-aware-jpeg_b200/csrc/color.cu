@@ -1,0 +1,505 @@
+// color.cu -- colour transforms (src/color/*.py), chroma resampling (jpeg.py:323-354), u8 cast
+// (edge_detection.py:70) for sm_100a.  HBM-bound elementwise work: one fused, coalesced,
+// float4-vectorised kernel per direction.
+//
+// Arithmetic contract (validated against the reference by the CPU oracle):
+//   * np.dot((N,3),M.T) == fma(x2,m2, fma(x1,m1, x0*m0)) in f32  -> dot3()
+//   * sRGB transfer functions and PQ are evaluated in f64 and stored as f32 (numba, Python-float consts)
+//   * INTER_AREA 2x2: ((a+b)+(c+d))*0.25f ; 1x4: (((a+b)+c)+d)*0.25f ; other ratios: OpenCV's table path
+//   * INTER_LINEAR: half-pixel centres, edge clamp, horizontal then vertical, a*(1-t)+b*t, no fma
+// The file is compiled with -fmad=false; every fused multiply-add below is explicit.
+#include "aeaj_internal.cuh"
+
+namespace {
+
+__device__ __forceinline__ void dot3(const float* m, float x0, float x1, float x2, float& o0, float& o1, float& o2) {
+    o0 = __fmaf_rn(x2, m[2], __fmaf_rn(x1, m[1], __fmul_rn(x0, m[0])));
+    o1 = __fmaf_rn(x2, m[5], __fmaf_rn(x1, m[4], __fmul_rn(x0, m[3])));
+    o2 = __fmaf_rn(x2, m[8], __fmaf_rn(x1, m[7], __fmul_rn(x0, m[6])));
+}
+
+__constant__ float c_rgb2xyz[9] = {0.4124564f, 0.3575761f, 0.1804375f, 0.2126729f, 0.7151522f, 0.0721750f,
+                                   0.0193339f, 0.1191920f, 0.9503041f};               // xyz.py:27-32
+__constant__ float c_xyz2rgb[9] = {3.2404542f, -1.5371385f, -0.4985314f, -0.9692660f, 1.8760108f, 0.0415560f,
+                                   0.0556434f, -0.2040259f, 1.0572252f};              // xyz.py:35-40
+
+// common.py:34-60.  lut (shared memory, 256 entries computed by the host libm) is exact for the
+// 8-bit-sourced inputs Image.load produces (image.py:80); anything else takes the f64 path.
+__device__ __forceinline__ float srgb_to_linear(float v, const float* lut) {
+    if (lut) {
+        float k = rintf(__fmul_rn(v, 255.0f));
+        if (k >= 0.0f && k <= 255.0f && __fdiv_rn(k, 255.0f) == v) return lut[(int)k];
+    }
+    double d = (double)v;
+    if (d <= 0.04045) return (float)(d / 12.92);
+    return (float)pow((d + 0.055) / 1.055, 2.4);
+}
+// common.py:62-92.  NaN -> 1.0 exactly like the reference's fastmath select chain (class T-NAN).
+__device__ __forceinline__ float linear_to_srgb(float v) {
+    double d = (double)v, r;
+    if (d <= 0.0031308) r = d * 12.92;
+    else r = 1.055 * pow(d, 1.0 / 2.4) - 0.055;
+    float f = (float)r;
+    f = (f < 1.0f) ? f : 1.0f;
+    f = (f > 0.0f) ? f : 0.0f;
+    return f;
+}
+// common.py:131-159
+__device__ __forceinline__ double pq_inv_eotf(double c, double m2) {
+    const double c1 = 3424.0 / 4096.0, c2 = 2413.0 / 128.0, c3 = 2392.0 / 128.0, m1 = 2610.0 / 16384.0;
+    double t = pow(c / 10000.0, m1);
+    return pow((c1 + c2 * t) / (1.0 + c3 * t), m2);
+}
+// common.py:94-129
+__device__ __forceinline__ double pq_eotf(double c, double m2) {
+    const double c1 = 3424.0 / 4096.0, c2 = 2413.0 / 128.0, c3 = 2392.0 / 128.0, m1 = 2610.0 / 16384.0;
+    double t = pow(c, 1.0 / m2);
+    double num = t - c1, den = c2 - c3 * t;
+    if (num < 0.0) num = 0.0;
+    if (den <= 0.0) den = 1e-12;
+    return 10000.0 * pow(num / den, 1.0 / m1);
+}
+#define PQ_M2 (2523.0 / 32.0)
+#define JZ_P (1.7 * 2523.0 / 32.0)
+#define JZ_B 1.15
+#define JZ_G 0.66
+#define JZ_D (-0.56)
+#define JZ_D0 1.6295499532821566e-11
+
+// no-contraction f64 helpers (nvcc would otherwise be free to fuse under -fmad=true; we compile with
+// -fmad=false, these just make the intent explicit)
+__device__ __forceinline__ double mul3add(double a0, double b0, double a1, double b1, double a2, double b2) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(a0, b0), __dmul_rn(a1, b1)), __dmul_rn(a2, b2));
+}
+
+template <int SPACE>
+__device__ __forceinline__ void color_fwd(const ColorConsts& C, const float* lut, float r, float g, float b,
+                                          float& o0, float& o1, float& o2) {
+    if (SPACE <= AEAJ_YCOCG_R) { dot3(C.fwd1, r, g, b, o0, o1, o2); return; }
+    float lr = srgb_to_linear(r, lut), lg = srgb_to_linear(g, lut), lb = srgb_to_linear(b, lut);
+    float X, Y, Z;
+    dot3(c_rgb2xyz, lr, lg, lb, X, Y, Z);
+    if (SPACE == AEAJ_XYZ) { o0 = X; o1 = Y; o2 = Z; return; }
+    if (SPACE == AEAJ_OKLAB) {                                   // oklab.py:71-75
+        float l, m, s;
+        dot3(C.fwd1, X, Y, Z, l, m, s);
+        const double e = (double)(float)(1.0 / 3.0);             // numpy casts the exponent to float32
+        float lp = (float)pow((double)l, e), mp = (float)pow((double)m, e), sp = (float)pow((double)s, e);
+        dot3(C.fwd2, lp, mp, sp, o0, o1, o2);
+    } else if (SPACE == AEAJ_ICACB || SPACE == AEAJ_ICTCP) {     // ictcp.py:47-79
+        float l, m, s;
+        dot3(C.fwd1, X, Y, Z, l, m, s);
+        double lp = pq_inv_eotf((double)l, PQ_M2), mp = pq_inv_eotf((double)m, PQ_M2), sp = pq_inv_eotf((double)s, PQ_M2);
+        const float* q = C.fwd2;
+        o0 = (float)mul3add((double)q[0], lp, (double)q[1], mp, (double)q[2], sp);
+        o1 = (float)mul3add((double)q[3], lp, (double)q[4], mp, (double)q[5], sp);
+        o2 = (float)mul3add((double)q[6], lp, (double)q[7], mp, (double)q[8], sp);
+    } else {                                                     // JzAzBz: jzazbz.py:57-97
+        double Xd = (double)X, Yd = (double)Y;
+        double Xp = __dsub_rn(__dmul_rn(JZ_B, Xd), __dmul_rn(JZ_B - 1.0, (double)Z));
+        double Yp = __dsub_rn(__dmul_rn(JZ_G, Yd), __dmul_rn(JZ_G - 1.0, Xd));
+        double lp[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float* m = C.fwd1 + 3 * k;
+            float mz = __fmul_rn(m[2], Z);                       // Z' stays f32 (jzazbz.py:63)
+            double L = __dadd_rn(__dadd_rn(__dmul_rn((double)m[0], Xp), __dmul_rn((double)m[1], Yp)), (double)mz);
+            lp[k] = pq_inv_eotf(L, JZ_P);
+        }
+        const float* q = C.fwd2;
+        double Iz = mul3add((double)q[0], lp[0], (double)q[1], lp[1], (double)q[2], lp[2]);
+        double Az = mul3add((double)q[3], lp[0], (double)q[4], lp[1], (double)q[5], lp[2]);
+        double Bz = mul3add((double)q[6], lp[0], (double)q[7], lp[1], (double)q[8], lp[2]);
+        double Jz = __dsub_rn(__ddiv_rn(__dmul_rn(1.0 + JZ_D, Iz), __dadd_rn(1.0, __dmul_rn(JZ_D, Iz))), JZ_D0);
+        o0 = (float)Jz; o1 = (float)Az; o2 = (float)Bz;
+    }
+}
+
+template <int SPACE>
+__device__ __forceinline__ void color_inv(const ColorConsts& C, float a, float b, float c, float& r, float& g, float& bl) {
+    if (SPACE <= AEAJ_YCOCG_R) {                                 // ycbcr.py:79-82: dot then np.clip
+        float t0, t1, t2;
+        dot3(C.inv1, a, b, c, t0, t1, t2);
+        r = fminf(fmaxf(t0, 0.0f), 1.0f); g = fminf(fmaxf(t1, 0.0f), 1.0f); bl = fminf(fmaxf(t2, 0.0f), 1.0f);
+        return;
+    }
+    float X, Y, Z;
+    if (SPACE == AEAJ_XYZ) { X = a; Y = b; Z = c; }
+    else if (SPACE == AEAJ_OKLAB) {                              // oklab.py:93-96
+        float lp, mp, sp;
+        dot3(C.inv1, a, b, c, lp, mp, sp);
+        float l = (float)pow((double)lp, 3.0), m = (float)pow((double)mp, 3.0), s = (float)pow((double)sp, 3.0);
+        dot3(C.inv2, l, m, s, X, Y, Z);
+    } else if (SPACE == AEAJ_ICACB || SPACE == AEAJ_ICTCP) {     // ictcp.py:103-137
+        float lp, mp, sp;
+        dot3(C.inv1, a, b, c, lp, mp, sp);
+        double l = pq_eotf((double)lp, PQ_M2), m = pq_eotf((double)mp, PQ_M2), s = pq_eotf((double)sp, PQ_M2);
+        const float* q = C.inv2;
+        X = (float)mul3add((double)q[0], l, (double)q[1], m, (double)q[2], s);
+        Y = (float)mul3add((double)q[3], l, (double)q[4], m, (double)q[5], s);
+        Z = (float)mul3add((double)q[6], l, (double)q[7], m, (double)q[8], s);
+    } else {                                                     // jzazbz.py:131-171
+        double jd = __dadd_rn((double)a, JZ_D0);
+        double Iz = __ddiv_rn(jd, __dsub_rn(1.0 + JZ_D, __dmul_rn(JZ_D, jd)));
+        double l[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float* m = C.inv1 + 3 * k;
+            float ta = __fmul_rn(m[1], b), tb = __fmul_rn(m[2], c);
+            double lp = __dadd_rn(__dadd_rn(__dmul_rn((double)m[0], Iz), (double)ta), (double)tb);
+            l[k] = pq_eotf(lp, JZ_P);
+        }
+        const float* q = C.inv2;
+        double Xp = mul3add((double)q[0], l[0], (double)q[1], l[1], (double)q[2], l[2]);
+        double Yp = mul3add((double)q[3], l[0], (double)q[4], l[1], (double)q[5], l[2]);
+        double Zp = mul3add((double)q[6], l[0], (double)q[7], l[1], (double)q[8], l[2]);
+        double Xd = __ddiv_rn(__dadd_rn(Xp, __dmul_rn(JZ_B - 1.0, Zp)), JZ_B);
+        double Yd = __ddiv_rn(__dadd_rn(Yp, __dmul_rn(JZ_G - 1.0, Xd)), JZ_G);
+        X = (float)Xd; Y = (float)Yd; Z = (float)Zp;
+    }
+    float lr, lg, lb;
+    dot3(c_xyz2rgb, X, Y, Z, lr, lg, lb);
+    r = linear_to_srgb(lr); g = linear_to_srgb(lg); bl = linear_to_srgb(lb);
+}
+
+__device__ __forceinline__ uint8_t cast_u8(float v) {            // (img*255).astype(np.uint8)
+    return (uint8_t)(__float2int_rz(__fmul_rn(v, 255.0f)) & 0xff);
+}
+
+__device__ __forceinline__ const float* load_lut(const float* lut_g, float* lut_s) {
+    if (!lut_g) return nullptr;
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 256; i += blockDim.x * blockDim.y) lut_s[i] = lut_g[i];
+    __syncthreads();
+    return lut_s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// (N,3) -> (N,3) pixel kernels: the `convert()` drop-in (conversion.py:95-124)
+// ---------------------------------------------------------------------------------------------
+template <int SPACE, bool INVERSE>
+__global__ void __launch_bounds__(256) k_color_pixels(const __grid_constant__ ColorConsts C, const float* __restrict__ lut_g,
+                                                      const float* __restrict__ in, float* __restrict__ out, size_t n) {
+    __shared__ float lut_s[256];
+    const float* lut = (SPACE > AEAJ_YCOCG_R && !INVERSE) ? load_lut(lut_g, lut_s) : nullptr;
+    // 4 pixels (12 floats = 3 x float4) per thread when possible
+    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t nq = n / 4;
+    for (; q < nq; q += (size_t)gridDim.x * blockDim.x) {
+        const float4* p = reinterpret_cast<const float4*>(in) + q * 3;
+        float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        float x[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w}, y[12];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (INVERSE) color_inv<SPACE>(C, x[3 * k], x[3 * k + 1], x[3 * k + 2], y[3 * k], y[3 * k + 1], y[3 * k + 2]);
+            else color_fwd<SPACE>(C, lut, x[3 * k], x[3 * k + 1], x[3 * k + 2], y[3 * k], y[3 * k + 1], y[3 * k + 2]);
+        }
+        float4* o = reinterpret_cast<float4*>(out) + q * 3;
+        o[0] = make_float4(y[0], y[1], y[2], y[3]); o[1] = make_float4(y[4], y[5], y[6], y[7]); o[2] = make_float4(y[8], y[9], y[10], y[11]);
+    }
+    // tail
+    size_t t = nq * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) {
+        float y0, y1, y2;
+        if (INVERSE) color_inv<SPACE>(C, in[3 * t], in[3 * t + 1], in[3 * t + 2], y0, y1, y2);
+        else color_fwd<SPACE>(C, lut, in[3 * t], in[3 * t + 1], in[3 * t + 2], y0, y1, y2);
+        out[3 * t] = y0; out[3 * t + 1] = y1; out[3 * t + 2] = y2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused forward: RGB (HWC) -> planar layers (+ chroma INTER_AREA) + u8 cast planes
+// MODE 0: chroma 2x2, needs H%2==0, W%4==0; thread = 4 px x 2 rows
+// MODE 1: chroma 1x4, needs W%4==0;          thread = 4 px x 1 row
+// MODE 2: anything: thread = 1 px, chroma written full-res to scratch (area kernel follows)
+// ---------------------------------------------------------------------------------------------
+struct FwdOut {
+    float* y; float* c1; float* c2;          // per-image strides below
+    uint8_t* y8; uint8_t* c18; uint8_t* c28;
+    size_t sy, sc;                           // elements per image for luma / chroma outputs
+};
+
+template <int SPACE, int MODE>
+__global__ void __launch_bounds__(256) k_color_forward_planar(const __grid_constant__ ColorConsts C, const float* __restrict__ lut_g,
+                                                              const float* __restrict__ rgb, int H, int W, FwdOut o) {
+    __shared__ float lut_s[256];
+    const float* lut = (SPACE > AEAJ_YCOCG_R) ? load_lut(lut_g, lut_s) : nullptr;
+    const int b = blockIdx.z;
+    const float* img = rgb + (size_t)b * H * W * 3;
+    if (MODE == 2) {
+        int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+        if (x >= W || y >= H) return;
+        size_t i = (size_t)y * W + x;
+        float v0, v1, v2;
+        color_fwd<SPACE>(C, lut, img[3 * i], img[3 * i + 1], img[3 * i + 2], v0, v1, v2);
+        o.y[b * o.sy + i] = v0; o.y8[b * o.sy + i] = cast_u8(v0);
+        o.c1[b * o.sc + i] = v1; o.c2[b * o.sc + i] = v2;     // full-res scratch (sc == H*W here)
+        return;
+    }
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int ROWS = (MODE == 0) ? 2 : 1;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * ROWS;
+    if (x0 >= W || y0 >= H) return;
+    float c1v[2][4], c2v[2][4];
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+        const float4* p = reinterpret_cast<const float4*>(img + ((size_t)(y0 + r) * W + x0) * 3);
+        float4 a = __ldg(p), bq = __ldg(p + 1), c = __ldg(p + 2);
+        float x[12] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w, c.x, c.y, c.z, c.w};
+        float yv[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) color_fwd<SPACE>(C, lut, x[3 * k], x[3 * k + 1], x[3 * k + 2], yv[k], c1v[r][k], c2v[r][k]);
+        size_t i = (size_t)b * o.sy + (size_t)(y0 + r) * W + x0;
+        *reinterpret_cast<float4*>(o.y + i) = make_float4(yv[0], yv[1], yv[2], yv[3]);
+        *reinterpret_cast<uchar4*>(o.y8 + i) = make_uchar4(cast_u8(yv[0]), cast_u8(yv[1]), cast_u8(yv[2]), cast_u8(yv[3]));
+    }
+    if (MODE == 0) {
+        // cv.resize INTER_AREA 2x2: ((a+b)+(c+d))*0.25f
+        const int cw = W >> 1;
+        size_t i = (size_t)b * o.sc + (size_t)(y0 >> 1) * cw + (x0 >> 1);
+        float u0 = __fmul_rn(__fadd_rn(__fadd_rn(c1v[0][0], c1v[0][1]), __fadd_rn(c1v[1][0], c1v[1][1])), 0.25f);
+        float u1 = __fmul_rn(__fadd_rn(__fadd_rn(c1v[0][2], c1v[0][3]), __fadd_rn(c1v[1][2], c1v[1][3])), 0.25f);
+        float w0 = __fmul_rn(__fadd_rn(__fadd_rn(c2v[0][0], c2v[0][1]), __fadd_rn(c2v[1][0], c2v[1][1])), 0.25f);
+        float w1 = __fmul_rn(__fadd_rn(__fadd_rn(c2v[0][2], c2v[0][3]), __fadd_rn(c2v[1][2], c2v[1][3])), 0.25f);
+        *reinterpret_cast<float2*>(o.c1 + i) = make_float2(u0, u1);
+        *reinterpret_cast<float2*>(o.c2 + i) = make_float2(w0, w1);
+        *reinterpret_cast<uchar2*>(o.c18 + i) = make_uchar2(cast_u8(u0), cast_u8(u1));
+        *reinterpret_cast<uchar2*>(o.c28 + i) = make_uchar2(cast_u8(w0), cast_u8(w1));
+    } else {
+        // 1x4: (((a+b)+c)+d)*0.25f
+        const int cw = W >> 2;
+        size_t i = (size_t)b * o.sc + (size_t)y0 * cw + (x0 >> 2);
+        float u = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(c1v[0][0], c1v[0][1]), c1v[0][2]), c1v[0][3]), 0.25f);
+        float w = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(c2v[0][0], c2v[0][1]), c2v[0][2]), c2v[0][3]), 0.25f);
+        o.c1[i] = u; o.c2[i] = w; o.c18[i] = cast_u8(u); o.c28[i] = cast_u8(w);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// general INTER_AREA (OpenCV ResizeArea_Invoker with computeResizeAreaTab), one thread per output
+// sample; used when a dimension is not divisible by the subsampling ratio (jpeg.py:686 floors).
+// ---------------------------------------------------------------------------------------------
+struct AreaAxis { int s1, s2; float aL, aM, aR; int hasL, hasR; };
+__device__ __forceinline__ AreaAxis area_axis(int d, int ssize, double scale) {
+    AreaAxis a;
+    double f1 = d * scale, f2 = f1 + scale;
+    double cell = fmin(scale, ssize - f1);
+    int s1 = (int)ceil(f1), s2 = (int)floor(f2);
+    s2 = min(s2, ssize - 1);
+    s1 = min(s1, s2);
+    a.s1 = s1; a.s2 = s2;
+    a.hasL = (s1 - f1 > 1e-3); a.aL = (float)((s1 - f1) / cell);
+    a.aM = (float)(1.0 / cell);
+    a.hasR = (f2 - s2 > 1e-3); a.aR = (float)(fmin(fmin(f2 - s2, 1.0), cell) / cell);
+    return a;
+}
+__global__ void __launch_bounds__(256) k_area(const float* __restrict__ src, int H, int W, float* __restrict__ dst, int dh, int dw,
+                                              uint8_t* __restrict__ u8, size_t src_stride, size_t dst_stride) {
+    int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (dx >= dw || dy >= dh) return;
+    const float* S = src + blockIdx.z * src_stride;
+    AreaAxis ax = area_axis(dx, W, (double)W / dw), ay = area_axis(dy, H, (double)H / dh);
+    float sum = 0.0f;
+    bool first = true;
+    int j0 = ay.hasL ? ay.s1 - 1 : ay.s1, j1 = ay.hasR ? ay.s2 : ay.s2 - 1;
+    for (int j = j0; j <= j1; j++) {
+        float beta = (j < ay.s1) ? ay.aL : ((j >= ay.s2) ? ay.aR : ay.aM);
+        const float* row = S + (size_t)j * W;
+        float buf = 0.0f;
+        if (ax.hasL) buf = __fadd_rn(buf, __fmul_rn(row[ax.s1 - 1], ax.aL));
+        for (int k = ax.s1; k < ax.s2; k++) buf = __fadd_rn(buf, __fmul_rn(row[k], ax.aM));
+        if (ax.hasR) buf = __fadd_rn(buf, __fmul_rn(row[ax.s2], ax.aR));
+        float t = __fmul_rn(beta, buf);
+        sum = first ? t : __fadd_rn(sum, t);
+        first = false;
+    }
+    size_t i = blockIdx.z * dst_stride + (size_t)dy * dw + dx;
+    dst[i] = sum;
+    if (u8) u8[i] = cast_u8(sum);
+}
+
+// ---------------------------------------------------------------------------------------------
+// INTER_LINEAR sample (half-pixel centres, edge clamp; horizontal then vertical; no fma)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lin_coord(int d, double scale, int ssize, int& s0, int& s1, float& f) {
+    float fx = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)floorf(fx);
+    fx -= (float)s;
+    if (s < 0) { fx = 0.0f; s = 0; }
+    if (s >= ssize - 1) { fx = 0.0f; s = ssize - 1; }
+    s0 = s; s1 = min(s + 1, ssize - 1); f = fx;
+}
+__device__ __forceinline__ float lin_sample(const float* __restrict__ p, int sw, int x0, int x1, float fx, int y0, int y1, float fy) {
+    const float* r0 = p + (size_t)y0 * sw;
+    const float* r1 = p + (size_t)y1 * sw;
+    float a0 = __fsub_rn(1.0f, fx), b0 = __fsub_rn(1.0f, fy);
+    float t0 = __fadd_rn(__fmul_rn(__ldg(r0 + x0), a0), __fmul_rn(__ldg(r0 + x1), fx));
+    float t1 = __fadd_rn(__fmul_rn(__ldg(r1 + x0), a0), __fmul_rn(__ldg(r1 + x1), fx));
+    return __fadd_rn(__fmul_rn(t0, b0), __fmul_rn(t1, fy));
+}
+__global__ void __launch_bounds__(256) k_resize_linear(const float* __restrict__ src, int sh, int sw, float* __restrict__ dst, int H, int W) {
+    int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (dx >= W || dy >= H) return;
+    if (sh == H && sw == W) { dst[(size_t)dy * W + dx] = src[(size_t)dy * W + dx]; return; }
+    int x0, x1, y0, y1; float fx, fy;
+    lin_coord(dx, (double)sw / W, sw, x0, x1, fx);
+    lin_coord(dy, (double)sh / H, sh, y0, y1, fy);
+    dst[(size_t)dy * W + dx] = lin_sample(src, sw, x0, x1, fx, y0, y1, fy);
+}
+
+// fused decode tail: per-layer INTER_LINEAR upsample (jpeg.py:340-354) + stack + inverse colour
+// (jpeg.py:290-297) -> RGB HWC
+struct UpIn { const float* p[3]; int h[3], w[3]; size_t stride[3]; };
+template <int SPACE>
+__global__ void __launch_bounds__(256) k_upsample_color_inverse(const __grid_constant__ ColorConsts C, UpIn in, int H, int W, float* __restrict__ rgb) {
+    int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (dx >= W || dy >= H) return;
+    int b = blockIdx.z;
+    float v[3];
+#pragma unroll
+    for (int l = 0; l < 3; l++) {
+        const float* p = in.p[l] + (size_t)b * in.stride[l];
+        if (in.h[l] == H && in.w[l] == W) v[l] = __ldg(p + (size_t)dy * W + dx);
+        else {
+            int x0, x1, y0, y1; float fx, fy;
+            lin_coord(dx, (double)in.w[l] / W, in.w[l], x0, x1, fx);
+            lin_coord(dy, (double)in.h[l] / H, in.h[l], y0, y1, fy);
+            v[l] = lin_sample(p, in.w[l], x0, x1, fx, y0, y1, fy);
+        }
+    }
+    float r, g, bl;
+    color_inv<SPACE>(C, v[0], v[1], v[2], r, g, bl);
+    float* o = rgb + ((size_t)b * H * W + (size_t)dy * W + dx) * 3;
+    o[0] = r; o[1] = g; o[2] = bl;
+}
+
+__global__ void __launch_bounds__(256) k_normalize(const float* __restrict__ in, float* __restrict__ out, size_t n, float mid, float scale, int inverse) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = inverse ? __fadd_rn(__fdiv_rn(in[i], scale), mid) : __fmul_rn(__fsub_rn(in[i], mid), scale);
+}
+__global__ void __launch_bounds__(256) k_cast_u8(const float* __restrict__ in, uint8_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = cast_u8(in[i]);
+}
+
+template <typename F>
+int dispatch_space(int space, F&& f) {
+    switch (space) {
+        case AEAJ_YCBCR: return f(std::integral_constant<int, AEAJ_YCBCR>());
+        case AEAJ_YCOCG: return f(std::integral_constant<int, AEAJ_YCOCG>());
+        case AEAJ_YCOCG_R: return f(std::integral_constant<int, AEAJ_YCOCG_R>());
+        case AEAJ_OKLAB: return f(std::integral_constant<int, AEAJ_OKLAB>());
+        case AEAJ_ICACB: return f(std::integral_constant<int, AEAJ_ICACB>());
+        case AEAJ_ICTCP: return f(std::integral_constant<int, AEAJ_ICTCP>());
+        case AEAJ_JZAZBZ: return f(std::integral_constant<int, AEAJ_JZAZBZ>());
+        case AEAJ_XYZ: return f(std::integral_constant<int, AEAJ_XYZ>());
+    }
+    aeaj_set_error("unknown colour space id %d", space);
+    return AEAJ_EINVAL;
+}
+
+}  // namespace
+
+int launch_color_pixels(aeaj_handle* h, int space, int inverse, const float* in, float* out, size_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    const ColorConsts& C = h->colors_host[space];
+    const float* lut = h->has_srgb_lut ? h->srgb_lut_dev : nullptr;
+    size_t nq = n / 4 > 0 ? n / 4 : 1;
+    int blocks = (int)std::min<size_t>((nq + 255) / 256, (size_t)h->sm_count * 16);
+    blocks = std::max(blocks, 1);
+    return dispatch_space(space, [&](auto S) {
+        constexpr int SP = decltype(S)::value;
+        if (inverse) k_color_pixels<SP, true><<<blocks, 256, 0, st>>>(C, lut, in, out, n);
+        else k_color_pixels<SP, false><<<blocks, 256, 0, st>>>(C, lut, in, out, n);
+        AEAJ_LAUNCH_CHECK();
+        return 0;
+    });
+}
+
+int launch_area(const float* src, int H, int W, float* dst, int dh, int dw, uint8_t* u8_out, int planes,
+                size_t src_stride, size_t dst_stride, cudaStream_t st) {
+    dim3 blk(32, 8), grd(aeaj_cdiv(dw, 32), aeaj_cdiv(dh, 8), planes);
+    k_area<<<grd, blk, 0, st>>>(src, H, W, dst, dh, dw, u8_out, src_stride, dst_stride);
+    AEAJ_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_resize_linear(const float* src, int sh, int sw, float* dst, int H, int W, cudaStream_t st) {
+    dim3 blk(32, 8), grd(aeaj_cdiv(W, 32), aeaj_cdiv(H, 8));
+    k_resize_linear<<<grd, blk, 0, st>>>(src, sh, sw, dst, H, W);
+    AEAJ_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_normalize(const float* in, float* out, size_t n, float mid, float scale, int inverse, cudaStream_t st) {
+    if (n == 0) return 0;
+    int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    k_normalize<<<blocks, 256, 0, st>>>(in, out, n, mid, scale, inverse);
+    AEAJ_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_cast_u8(const float* in, uint8_t* out, size_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    k_cast_u8<<<blocks, 256, 0, st>>>(in, out, n);
+    AEAJ_LAUNCH_CHECK();
+    return 0;
+}
+
+// planes_host: [B*3] plane descriptors, plane index = b*3 + layer; layers of one kind are contiguous
+// across the batch (stride = h*w), which is what FwdOut's per-image strides assume.
+int launch_color_forward_planar(aeaj_handle* h, int space, const float* rgb, int B, int H, int W,
+                                const PlaneDesc* planes_dev, const PlaneDesc* P, float* full_c1, float* full_c2,
+                                cudaStream_t st, int* launches) {
+    (void)planes_dev;
+    const ColorConsts& C = h->colors_host[space];
+    const float* lut = h->has_srgb_lut ? h->srgb_lut_dev : nullptr;
+    const int ch = P[1].h, cw = P[1].w;
+    int mode;
+    if (ch * 2 == H && cw * 2 == W && (W % 4) == 0) mode = 0;
+    else if (ch == H && cw * 4 == W) mode = 1;
+    else mode = 2;
+    FwdOut o;
+    o.y = P[0].layer_f32; o.y8 = P[0].u8a; o.sy = (size_t)H * W;
+    if (mode == 2) { o.c1 = full_c1; o.c2 = full_c2; o.c18 = nullptr; o.c28 = nullptr; o.sc = (size_t)H * W; }
+    else { o.c1 = P[1].layer_f32; o.c2 = P[2].layer_f32; o.c18 = P[1].u8a; o.c28 = P[2].u8a; o.sc = (size_t)ch * cw; }
+    int rc = dispatch_space(space, [&](auto S) {
+        constexpr int SP = decltype(S)::value;
+        if (mode == 0) {
+            dim3 blk(32, 8), grd(aeaj_cdiv(W / 4, 32), aeaj_cdiv(H / 2, 8), B);
+            k_color_forward_planar<SP, 0><<<grd, blk, 0, st>>>(C, lut, rgb, H, W, o);
+        } else if (mode == 1) {
+            dim3 blk(32, 8), grd(aeaj_cdiv(W / 4, 32), aeaj_cdiv(H, 8), B);
+            k_color_forward_planar<SP, 1><<<grd, blk, 0, st>>>(C, lut, rgb, H, W, o);
+        } else {
+            dim3 blk(32, 8), grd(aeaj_cdiv(W, 32), aeaj_cdiv(H, 8), B);
+            k_color_forward_planar<SP, 2><<<grd, blk, 0, st>>>(C, lut, rgb, H, W, o);
+        }
+        AEAJ_LAUNCH_CHECK();
+        return 0;
+    });
+    if (rc) return rc;
+    (*launches)++;
+    if (mode == 2) {
+        rc = launch_area(full_c1, H, W, P[1].layer_f32, ch, cw, P[1].u8a, B, (size_t)H * W, (size_t)ch * cw, st);
+        if (rc) return rc;
+        rc = launch_area(full_c2, H, W, P[2].layer_f32, ch, cw, P[2].u8a, B, (size_t)H * W, (size_t)ch * cw, st);
+        if (rc) return rc;
+        (*launches) += 2;
+    }
+    return 0;
+}
+
+int launch_upsample_color_inverse(aeaj_handle* h, int space, const PlaneDesc* P, int B, int H, int W, float* rgb, cudaStream_t st) {
+    const ColorConsts& C = h->colors_host[space];
+    UpIn in;
+    for (int l = 0; l < 3; l++) { in.p[l] = P[l].layer_f32; in.h[l] = P[l].h; in.w[l] = P[l].w; in.stride[l] = (size_t)P[l].h * P[l].w; }
+    dim3 blk(32, 8), grd(aeaj_cdiv(W, 32), aeaj_cdiv(H, 8), B);
+    return dispatch_space(space, [&](auto S) {
+        constexpr int SP = decltype(S)::value;
+        k_upsample_color_inverse<SP><<<grd, blk, 0, st>>>(C, in, H, W, rgb);
+        AEAJ_LAUNCH_CHECK();
+        return 0;
+    });
+}

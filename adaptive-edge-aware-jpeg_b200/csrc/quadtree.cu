@@ -1,0 +1,269 @@
+// quadtree.cu -- QuadTree(edge, max, min).get_leaves_and_states() (quadtree.py:68-165) for sm_100a.
+//
+// The reference walks the tree with a Python stack, calling a numba `np.any` per node.  Here the
+// tree is never materialised:
+//   1. per "top block" (T = min(max_size, root) pixels square) an OR-pyramid of edge presence over
+//      min_size cells is reduced bottom-up in shared memory from the bit-packed edge map;
+//   2. split(node) = size > max || (size > min && any_edge(node)); a node exists iff its parent
+//      splits; DFS pre-order == ascending Morton order of the node's first cell, larger nodes first;
+//   3. exclusive scans in Morton order (inside a block: warp-shuffle scan; across top blocks: one
+//      block per plane) give every node its position in the state stream and every leaf its index
+//      and coefficient offset; leaves are also appended to per-size-class work lists for the DCT.
+// Equivalence with the reference's traversal (incl. '10' states for out-of-bounds children and the
+// all-split levels above max_size) is validated by the oracle tests on degenerate shapes.
+#include "aeaj_internal.cuh"
+
+namespace {
+
+constexpr int QT_THREADS = 256;
+constexpr int QT_MAX_CELLS = 128;                    // T / min_size <= 128 (e.g. 256 / 2)
+constexpr int QT_OCC_BYTES = 22016;                  // sum_{l} (128 >> l)^2 = 21845, padded
+
+struct QtParams { int min_size, lg_min, max_size; };
+
+struct Scan3 { int a, b, c; };
+__device__ __forceinline__ Scan3 block_excl_scan3(Scan3 v, Scan3& total, int* smem /* 3*8 + 3 ints */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Scan3 inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int ta = __shfl_up_sync(0xffffffffu, inc.a, o), tb = __shfl_up_sync(0xffffffffu, inc.b, o), tc = __shfl_up_sync(0xffffffffu, inc.c, o);
+        if (lane >= o) { inc.a += ta; inc.b += tb; inc.c += tc; }
+    }
+    __syncthreads();                                   // protect smem reuse across calls
+    if (lane == 31) { smem[warp * 3] = inc.a; smem[warp * 3 + 1] = inc.b; smem[warp * 3 + 2] = inc.c; }
+    __syncthreads();
+    Scan3 off = {0, 0, 0}, tot = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < QT_THREADS / 32; k++) {
+        int a = smem[k * 3], b = smem[k * 3 + 1], c = smem[k * 3 + 2];
+        if (k < warp) { off.a += a; off.b += b; off.c += c; }
+        tot.a += a; tot.b += b; tot.c += c;
+    }
+    total = tot;
+    Scan3 ex = {off.a + inc.a - v.a, off.b + inc.b - v.b, off.c + inc.c - v.c};
+    return ex;
+}
+
+__device__ __forceinline__ bool cell_has_edge(const uint32_t* __restrict__ bits, int wpr, int h, int w, int x0, int y0, int c) {
+    int y1 = min(y0 + c, h), x1 = min(x0 + c, w);
+    if (x0 >= w || y0 >= h) return false;
+    int w0 = x0 >> 5, w1 = (x1 - 1) >> 5;
+    for (int y = y0; y < y1; y++)
+        for (int wi = w0; wi <= w1; wi++) {
+            unsigned v = __ldg(bits + (size_t)y * wpr + wi);
+            int lo = max(x0 - wi * 32, 0), hi = min(x1 - wi * 32, 32);   // bit range [lo, hi)
+            unsigned m = (hi - lo >= 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+            if (v & m) return true;
+        }
+    return false;
+}
+
+// phase 0: totals per top block.  phase 1: emit states / leaves / class entries.
+// grid: (max top blocks over planes, nplanes)
+__global__ void __launch_bounds__(QT_THREADS) k_qt_blocks(const PlaneDesc* __restrict__ planes, QtParams q, int phase,
+                                                          ClassEntry* __restrict__ class_lists, int* __restrict__ class_counts,
+                                                          const long long* __restrict__ class_offsets) {
+    const PlaneDesc& P = planes[blockIdx.y];
+    const int tb = blockIdx.x;
+    if (tb >= P.ntx * P.nty) return;
+    const int T = P.top, c = q.min_size;
+    const int n = T / c;                               // cells per side (power of two, >= 1)
+    int L = 0; while ((1 << L) < n) L++;
+    const int bx = tb % P.ntx, by = tb / P.ntx;
+    const int X0 = bx * T, Y0 = by * T;
+    __shared__ uint8_t occ[QT_OCC_BYTES];
+    __shared__ int lvl_off[9];
+    __shared__ int s_scan[3 * 8 + 4];
+    __shared__ int s_cls[9], s_cls_base[9];
+    const int tid = threadIdx.x;
+    if (tid == 0) { int o = 0; for (int l = 0; l <= L; l++) { lvl_off[l] = o; o += (n >> l) * (n >> l); } }
+    if (tid < 9) { s_cls[tid] = 0; s_cls_base[tid] = 0; }
+    __syncthreads();
+    // level 0 from the bitmap
+    for (int i = tid; i < n * n; i += QT_THREADS) {
+        int cy = i / n, cx = i - cy * n;
+        occ[i] = cell_has_edge(P.strong, P.wpr, P.h, P.w, X0 + cx * c, Y0 + cy * c, c);
+    }
+    __syncthreads();
+    for (int l = 1; l <= L; l++) {
+        const int nl = n >> l, np = n >> (l - 1);
+        const uint8_t* prev = occ + lvl_off[l - 1];
+        uint8_t* cur = occ + lvl_off[l];
+        for (int i = tid; i < nl * nl; i += QT_THREADS) {
+            int j = i / nl, k = i - j * nl;
+            cur[i] = prev[(2 * j) * np + 2 * k] | prev[(2 * j) * np + 2 * k + 1] | prev[(2 * j + 1) * np + 2 * k] | prev[(2 * j + 1) * np + 2 * k + 1];
+        }
+        __syncthreads();
+    }
+    // node predicates ---------------------------------------------------------------------------
+    auto node_split = [&](int l, int j, int k) -> bool { return l > 0 && occ[lvl_off[l] + j * (n >> l) + k]; };
+    auto node_exists = [&](int l, int j, int k) -> bool { return l == L ? true : node_split(l + 1, j >> 1, k >> 1); };
+    auto node_inb = [&](int l, int j, int k) -> bool { return (X0 + (k << l) * c) < P.w && (Y0 + (j << l) * c) < P.h; };
+
+    if (phase == 1) {
+        // per-class leaf counts for this block -> reserve ranges in the global class lists
+        int tot_nodes = lvl_off[L] + 1;
+        for (int i = tid; i < tot_nodes; i += QT_THREADS) {
+            int l = 0; while (l < L && i >= lvl_off[l + 1]) l++;
+            int r = i - lvl_off[l], nl = n >> l, j = r / nl, k = r - j * nl;
+            if (node_exists(l, j, k) && node_inb(l, j, k) && !node_split(l, j, k)) atomicAdd(&s_cls[l], 1);
+        }
+        __syncthreads();
+        if (tid <= L && s_cls[tid] > 0) s_cls_base[tid] = atomicAdd(&class_counts[q.lg_min + tid], s_cls[tid]);
+        __syncthreads();
+        if (tid < 9) s_cls[tid] = 0;
+        __syncthreads();
+    }
+    const int4 base = (phase == 1) ? P.tb_base[tb] : make_int4(0, 0, 0, 0);
+    Scan3 carry = {0, 0, 0};
+    const int ncell = n * n;
+    for (int z0 = 0; z0 < ncell; z0 += QT_THREADS) {
+        const int z = z0 + tid;
+        Scan3 cnt = {0, 0, 0};
+        int cx = 0, cy = 0;
+        if (z < ncell) {
+            cx = (int)compact1by1((uint32_t)z); cy = (int)compact1by1((uint32_t)z >> 1);
+            for (int l = L; l >= 0; l--) {
+                if (z & ((1 << (2 * l)) - 1)) continue;
+                int j = cy >> l, k = cx >> l;
+                if (!node_exists(l, j, k)) continue;
+                cnt.a++;
+                if (node_inb(l, j, k) && !node_split(l, j, k)) { cnt.b++; int s = c << l; cnt.c += s * s; }
+            }
+        }
+        Scan3 tot;
+        Scan3 ex = block_excl_scan3(cnt, tot, s_scan);
+        if (phase == 1 && z < ncell && cnt.a) {
+            int spos = base.x + carry.a + ex.a;
+            for (int l = L; l >= 0; l--) {
+                if (z & ((1 << (2 * l)) - 1)) continue;
+                int j = cy >> l, k = cx >> l;
+                if (!node_exists(l, j, k)) continue;
+                bool inb = node_inb(l, j, k), sp = node_split(l, j, k);
+                P.states[spos++] = inb ? (sp ? 1 : 0) : 2;
+                if (inb && !sp) {
+                    int li = base.y + carry.b + ex.b, co = base.z + carry.c + ex.c;
+                    int s = c << l, x = X0 + (k << l) * c, y = Y0 + (j << l) * c;
+                    reinterpret_cast<int4*>(P.leaves)[li] = make_int4(x, y, s, co);
+                    int r = s_cls_base[l] + atomicAdd(&s_cls[l], 1);
+                    ClassEntry e; e.x = x; e.y = y; e.plane = blockIdx.y; e.coef_off = co;
+                    class_lists[class_offsets[q.lg_min + l] + r] = e;
+                }
+            }
+        }
+        carry.a += tot.a; carry.b += tot.b; carry.c += tot.c;
+    }
+    if (phase == 0 && tid == 0) { P.tb_tot[tb] = make_int2(carry.a, carry.b); P.tb_coef[tb] = carry.c; }
+}
+
+// one block per plane: Morton-order scan over all (root/T)^2 top positions, emitting the states of
+// the all-split levels above T and the '10' states of out-of-bounds positions.
+__global__ void __launch_bounds__(QT_THREADS) k_qt_scan(const PlaneDesc* __restrict__ planes) {
+    const PlaneDesc& P = planes[blockIdx.x];
+    __shared__ int s_scan[3 * 8 + 4];
+    const int T = P.top, R = P.root;
+    const int side = R / T;                            // power of two
+    int U = 0; while ((1 << U) < side) U++;
+    const int M = side * side;
+    Scan3 carry = {0, 0, 0};
+    for (int m0 = 0; m0 < M; m0 += QT_THREADS) {
+        const int m = m0 + threadIdx.x;
+        Scan3 cnt = {0, 0, 0};
+        int n_upper = 0, top_kind = 0;                 // 0 none, 1 in-bounds subtree, 2 single '10'
+        int bx = 0, by = 0;
+        if (m < M) {
+            bx = (int)compact1by1((uint32_t)m); by = (int)compact1by1((uint32_t)m >> 1);
+            const int x = bx * T, y = by * T;
+            for (int u = U; u >= 1; u--) {
+                if (m & ((1 << (2 * u)) - 1)) continue;
+                long long size = (long long)T << u;
+                bool inb = x < P.w && y < P.h;
+                bool pinb = true;
+                if (u < U) { long long ps = size * 2; long long px = (x / ps) * ps, py = (y / ps) * ps; pinb = px < P.w && py < P.h; }
+                if (inb || pinb) n_upper++;
+            }
+            bool inb = x < P.w && y < P.h, pinb = true;
+            if (U >= 1) { long long ps = (long long)T * 2; long long px = (x / ps) * ps, py = (y / ps) * ps; pinb = px < P.w && py < P.h; }
+            if (inb) {
+                int tb = by * P.ntx + bx;
+                int2 t = P.tb_tot[tb];
+                cnt.a = t.x; cnt.b = t.y; cnt.c = P.tb_coef[tb];
+                top_kind = 1;
+            } else if (pinb) { cnt.a = 1; top_kind = 2; }
+            cnt.a += n_upper;
+        }
+        Scan3 tot;
+        Scan3 ex = block_excl_scan3(cnt, tot, s_scan);
+        if (m < M) {
+            int pos = carry.a + ex.a;
+            const int x = bx * T, y = by * T;
+            for (int u = U; u >= 1; u--) {
+                if (m & ((1 << (2 * u)) - 1)) continue;
+                long long size = (long long)T << u;
+                bool inb = x < P.w && y < P.h;
+                bool pinb = true;
+                if (u < U) { long long ps = size * 2; long long px = (x / ps) * ps, py = (y / ps) * ps; pinb = px < P.w && py < P.h; }
+                if (inb) P.states[pos++] = 1;          // size > max: always split (quadtree.py:118)
+                else if (pinb) P.states[pos++] = 2;
+            }
+            if (top_kind == 1) P.tb_base[by * P.ntx + bx] = make_int4(pos, carry.b + ex.b, carry.c + ex.c, 0);
+            else if (top_kind == 2) P.states[pos] = 2;
+        }
+        carry.a += tot.a; carry.b += tot.b; carry.c += tot.c;
+    }
+    if (threadIdx.x == 0) { P.counts[0] = carry.b; P.counts[1] = carry.a; P.counts[2] = carry.c; P.counts[3] = R; }
+}
+
+// decode side: leaves (x,y,size,coef_off) -> per-size-class work lists
+__global__ void __launch_bounds__(256) k_bucket_leaves(const PlaneDesc* __restrict__ planes, ClassEntry* __restrict__ class_lists,
+                                                       int* __restrict__ class_counts, const long long* __restrict__ class_offsets) {
+    const PlaneDesc& P = planes[blockIdx.y];
+    const int nl = P.counts[0];
+    __shared__ int s_cls[9], s_base[9];
+    if (threadIdx.x < 9) s_cls[threadIdx.x] = 0;
+    __syncthreads();
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    int4 lf = make_int4(0, 0, 0, 0);
+    int lg = -1, rank = 0;
+    if (i < nl) {
+        lf = reinterpret_cast<const int4*>(P.leaves)[i];
+        lg = 31 - __clz(lf.z);
+        rank = atomicAdd(&s_cls[lg], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 9 && s_cls[threadIdx.x] > 0) s_base[threadIdx.x] = atomicAdd(&class_counts[threadIdx.x], s_cls[threadIdx.x]);
+    __syncthreads();
+    if (i < nl) {
+        ClassEntry e; e.x = lf.x; e.y = lf.y; e.plane = blockIdx.y; e.coef_off = lf.w;
+        class_lists[class_offsets[lg] + s_base[lg] + rank] = e;
+    }
+}
+
+}  // namespace
+
+int launch_quadtree(const PlaneDesc* planes_dev, const PlaneDesc* P, int nplanes, int min_size, int max_size,
+                    ClassEntry* class_lists, int* class_counts, const long long* class_offsets_dev, cudaStream_t st, int* launches) {
+    int maxtb = 0;
+    for (int i = 0; i < nplanes; i++) maxtb = std::max(maxtb, P[i].ntx * P[i].nty);
+    QtParams q; q.min_size = min_size; q.lg_min = ilog2i(min_size); q.max_size = max_size;
+    dim3 grd(maxtb, nplanes);
+    k_qt_blocks<<<grd, QT_THREADS, 0, st>>>(planes_dev, q, 0, class_lists, class_counts, class_offsets_dev);
+    AEAJ_LAUNCH_CHECK();
+    k_qt_scan<<<nplanes, QT_THREADS, 0, st>>>(planes_dev);
+    AEAJ_LAUNCH_CHECK();
+    k_qt_blocks<<<grd, QT_THREADS, 0, st>>>(planes_dev, q, 1, class_lists, class_counts, class_offsets_dev);
+    AEAJ_LAUNCH_CHECK();
+    if (launches) *launches += 3;
+    return 0;
+}
+
+int launch_bucket_leaves(const PlaneDesc* planes_dev, const PlaneDesc* P, int nplanes, ClassEntry* class_lists,
+                         int* class_counts, const long long* class_offsets_dev, cudaStream_t st) {
+    int64_t maxl = 1;
+    for (int i = 0; i < nplanes; i++) maxl = std::max<int64_t>(maxl, P[i].cap_leaves);
+    dim3 grd((unsigned)aeaj_cdiv64(maxl, 256), nplanes);
+    k_bucket_leaves<<<grd, 256, 0, st>>>(planes_dev, class_lists, class_counts, class_offsets_dev);
+    AEAJ_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,184 @@
+/*
+ * aeaj.h -- C ABI of libaeaj.so: the B200 (sm_100a) implementation of the adaptive edge-aware
+ * JPEG hot path.  This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ *
+ * The reference (fevzibabaoglu/adaptive-edge-aware-jpeg) is pure Python and has no FFI of its own;
+ * each entry point below replaces the reference call site cited beside it (paths under
+ * /root/reference/src).  The Python host shim that binds these with ctypes lives in
+ * adaptive-edge-aware-jpeg_b200/aeaj/native.py; INTEGRATION.md shows the binding a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - every export returns int: 0 = ok, <0 = AEAJ_E*, >0 = cudaError_t; aeaj_last_error() gives text.
+ *   - all data pointers are DEVICE pointers unless the name ends in _host.
+ *   - every call is asynchronous on the cudaStream_t passed as `void* stream` (NULL = default stream)
+ *     unless documented otherwise; the caller owns every buffer; the library owns only handles/plans.
+ *   - a handle/plan is not re-entrant; distinct handles are independent.
+ *   - images are float32 HWC in [0,1] (image.py:80); layers are planar float32 (jpeg.py:263-264);
+ *     edge maps are uint8 {0,1}; quantised coefficients are int32 (jpeg.py:501).
+ */
+#ifndef AEAJ_H
+#define AEAJ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AEAJ_VERSION 1
+
+#if defined(__GNUC__)
+#define AEAJ_API __attribute__((visibility("default")))
+#else
+#define AEAJ_API
+#endif
+
+enum {
+    AEAJ_OK = 0,
+    AEAJ_EINVAL = -1,      /* bad argument (the Python shim raises ValueError/TypeError before this) */
+    AEAJ_ENOMEM = -2,
+    AEAJ_ENOCUDA = -3,     /* no usable sm_100 device: there is NO CPU fallback */
+    AEAJ_ECAPACITY = -4,   /* a caller-provided output buffer was too small */
+    AEAJ_ENOTCONVERGED = -5
+};
+
+/* colour spaces: keys of COLOR_SPACE_SETTINGS (jpeg.py:62-147) + XYZ (conversion.py:65-70) */
+enum {
+    AEAJ_YCBCR = 0, AEAJ_YCOCG = 1, AEAJ_YCOCG_R = 2, AEAJ_OKLAB = 3,
+    AEAJ_ICACB = 4, AEAJ_ICTCP = 5, AEAJ_JZAZBZ = 6, AEAJ_XYZ = 7
+};
+
+typedef struct aeaj_handle aeaj_handle;
+typedef struct aeaj_plan aeaj_plan;
+
+AEAJ_API const char* aeaj_last_error(void);
+AEAJ_API int aeaj_version(void);
+
+/* one handle per (device, stream user). Uploads DCT matrices and colour constants. */
+AEAJ_API int aeaj_create(int device, aeaj_handle** out);
+AEAJ_API int aeaj_destroy(aeaj_handle* h);
+
+/* Colour constants that the reference derives with numpy at import time (np.linalg.inv of float32
+ * matrices: oklab.py:35,47; icacb.py:149,159; ictcp.py:149,159; jzazbz.py:196,206) and the
+ * 256-entry sRGB->linear table evaluated with the host libm exactly as common.py:34-60 does.
+ * fwd1/fwd2/inv1/inv2: 3x3 row-major float32 for `space`; srgb_lut: 256 float32 or NULL. */
+AEAJ_API int aeaj_set_color_tables(aeaj_handle* h, int space, const float* fwd1_host, const float* fwd2_host,
+                          const float* inv1_host, const float* inv2_host, const float* mid_host,
+                          const float* scale_host);
+AEAJ_API int aeaj_set_srgb_lut(aeaj_handle* h, const float* lut256_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * stage entry points (stage-isolated parity; each is the kernel the fused path uses)
+ * ------------------------------------------------------------------------------------------- */
+
+/* convert("sRGB", space, x) / convert(space, "sRGB", x)  (conversion.py:95-124); x is (n,3) */
+AEAJ_API int aeaj_color_forward(aeaj_handle* h, int space, const float* rgb, float* out, size_t n, void* stream);
+AEAJ_API int aeaj_color_inverse(aeaj_handle* h, int space, const float* in, float* rgb, size_t n, void* stream);
+/* apply_normalization(space, x, inverse) on one channel (conversion.py:126-157; jpeg.py:387-390,452-455) */
+AEAJ_API int aeaj_normalize(aeaj_handle* h, int space, int channel, int inverse, const float* in, float* out,
+                   size_t n, void* stream);
+/* cv.resize(INTER_AREA) (jpeg.py:336) and cv.resize(INTER_LINEAR) (jpeg.py:352) on one plane */
+AEAJ_API int aeaj_downsample_area(aeaj_handle* h, const float* src, int H, int W, float* dst, int dh, int dw, void* stream);
+AEAJ_API int aeaj_resize_linear(aeaj_handle* h, const float* src, int sh, int sw, float* dst, int H, int W, void* stream);
+
+/* Device scratch for ANY single-plane stage call below on an (h,w) plane with the given block range
+ * (upper bound over all stages; pass min_size = max_size = 0 if no quadtree/DCT call is made). */
+AEAJ_API size_t aeaj_stage_workspace_bytes(int h, int w, int min_size, int max_size);
+
+/* EdgeDetection.canny stages (edge_detection.py:70-86), one (h,w) plane each. */
+AEAJ_API int aeaj_cast_u8(aeaj_handle* hd, const float* layer, uint8_t* out, size_t n, void* stream);               /* :70 */
+AEAJ_API int aeaj_clahe(aeaj_handle* hd, const uint8_t* src, int h, int w, uint8_t* dst, void* ws, void* stream);   /* :73-74 */
+AEAJ_API int aeaj_gauss3(aeaj_handle* hd, const uint8_t* src, int h, int w, uint8_t* dst, void* ws, void* stream);  /* :77 */
+AEAJ_API int aeaj_bilateral5(aeaj_handle* hd, const uint8_t* src, int h, int w, uint8_t* dst, void* ws, void* stream); /* :78 */
+/* np.percentile(img,10), np.percentile(img,30) (:81-82) -> thr[0], thr[1] as float64 on the device */
+AEAJ_API int aeaj_percentile_thresholds(aeaj_handle* hd, const uint8_t* src, int h, int w, double* thr, void* ws, void* stream);
+/* cv.Canny(img, lo, hi, apertureSize=3, L2gradient=True) (:85); thr = 2 float64 on the device; edge uint8 {0,1} */
+AEAJ_API int aeaj_canny_u8(aeaj_handle* hd, const uint8_t* src, int h, int w, const double* thr, uint8_t* edge,
+                  void* ws, void* stream);
+/* the whole of EdgeDetection.canny(layer) -> uint8 {0,1} */
+AEAJ_API int aeaj_canny(aeaj_handle* hd, const float* layer, int h, int w, uint8_t* edge, void* ws, void* stream);
+
+/* QuadTree(edge, max, min).get_leaves_and_states() (quadtree.py:71-165).
+ * edge: uint8 {0,1} (h,w).  leaves: int32 [cap_leaves][4] = x, y, size, coefficient offset (DFS order).
+ * states: uint8 [cap_states] in {0 leaf, 1 split, 2 absent} (DFS pre-order).
+ * counts: int32[4] on the device = n_leaves, n_states, n_coef, root size. */
+AEAJ_API int aeaj_quadtree_caps(int h, int w, int min_size, int max_size, int64_t* cap_leaves, int64_t* cap_states,
+                       int64_t* cap_coef, int* root);
+AEAJ_API int aeaj_quadtree(aeaj_handle* hd, const uint8_t* edge, int h, int w, int min_size, int max_size,
+                  int32_t* leaves, uint8_t* states, int32_t* counts, void* ws, void* stream);
+
+/* normalise + leaf extraction with reflect padding + cv.dct + quantise (jpeg.py:387-404,471,497-504)
+ * for the leaves of one layer.  qtab_dev_ptrs_host: HOST array of 9 DEVICE pointers, entry log2(s) is the
+ * s*s int32 table quantization_matrix_cache[layer][s] (jpeg.py:228-238), NULL for unused sizes.
+ * counts: the device int32[4] written by aeaj_quadtree (no host sync needed in between). */
+AEAJ_API int aeaj_dct_quant(aeaj_handle* hd, const float* layer, int h, int w, float mid, float scale,
+                   const int32_t* leaves, const int32_t* counts, int min_size, int max_size,
+                   const int32_t* const* qtab_dev_ptrs_host, int32_t* coef, void* ws, void* stream);
+/* dequantise + cv.idct + merge + crop + denormalise (jpeg.py:508-529,483,410-459) */
+AEAJ_API int aeaj_dequant_idct(aeaj_handle* hd, const int32_t* coef, const int32_t* leaves, const int32_t* counts,
+                      int min_size, int max_size, const int32_t* const* qtab_dev_ptrs_host, int h, int w,
+                      float mid, float scale, float* layer, void* ws, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * fused batch path: Jpeg.compress minus _entropy_encode (jpeg.py:262-270) and
+ * Jpeg.decompress minus _entropy_decode (jpeg.py:285-297) for `batch` images of one shape.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int batch, height, width, space, block_min, block_max;
+    int layer_h[3], layer_w[3], root[3];
+    int64_t cap_leaves[3];   /* per image, per layer */
+    int64_t cap_states[3];
+    int64_t cap_coef[3];
+    int64_t workspace_bytes; /* device scratch the caller must provide to encode/decode */
+} aeaj_plan_info;
+
+AEAJ_API int aeaj_plan_create(aeaj_handle* h, int batch, int height, int width, int space, int block_min,
+                     int block_max, aeaj_plan** out);
+AEAJ_API int aeaj_plan_destroy(aeaj_plan* p);
+AEAJ_API int aeaj_plan_get_info(const aeaj_plan* p, aeaj_plan_info* info);
+/* quantisation tables computed on the host exactly as jpeg.py:688-724 does (Python math.log, int()):
+ * for table t in {0 luma, 1 chroma} and each size class s = block_min..block_max the s*s int32
+ * entries, concatenated in ascending size order: [luma sizes...][chroma sizes...]. */
+AEAJ_API int aeaj_plan_set_qtables(aeaj_plan* p, const int32_t* tables_host, size_t n_entries, void* stream);
+
+typedef struct {
+    const float* rgb;        /* [batch][H][W][3] */
+    int32_t* coef[3];        /* [batch][cap_coef[l]]  leaf order, row-major blocks */
+    int32_t* leaves[3];      /* [batch][cap_leaves[l]][4] x,y,size,coef offset */
+    uint8_t* states[3];      /* [batch][cap_states[l]] */
+    int32_t* counts;         /* [batch][3][4] n_leaves, n_states, n_coef, root */
+    float* tap_layers[3];    /* optional [batch][h_l][w_l]: downsampled un-normalised layers */
+    uint8_t* tap_edges[3];   /* optional [batch][h_l][w_l]: edge maps {0,1} */
+    int32_t* status;         /* device int32[2]: hysteresis rounds used, converged flag */
+} aeaj_encode_io;
+
+typedef struct {
+    const int32_t* coef[3];
+    const int32_t* leaves[3];
+    const int32_t* counts;   /* [batch][3][4] (only n_leaves is read) */
+    float* rgb;              /* [batch][H][W][3] */
+    float* tap_layers[3];    /* optional [batch][h_l][w_l]: merged + denormalised layers */
+} aeaj_decode_io;
+
+AEAJ_API int aeaj_encode(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, void* stream);
+AEAJ_API int aeaj_decode(aeaj_plan* p, const aeaj_decode_io* io, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * host-side helpers for the entropy-coding side (plain CPU code, no device work):
+ * the 2-bit state stream (jpeg.py:563-571) and its inverse (jpeg.py:768-800 + 428-448).
+ * ------------------------------------------------------------------------------------------- */
+/* states (0 leaf, 1 split, 2 absent; DFS pre-order) -> leaves_host[n][4] = x, y, size, coef offset */
+AEAJ_API int aeaj_states_to_leaves_host(const uint8_t* states_host, int n_states, int root, int h, int w,
+                               int32_t* leaves_host, int* n_leaves, int64_t* n_coef);
+/* 2 bits per state, MSB first, zero padded; packed_host holds ceil(n_states/4) bytes */
+AEAJ_API int aeaj_pack_states_host(const uint8_t* states_host, int n_states, uint8_t* packed_host);
+
+/* number of kernel launches issued by the last aeaj_encode / aeaj_decode on this plan */
+AEAJ_API int aeaj_plan_last_launches(const aeaj_plan* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AEAJ_H */
