@@ -149,6 +149,79 @@ class DeviceCodec:
         self.last_launches = self.lib.aeaj_plan_last_launches(p.ptr)
         return (p.rgb_out, tl) if taps else p.rgb_out
 
+    # ------------------------------------------------------------------------------------------
+    # measurement support
+    # ------------------------------------------------------------------------------------------
+    def enable_timing(self, B, H, W, space, brange, qrange, on: bool):
+        p = self._plan(B, H, W, space, brange, qrange)
+        native.check(self.lib.aeaj_plan_enable_timing(p.ptr, int(on)), "aeaj_plan_enable_timing")
+
+    def read_timing(self, B, H, W, space, brange, qrange) -> Dict[str, float]:
+        """Stage durations (ms) of the last encode or decode call on this plan (CUDA events)."""
+        p = self._plan(B, H, W, space, brange, qrange)
+        names = C.create_string_buffer(4096)
+        ms = (C.c_float * 64)()
+        n = C.c_int()
+        native.check(self.lib.aeaj_plan_read_timing(p.ptr, names, 4096, ms, 64, C.byref(n)), "aeaj_plan_read_timing")
+        return {nm: float(ms[i]) for i, nm in enumerate(names.value.decode().split("\n")[: n.value])}
+
+    # ------------------------------------------------------------------------------------------
+    # host-buffer path (what a caller holding numpy / pinned host memory uses; bench.py e2e leg)
+    # ------------------------------------------------------------------------------------------
+    def _host_staging(self, p: _Plan):
+        if not p.keep:
+            B = p.info.batch
+            st = dict(
+                rgb_in=torch.empty((B, p.info.height, p.info.width, 3), dtype=torch.float32).pin_memory(),
+                rgb_out=torch.empty((B, p.info.height, p.info.width, 3), dtype=torch.float32).pin_memory(),
+                coef=[torch.empty((B, int(p.info.cap_coef[l])), dtype=torch.int32).pin_memory() for l in range(3)],
+                leaves=[torch.empty((B, int(p.info.cap_leaves[l]), 4), dtype=torch.int32).pin_memory() for l in range(3)],
+                states=[torch.empty((B, int(p.info.cap_states[l])), dtype=torch.uint8).pin_memory() for l in range(3)],
+                counts=torch.empty((B, 3, 4), dtype=torch.int32).pin_memory(),
+                rgb_dev=torch.empty((B, p.info.height, p.info.width, 3), dtype=torch.float32, device=p.rgb_out.device))
+            p.keep.append(st)
+        return p.keep[0]
+
+    def host_staging(self, B, H, W, space, brange, qrange):
+        return self._host_staging(self._plan(B, H, W, space, brange, qrange))
+
+    def encode_host(self, rgb_host: torch.Tensor, space, qrange, brange):
+        """rgb_host: pinned float32 CPU tensor [B,H,W,3].  H2D, encode, D2H of the used parts of the
+        coefficient / leaf / state buffers into pinned staging.  Returns (staging dict, counts ndarray, bytes h2d, bytes d2h)."""
+        B, H, W, _ = rgb_host.shape
+        p = self._plan(B, H, W, space, brange, qrange)
+        st = self._host_staging(p)
+        st["rgb_dev"].copy_(rgb_host, non_blocking=True)
+        enc = self.encode(st["rgb_dev"], space, qrange, brange)
+        st["counts"].copy_(enc.counts, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        counts = st["counts"].numpy()
+        d2h = st["counts"].numel() * 4
+        for l in range(3):
+            nl, ns, nc = (int(counts[:, l, k].max()) for k in range(3))
+            st["coef"][l][:, :nc].copy_(enc.coef[l][:, :nc], non_blocking=True)
+            st["leaves"][l][:, :nl].copy_(enc.leaves[l][:, :nl], non_blocking=True)
+            st["states"][l][:, :ns].copy_(enc.states[l][:, :ns], non_blocking=True)
+            d2h += B * (nc * 4 + nl * 16 + ns)
+        torch.cuda.current_stream().synchronize()
+        return st, counts, rgb_host.numel() * 4, d2h
+
+    def decode_host(self, st, counts: np.ndarray, B, H, W, space, qrange, brange):
+        """Inverse of encode_host: H2D of the used parts, decode, D2H of the RGB batch into pinned staging."""
+        p = self._plan(B, H, W, space, brange, qrange)
+        o = p.out
+        h2d = st["counts"].numel() * 4
+        for l in range(3):
+            nl, nc = int(counts[:, l, 0].max()), int(counts[:, l, 2].max())
+            o.coef[l][:, :nc].copy_(st["coef"][l][:, :nc], non_blocking=True)
+            o.leaves[l][:, :nl].copy_(st["leaves"][l][:, :nl], non_blocking=True)
+            h2d += B * (nc * 4 + nl * 16)
+        o.counts.copy_(st["counts"], non_blocking=True)
+        rgb = self.decode(o.coef, o.leaves, o.counts, B, H, W, space, qrange, brange)
+        st["rgb_out"].copy_(rgb, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return st["rgb_out"], h2d, st["rgb_out"].numel() * 4
+
     def decode_encoded(self, enc: EncodedBatch, space, qrange, brange):
         B, H, W = enc.shape
         return self.decode(enc.coef, enc.leaves, enc.counts, B, H, W, space, qrange, brange)

@@ -20,6 +20,7 @@ EXPORTS = [
     "aeaj_percentile_thresholds", "aeaj_canny_u8", "aeaj_canny", "aeaj_quadtree_caps", "aeaj_quadtree",
     "aeaj_dct_quant", "aeaj_dequant_idct", "aeaj_plan_create", "aeaj_plan_destroy", "aeaj_plan_get_info",
     "aeaj_plan_set_qtables", "aeaj_encode", "aeaj_decode", "aeaj_plan_last_launches",
+    "aeaj_plan_enable_timing", "aeaj_plan_read_timing",
     "aeaj_states_to_leaves_host", "aeaj_pack_states_host",
 ]
 
@@ -93,6 +94,8 @@ def load():
         lib.aeaj_encode.argtypes = [vp, C.POINTER(EncodeIO), vp, vp]
         lib.aeaj_decode.argtypes = [vp, C.POINTER(DecodeIO), vp, vp]
         lib.aeaj_plan_last_launches.argtypes = [vp]
+        lib.aeaj_plan_enable_timing.argtypes = [vp, i]
+        lib.aeaj_plan_read_timing.argtypes = [vp, C.c_char_p, sz, vp, i, C.POINTER(i)]
         lib.aeaj_states_to_leaves_host.argtypes = [vp, i, i, i, i, vp, C.POINTER(i), C.POINTER(C.c_int64)]
         lib.aeaj_pack_states_host.argtypes = [vp, i, vp]
         _lib = lib

@@ -183,7 +183,7 @@ int launch_bucket_leaves(const PlaneDesc* planes_dev, const PlaneDesc* planes_ho
                          int* class_counts, const long long* class_offsets_dev, cudaStream_t st);
 int launch_dct_quant(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,
                      const int64_t* class_offsets_host, const int64_t* class_caps_host, int lg_min, int lg_max,
-                     cudaStream_t st, int* launches);
+                     cudaStream_t st, int* launches, void (*mark)(void*, const char*), void* mark_ctx);
 int launch_dequant_idct(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,
                         const int64_t* class_offsets_host, const int64_t* class_caps_host, int lg_min, int lg_max,
-                        cudaStream_t st, int* launches);
+                        cudaStream_t st, int* launches, void (*mark)(void*, const char*), void* mark_ctx);

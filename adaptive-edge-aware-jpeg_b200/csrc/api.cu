@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <string>
 #include <vector>
 #include "aeaj_internal.cuh"
 
@@ -159,14 +160,17 @@ extern "C" int aeaj_set_srgb_lut(aeaj_handle* h, const float* lut) {
 #define ST(stream) ((cudaStream_t)(stream))
 
 extern "C" int aeaj_color_forward(aeaj_handle* h, int space, const float* rgb, float* out, size_t n, void* stream) {
+    if (h && n == 0) return 0;
     AEAJ_REQUIRE(h && rgb && out && space >= 0 && space < 8, "aeaj_color_forward: bad arguments");
     return launch_color_pixels(h, space, 0, rgb, out, n, ST(stream));
 }
 extern "C" int aeaj_color_inverse(aeaj_handle* h, int space, const float* in, float* rgb, size_t n, void* stream) {
+    if (h && n == 0) return 0;
     AEAJ_REQUIRE(h && rgb && in && space >= 0 && space < 8, "aeaj_color_inverse: bad arguments");
     return launch_color_pixels(h, space, 1, in, rgb, n, ST(stream));
 }
 extern "C" int aeaj_normalize(aeaj_handle* h, int space, int channel, int inverse, const float* in, float* out, size_t n, void* stream) {
+    if (h && n == 0) return 0;
     AEAJ_REQUIRE(h && in && out && space >= 0 && space < 8 && channel >= 0 && channel < 3, "aeaj_normalize: bad arguments");
     return launch_normalize(in, out, n, h->colors_host[space].mid[channel], h->colors_host[space].scale[channel], inverse, ST(stream));
 }
@@ -180,6 +184,7 @@ extern "C" int aeaj_resize_linear(aeaj_handle* h, const float* src, int sh, int 
     return launch_resize_linear(src, sh, sw, dst, H, W, ST(stream));
 }
 extern "C" int aeaj_cast_u8(aeaj_handle* h, const float* layer, uint8_t* out, size_t n, void* stream) {
+    if (h && n == 0) return 0;
     AEAJ_REQUIRE(h && layer && out, "aeaj_cast_u8: bad arguments");
     return launch_cast_u8(layer, out, n, ST(stream));
 }
@@ -336,8 +341,8 @@ static int stage_blocks(aeaj_handle* hd, bool inverse, float* layer, int h, int 
     AEAJ_CUDA(cudaMemcpyAsync(hd->stage_class_off_dev, off, sizeof off, cudaMemcpyHostToDevice, st));
     AEAJ_CUDA(cudaMemsetAsync(S.class_counts, 0, 16 * sizeof(int), st));
     rc = launch_bucket_leaves(hd->stage_plane_dev, &S.P, 1, S.class_lists, S.class_counts, hd->stage_class_off_dev, st); if (rc) return rc;
-    if (inverse) return launch_dequant_idct(hd, hd->stage_plane_dev, S.class_lists, S.class_counts, S.cg.off, S.cg.cap, ilog2i(mn), ilog2i(mx), st, nullptr);
-    return launch_dct_quant(hd, hd->stage_plane_dev, S.class_lists, S.class_counts, S.cg.off, S.cg.cap, ilog2i(mn), ilog2i(mx), st, nullptr);
+    if (inverse) return launch_dequant_idct(hd, hd->stage_plane_dev, S.class_lists, S.class_counts, S.cg.off, S.cg.cap, ilog2i(mn), ilog2i(mx), st, nullptr, nullptr, nullptr);
+    return launch_dct_quant(hd, hd->stage_plane_dev, S.class_lists, S.class_counts, S.cg.off, S.cg.cap, ilog2i(mn), ilog2i(mx), st, nullptr, nullptr, nullptr);
 }
 extern "C" int aeaj_dct_quant(aeaj_handle* hd, const float* layer, int h, int w, float mid, float scale, const int32_t* leaves,
                               const int32_t* counts, int mn, int mx, const int32_t* const* qtab, int32_t* coef, void* ws, void* stream) {
@@ -367,7 +372,21 @@ struct aeaj_plan {
     uint8_t** outs_dev;                  // tap pointers [nplanes]
     int last_launches;
     bool need_full_chroma;
+    // optional per-stage CUDA-event timing (bench.py roofline leg)
+    bool timing_on = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<std::string> ev_name;
+    int ev_n = 0;
+    cudaStream_t ev_stream = 0;
+    void mark(const char* name) {
+        if (!timing_on) return;
+        if ((int)ev.size() <= ev_n) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); ev_name.push_back(""); }
+        cudaEventRecord(ev[ev_n], ev_stream);
+        ev_name[ev_n] = name;
+        ev_n++;
+    }
 };
+static void plan_mark_cb(void* ctx, const char* name) { ((aeaj_plan*)ctx)->mark(name); }
 
 static int sub_ratio(int space, int& rh, int& rw) {
     switch (space) {
@@ -490,6 +509,32 @@ extern "C" int aeaj_plan_get_info(const aeaj_plan* p, aeaj_plan_info* info) {
 }
 extern "C" int aeaj_plan_last_launches(const aeaj_plan* p) { return p ? p->last_launches : 0; }
 
+extern "C" int aeaj_plan_enable_timing(aeaj_plan* p, int enable) {
+    AEAJ_REQUIRE(p, "aeaj_plan_enable_timing: NULL plan");
+    p->timing_on = enable != 0;
+    p->ev_n = 0;
+    return 0;
+}
+// durations (ms) of the stages of the LAST encode or decode call on this plan; synchronises its stream.
+// names_buf receives '\n'-separated stage names.
+extern "C" int aeaj_plan_read_timing(aeaj_plan* p, char* names_buf, size_t names_cap, float* ms, int cap, int* n) {
+    AEAJ_REQUIRE(p && names_buf && ms && n, "aeaj_plan_read_timing: bad arguments");
+    *n = 0;
+    names_buf[0] = 0;
+    if (!p->timing_on || p->ev_n < 2) return 0;
+    AEAJ_CUDA(cudaEventSynchronize(p->ev[p->ev_n - 1]));
+    size_t used = 0;
+    for (int i = 1; i < p->ev_n && *n < cap; i++) {
+        float t = 0;
+        AEAJ_CUDA(cudaEventElapsedTime(&t, p->ev[i - 1], p->ev[i]));
+        const std::string& nm = p->ev_name[i];
+        if (used + nm.size() + 2 > names_cap) break;
+        memcpy(names_buf + used, nm.c_str(), nm.size()); used += nm.size(); names_buf[used++] = '\n'; names_buf[used] = 0;
+        ms[(*n)++] = t;
+    }
+    return 0;
+}
+
 extern "C" int aeaj_plan_set_qtables(aeaj_plan* p, const int32_t* tables, size_t n_entries, void* stream) {
     AEAJ_REQUIRE(p && tables, "aeaj_plan_set_qtables: bad arguments");
     size_t per = 0;
@@ -540,17 +585,25 @@ extern "C" int aeaj_encode(aeaj_plan* p, const aeaj_encode_io* io, void* workspa
     AEAJ_CUDA(cudaMemsetAsync(p->planes[0].clahe_hist, 0, (size_t)NP * 16 * 256 * sizeof(uint32_t), st));
     AEAJ_CUDA(cudaMemsetAsync(p->planes[0].hist, 0, (size_t)NP * 256 * sizeof(uint32_t), st));
     AEAJ_CUDA(cudaMemsetAsync(A.class_counts, 0, 16 * sizeof(int), st));
+    p->ev_n = 0; p->ev_stream = st; p->mark("start");
     // colour + chroma subsampling + u8 cast
     rc = launch_color_forward_planar(h, p->info.space, io->rgb, B, p->info.height, p->info.width, p->planes_dev, p->planes.data(),
                                      A.full_c1, A.full_c2, st, &launches);
     if (rc) return rc;
+    p->mark("color_forward_planar");
     // Canny pipeline on all planes of the batch at once
     rc = launch_clahe_hist(p->planes_dev, p->planes.data(), NP, st); if (rc) return rc;
+    p->mark("clahe_hist");
     rc = launch_clahe_lut(p->planes_dev, NP, st); if (rc) return rc;
+    p->mark("clahe_lut");
     rc = launch_prefilter(p->planes_dev, p->planes.data(), NP, 7, 1, st); if (rc) return rc;
+    p->mark("prefilter");
     rc = launch_thresholds(p->planes_dev, NP, st); if (rc) return rc;
+    p->mark("thresholds");
     rc = launch_canny_nms(p->planes_dev, p->planes.data(), NP, st); if (rc) return rc;
+    p->mark("canny_nms");
     rc = launch_hysteresis(h, p->planes_dev, NP, p->tile_base_dev, p->ntiles, A.flags, A.ctrl, io->status, st); if (rc) return rc;
+    p->mark("hysteresis");
     launches += 6;
     if (any_tap_edge) {
         AEAJ_CUDA(cudaMemcpyAsync(p->outs_dev, outs.data(), sizeof(uint8_t*) * NP, cudaMemcpyHostToDevice, st));
@@ -565,7 +618,9 @@ extern "C" int aeaj_encode(aeaj_plan* p, const aeaj_encode_io* io, void* workspa
     rc = launch_quadtree(p->planes_dev, p->planes.data(), NP, p->info.block_min, p->info.block_max, A.class_lists, A.class_counts,
                          p->class_off_dev, st, &launches);
     if (rc) return rc;
-    rc = launch_dct_quant(h, p->planes_dev, A.class_lists, A.class_counts, p->cg.off, p->cg.cap, p->lg_min, p->lg_max, st, &launches);
+    p->mark("quadtree");
+    rc = launch_dct_quant(h, p->planes_dev, A.class_lists, A.class_counts, p->cg.off, p->cg.cap, p->lg_min, p->lg_max, st, &launches,
+                          plan_mark_cb, p);
     if (rc) return rc;
     p->last_launches = launches;
     return 0;
@@ -592,9 +647,12 @@ extern "C" int aeaj_decode(aeaj_plan* p, const aeaj_decode_io* io, void* workspa
     }
     int rc = plan_push_planes(p, st); if (rc) return rc;
     AEAJ_CUDA(cudaMemsetAsync(A.class_counts, 0, 16 * sizeof(int), st));
+    p->ev_n = 0; p->ev_stream = st; p->mark("start");
     rc = launch_bucket_leaves(p->planes_dev, p->planes.data(), NP, A.class_lists, A.class_counts, p->class_off_dev, st); if (rc) return rc;
     launches++;
-    rc = launch_dequant_idct(h, p->planes_dev, A.class_lists, A.class_counts, p->cg.off, p->cg.cap, p->lg_min, p->lg_max, st, &launches);
+    p->mark("bucket_leaves");
+    rc = launch_dequant_idct(h, p->planes_dev, A.class_lists, A.class_counts, p->cg.off, p->cg.cap, p->lg_min, p->lg_max, st, &launches,
+                             plan_mark_cb, p);
     if (rc) return rc;
     for (int l = 0; l < 3; l++)
         if (io->tap_layers[l])
@@ -602,6 +660,7 @@ extern "C" int aeaj_decode(aeaj_plan* p, const aeaj_decode_io* io, void* workspa
                                       cudaMemcpyDeviceToDevice, st));
     rc = launch_upsample_color_inverse(h, p->info.space, p->planes.data(), B, p->info.height, p->info.width, io->rgb, st); if (rc) return rc;
     launches++;
+    p->mark("upsample_color_inverse");
     p->last_launches = launches;
     return 0;
 }

@@ -284,7 +284,10 @@ int launch_cta(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* li
 
 template <bool INV>
 int launch_all(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,
-               const int64_t* off, const int64_t* caps, int lg_min, int lg_max, cudaStream_t st, int* launches) {
+               const int64_t* off, const int64_t* caps, int lg_min, int lg_max, cudaStream_t st, int* launches,
+               void (*mark)(void*, const char*), void* mark_ctx) {
+    static const char* fwd_names[9] = {"", "dct_quant_2", "dct_quant_4", "dct_quant_8", "dct_quant_16", "dct_quant_32", "dct_quant_64", "dct_quant_128", ""};
+    static const char* inv_names[9] = {"", "dequant_idct_2", "dequant_idct_4", "dequant_idct_8", "dequant_idct_16", "dequant_idct_32", "dequant_idct_64", "dequant_idct_128", ""};
     for (int lg = lg_min; lg <= lg_max; lg++) {
         if (caps[lg] <= 0) continue;
         const ClassEntry* list = class_lists + off[lg];
@@ -302,6 +305,7 @@ int launch_all(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* cl
         }
         if (rc) return rc;
         if (launches) (*launches)++;
+        if (mark) mark(mark_ctx, INV ? inv_names[lg] : fwd_names[lg]);
     }
     return 0;
 }
@@ -336,10 +340,12 @@ int aeaj_dct_init(aeaj_handle* h) {
 }
 
 int launch_dct_quant(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,
-                     const int64_t* off, const int64_t* caps, int lg_min, int lg_max, cudaStream_t st, int* launches) {
-    return launch_all<false>(h, planes_dev, class_lists, class_counts, off, caps, lg_min, lg_max, st, launches);
+                     const int64_t* off, const int64_t* caps, int lg_min, int lg_max, cudaStream_t st, int* launches,
+                     void (*mark)(void*, const char*), void* mark_ctx) {
+    return launch_all<false>(h, planes_dev, class_lists, class_counts, off, caps, lg_min, lg_max, st, launches, mark, mark_ctx);
 }
 int launch_dequant_idct(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,
-                        const int64_t* off, const int64_t* caps, int lg_min, int lg_max, cudaStream_t st, int* launches) {
-    return launch_all<true>(h, planes_dev, class_lists, class_counts, off, caps, lg_min, lg_max, st, launches);
+                        const int64_t* off, const int64_t* caps, int lg_min, int lg_max, cudaStream_t st, int* launches,
+                        void (*mark)(void*, const char*), void* mark_ctx) {
+    return launch_all<true>(h, planes_dev, class_lists, class_counts, off, caps, lg_min, lg_max, st, launches, mark, mark_ctx);
 }

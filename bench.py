@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- encode+decode megapixels/s of the adaptive edge-aware JPEG hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1], "C2"): synthetic 3840x2160 RGB frames (tests/synth.py, seeds
+rank*B+i), YCbCr, quality (30,95), blocks (4,128).  One step = one pass of the hot path -- encode
+(colour -> quantised coefficients + quadtree) and decode (coefficients -> RGB) -- over a batch of B
+distinct frames; B*99.5 MB of input per step is larger than the 126 MB L2 (no flush needed).
+Entropy coding / .ajpg framing are host-side and outside the timed region (north_star).
+
+  value   : whole-job MP/s with inputs resident in HBM, CUDA events, max over ranks
+  e2e     : the same through the host-buffer API (pinned host RGB in, pinned host RGB out; every
+            host<->device copy inside the timed region)
+  roofline: the dominant kernel, per-launch algorithmic bytes / its CUDA-event duration
+  cpu_baseline: the CPU oracle port on the same frames, on this box's host cores
+
+N>1: launched by torchrun, one rank per GPU; frames are sharded across ranks, no data-path
+collective (the path shards by image); timing = max over ranks (all_reduce MAX).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "adaptive-edge-aware-jpeg_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+
+H, W = 2160, 3840
+SPACE, QRANGE, BRANGE = "YCbCr", (30, 95), (4, 128)
+WORKLOAD = "C2: synthetic 3840x2160 RGB f32, YCbCr, quality 30-95, blocks 4-128"
+ALG_BYTES_PER_PX = 36.0          # 12 B RGB in + 6 B coefficients out, both directions
+
+
+def _oracle():
+    """CPU oracle (test infrastructure) -- only the cpu_baseline / reference legs may touch it."""
+    p = os.path.join(ROOT, "oracle")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    import oracle as O
+    return O
+
+
+def _frames(n, first_seed):
+    from synth import synth
+    return np.stack([synth(H, W, seed=first_seed + i) for i in range(n)])
+
+
+def cpu_baseline(frames: np.ndarray, threads: int):
+    """encode+decode of the oracle port on `frames` with `threads` OpenMP threads -> (MP/s, seconds)."""
+    O = _oracle()
+    O.set_threads(threads)
+    O.encode_hot(frames[0][:256, :256].copy(), SPACE, QRANGE, BRANGE)          # warm-up (tables, page-in)
+    t0 = time.perf_counter()
+    for f in frames:
+        enc = O.encode_hot(f, SPACE, QRANGE, BRANGE)
+        O.decode_hot(enc, H, W, SPACE, QRANGE, BRANGE)
+    dt = time.perf_counter() - t0
+    return len(frames) * H * W / 1e6 / dt, dt
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(gpu_index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is Python over
+    un-vendored wheels and /root/reference does not exist on the GPU box, so this arm times the
+    validated CPU port (oracle/, pinned against the reference) with every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    O = _oracle()
+    cores = os.cpu_count() or 1
+    O.set_threads(cores)
+    frames = _frames(1, 0)
+    for _ in range(max(args.warmup, 1)):
+        O.decode_hot(O.encode_hot(frames[0], SPACE, QRANGE, BRANGE), H, W, SPACE, QRANGE, BRANGE)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.decode_hot(O.encode_hot(frames[0], SPACE, QRANGE, BRANGE), H, W, SPACE, QRANGE, BRANGE)
+    dt = time.perf_counter() - t0
+    v = args.steps * H * W / 1e6 / dt
+    line = {"impl": "reference", "metric": "encode+decode megapixels/sec", "value": v, "unit": "MP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": 1},
+            "cpu_baseline": {"value": v, "unit": "MP/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} x 1 frame 3840x2160 (seed 0), encode+decode hot path, OpenMP {cores} threads"},
+            "e2e": {"value": v, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=4, help="frames per step per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-frames", type=int, default=2, help="frames in the bounded cpu_baseline sample (0 = skip)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from aeaj.codec import get_codec
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.batch
+    codec = get_codec(local)
+    frames_np = _frames(B, rank * B)
+    host_in = torch.from_numpy(frames_np).pin_memory()
+    rgb = host_in.to(f"cuda:{local}")
+    mp_per_step = B * H * W / 1e6
+
+    def step():
+        enc = codec.encode(rgb, SPACE, QRANGE, BRANGE)
+        return codec.decode_encoded(enc, SPACE, QRANGE, BRANGE)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches_per_step = 0
+    codec.encode(rgb, SPACE, QRANGE, BRANGE); launches_per_step += codec.last_launches
+    codec.decode_encoded(codec._plan(B, H, W, SPACE, BRANGE, QRANGE).out, SPACE, QRANGE, BRANGE); launches_per_step += codec.last_launches
+    torch.cuda.synchronize()
+    status = codec._plan(B, H, W, SPACE, BRANGE, QRANGE).out.status.cpu().numpy()
+
+    # ---- e2e: host buffers in, host buffers out ------------------------------------------------
+    for _ in range(2):
+        st, counts, _, _ = codec.encode_host(host_in, SPACE, QRANGE, BRANGE)
+        codec.decode_host(st, counts, B, H, W, SPACE, QRANGE, BRANGE)
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(args.steps):
+        st, counts, a, b_ = codec.encode_host(host_in, SPACE, QRANGE, BRANGE)
+        _, c, d = codec.decode_host(st, counts, B, H, W, SPACE, QRANGE, BRANGE)
+        h2d, d2h = a + c, b_ + d
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if sampler else None
+
+    # ---- per-stage timing (separate instrumented passes; CUDA events on the launching stream) --
+    codec.enable_timing(B, H, W, SPACE, BRANGE, QRANGE, True)
+    stage_ms = {}
+    reps = max(3, min(args.steps, 10))
+    for _ in range(reps):
+        enc = codec.encode(rgb, SPACE, QRANGE, BRANGE)
+        for k, v in codec.read_timing(B, H, W, SPACE, BRANGE, QRANGE).items():
+            stage_ms[k] = stage_ms.get(k, 0.0) + v / reps
+        codec.decode_encoded(enc, SPACE, QRANGE, BRANGE)
+        for k, v in codec.read_timing(B, H, W, SPACE, BRANGE, QRANGE).items():
+            stage_ms[k] = stage_ms.get(k, 0.0) + v / reps
+    codec.enable_timing(B, H, W, SPACE, BRANGE, QRANGE, False)
+    counts_np = codec._plan(B, H, W, SPACE, BRANGE, QRANGE).out.counts.cpu().numpy()
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * mp_per_step * args.steps / (ms / 1e3)
+    e2e_value = world * mp_per_step * args.steps / (e2e_ms / 1e3)
+    # roofline: dominant stage of the step
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    dom = max(stage_ms, key=stage_ms.get)
+    n_samples = float(counts_np[:, :, 2].sum())                       # coefficients = samples incl. padding, whole batch
+    full_px = B * H * W
+    alg = {  # algorithmic bytes per launch of each stage (DESIGN.md "kernels")
+        "color_forward_planar": full_px * (12 + 6 + 1.5), "upsample_color_inverse": full_px * (6 + 12),
+        "prefilter": full_px * 1.5 * 2, "clahe_hist": full_px * 1.5, "canny_nms": full_px * 1.5 * (1 + 0.25),
+    }
+    if dom.startswith("dct_quant_") or dom.startswith("dequant_idct_"):
+        s = int(dom.rsplit("_", 1)[1])
+        lg = int(np.log2(s))
+        # samples of this size class: recount from the leaf lists
+        plan = codec._plan(B, H, W, SPACE, BRANGE, QRANGE)
+        ns = 0
+        for l in range(3):
+            lv = plan.out.leaves[l].cpu().numpy()
+            for b in range(B):
+                sz = lv[b, : counts_np[b, l, 0], 2]
+                ns += int((sz == s).sum()) * s * s
+        alg[dom] = ns * 8.0                                            # 4 B in + 4 B out per sample
+    alg_bytes = alg.get(dom)
+    dom_ms = stage_ms[dom]
+    roof = {"bound": "hbm", "kernel": dom, "achieved": (alg_bytes / 1e9) / (dom_ms / 1e3) if alg_bytes else None, "peak": peak,
+            "unit": "GB/s", "frac": ((alg_bytes / 1e9) / (dom_ms / 1e3) / peak) if alg_bytes else None, "traffic": None,
+            "peak_source": peak_src, "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / sum(stage_ms.values()),
+            "pipeline_achieved": (ALG_BYTES_PER_PX * full_px * world / 1e9) / (ms / args.steps / 1e3),
+            "pipeline_frac": (ALG_BYTES_PER_PX * full_px / 1e9) / (ms / args.steps / 1e3) / peak,
+            "stage_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])}}
+
+    cpu = None
+    if args.cpu_frames > 0:
+        cores = os.cpu_count() or 1
+        v, dt = cpu_baseline(frames_np[: min(args.cpu_frames, B)], cores)
+        cpu = {"value": v, "unit": "MP/s", "cores": cores, "kind": "port",
+               "sample": f"{min(args.cpu_frames, B)} of this step's frames, encode+decode hot path, oracle port (C, OpenMP {cores} threads), {dt:.1f} s"}
+
+    line = {"metric": "encode+decode megapixels/sec", "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "l2": "inputs larger than L2 (no flush)",
+                       "parallelism": f"batch-sharded x{world}", "hysteresis_rounds": int(status[0]), "hysteresis_converged": int(status[1])},
+            "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -178,6 +178,12 @@ AEAJ_API int aeaj_pack_states_host(const uint8_t* states_host, int n_states, uin
 /* number of kernel launches issued by the last aeaj_encode / aeaj_decode on this plan */
 AEAJ_API int aeaj_plan_last_launches(const aeaj_plan* p);
 
+/* optional per-stage timing with CUDA events on the launching stream (measurement only).
+ * aeaj_plan_read_timing returns the stage durations (ms) of the LAST encode or decode call;
+ * names_buf receives newline-separated stage names.  It synchronises that call's last event. */
+AEAJ_API int aeaj_plan_enable_timing(aeaj_plan* p, int enable);
+AEAJ_API int aeaj_plan_read_timing(aeaj_plan* p, char* names_buf, size_t names_cap, float* ms, int cap, int* n);
+
 #ifdef __cplusplus
 }
 #endif
