@@ -198,11 +198,12 @@ class DeviceCodec:
         counts = st["counts"].numpy()
         d2h = st["counts"].numel() * 4
         for l in range(3):
-            nl, ns, nc = (int(counts[:, l, k].max()) for k in range(3))
-            st["coef"][l][:, :nc].copy_(enc.coef[l][:, :nc], non_blocking=True)
-            st["leaves"][l][:, :nl].copy_(enc.leaves[l][:, :nl], non_blocking=True)
-            st["states"][l][:, :ns].copy_(enc.states[l][:, :ns], non_blocking=True)
-            d2h += B * (nc * 4 + nl * 16 + ns)
+            for b in range(B):                              # contiguous per-image slices -> plain async memcpys
+                nl, ns, nc = (int(counts[b, l, k]) for k in range(3))
+                st["coef"][l][b, :nc].copy_(enc.coef[l][b, :nc], non_blocking=True)
+                st["leaves"][l][b, :nl].copy_(enc.leaves[l][b, :nl], non_blocking=True)
+                st["states"][l][b, :ns].copy_(enc.states[l][b, :ns], non_blocking=True)
+                d2h += nc * 4 + nl * 16 + ns
         torch.cuda.current_stream().synchronize()
         return st, counts, rgb_host.numel() * 4, d2h
 
@@ -212,10 +213,11 @@ class DeviceCodec:
         o = p.out
         h2d = st["counts"].numel() * 4
         for l in range(3):
-            nl, nc = int(counts[:, l, 0].max()), int(counts[:, l, 2].max())
-            o.coef[l][:, :nc].copy_(st["coef"][l][:, :nc], non_blocking=True)
-            o.leaves[l][:, :nl].copy_(st["leaves"][l][:, :nl], non_blocking=True)
-            h2d += B * (nc * 4 + nl * 16)
+            for b in range(B):
+                nl, nc = int(counts[b, l, 0]), int(counts[b, l, 2])
+                o.coef[l][b, :nc].copy_(st["coef"][l][b, :nc], non_blocking=True)
+                o.leaves[l][b, :nl].copy_(st["leaves"][l][b, :nl], non_blocking=True)
+                h2d += nc * 4 + nl * 16
         o.counts.copy_(st["counts"], non_blocking=True)
         rgb = self.decode(o.coef, o.leaves, o.counts, B, H, W, space, qrange, brange)
         st["rgb_out"].copy_(rgb, non_blocking=True)

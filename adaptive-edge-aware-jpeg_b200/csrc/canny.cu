@@ -129,40 +129,87 @@ __device__ __forceinline__ uint8_t clahe_apply_px(const uint8_t (*lut)[256], con
 // stages: bit0 CLAHE apply, bit1 Gaussian, bit2 bilateral.   grid: (tiles x, tiles y, planes)
 // ---------------------------------------------------------------------------------------------
 constexpr int PF_TW = 64, PF_TH = 32;
+constexpr int PF_AS = PF_TW + 8;                     // row stride of both staging tiles (4-byte aligned rows)
+// tap k of the 13-tap bilateral window in raster order -> (dy, dx, weight class r^2 in {0,1,2,4} -> 0..3)
+#define BIL_TAPS(X) X(0,-2,0,3) X(1,-1,-1,2) X(2,-1,0,1) X(3,-1,1,2) X(4,0,-2,3) X(5,0,-1,1) X(6,0,0,0) X(7,0,1,1) X(8,0,2,3) \
+                    X(9,1,-1,2) X(10,1,0,1) X(11,1,1,2) X(12,2,0,3)
+
 __global__ void __launch_bounds__(256) k_prefilter(const PlaneDesc* __restrict__ planes, int stages, int do_hist) {
     const PlaneDesc& P = planes[blockIdx.z];
     const int X0 = blockIdx.x * PF_TW, Y0 = blockIdx.y * PF_TH;
     if (X0 >= P.w || Y0 >= P.h) return;
-    __shared__ uint8_t sA[PF_TH + 6][PF_TW + 8];     // CLAHE output (or source), halo 3
-    __shared__ uint8_t sG[PF_TH + 4][PF_TW + 4];     // Gaussian output, halo 2
-    __shared__ uint8_t sLut[16][256];
-    __shared__ float sColor[256];
+    __shared__ __align__(16) uint8_t sA[PF_TH + 6][PF_AS];     // CLAHE output (or source), halo 3
+    __shared__ __align__(16) uint8_t sG[PF_TH + 4][PF_AS];     // Gaussian output, halo 2
+    __shared__ __align__(16) uint8_t sLut[16][256];
+    __shared__ float sW[4][256];                               // space weight (r^2 = 0,1,2,4) x colour weight, rounded product
     __shared__ unsigned int sHist[256];
+    __shared__ float sXa[PF_TW + 6], sYa[PF_TH + 6];           // CLAHE interpolation weights per tile column / row
+    __shared__ uint8_t sTx[PF_TW + 6][2], sTy[PF_TH + 6][2];   // CLAHE tile indices per tile column / row
     const int tid = threadIdx.x;
-    if (stages & 1) for (int i = tid; i < 16 * 256 / 4; i += 256) reinterpret_cast<uint32_t*>(&sLut[0][0])[i] = reinterpret_cast<const uint32_t*>(P.clahe_lut)[i];
-    sColor[tid] = c_bil_color[tid];
-    sHist[tid] = 0;
-    __syncthreads();
     const ClaheGeom g = clahe_geom(P.h, P.w);
+    if (stages & 1) {
+        for (int i = tid; i < 16 * 256 / 4; i += 256) reinterpret_cast<uint32_t*>(&sLut[0][0])[i] = reinterpret_cast<const uint32_t*>(P.clahe_lut)[i];
+        if (tid < PF_TW + 6) {
+            int x = reflect101(X0 + tid - 3, P.w);
+            float txf = __fsub_rn(__fmul_rn((float)x, g.inv_tw), 0.5f);
+            int t1 = (int)floorf(txf);
+            sXa[tid] = __fsub_rn(txf, (float)t1);
+            sTx[tid][0] = (uint8_t)max(t1, 0); sTx[tid][1] = (uint8_t)min(t1 + 1, 3);
+        } else if (tid >= 128 && tid < 128 + PF_TH + 6) {
+            int r = tid - 128;
+            int y = reflect101(Y0 + r - 3, P.h);
+            float tyf = __fsub_rn(__fmul_rn((float)y, g.inv_th), 0.5f);
+            int t1 = (int)floorf(tyf);
+            sYa[r] = __fsub_rn(tyf, (float)t1);
+            sTy[r][0] = (uint8_t)max(t1, 0); sTy[r][1] = (uint8_t)min(t1 + 1, 3);
+        }
+    }
+    {
+        float cw = c_bil_color[tid];
+        sW[0][tid] = cw;                                       // centre tap: space weight exp(0) = 1
+        sW[1][tid] = __fmul_rn(c_bil_space[2], cw);            // r^2 = 1
+        sW[2][tid] = __fmul_rn(c_bil_space[1], cw);            // r^2 = 2
+        sW[3][tid] = __fmul_rn(c_bil_space[0], cw);            // r^2 = 4
+        sHist[tid] = 0;
+    }
+    __syncthreads();
     const uint8_t* src = P.u8a;
+    // stage A: source (folded coordinates) -> CLAHE
     for (int i = tid; i < (PF_TH + 6) * (PF_TW + 6); i += 256) {
-        int ry = i / (PF_TW + 6), rx = i - ry * (PF_TW + 6);
-        int y = reflect101(Y0 + ry - 3, P.h), x = reflect101(X0 + rx - 3, P.w);
-        int v = src[(size_t)y * P.w + x];
-        sA[ry][rx] = (stages & 1) ? clahe_apply_px(sLut, g, y, x, v) : (uint8_t)v;
+        const int ry = i / (PF_TW + 6), rx = i - ry * (PF_TW + 6);
+        const int y = reflect101(Y0 + ry - 3, P.h), x = reflect101(X0 + rx - 3, P.w);
+        const int v = src[(size_t)y * P.w + x];
+        int outv = v;
+        if (stages & 1) {
+            const float xa = sXa[rx], xa1 = __fsub_rn(1.0f, xa), ya = sYa[ry], ya1 = __fsub_rn(1.0f, ya);
+            const int t00 = sTy[ry][0] * 4 + sTx[rx][0], t01 = sTy[ry][0] * 4 + sTx[rx][1];
+            const int t10 = sTy[ry][1] * 4 + sTx[rx][0], t11 = sTy[ry][1] * 4 + sTx[rx][1];
+            const float a = __fmul_rn((float)sLut[t00][v], xa1), b = __fmul_rn((float)sLut[t01][v], xa);
+            const float c = __fmul_rn((float)sLut[t10][v], xa1), d = __fmul_rn((float)sLut[t11][v], xa);
+            const float r = __fadd_rn(__fmul_rn(__fadd_rn(a, b), ya1), __fmul_rn(__fadd_rn(c, d), ya));
+            outv = min(max(__float2int_rn(r), 0), 255);
+        }
+        sA[ry][rx] = (uint8_t)outv;
     }
     __syncthreads();
-    for (int i = tid; i < (PF_TH + 4) * (PF_TW + 4); i += 256) {
-        int ry = i / (PF_TW + 4), rx = i - ry * (PF_TW + 4);
+    // stage B: Gaussian [1 2 1]x[1 2 1], 4 outputs per thread sharing the 6 column sums
+    for (int i = tid; i < (PF_TH + 4) * 17; i += 256) {
+        const int ry = i / 17, gx = (i - ry * 17) * 4;            // output cells (ry, gx..gx+3) of the halo-2 region
+        uchar4 o;
         if (stages & 2) {
-            const uint8_t* r0 = &sA[ry][rx]; const uint8_t* r1 = &sA[ry + 1][rx]; const uint8_t* r2 = &sA[ry + 2][rx];
-            int s = (r0[0] + 2 * r0[1] + r0[2]) + 2 * (r1[0] + 2 * r1[1] + r1[2]) + (r2[0] + 2 * r2[1] + r2[2]);
-            sG[ry][rx] = (uint8_t)((s + 8) >> 4);
-        } else sG[ry][rx] = sA[ry + 1][rx + 1];
+            int cs[6];
+#pragma unroll
+            for (int j = 0; j < 6; j++) cs[j] = sA[ry][gx + j] + 2 * sA[ry + 1][gx + j] + sA[ry + 2][gx + j];
+            o.x = (uint8_t)((cs[0] + 2 * cs[1] + cs[2] + 8) >> 4); o.y = (uint8_t)((cs[1] + 2 * cs[2] + cs[3] + 8) >> 4);
+            o.z = (uint8_t)((cs[2] + 2 * cs[3] + cs[4] + 8) >> 4); o.w = (uint8_t)((cs[3] + 2 * cs[4] + cs[5] + 8) >> 4);
+        } else {
+            o = make_uchar4(sA[ry + 1][gx + 1], sA[ry + 1][gx + 2], sA[ry + 1][gx + 3], sA[ry + 1][gx + 4]);
+        }
+        *reinterpret_cast<uchar4*>(&sG[ry][gx]) = o;
     }
     __syncthreads();
+    // stage C: bilateral, thread -> 4 consecutive px in rows (tid/16) and (tid/16 + 16)
     uint8_t* dst = P.u8b;
-    // thread -> 4 consecutive px in rows (tid/16) and (tid/16 + 16)
     const int tx = (tid & 15) * 4;
 #pragma unroll
     for (int half = 0; half < 2; half++) {
@@ -170,38 +217,49 @@ __global__ void __launch_bounds__(256) k_prefilter(const PlaneDesc* __restrict__
         const int y = Y0 + ty;
         if (y >= P.h) continue;
         uint8_t outv[4];
+        if (stages & 4) {
+            // 5 rows x 8 bytes window: rows ty..ty+4, cols tx..tx+7 of sG
+            int win[5][8];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int lx = tx + k;
-            int res;
-            if (stages & 4) {
-                const int v0 = sG[ty + 2][lx + 2];
+            for (int r = 0; r < 5; r++) {
+                const uchar4 a = *reinterpret_cast<const uchar4*>(&sG[ty + r][tx]);
+                const uchar4 b = *reinterpret_cast<const uchar4*>(&sG[ty + r][tx + 4]);
+                win[r][0] = a.x; win[r][1] = a.y; win[r][2] = a.z; win[r][3] = a.w;
+                win[r][4] = b.x; win[r][5] = b.y; win[r][6] = b.z; win[r][7] = b.w;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int v0 = win[2][k + 2];
                 float sum = 0.0f, wsum = 0.0f;
+#define BIL_ONE(idx, dy, dx, cls) { const int v = win[2 + (dy)][k + 2 + (dx)]; const float wgt = sW[cls][__sad(v, v0, 0u)]; \
+                                    sum = __fmaf_rn((float)v, wgt, sum); wsum = __fadd_rn(wsum, wgt); }
+                BIL_TAPS(BIL_ONE)
+#undef BIL_ONE
+                const int res = __float2int_rn(__fdiv_rn(sum, wsum));
+                outv[k] = (uint8_t)min(max(res, 0), 255);
+            }
+        } else {
 #pragma unroll
-                for (int t = 0; t < 13; t++) {
-                    int v = sG[ty + 2 + c_bil_dy[t]][lx + 2 + c_bil_dx[t]];
-                    float wgt = __fmul_rn(c_bil_space[t], sColor[abs(v - v0)]);
-                    sum = __fmaf_rn((float)v, wgt, sum);
-                    wsum = __fadd_rn(wsum, wgt);
-                }
-                res = __float2int_rn(__fdiv_rn(sum, wsum));
-                res = res < 0 ? 0 : (res > 255 ? 255 : res);
-            } else res = sG[ty + 2][lx + 2];
-            outv[k] = (uint8_t)res;
+            for (int k = 0; k < 4; k++) outv[k] = sG[ty + 2][tx + k + 2];
         }
         const int x = X0 + tx;
-        int prev = -1, cnt = 0;
+        uint8_t* drow = dst + (size_t)y * P.w;
+        if (x + 3 < P.w && ((P.w & 3) == 0)) *reinterpret_cast<uchar4*>(drow + x) = make_uchar4(outv[0], outv[1], outv[2], outv[3]);
+        else {
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (x + k < P.w) {
-                dst[(size_t)y * P.w + x + k] = outv[k];
-                if (do_hist) {
+            for (int k = 0; k < 4; k++) if (x + k < P.w) drow[x + k] = outv[k];
+        }
+        if (do_hist) {
+            int prev = -1, cnt = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (x + k < P.w) {
                     if (outv[k] == prev) cnt++;
                     else { if (cnt) atomicAdd(&sHist[prev], (unsigned)cnt); prev = outv[k]; cnt = 1; }
                 }
             }
+            if (cnt) atomicAdd(&sHist[prev], (unsigned)cnt);
         }
-        if (do_hist && cnt) atomicAdd(&sHist[prev], (unsigned)cnt);
     }
     if (do_hist) {
         __syncthreads();

@@ -372,6 +372,51 @@ __global__ void __launch_bounds__(256) k_upsample_color_inverse(const __grid_con
     o[0] = r; o[1] = g; o[2] = bl;
 }
 
+// 2x2 chroma specialisation (H == 2h, W == 2w, W % 4 == 0): 4 output px per thread, float4 stores.
+// The half-pixel coordinates are exact dyadic numbers here -- even dx: source k-1 with t = .75, odd dx:
+// source k with t = .25, clamped with t = 0 at the borders -- so this reproduces lin_coord() bit for bit.
+__device__ __forceinline__ void up2_coord(int d, int ssize, int& s0, int& s1, float& f) {
+    int k = d >> 1;
+    int s = (d & 1) ? k : k - 1;
+    float fx = (d & 1) ? 0.25f : 0.75f;
+    if (s < 0) { fx = 0.0f; s = 0; }
+    if (s >= ssize - 1) { fx = 0.0f; s = ssize - 1; }
+    s0 = s; s1 = min(s + 1, ssize - 1); f = fx;
+}
+template <int SPACE>
+__global__ void __launch_bounds__(256) k_upsample2x_color_inverse(const __grid_constant__ ColorConsts C, UpIn in, int H, int W, float* __restrict__ rgb) {
+    const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, dy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (dx0 >= W || dy >= H) return;
+    const int b = blockIdx.z;
+    const int cw = in.w[1], chh = in.h[1];
+    const float4 yv = __ldg(reinterpret_cast<const float4*>(in.p[0] + (size_t)b * in.stride[0] + (size_t)dy * W + dx0));
+    const float lum[4] = {yv.x, yv.y, yv.z, yv.w};
+    int y0, y1; float fy;
+    up2_coord(dy, chh, y0, y1, fy);
+    const float b0 = __fsub_rn(1.0f, fy);
+    float cv[2][4];
+#pragma unroll
+    for (int l = 1; l <= 2; l++) {
+        const float* p = in.p[l] + (size_t)b * in.stride[l];
+        const float* r0 = p + (size_t)y0 * cw;
+        const float* r1 = p + (size_t)y1 * cw;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int x0, x1; float fx;
+            up2_coord(dx0 + k, cw, x0, x1, fx);
+            const float a0 = __fsub_rn(1.0f, fx);
+            float t0 = __fadd_rn(__fmul_rn(__ldg(r0 + x0), a0), __fmul_rn(__ldg(r0 + x1), fx));
+            float t1 = __fadd_rn(__fmul_rn(__ldg(r1 + x0), a0), __fmul_rn(__ldg(r1 + x1), fx));
+            cv[l - 1][k] = __fadd_rn(__fmul_rn(t0, b0), __fmul_rn(t1, fy));
+        }
+    }
+    float o[12];
+#pragma unroll
+    for (int k = 0; k < 4; k++) color_inv<SPACE>(C, lum[k], cv[0][k], cv[1][k], o[3 * k], o[3 * k + 1], o[3 * k + 2]);
+    float4* out = reinterpret_cast<float4*>(rgb + ((size_t)b * H * W + (size_t)dy * W + dx0) * 3);
+    out[0] = make_float4(o[0], o[1], o[2], o[3]); out[1] = make_float4(o[4], o[5], o[6], o[7]); out[2] = make_float4(o[8], o[9], o[10], o[11]);
+}
+
 __global__ void __launch_bounds__(256) k_normalize(const float* __restrict__ in, float* __restrict__ out, size_t n, float mid, float scale, int inverse) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -495,10 +540,17 @@ int launch_upsample_color_inverse(aeaj_handle* h, int space, const PlaneDesc* P,
     const ColorConsts& C = h->colors_host[space];
     UpIn in;
     for (int l = 0; l < 3; l++) { in.p[l] = P[l].layer_f32; in.h[l] = P[l].h; in.w[l] = P[l].w; in.stride[l] = (size_t)P[l].h * P[l].w; }
-    dim3 blk(32, 8), grd(aeaj_cdiv(W, 32), aeaj_cdiv(H, 8), B);
+    const bool fast2x = (in.h[1] * 2 == H && in.w[1] * 2 == W && in.h[2] == in.h[1] && in.w[2] == in.w[1] && (W % 4) == 0 &&
+                         in.h[0] == H && in.w[0] == W);
     return dispatch_space(space, [&](auto S) {
         constexpr int SP = decltype(S)::value;
-        k_upsample_color_inverse<SP><<<grd, blk, 0, st>>>(C, in, H, W, rgb);
+        if (fast2x) {
+            dim3 blk(32, 8), grd(aeaj_cdiv(W / 4, 32), aeaj_cdiv(H, 8), B);
+            k_upsample2x_color_inverse<SP><<<grd, blk, 0, st>>>(C, in, H, W, rgb);
+        } else {
+            dim3 blk(32, 8), grd(aeaj_cdiv(W, 32), aeaj_cdiv(H, 8), B);
+            k_upsample_color_inverse<SP><<<grd, blk, 0, st>>>(C, in, H, W, rgb);
+        }
         AEAJ_LAUNCH_CHECK();
         return 0;
     });
