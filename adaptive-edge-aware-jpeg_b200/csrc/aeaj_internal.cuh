@@ -112,6 +112,8 @@ struct aeaj_handle {
     int has_srgb_lut;
     float* dct_dev[9];            // DCT-II matrices C (s x s, row-major) for s = 2^k, k = 1..8
     float* dct_all_dev;
+    float* dct_half_dev[9];       // even/odd half tables for the CTA kernels (sizes 64, 128)
+    float* dct_half_all_dev;
     // device scratch for single-plane stage calls
     struct PlaneDesc* stage_plane_dev;
     long long* stage_class_off_dev;   // [9]

@@ -146,107 +146,227 @@ __global__ void __launch_bounds__(256) k_dct_rows(const PlaneDesc* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// CTA kernel, S in {64,128}: 256 threads, (S/16 x S/16) register tile per thread.
-//   pass 1: V = A1 . In   with A1^T staged in sA (sA[i][k] = M[k][i] = M^T row-major)
-//   pass 2: Out = V . M^T with V^T staged in sB (aliasing In) and B2 = M^T = sA again
+// CTA kernel, S in {64,128}: one CTA (256 threads) per leaf, FP32 FMA, using the even/odd symmetry of
+// the DCT matrix, C[k][N-1-i] = (-1)^k C[k][i]: with Ce[m][i] = C[2m][i], Co[m][i] = C[2m+1][i]
+// (m, i < h = N/2) every 1-D transform is two h x h products on folded data -- half the FLOPs.
+//
+//   forward  (cv.dct):  U = X[i]+X[N-1-i], D = X[i]-X[N-1-i] (fold rows while loading);
+//                       V[2m] = Ce.U, V[2m+1] = Co.D; fold V's columns in registers;
+//                       Out[k][2m] = sum_j P[k][j] Ce[m][j], Out[k][2m+1] = sum_j Q[k][j] Co[m][j]
+//   inverse  (cv.idct): E = Ce^T.Z[even rows], O = Co^T.Z[odd rows]; V[i] = E+O, V[N-1-i] = E-O;
+//                       E' = V[:, even].Ce, O' = V[:, odd].Co; X[i][j] = E'+O', X[i][N-1-j] = E'-O'
+//
+// Thread t: parity g = t & 1 (even / odd half), pair p = t >> 1.  The two lanes of a pair hold the even
+// and the odd partial results for the same tile and exchange them with __shfl_xor(.., 1).
+// Shared memory: sA = [Ae | Ao] (2 x h x h: the half matrices in the orientation the pass needs),
+// sB = N x N staging (folded input, then the transposed intermediate).  1.5 N^2 floats = 96 KB at N=128.
 // ---------------------------------------------------------------------------------------------
 template <int S, bool INVERSE>
 __global__ void __launch_bounds__(256) k_dct_cta(const PlaneDesc* __restrict__ planes, const ClassEntry* __restrict__ list,
-                                                 const int* __restrict__ count_ptr, const float* __restrict__ Mtg) {
-    constexpr int TM = S / 16, TN = S / 16;
+                                                 const int* __restrict__ count_ptr, const float* __restrict__ half_tab) {
+    constexpr int N = S, Hh = S / 2;
     constexpr int LG = (S == 64) ? 6 : 7;
+    constexpr int T = S / 16;                          // tile edge per thread: 8 (N=128) or 4 (N=64)
+    constexpr int RC = T / 4;                          // number of 4-wide chunks along the "4-chunk" axis
+    constexpr int CW = T / 2;                          // width of the two mirrored column chunks (forward pass 1)
     extern __shared__ __align__(16) float smem[];
-    float* sA = smem;                                  // M^T row-major: sA[i*S + k] = M[k][i]
-    float* sB = smem + S * S;                          // In (row-major), later V^T
-    const int tid = threadIdx.x;
-    for (int i = tid; i < S * S / 4; i += 256) reinterpret_cast<float4*>(sA)[i] = __ldg(reinterpret_cast<const float4*>(Mtg) + i);
+    float* sA = smem;                                  // [2][Hh][Hh]
+    float* sB = smem + 2 * Hh * Hh;                    // [N][N]
+    const int tid = threadIdx.x, g = tid & 1, p = tid >> 1;
+    for (int i = tid; i < 2 * Hh * Hh / 4; i += 256) reinterpret_cast<float4*>(sA)[i] = __ldg(reinterpret_cast<const float4*>(half_tab) + i);
+    const float* sAg = sA + g * Hh * Hh;
     const int count = *count_ptr;
-    const int tr = tid / 16, tc = tid % 16;            // thread tile: rows tr*4 + 64*c + (0..3), cols tc*4 + 64*c + (0..3)
-    auto ridx = [&](int a) { return tr * 4 + (a & 3) + (a >> 2) * 64; };
-    auto cidx = [&](int b) { return tc * 4 + (b & 3) + (b >> 2) * 64; };
+    // pass-1 tile: rows (h of them) in chunks of 4 at stride 32, columns (N of them)
+    const int tr = p / 16, tc = p % 16;
+    // pass-2 tile: rows (N of them) in chunks of 4 at stride 64, columns (h of them) in chunks of 4 at stride 32
+    const int tr2 = p / 8, tc2 = p % 8;
     for (int li = blockIdx.x; li < count; li += gridDim.x) {
         const ClassEntry e = list[li];
         const PlaneDesc& P = planes[e.plane];
         __syncthreads();                               // previous leaf done with sB
         if (!INVERSE) {
-            const int bh = min(S, P.h - e.y), bw = min(S, P.w - e.x);
+            // load X, fold rows: sB[i][j] = X[i][j] + X[N-1-i][j] (i < h), sB[h+i][j] = X[i][j] - X[N-1-i][j]
+            const int bh = min(N, P.h - e.y), bw = min(N, P.w - e.x);
             const float mid = P.mid, sc = P.scale;
-            for (int i = tid; i < S * S; i += 256) {
-                int rr = i / S, cc = i - rr * S;
-                float v = __ldg(P.layer_f32 + (size_t)(e.y + pad_reflect(rr, bh)) * P.w + e.x + pad_reflect(cc, bw));
-                sB[i] = __fmul_rn(__fsub_rn(v, mid), sc);
+            for (int i = tid; i < Hh * N; i += 256) {
+                const int rr = i / N, cc = i - rr * N;
+                const int xx = e.x + pad_reflect(cc, bw);
+                float a = __ldg(P.layer_f32 + (size_t)(e.y + pad_reflect(rr, bh)) * P.w + xx);
+                float b = __ldg(P.layer_f32 + (size_t)(e.y + pad_reflect(N - 1 - rr, bh)) * P.w + xx);
+                a = __fmul_rn(__fsub_rn(a, mid), sc); b = __fmul_rn(__fsub_rn(b, mid), sc);
+                sB[i] = __fadd_rn(a, b); sB[Hh * N + i] = __fsub_rn(a, b);
             }
         } else {
+            // load Z dequantised, rows in split order: even rows first, then odd rows
             const int* cf = P.coef + (size_t)e.coef_off;
             const int* qt = P.qtab[LG];
-            for (int i = tid; i < S * S; i += 256) sB[i] = (float)(__ldg(cf + i) * __ldg(qt + i));
+            for (int i = tid; i < N * N / 4; i += 256) {
+                const int k = (i * 4) / N, l = (i * 4) - k * N;
+                int4 cv = __ldg(reinterpret_cast<const int4*>(cf) + i), qv = __ldg(reinterpret_cast<const int4*>(qt) + i);
+                *reinterpret_cast<float4*>(sB + ((k & 1) * Hh + (k >> 1)) * N + l) =
+                    make_float4((float)(cv.x * qv.x), (float)(cv.y * qv.y), (float)(cv.z * qv.z), (float)(cv.w * qv.w));
+            }
         }
         __syncthreads();
-        float acc[TM][TN];
+        float acc[T][T];
 #pragma unroll
-        for (int a = 0; a < TM; a++)
+        for (int a = 0; a < T; a++)
 #pragma unroll
-            for (int b = 0; b < TN; b++) acc[a][b] = 0.0f;
-        // pass 1: V[k][j] = sum_i M[k][i] In[i][j]
-        for (int i = 0; i < S; i++) {
-            float av[TM], bv[TN];
-#pragma unroll
-            for (int a = 0; a < TM; a += 4) { float4 t = *reinterpret_cast<const float4*>(sA + i * S + ridx(a)); av[a] = t.x; av[a + 1] = t.y; av[a + 2] = t.z; av[a + 3] = t.w; }
-#pragma unroll
-            for (int b = 0; b < TN; b += 4) { float4 t = *reinterpret_cast<const float4*>(sB + i * S + cidx(b)); bv[b] = t.x; bv[b + 1] = t.y; bv[b + 2] = t.z; bv[b + 3] = t.w; }
-#pragma unroll
-            for (int a = 0; a < TM; a++)
-#pragma unroll
-                for (int b = 0; b < TN; b++) acc[a][b] = __fmaf_rn(av[a], bv[b], acc[a][b]);
-        }
-        __syncthreads();                               // everyone finished reading In
-        // store V transposed: sB[j*S + k] = V[k][j]
-#pragma unroll
-        for (int b = 0; b < TN; b++)
-#pragma unroll
-            for (int a = 0; a < TM; a += 4)
-                *reinterpret_cast<float4*>(sB + cidx(b) * S + ridx(a)) = make_float4(acc[a][b], acc[a + 1][b], acc[a + 2][b], acc[a + 3][b]);
-        __syncthreads();
-#pragma unroll
-        for (int a = 0; a < TM; a++)
-#pragma unroll
-            for (int b = 0; b < TN; b++) acc[a][b] = 0.0f;
-        // pass 2: Out[k][l] = sum_j V[k][j] M[l][j] = sum_j sB[j][k] * sA[j][l]
-        for (int j = 0; j < S; j++) {
-            float av[TM], bv[TN];
-#pragma unroll
-            for (int a = 0; a < TM; a += 4) { float4 t = *reinterpret_cast<const float4*>(sB + j * S + ridx(a)); av[a] = t.x; av[a + 1] = t.y; av[a + 2] = t.z; av[a + 3] = t.w; }
-#pragma unroll
-            for (int b = 0; b < TN; b += 4) { float4 t = *reinterpret_cast<const float4*>(sA + j * S + cidx(b)); bv[b] = t.x; bv[b + 1] = t.y; bv[b + 2] = t.z; bv[b + 3] = t.w; }
-#pragma unroll
-            for (int a = 0; a < TM; a++)
-#pragma unroll
-                for (int b = 0; b < TN; b++) acc[a][b] = __fmaf_rn(av[a], bv[b], acc[a][b]);
-        }
+            for (int b = 0; b < T; b++) acc[a][b] = 0.0f;
+        const float* sBg = sB + g * Hh * N;
         if (!INVERSE) {
+            // pass 1: Vg[m][j] = sum_i Cg[m][i] * Fg[i][j]; sAg[i][m] = Cg[m][i]; columns = two mirrored chunks
+            for (int i = 0; i < Hh; i++) {
+                float av[T], bv[T];
+#pragma unroll
+                for (int c = 0; c < RC; c++) { float4 t = *reinterpret_cast<const float4*>(sAg + i * Hh + tr * 4 + c * 32); av[4 * c] = t.x; av[4 * c + 1] = t.y; av[4 * c + 2] = t.z; av[4 * c + 3] = t.w; }
+                if (CW == 4) {
+                    float4 t = *reinterpret_cast<const float4*>(sBg + i * N + tc * 4);
+                    float4 u = *reinterpret_cast<const float4*>(sBg + i * N + N - 4 - tc * 4);
+                    bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w; bv[4] = u.w; bv[5] = u.z; bv[6] = u.y; bv[7] = u.x;
+                } else {
+                    float2 t = *reinterpret_cast<const float2*>(sBg + i * N + tc * 2);
+                    float2 u = *reinterpret_cast<const float2*>(sBg + i * N + N - 2 - tc * 2);
+                    bv[0] = t.x; bv[1] = t.y; bv[2] = u.y; bv[3] = u.x;
+                }
+#pragma unroll
+                for (int a = 0; a < T; a++)
+#pragma unroll
+                    for (int b = 0; b < T; b++) acc[a][b] = __fmaf_rn(av[a], bv[b], acc[a][b]);
+            }
+            __syncthreads();                           // everyone finished reading the folded input
+            // fold V's columns in registers and store transposed, rows in split order k' = g*h + m:
+            //   sB[j][k']       = P[k][j] = V[k][j] + V[k][N-1-j]      (j < h)
+            //   sB[h + j][k']   = Q[k][j] = V[k][j] - V[k][N-1-j]
+#pragma unroll
+            for (int b = 0; b < CW; b++) {
+                const int j = tc * CW + b;
+#pragma unroll
+                for (int c = 0; c < RC; c++) {
+                    float pv[4], qv[4];
+#pragma unroll
+                    for (int a = 0; a < 4; a++) { pv[a] = __fadd_rn(acc[4 * c + a][b], acc[4 * c + a][b + CW]); qv[a] = __fsub_rn(acc[4 * c + a][b], acc[4 * c + a][b + CW]); }
+                    const int kk = g * Hh + tr * 4 + c * 32;
+                    *reinterpret_cast<float4*>(sB + j * N + kk) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+                    *reinterpret_cast<float4*>(sB + (Hh + j) * N + kk) = make_float4(qv[0], qv[1], qv[2], qv[3]);
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int a = 0; a < T; a++)
+#pragma unroll
+                for (int b = 0; b < T; b++) acc[a][b] = 0.0f;
+            // pass 2: Out[k'][2m+g] = sum_j F2g[j][k'] * Cg[m][j]   (F2e = P, F2o = Q; sAg[j][m] = Cg[m][j])
+            for (int j = 0; j < Hh; j++) {
+                float av[T], bv[T];
+#pragma unroll
+                for (int c = 0; c < RC; c++) { float4 t = *reinterpret_cast<const float4*>(sBg + j * N + tr2 * 4 + c * 64); av[4 * c] = t.x; av[4 * c + 1] = t.y; av[4 * c + 2] = t.z; av[4 * c + 3] = t.w; }
+#pragma unroll
+                for (int c = 0; c < RC; c++) { float4 t = *reinterpret_cast<const float4*>(sAg + j * Hh + tc2 * 4 + c * 32); bv[4 * c] = t.x; bv[4 * c + 1] = t.y; bv[4 * c + 2] = t.z; bv[4 * c + 3] = t.w; }
+#pragma unroll
+                for (int a = 0; a < T; a++)
+#pragma unroll
+                    for (int b = 0; b < T; b++) acc[a][b] = __fmaf_rn(av[a], bv[b], acc[a][b]);
+            }
+            // quantise, interleave even/odd columns with the pair lane, store int4
             int* cf = P.coef + (size_t)e.coef_off;
             const int* qt = P.qtab[LG];
 #pragma unroll
-            for (int a = 0; a < TM; a++) {
-                const int k = ridx(a);
+            for (int a = 0; a < T; a++) {
+                const int kp = tr2 * 4 + (a & 3) + (a >> 2) * 64;           // split-order row
+                const int k = (kp < Hh) ? 2 * kp : 2 * (kp - Hh) + 1;       // natural row
 #pragma unroll
-                for (int b = 0; b < TN; b += 4) {
-                    const int l = cidx(b);
-                    int4 qv = __ldg(reinterpret_cast<const int4*>(qt + k * S + l));
-                    int4 o = make_int4(quantize(acc[a][b], qv.x), quantize(acc[a][b + 1], qv.y), quantize(acc[a][b + 2], qv.z), quantize(acc[a][b + 3], qv.w));
-                    *reinterpret_cast<int4*>(cf + k * S + l) = o;
+                for (int c = 0; c < RC; c++) {
+                    const int m0 = tc2 * 4 + c * 32;
+                    int qv[4];
+#pragma unroll
+                    for (int b = 0; b < 4; b++) qv[b] = quantize(acc[a][4 * c + b], __ldg(qt + k * N + 2 * (m0 + b) + g));
+                    const int x0 = g ? qv[0] : qv[2], x1 = g ? qv[1] : qv[3];
+                    const int r0 = __shfl_xor_sync(0xffffffffu, x0, 1), r1 = __shfl_xor_sync(0xffffffffu, x1, 1);
+                    const int4 o = g ? make_int4(r0, qv[2], r1, qv[3]) : make_int4(qv[0], r0, qv[1], r1);
+                    *reinterpret_cast<int4*>(cf + k * N + 2 * m0 + 4 * g) = o;
                 }
             }
         } else {
+            // pass 1: Rg[i][l] = sum_m Cg[m][i] * Zg[m][l]; sAg[m][i] = Cg[m][i]; columns l natural in chunks of 4
+            for (int m = 0; m < Hh; m++) {
+                float av[T], bv[T];
+#pragma unroll
+                for (int c = 0; c < RC; c++) { float4 t = *reinterpret_cast<const float4*>(sAg + m * Hh + tr * 4 + c * 32); av[4 * c] = t.x; av[4 * c + 1] = t.y; av[4 * c + 2] = t.z; av[4 * c + 3] = t.w; }
+#pragma unroll
+                for (int c = 0; c < RC; c++) { float4 t = *reinterpret_cast<const float4*>(sBg + m * N + tc * 4 + c * 64); bv[4 * c] = t.x; bv[4 * c + 1] = t.y; bv[4 * c + 2] = t.z; bv[4 * c + 3] = t.w; }
+#pragma unroll
+                for (int a = 0; a < T; a++)
+#pragma unroll
+                    for (int b = 0; b < T; b++) acc[a][b] = __fmaf_rn(av[a], bv[b], acc[a][b]);
+            }
+            __syncthreads();                           // everyone finished reading Z
+            // V[i][l] = E + O (even lane), V[N-1-i][l] = E - O (odd lane); store transposed with the columns in
+            // split order: sB[(l&1)*h + (l>>1)][row]
+#pragma unroll
+            for (int b = 0; b < T; b++) {
+                const int l = tc * 4 + (b & 3) + (b >> 2) * 64;
+                const int lrow = (l & 1) * Hh + (l >> 1);
+#pragma unroll
+                for (int c = 0; c < RC; c++) {
+                    float v[4];
+#pragma unroll
+                    for (int a = 0; a < 4; a++) {
+                        const float mine = acc[4 * c + a][b];
+                        const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+                        v[a] = g ? __fsub_rn(other, mine) : __fadd_rn(mine, other);     // g=0: E+O ; g=1: E-O
+                    }
+                    const int i0 = tr * 4 + c * 32;
+                    if (!g) *reinterpret_cast<float4*>(sB + lrow * N + i0) = make_float4(v[0], v[1], v[2], v[3]);
+                    else *reinterpret_cast<float4*>(sB + lrow * N + (N - 4 - i0)) = make_float4(v[3], v[2], v[1], v[0]);
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int a = 0; a < T; a++)
+#pragma unroll
+                for (int b = 0; b < T; b++) acc[a][b] = 0.0f;
+            // pass 2: R2g[i'][j] = sum_m V[i'][2m+g] * Cg[m][j] = sum_m sBg[m][i'] * sAg[m][j]
+            for (int m = 0; m < Hh; m++) {
+                float av[T], bv[T];
+#pragma unroll
+                for (int c = 0; c < RC; c++) { float4 t = *reinterpret_cast<const float4*>(sBg + m * N + tr2 * 4 + c * 64); av[4 * c] = t.x; av[4 * c + 1] = t.y; av[4 * c + 2] = t.z; av[4 * c + 3] = t.w; }
+#pragma unroll
+                for (int c = 0; c < RC; c++) { float4 t = *reinterpret_cast<const float4*>(sAg + m * Hh + tc2 * 4 + c * 32); bv[4 * c] = t.x; bv[4 * c + 1] = t.y; bv[4 * c + 2] = t.z; bv[4 * c + 3] = t.w; }
+#pragma unroll
+                for (int a = 0; a < T; a++)
+#pragma unroll
+                    for (int b = 0; b < T; b++) acc[a][b] = __fmaf_rn(av[a], bv[b], acc[a][b]);
+            }
+            // X[i'][j] = E' + O' (even lane), X[i'][N-1-j] = E' - O' (odd lane); denormalise, crop, store
             const float mid = P.mid, sc = P.scale;
+            const bool vec_ok = ((P.w & 3) == 0);
 #pragma unroll
-            for (int a = 0; a < TM; a++) {
-                const int y = e.y + ridx(a);
-                if (y >= P.h) continue;
+            for (int a = 0; a < T; a++) {
+                const int y = e.y + tr2 * 4 + (a & 3) + (a >> 2) * 64;
 #pragma unroll
-                for (int b = 0; b < TN; b++) {
-                    const int x = e.x + cidx(b);
-                    if (x < P.w) P.layer_f32[(size_t)y * P.w + x] = __fadd_rn(__fdiv_rn(acc[a][b], sc), mid);
+                for (int c = 0; c < RC; c++) {
+                    float v[4];
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const float mine = acc[a][4 * c + b];
+                        const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+                        const float x = g ? __fsub_rn(other, mine) : __fadd_rn(mine, other);
+                        v[b] = __fadd_rn(__fdiv_rn(x, sc), mid);
+                    }
+                    const int j0 = tc2 * 4 + c * 32;
+                    const int xs = e.x + (g ? (N - 4 - j0) : j0);
+                    if (y < P.h) {
+                        float* row = P.layer_f32 + (size_t)y * P.w;
+                        const float4 o = g ? make_float4(v[3], v[2], v[1], v[0]) : make_float4(v[0], v[1], v[2], v[3]);
+                        if (vec_ok && xs + 3 < P.w) *reinterpret_cast<float4*>(row + xs) = o;
+                        else {
+                            if (xs < P.w) row[xs] = o.x;
+                            if (xs + 1 < P.w) row[xs + 1] = o.y;
+                            if (xs + 2 < P.w) row[xs + 2] = o.z;
+                            if (xs + 3 < P.w) row[xs + 3] = o.w;
+                        }
+                    }
                 }
             }
         }
@@ -267,17 +387,17 @@ int launch_rows(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* l
 }
 template <int S, bool INV>
 int launch_cta(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* list, const int* count, int64_t cap, cudaStream_t st) {
-    const size_t smem = 2 * (size_t)S * S * sizeof(float);
+    const size_t smem = (size_t)(S * S + S * S / 2) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         AEAJ_CUDA(cudaFuncSetAttribute(k_dct_cta<S, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    int per_sm = (smem > 100 * 1024) ? 1 : 4;
+    int per_sm = (smem > 110 * 1024) ? 1 : ((smem > 56 * 1024) ? 2 : 4);
     int blocks = (int)std::min<int64_t>(std::max<int64_t>(cap, 1), (int64_t)h->sm_count * per_sm);
     const int lg = ilog2i(S);
-    // forward: M = C  -> M^T = C^T (second half of the table); inverse: M = C^T -> M^T = C (first half)
-    k_dct_cta<S, INV><<<blocks, 256, smem, st>>>(planes_dev, list, count, INV ? h->dct_dev[lg] : h->dct_dev[lg] + S * S);
+    // half tables [Ae | Ao]: forward needs Cg^T (sAg[i][m] = Cg[m][i]), inverse needs Cg (sAg[m][i] = Cg[m][i])
+    k_dct_cta<S, INV><<<blocks, 256, smem, st>>>(planes_dev, list, count, h->dct_half_dev[lg] + (INV ? (S * S / 2) : 0));
     AEAJ_LAUNCH_CHECK();
     return 0;
 }
@@ -336,6 +456,33 @@ int aeaj_dct_init(aeaj_handle* h) {
     h->dct_dev[0] = nullptr; h->dct_dev[8] = nullptr;
     AEAJ_CUDA(cudaMemcpy(h->dct_all_dev, host, total * sizeof(float), cudaMemcpyHostToDevice));
     free(host);
+    // half tables for the even/odd CTA kernels (sizes 64, 128):
+    //   [Ce^T | Co^T] (forward)  then  [Ce | Co] (inverse), each h x h row-major, Cg[m][i] = C[2m+g][i], i < h
+    size_t htotal = 0;
+    for (int lg = 6; lg <= 7; lg++) htotal += (size_t)1 << (2 * lg);
+    float* hh = (float*)malloc(htotal * sizeof(float));
+    if (!hh) return AEAJ_ENOMEM;
+    AEAJ_CUDA(cudaMalloc(&h->dct_half_all_dev, htotal * sizeof(float)));
+    size_t ho = 0;
+    for (int k = 0; k < 9; k++) h->dct_half_dev[k] = nullptr;
+    for (int lg = 6; lg <= 7; lg++) {
+        const int s = 1 << lg, hf = s / 2;
+        float* fwd = hh + ho;                       // [2][hf][hf] transposed halves
+        float* inv = hh + ho + (size_t)s * s / 2;   // [2][hf][hf] plain halves
+        for (int g = 0; g < 2; g++)
+            for (int m = 0; m < hf; m++)
+                for (int i = 0; i < hf; i++) {
+                    const int k = 2 * m + g;
+                    double v = sqrt(2.0 / s) * cos(M_PI * (2 * i + 1) * k / (2.0 * s));
+                    if (k == 0) v *= sqrt(0.5);
+                    fwd[(size_t)g * hf * hf + (size_t)i * hf + m] = (float)v;
+                    inv[(size_t)g * hf * hf + (size_t)m * hf + i] = (float)v;
+                }
+        h->dct_half_dev[lg] = h->dct_half_all_dev + ho;
+        ho += (size_t)s * s;
+    }
+    AEAJ_CUDA(cudaMemcpy(h->dct_half_all_dev, hh, htotal * sizeof(float), cudaMemcpyHostToDevice));
+    free(hh);
     return 0;
 }
 
