@@ -40,29 +40,48 @@ __host__ __device__ inline ClaheGeom clahe_geom(int h, int w) {
 }
 
 constexpr int HIST_ROWS = 32;   // rows of one CLAHE tile handled by one block
-// grid: (row chunks, 16 tiles, planes)
+// 16 consecutive pixels from one 128-bit load, equal neighbours merged into one shared-memory atomic
+__device__ __forceinline__ void hist_add16(unsigned int* wh, uint4 q) {
+    const unsigned w[4] = {q.x, q.y, q.z, q.w};
+    int prev = w[0] & 0xff, cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int v = (w[k >> 2] >> (8 * (k & 3))) & 0xff;
+        if (v == prev) cnt++;
+        else { atomicAdd(&wh[prev], (unsigned)cnt); prev = v; cnt = 1; }
+    }
+    atomicAdd(&wh[prev], (unsigned)cnt);
+}
+// grid: (row chunks, 16 tiles, planes).  Each warp walks rows of the tile with 128-bit loads over the
+// 16-byte-aligned middle of the row segment; head / tail / reflected padding go byte by byte.
 __global__ void __launch_bounds__(256) k_clahe_hist(const PlaneDesc* __restrict__ planes) {
     const PlaneDesc& P = planes[blockIdx.z];
     ClaheGeom g = clahe_geom(P.h, P.w);
     const int tile = blockIdx.y, ty = tile >> 2, tx = tile & 3;
     const int r0 = blockIdx.x * HIST_ROWS;
     if (r0 >= g.th) return;
-    __shared__ unsigned int wh[8][257];
-    for (int i = threadIdx.x; i < 8 * 257; i += 256) (&wh[0][0])[i] = 0;
+    __shared__ unsigned int wh[8][256];
+    for (int i = threadIdx.x; i < 8 * 256; i += 256) (&wh[0][0])[i] = 0;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r1 = min(r0 + HIST_ROWS, g.th);
     const uint8_t* src = P.u8a;
+    unsigned int* my = wh[warp];
+    const int cx0 = tx * g.tw, cx1 = cx0 + g.tw;
     for (int r = r0 + warp; r < r1; r += 8) {
-        int sy = reflect101(ty * g.th + r, P.h);
-        const uint8_t* row = src + (size_t)sy * P.w;
-        for (int c0 = 0; c0 < g.tw; c0 += 32) {
-            int c = c0 + lane;
-            int v = 256;
-            if (c < g.tw) v = row[reflect101(tx * g.tw + c, P.w)];
-            unsigned m = __match_any_sync(0xffffffffu, v);
-            if (lane == __ffs(m) - 1) atomicAdd(&wh[warp][v], (unsigned)__popc(m));
+        const int sy = reflect101(ty * g.th + r, P.h);
+        const uint8_t* rowp = src + (size_t)sy * P.w;
+        const int xa = cx0, xb = min(cx1, P.w);
+        if (xa < xb) {
+            const int head = min((int)((16 - ((uintptr_t)(rowp + xa) & 15)) & 15), xb - xa);
+            const int nvec = (xb - xa - head) >> 4;
+            const int tail0 = xa + head + nvec * 16;
+            for (int x = xa + lane; x < xa + head; x += 32) atomicAdd(&my[rowp[x]], 1u);
+            for (int x = tail0 + lane; x < xb; x += 32) atomicAdd(&my[rowp[x]], 1u);
+            const uint4* vp = reinterpret_cast<const uint4*>(rowp + xa + head);
+            for (int c = lane; c < nvec; c += 32) hist_add16(my, __ldg(vp + c));
         }
+        for (int x = max(cx0, P.w) + lane; x < cx1; x += 32) atomicAdd(&my[rowp[reflect101(x, P.w)]], 1u);
     }
     __syncthreads();
     unsigned s = 0;
@@ -143,27 +162,29 @@ __global__ void __launch_bounds__(256) k_prefilter(const PlaneDesc* __restrict__
     __shared__ __align__(16) uint8_t sLut[16][256];
     __shared__ float sW[4][256];                               // space weight (r^2 = 0,1,2,4) x colour weight, rounded product
     __shared__ unsigned int sHist[256];
-    __shared__ float sXa[PF_TW + 6], sYa[PF_TH + 6];           // CLAHE interpolation weights per tile column / row
-    __shared__ uint8_t sTx[PF_TW + 6][2], sTy[PF_TH + 6][2];   // CLAHE tile indices per tile column / row
+    __shared__ float sXa[PF_AS], sYa[PF_TH + 6];               // CLAHE interpolation weights per tile column / row
+    __shared__ uint8_t sTx[PF_AS][2], sTy[PF_TH + 6][2];       // CLAHE tile indices per tile column / row
+    __shared__ int sFx[PF_AS], sFy[PF_TH + 6];                 // REFLECT_101-folded source coordinates
     const int tid = threadIdx.x;
     const ClaheGeom g = clahe_geom(P.h, P.w);
-    if (stages & 1) {
-        for (int i = tid; i < 16 * 256 / 4; i += 256) reinterpret_cast<uint32_t*>(&sLut[0][0])[i] = reinterpret_cast<const uint32_t*>(P.clahe_lut)[i];
-        if (tid < PF_TW + 6) {
-            int x = reflect101(X0 + tid - 3, P.w);
-            float txf = __fsub_rn(__fmul_rn((float)x, g.inv_tw), 0.5f);
-            int t1 = (int)floorf(txf);
-            sXa[tid] = __fsub_rn(txf, (float)t1);
-            sTx[tid][0] = (uint8_t)max(t1, 0); sTx[tid][1] = (uint8_t)min(t1 + 1, 3);
-        } else if (tid >= 128 && tid < 128 + PF_TH + 6) {
-            int r = tid - 128;
-            int y = reflect101(Y0 + r - 3, P.h);
-            float tyf = __fsub_rn(__fmul_rn((float)y, g.inv_th), 0.5f);
-            int t1 = (int)floorf(tyf);
-            sYa[r] = __fsub_rn(tyf, (float)t1);
-            sTy[r][0] = (uint8_t)max(t1, 0); sTy[r][1] = (uint8_t)min(t1 + 1, 3);
-        }
+    if (tid < PF_AS) {
+        const int x = reflect101(X0 + tid - 3, P.w);
+        sFx[tid] = x;
+        const float txf = __fsub_rn(__fmul_rn((float)x, g.inv_tw), 0.5f);
+        const int t1 = (int)floorf(txf);
+        sXa[tid] = __fsub_rn(txf, (float)t1);
+        sTx[tid][0] = (uint8_t)max(t1, 0); sTx[tid][1] = (uint8_t)min(t1 + 1, 3);
+    } else if (tid >= 128 && tid < 128 + PF_TH + 6) {
+        const int r = tid - 128;
+        const int y = reflect101(Y0 + r - 3, P.h);
+        sFy[r] = y;
+        const float tyf = __fsub_rn(__fmul_rn((float)y, g.inv_th), 0.5f);
+        const int t1 = (int)floorf(tyf);
+        sYa[r] = __fsub_rn(tyf, (float)t1);
+        sTy[r][0] = (uint8_t)(max(t1, 0) * 4); sTy[r][1] = (uint8_t)(min(t1 + 1, 3) * 4);
     }
+    if (stages & 1)
+        for (int i = tid; i < 16 * 256 / 4; i += 256) reinterpret_cast<uint32_t*>(&sLut[0][0])[i] = reinterpret_cast<const uint32_t*>(P.clahe_lut)[i];
     {
         float cw = c_bil_color[tid];
         sW[0][tid] = cw;                                       // centre tap: space weight exp(0) = 1
@@ -174,18 +195,19 @@ __global__ void __launch_bounds__(256) k_prefilter(const PlaneDesc* __restrict__
     }
     __syncthreads();
     const uint8_t* src = P.u8a;
-    // stage A: source (folded coordinates) -> CLAHE
-    for (int i = tid; i < (PF_TH + 6) * (PF_TW + 6); i += 256) {
-        const int ry = i / (PF_TW + 6), rx = i - ry * (PF_TW + 6);
-        const int y = reflect101(Y0 + ry - 3, P.h), x = reflect101(X0 + rx - 3, P.w);
-        const int v = src[(size_t)y * P.w + x];
+    // stage A: source (folded coordinates) -> CLAHE; the staging region is 38 rows x 72 columns (2 spare
+    // columns keep the index arithmetic to shifts; they hold valid folded pixels and are never read)
+    for (int i = tid; i < (PF_TH + 6) * PF_AS; i += 256) {
+        const int ry = i / PF_AS, rx = i - ry * PF_AS;
+        const int v = src[(size_t)sFy[ry] * P.w + sFx[rx]];
         int outv = v;
         if (stages & 1) {
             const float xa = sXa[rx], xa1 = __fsub_rn(1.0f, xa), ya = sYa[ry], ya1 = __fsub_rn(1.0f, ya);
-            const int t00 = sTy[ry][0] * 4 + sTx[rx][0], t01 = sTy[ry][0] * 4 + sTx[rx][1];
-            const int t10 = sTy[ry][1] * 4 + sTx[rx][0], t11 = sTy[ry][1] * 4 + sTx[rx][1];
-            const float a = __fmul_rn((float)sLut[t00][v], xa1), b = __fmul_rn((float)sLut[t01][v], xa);
-            const float c = __fmul_rn((float)sLut[t10][v], xa1), d = __fmul_rn((float)sLut[t11][v], xa);
+            const uint8_t* l0 = &sLut[sTy[ry][0]][v];
+            const uint8_t* l1 = &sLut[sTy[ry][1]][v];
+            const int c0 = sTx[rx][0] * 256, c1 = sTx[rx][1] * 256;
+            const float a = __fmul_rn((float)l0[c0], xa1), b = __fmul_rn((float)l0[c1], xa);
+            const float c = __fmul_rn((float)l1[c0], xa1), d = __fmul_rn((float)l1[c1], xa);
             const float r = __fadd_rn(__fmul_rn(__fadd_rn(a, b), ya1), __fmul_rn(__fadd_rn(c, d), ya));
             outv = min(max(__float2int_rn(r), 0), 255);
         }
@@ -384,18 +406,19 @@ __global__ void __launch_bounds__(256) k_canny_nms(const PlaneDesc* __restrict__
 
 // ---------------------------------------------------------------------------------------------
 // hysteresis: strong |= weak pixels 8-connected (through weak pixels) to a strong pixel.
-// Bit-packed frontier propagation.  A block owns a tile of 8 words x 128 rows (256 x 128 px), one
+// Bit-packed frontier propagation.  A block owns a tile of 8 words x 32 rows (256 x 32 px), one
 // word per thread; it iterates to local convergence in shared memory.  A cooperative grid loop
 // repeats until no tile's border changed; tiles whose neighbours did not change are skipped.
 // ---------------------------------------------------------------------------------------------
-constexpr int HY_WW = 8, HY_TR = 128;
+constexpr int HY_WW = 8, HY_TR = 32;                 // tile = 256 px x 32 rows, one word per thread (256 threads)
+constexpr int HY_THREADS = HY_WW * HY_TR;
 struct HystTileMap { int nplanes; int ntiles; };
 
 __device__ __forceinline__ unsigned spread3(unsigned L, unsigned Cw, unsigned R) {
     return Cw | (Cw << 1) | (Cw >> 1) | (L >> 31) | (R << 31);
 }
 
-__global__ void __launch_bounds__(1024, 1) k_hysteresis(const PlaneDesc* __restrict__ planes, int nplanes, const int* __restrict__ tile_base,
+__global__ void __launch_bounds__(HY_THREADS) k_hysteresis(const PlaneDesc* __restrict__ planes, int nplanes, const int* __restrict__ tile_base,
                                                         int ntiles, int* __restrict__ flags, int* __restrict__ ctrl, int* __restrict__ status, int max_rounds) {
     cg::grid_group grid = cg::this_grid();
     __shared__ unsigned sS[HY_TR + 2][HY_WW + 2];
@@ -408,7 +431,7 @@ __global__ void __launch_bounds__(1024, 1) k_hysteresis(const PlaneDesc* __restr
         int* c_nxt = ctrl + (round + 1) % 3;
         if (blockIdx.x == 0 && tid == 0) ctrl[(round + 2) % 3] = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            if (round > 0 && fl_cur[tile] == 0) continue;        // uniform per block
+            if (round > 0 && __ldcg(fl_cur + tile) == 0) continue;   // uniform per block
             __syncthreads();
             if (tid == 0) {
                 fl_cur[tile] = 0;
@@ -423,11 +446,11 @@ __global__ void __launch_bounds__(1024, 1) k_hysteresis(const PlaneDesc* __restr
             const int tyi = local / ntx, txi = local - tyi * ntx;
             const int gy0 = tyi * HY_TR, gw0 = txi * HY_WW;
             // load strong words incl. 1-row / 1-word halo
-            for (int i = tid; i < (HY_TR + 2) * (HY_WW + 2); i += 1024) {
+            for (int i = tid; i < (HY_TR + 2) * (HY_WW + 2); i += HY_THREADS) {
                 int ry = i / (HY_WW + 2), rw = i - ry * (HY_WW + 2);
                 int gy = gy0 + ry - 1, gw = gw0 + rw - 1;
                 unsigned v = 0;
-                if (gy >= 0 && gy < P.h && gw >= 0 && gw < P.wpr) v = P.strong[(size_t)gy * P.wpr + gw];
+                if (gy >= 0 && gy < P.h && gw >= 0 && gw < P.wpr) v = __ldcg(P.strong + (size_t)gy * P.wpr + gw);
                 sS[ry][rw] = v;
             }
             const int gy = gy0 + tr, gw = gw0 + tc;
@@ -575,13 +598,13 @@ int launch_hysteresis(aeaj_handle* h, const PlaneDesc* planes_dev, int nplanes, 
     AEAJ_CUDA(cudaMemsetAsync(ctrl, 0, sizeof(int) * 3, st));
     static int blocks_per_sm = 0;
     if (!blocks_per_sm) {
-        AEAJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_hysteresis, 1024, 0));
+        AEAJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_hysteresis, HY_THREADS, 0));
         if (blocks_per_sm < 1) { aeaj_set_error("hysteresis kernel cannot be resident"); return AEAJ_EINVAL; }
     }
     int grid = std::min(ntiles, blocks_per_sm * h->sm_count);
     int max_rounds = 1 << 20;
     void* args[] = {(void*)&planes_dev, (void*)&nplanes, (void*)&tile_base_dev, (void*)&ntiles, (void*)&flags, (void*)&ctrl, (void*)&status, (void*)&max_rounds};
-    AEAJ_CUDA(cudaLaunchCooperativeKernel((void*)k_hysteresis, dim3(grid), dim3(1024), args, 0, st));
+    AEAJ_CUDA(cudaLaunchCooperativeKernel((void*)k_hysteresis, dim3(grid), dim3(HY_THREADS), args, 0, st));
     return 0;
 }
 

@@ -80,10 +80,29 @@ __global__ void __launch_bounds__(QT_THREADS) k_qt_blocks(const PlaneDesc* __res
     if (tid == 0) { int o = 0; for (int l = 0; l <= L; l++) { lvl_off[l] = o; o += (n >> l) * (n >> l); } }
     if (tid < 9) { s_cls[tid] = 0; s_cls_base[tid] = 0; }
     __syncthreads();
-    // level 0 from the bitmap
-    for (int i = tid; i < n * n; i += QT_THREADS) {
-        int cy = i / n, cx = i - cy * n;
-        occ[i] = cell_has_edge(P.strong, P.wpr, P.h, P.w, X0 + cx * c, Y0 + cy * c, c);
+    // level 0 from the bitmap.  For cells narrower than a word, one thread ORs the c rows of a
+    // (cell row, bitmap word) pair and splits the word into 32/c cell flags.
+    if (c <= 32) {
+        const int cpw = 32 / c;                                    // cells per word
+        const int wpt = (T + 31) / 32;                             // words per top-block row
+        const int w0 = X0 >> 5;                                    // X0 is a multiple of T; if T < 32, bits are offset
+        const int bit0 = X0 & 31;
+        for (int i = tid; i < n * wpt; i += QT_THREADS) {
+            const int cy = i / wpt, wi = i - cy * wpt;
+            const int y0 = Y0 + cy * c, y1 = min(y0 + c, P.h);
+            unsigned acc = 0;
+            if (w0 + wi < P.wpr)
+                for (int y = y0; y < y1; y++) acc |= __ldg(P.strong + (size_t)y * P.wpr + w0 + wi);
+            acc >>= bit0;                                          // only non-zero when T < 32 (then wpt == 1)
+            const int ncell = min(cpw, n - wi * cpw);
+            const unsigned m = (c == 32) ? 0xffffffffu : ((1u << c) - 1u);
+            for (int k = 0; k < ncell; k++) occ[cy * n + wi * cpw + k] = ((acc >> (k * c)) & m) != 0;
+        }
+    } else {
+        for (int i = tid; i < n * n; i += QT_THREADS) {
+            int cy = i / n, cx = i - cy * n;
+            occ[i] = cell_has_edge(P.strong, P.wpr, P.h, P.w, X0 + cx * c, Y0 + cy * c, c);
+        }
     }
     __syncthreads();
     for (int l = 1; l <= L; l++) {
