@@ -82,7 +82,7 @@ class DeviceCodec:
                 leaves=[torch.empty((B, int(info.cap_leaves[l]), 4), dtype=torch.int32, device=dev) for l in range(3)],
                 states=[torch.empty((B, int(info.cap_states[l])), dtype=torch.uint8, device=dev) for l in range(3)],
                 counts=torch.zeros((B, 3, 4), dtype=torch.int32, device=dev),
-                status=torch.zeros(2, dtype=torch.int32, device=dev), shape=(B, H, W))
+                status=torch.zeros(64, dtype=torch.int32, device=dev), shape=(B, H, W))
             rgb_out = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
             p = _Plan(ptr, info, ws, out, rgb_out)
             self._plans[key] = p

@@ -124,6 +124,7 @@ struct aeaj_handle {
 // device-side description of every plane of a batch; lives in the plan's device memory
 struct PlaneDesc {
     int h, w, wpr, root, top, ntx, nty, layer;
+    int hy_base_small, hy_base_big;   // first hysteresis tile of this plane in the small / big tiling
     float mid, scale;
     float* layer_f32;        // downsampled un-normalised layer
     uint8_t* u8a;            // cast / stage ping
@@ -148,6 +149,32 @@ struct PlaneDesc {
 
 struct ClassEntry { int x, y, plane, coef_off; };
 
+// exact 1-D grids over the tiles of all planes of a batch (no empty blocks for the smaller chroma planes):
+// planes are ordered image-major with `nl` layers per image and identical geometry per layer.
+struct TileMap { int per_image, nl; int cum[4]; int ntx[3]; };
+static inline TileMap make_tile_map(const PlaneDesc* P, int nplanes, int tw, int th, bool square_top = false) {
+    TileMap m;
+    m.nl = nplanes >= 3 && (nplanes % 3) == 0 && P[0].layer == 0 && P[1].layer == 1 ? 3 : 1;
+    int c = 0;
+    for (int l = 0; l < 3; l++) {
+        m.cum[l] = c;
+        if (l < m.nl) {
+            int nx = square_top ? P[l].ntx : aeaj_cdiv(P[l].w, tw), ny = square_top ? P[l].nty : aeaj_cdiv(P[l].h, th);
+            m.ntx[l] = nx; c += nx * ny;
+        } else m.ntx[l] = 1;
+    }
+    m.cum[3] = c; m.per_image = c;
+    return m;
+}
+static inline int tile_map_total(const TileMap& m, int nplanes) { return m.per_image * (nplanes / m.nl); }
+static inline __device__ void tile_decode(const TileMap& m, int bid, int& plane, int& tx, int& ty) {
+    const int b = bid / m.per_image, r = bid - b * m.per_image;
+    const int l = (r >= m.cum[2] && m.nl > 2) ? 2 : ((r >= m.cum[1] && m.nl > 1) ? 1 : 0);
+    const int t = r - m.cum[l];
+    ty = t / m.ntx[l]; tx = t - ty * m.ntx[l];
+    plane = b * m.nl + l;
+}
+
 // kernels' host launchers (defined in the .cu files)
 int aeaj_canny_init_constants();
 int aeaj_dct_init(aeaj_handle* h);
@@ -171,8 +198,8 @@ int launch_hist_u8(const uint8_t* src, size_t n, unsigned int* hist, cudaStream_
 int launch_thresholds(const PlaneDesc* planes_dev, int nplanes, cudaStream_t st);
 int launch_thresholds_from_double(const double* thr_d, int* thr, cudaStream_t st);
 int launch_canny_nms(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, cudaStream_t st);
-int hysteresis_tiles(const PlaneDesc* planes_host, int nplanes, int* tile_base_host);
-int launch_hysteresis(aeaj_handle* h, const PlaneDesc* planes_dev, int nplanes, const int* tile_base_dev, int ntiles,
+int hysteresis_tiles(PlaneDesc* planes_host, int nplanes, int* nbig);
+int launch_hysteresis(aeaj_handle* h, const PlaneDesc* planes_dev, int nplanes, int nsmall, int nbig,
                       int* flags, int* ctrl, int* status, cudaStream_t st);
 int launch_bitmap_to_u8(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes,
                         uint8_t* const* outs_dev, cudaStream_t st);

@@ -196,7 +196,7 @@ struct StageWs {
     int* flags; int* ctrl; int* status;
     ClassEntry* class_lists; int* class_counts;
     ClassGeom cg;
-    int ntiles;
+    int ntiles, nbig;
     size_t bytes;
 };
 static void stage_ws(void* ws, int h, int w, int mn, int mx, StageWs& S) {
@@ -206,9 +206,8 @@ static void stage_ws(void* ws, int h, int w, int mn, int mx, StageWs& S) {
     carve_plane_scratch(b, S.P, true, mx > 0);
     S.u8a = b.take<uint8_t>((size_t)h * w);
     S.u8b = b.take<uint8_t>((size_t)h * w);
-    int tb = 0;
-    S.ntiles = hysteresis_tiles(&S.P, 1, &tb);
-    S.flags = b.take<int>(2 * (size_t)S.ntiles);
+    S.ntiles = hysteresis_tiles(&S.P, 1, &S.nbig);
+    S.flags = b.take<int>(2 * (size_t)S.nbig);
     S.ctrl = b.take<int>(4);
     S.status = b.take<int>(2);
     S.class_counts = b.take<int>(16);
@@ -270,7 +269,7 @@ extern "C" int aeaj_percentile_thresholds(aeaj_handle* hd, const uint8_t* src, i
 
 static int run_nms_hysteresis(aeaj_handle* hd, StageWs& S, uint8_t* edge, cudaStream_t st) {
     int rc = launch_canny_nms(hd->stage_plane_dev, &S.P, 1, st); if (rc) return rc;
-    rc = launch_hysteresis(hd, hd->stage_plane_dev, 1, hd->stage_tile_base_dev, S.ntiles, S.flags, S.ctrl, S.status, st);
+    rc = launch_hysteresis(hd, hd->stage_plane_dev, 1, S.ntiles, S.nbig, S.flags, S.ctrl, S.status, st);
     if (rc) return rc;
     if (edge) {
         AEAJ_CUDA(cudaMemcpyAsync(hd->stage_outs_dev, &edge, sizeof(uint8_t*), cudaMemcpyHostToDevice, st));
@@ -364,7 +363,7 @@ struct aeaj_plan {
     int nplanes, lg_min, lg_max;
     std::vector<PlaneDesc> planes;       // host copy, index b*3 + l
     PlaneDesc* planes_dev;
-    int* tile_base_dev; int ntiles;
+    int ntiles, nbig;
     long long* class_off_dev;
     ClassGeom cg;
     int32_t* qtab_dev; size_t qtab_entries;
@@ -436,7 +435,7 @@ static size_t plan_carve_aux(aeaj_plan* p, void* ws, size_t start, PlanAux& A) {
     const size_t HW = (size_t)p->info.height * p->info.width;
     if (p->need_full_chroma) { A.full_c1 = b.take<float>(HW * p->info.batch); A.full_c2 = b.take<float>(HW * p->info.batch); }
     else { A.full_c1 = A.full_c2 = nullptr; }
-    A.flags = b.take<int>(2 * (size_t)p->ntiles);
+    A.flags = b.take<int>(2 * (size_t)p->nbig);
     A.ctrl = b.take<int>(4);
     A.class_counts = b.take<int>(16);
     A.class_lists = b.take<ClassEntry>((size_t)p->cg.total);
@@ -476,16 +475,13 @@ extern "C" int aeaj_plan_create(aeaj_handle* h, int batch, int height, int width
     const int ch = p->info.layer_h[1], cw = p->info.layer_w[1];
     p->need_full_chroma = !((ch * 2 == height && cw * 2 == width && (width % 4) == 0) || (ch == height && cw * 4 == width));
     class_geom(p->planes.data(), p->nplanes, p->lg_min, p->lg_max, p->cg);
-    std::vector<int> tile_base(p->nplanes);
-    p->ntiles = hysteresis_tiles(p->planes.data(), p->nplanes, tile_base.data());
+    p->ntiles = hysteresis_tiles(p->planes.data(), p->nplanes, &p->nbig);
     size_t s1 = plan_carve(p, nullptr);
     PlanAux A;
     p->info.workspace_bytes = (int64_t)plan_carve_aux(p, nullptr, s1, A) + 256;
     AEAJ_CUDA(cudaMalloc(&p->planes_dev, sizeof(PlaneDesc) * p->nplanes));
-    AEAJ_CUDA(cudaMalloc(&p->tile_base_dev, sizeof(int) * p->nplanes));
     AEAJ_CUDA(cudaMalloc(&p->class_off_dev, sizeof(long long) * 9));
     AEAJ_CUDA(cudaMalloc(&p->outs_dev, sizeof(uint8_t*) * p->nplanes));
-    AEAJ_CUDA(cudaMemcpy(p->tile_base_dev, tile_base.data(), sizeof(int) * p->nplanes, cudaMemcpyHostToDevice));
     long long off[9]; for (int k = 0; k < 9; k++) off[k] = p->cg.off[k];
     AEAJ_CUDA(cudaMemcpy(p->class_off_dev, off, sizeof off, cudaMemcpyHostToDevice));
     p->qtab_dev = nullptr; p->qtab_entries = 0;
@@ -498,7 +494,7 @@ extern "C" int aeaj_plan_create(aeaj_handle* h, int batch, int height, int width
 extern "C" int aeaj_plan_destroy(aeaj_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->h->device);
-    cudaFree(p->planes_dev); cudaFree(p->tile_base_dev); cudaFree(p->class_off_dev); cudaFree(p->outs_dev); cudaFree(p->qtab_dev);
+    cudaFree(p->planes_dev); cudaFree(p->class_off_dev); cudaFree(p->outs_dev); cudaFree(p->qtab_dev);
     delete p;
     return 0;
 }
@@ -602,9 +598,9 @@ extern "C" int aeaj_encode(aeaj_plan* p, const aeaj_encode_io* io, void* workspa
     p->mark("thresholds");
     rc = launch_canny_nms(p->planes_dev, p->planes.data(), NP, st); if (rc) return rc;
     p->mark("canny_nms");
-    rc = launch_hysteresis(h, p->planes_dev, NP, p->tile_base_dev, p->ntiles, A.flags, A.ctrl, io->status, st); if (rc) return rc;
+    rc = launch_hysteresis(h, p->planes_dev, NP, p->ntiles, p->nbig, A.flags, A.ctrl, io->status, st); if (rc) return rc;
     p->mark("hysteresis");
-    launches += 6;
+    launches += 7;
     if (any_tap_edge) {
         AEAJ_CUDA(cudaMemcpyAsync(p->outs_dev, outs.data(), sizeof(uint8_t*) * NP, cudaMemcpyHostToDevice, st));
         rc = launch_bitmap_to_u8(p->planes_dev, p->planes.data(), NP, p->outs_dev, st); if (rc) return rc;

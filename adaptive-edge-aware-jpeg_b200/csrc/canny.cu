@@ -153,10 +153,11 @@ constexpr int PF_AS = PF_TW + 8;                     // row stride of both stagi
 #define BIL_TAPS(X) X(0,-2,0,3) X(1,-1,-1,2) X(2,-1,0,1) X(3,-1,1,2) X(4,0,-2,3) X(5,0,-1,1) X(6,0,0,0) X(7,0,1,1) X(8,0,2,3) \
                     X(9,1,-1,2) X(10,1,0,1) X(11,1,1,2) X(12,2,0,3)
 
-__global__ void __launch_bounds__(256) k_prefilter(const PlaneDesc* __restrict__ planes, int stages, int do_hist) {
-    const PlaneDesc& P = planes[blockIdx.z];
-    const int X0 = blockIdx.x * PF_TW, Y0 = blockIdx.y * PF_TH;
-    if (X0 >= P.w || Y0 >= P.h) return;
+__global__ void __launch_bounds__(256) k_prefilter(const PlaneDesc* __restrict__ planes, const __grid_constant__ TileMap tm, int stages, int do_hist) {
+    int plane_i, txi, tyi;
+    tile_decode(tm, blockIdx.x, plane_i, txi, tyi);
+    const PlaneDesc& P = planes[plane_i];
+    const int X0 = txi * PF_TW, Y0 = tyi * PF_TH;
     __shared__ __align__(16) uint8_t sA[PF_TH + 6][PF_AS];     // CLAHE output (or source), halo 3
     __shared__ __align__(16) uint8_t sG[PF_TH + 4][PF_AS];     // Gaussian output, halo 2
     __shared__ __align__(16) uint8_t sLut[16][256];
@@ -340,66 +341,117 @@ __global__ void k_thresholds_from_double(const double* thr_d, int* thr) { canny_
 // one bitmap word.   grid: (tiles x, tiles y, planes)
 // ---------------------------------------------------------------------------------------------
 constexpr int NM_TW = 64, NM_TH = 32;
-__global__ void __launch_bounds__(256) k_canny_nms(const PlaneDesc* __restrict__ planes) {
-    const PlaneDesc& P = planes[blockIdx.z];
-    const int X0 = blockIdx.x * NM_TW, Y0 = blockIdx.y * NM_TH;
-    if (X0 >= P.w || Y0 >= P.h) return;
-    __shared__ uint8_t sS[NM_TH + 4][NM_TW + 4];
-    __shared__ int sM[NM_TH + 2][NM_TW + 2];
-    __shared__ short sDx[NM_TH + 2][NM_TW + 2];
-    __shared__ short sDy[NM_TH + 2][NM_TW + 2];
+constexpr int NM_SS = NM_TW + 8;                      // source tile: 72 columns starting at X0-4 (4-byte aligned)
+constexpr int NM_MS = NM_TW + 4;                      // magnitude tile: 68 columns starting at X0-1
+__global__ void __launch_bounds__(256) k_canny_nms(const PlaneDesc* __restrict__ planes, const __grid_constant__ TileMap tm) {
+    int plane_i, txi, tyi;
+    tile_decode(tm, blockIdx.x, plane_i, txi, tyi);
+    const PlaneDesc& P = planes[plane_i];
+    const int X0 = txi * NM_TW, Y0 = tyi * NM_TH;
+    __shared__ __align__(16) uint8_t sS[NM_TH + 4][NM_SS];       // rows Y0-2.., cols X0-4.. (BORDER_REPLICATE)
+    __shared__ __align__(16) int sM[NM_TH + 2][NM_MS];           // magnitude, rows Y0-1.., cols X0-1.. (0 outside the image)
+    __shared__ __align__(16) int sD[NM_TH + 2][NM_MS];           // dx | dy << 16
     const int tid = threadIdx.x;
     const uint8_t* src = P.u8b;
-    for (int i = tid; i < (NM_TH + 4) * (NM_TW + 4); i += 256) {
-        int ry = i / (NM_TW + 4), rx = i - ry * (NM_TW + 4);
-        int y = clampi(Y0 + ry - 2, 0, P.h - 1), x = clampi(X0 + rx - 2, 0, P.w - 1);
-        sS[ry][rx] = src[(size_t)y * P.w + x];
-    }
-    __syncthreads();
-    for (int i = tid; i < (NM_TH + 2) * (NM_TW + 2); i += 256) {
-        int ry = i / (NM_TW + 2), rx = i - ry * (NM_TW + 2);
-        int y = Y0 + ry - 1, x = X0 + rx - 1;
-        int gx = 0, gy = 0, m = 0;
-        if (y >= 0 && y < P.h && x >= 0 && x < P.w) {
-            const uint8_t* r0 = &sS[ry][rx]; const uint8_t* r1 = &sS[ry + 1][rx]; const uint8_t* r2 = &sS[ry + 2][rx];
-            gx = (r0[2] + 2 * r1[2] + r2[2]) - (r0[0] + 2 * r1[0] + r2[0]);
-            gy = (r2[0] + 2 * r2[1] + r2[2]) - (r0[0] + 2 * r0[1] + r0[2]);
-            m = gx * gx + gy * gy;
+    // stage 1: source tile.  Interior tiles of 4-aligned planes use 32-bit loads.
+    if (X0 >= 4 && X0 + NM_SS - 4 <= P.w && (P.w & 3) == 0) {
+        for (int i = tid; i < (NM_TH + 4) * (NM_SS / 4); i += 256) {
+            const int ry = i / (NM_SS / 4), rw = i - ry * (NM_SS / 4);
+            const int y = clampi(Y0 + ry - 2, 0, P.h - 1);
+            reinterpret_cast<uint32_t*>(&sS[ry][0])[rw] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)y * P.w + X0 - 4) + rw);
         }
-        sM[ry][rx] = m; sDx[ry][rx] = (short)gx; sDy[ry][rx] = (short)gy;
+    } else {
+        for (int i = tid; i < (NM_TH + 4) * NM_SS; i += 256) {
+            const int ry = i / NM_SS, rx = i - ry * NM_SS;
+            const int y = clampi(Y0 + ry - 2, 0, P.h - 1), x = clampi(X0 + rx - 4, 0, P.w - 1);
+            sS[ry][rx] = src[(size_t)y * P.w + x];
+        }
     }
     __syncthreads();
+    // stage 2: Sobel + L2 magnitude for 4 cells per task; cell (ry, c) <-> pixel (Y0-1+ry, X0-1+c),
+    // its 3x3 window starts at source tile row ry, column c+2
+    for (int i = tid; i < (NM_TH + 2) * (NM_MS / 4); i += 256) {
+        const int ry = i / (NM_MS / 4), c0 = (i - ry * (NM_MS / 4)) * 4;
+        int r[3][6];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            // columns c0+2 .. c0+7 of the source tile: two aligned words starting at c0 (c0 % 4 == 0)
+            const uchar4 a = *reinterpret_cast<const uchar4*>(&sS[ry + k][c0]);
+            const uchar4 b = *reinterpret_cast<const uchar4*>(&sS[ry + k][c0 + 4]);
+            r[k][0] = a.z; r[k][1] = a.w; r[k][2] = b.x; r[k][3] = b.y; r[k][4] = b.z; r[k][5] = b.w;
+        }
+        int cs[6], cd[6];
+#pragma unroll
+        for (int j = 0; j < 6; j++) { cs[j] = r[0][j] + 2 * r[1][j] + r[2][j]; cd[j] = r[2][j] - r[0][j]; }
+        int m[4], d[4];
+        const int y = Y0 - 1 + ry;
+        const bool yin = (y >= 0 && y < P.h);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int x = X0 - 1 + c0 + k;
+            int gx = cs[k + 2] - cs[k], gy = cd[k] + 2 * cd[k + 1] + cd[k + 2];
+            const bool in = yin && x >= 0 && x < P.w;
+            gx = in ? gx : 0; gy = in ? gy : 0;
+            m[k] = gx * gx + gy * gy;
+            d[k] = (int)((unsigned)(gx & 0xffff) | ((unsigned)gy << 16));
+        }
+        *reinterpret_cast<int4*>(&sM[ry][c0]) = make_int4(m[0], m[1], m[2], m[3]);
+        *reinterpret_cast<int4*>(&sD[ry][c0]) = make_int4(d[0], d[1], d[2], d[3]);
+    }
+    __syncthreads();
+    // stage 3: NMS + double threshold, 4 px per thread; a warp covers 2 rows x 64 px = 4 bitmap words
     const int low = P.thr[0], high = P.thr[1];
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int seg = warp; seg < NM_TH * 2; seg += 8) {
-        const int ty = seg >> 1, hx = (seg & 1) * 32;
-        const int y = Y0 + ty, x = X0 + hx + lane;
-        int cls = 0;
-        if (y < P.h && x < P.w) {
-            const int ry = ty + 1, rx = hx + lane + 1;
-            const int m = sM[ry][rx];
-            if (m > low) {
-                const int xs = sDx[ry][rx], ys = sDy[ry][rx];
+    const int lane = tid & 31;
+    const int gx4 = (tid & 15) * 4;                                // first of the 4 px inside the tile row
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const int ty = (tid >> 4) + half * 16;
+        const int y = Y0 + ty;
+        // magnitude rows ty, ty+1, ty+2 of sM (pixel rows y-1, y, y+1), columns gx4 .. gx4+5 (pixel x-1 .. x+4)
+        int mg[3][6];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int4 a = *reinterpret_cast<const int4*>(&sM[ty + k][gx4]);
+            mg[k][0] = a.x; mg[k][1] = a.y; mg[k][2] = a.z; mg[k][3] = a.w;
+            mg[k][4] = sM[ty + k][gx4 + 4]; mg[k][5] = sM[ty + k][gx4 + 5];
+        }
+        const int4 dq = *reinterpret_cast<const int4*>(&sD[ty + 1][gx4]);   // cells gx4..gx4+3 = pixels x-1..x+2
+        const int dd[5] = {dq.x, dq.y, dq.z, dq.w, sD[ty + 1][gx4 + 4]};
+        unsigned sb = 0, wb = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int x = X0 + gx4 + k;
+            const int mm = mg[1][k + 1];
+            int cls = 0;
+            if (y < P.h && x < P.w && mm > low) {
+                const int dv = dd[k + 1];
+                const int xs = (int)(short)(dv & 0xffff), ys = dv >> 16;
                 const int ax = abs(xs), ay = abs(ys) << 15;
                 const int tg22x = ax * 13573;
                 bool keep;
-                if (ay < tg22x) keep = (m > sM[ry][rx - 1]) && (m >= sM[ry][rx + 1]);
+                if (ay < tg22x) keep = (mm > mg[1][k]) && (mm >= mg[1][k + 2]);
                 else {
                     const int tg67x = tg22x + (ax << 16);
-                    if (ay > tg67x) keep = (m > sM[ry - 1][rx]) && (m >= sM[ry + 1][rx]);
+                    if (ay > tg67x) keep = (mm > mg[0][k + 1]) && (mm >= mg[2][k + 1]);
                     else {
-                        const int s = ((xs ^ ys) < 0) ? -1 : 1;
-                        keep = (m > sM[ry - 1][rx - s]) && (m > sM[ry + 1][rx + s]);
+                        const bool neg = (xs ^ ys) < 0;                      // s = -1: up-right / down-left
+                        const int up = neg ? mg[0][k + 2] : mg[0][k], dn = neg ? mg[2][k] : mg[2][k + 2];
+                        keep = (mm > up) && (mm > dn);
                     }
                 }
-                if (keep) cls = (m > high) ? 2 : 1;
+                if (keep) cls = (mm > high) ? 2 : 1;
             }
+            sb |= (unsigned)(cls == 2) << k;
+            wb |= (unsigned)(cls == 1) << k;
         }
-        unsigned bs = __ballot_sync(0xffffffffu, cls == 2), bw = __ballot_sync(0xffffffffu, cls == 1);
-        const int word = (X0 + hx) >> 5;
-        if (lane == 0 && y < P.h && word < P.wpr) {
-            P.strong[(size_t)y * P.wpr + word] = bs;
-            P.weak[(size_t)y * P.wpr + word] = bw;
+        // OR the nibbles of 8 neighbouring lanes into one 32-bit word
+        sb <<= 4 * (lane & 7); wb <<= 4 * (lane & 7);
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) { sb |= __shfl_xor_sync(0xffffffffu, sb, o); wb |= __shfl_xor_sync(0xffffffffu, wb, o); }
+        const int word = (X0 + gx4) >> 5;
+        if ((lane & 7) == 0 && y < P.h && word < P.wpr) {
+            P.strong[(size_t)y * P.wpr + word] = sb;
+            P.weak[(size_t)y * P.wpr + word] = wb;
         }
     }
 }
@@ -410,85 +462,176 @@ __global__ void __launch_bounds__(256) k_canny_nms(const PlaneDesc* __restrict__
 // word per thread; it iterates to local convergence in shared memory.  A cooperative grid loop
 // repeats until no tile's border changed; tiles whose neighbours did not change are skipped.
 // ---------------------------------------------------------------------------------------------
-constexpr int HY_WW = 8, HY_TR = 32;                 // tile = 256 px x 32 rows, one word per thread (256 threads)
+// Two tilings of every plane's bitmap, both 8 words (256 px) wide, one word-row per thread-row:
+//   small tiles: 32 rows  (round 0: every tile once, one block per tile, maximal parallelism)
+//   big tiles  : 128 rows (rounds 1..: only dirty tiles, 4 rows per thread; a chain advances 128 rows
+//                per round instead of 32, so the number of grid-wide rounds drops ~4x)
+// Dirty flags always refer to the big tiling.
+constexpr int HY_WW = 8, HY_TR = 32, HY_BIG = 1;
 constexpr int HY_THREADS = HY_WW * HY_TR;
-struct HystTileMap { int nplanes; int ntiles; };
+constexpr bool HY_VFLOOD = false;                   // bit-transposed column flood: measured slower on the 4K workload
 
+constexpr int HY_SS = HY_WW + 3;                      // smem row stride (odd: lanes that differ in the row hit different banks)
 __device__ __forceinline__ unsigned spread3(unsigned L, unsigned Cw, unsigned R) {
     return Cw | (Cw << 1) | (Cw >> 1) | (L >> 31) | (R << 31);
 }
+// 32x32 bit-matrix transpose inside a warp: lane i holds row i, returns column i (5 shuffle stages)
+__device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
+    const unsigned mlo[5] = {0x0000ffffu, 0x00ff00ffu, 0x0f0f0f0fu, 0x33333333u, 0x55555555u};
+#pragma unroll
+    for (int st = 0; st < 5; st++) {
+        const int k = 16 >> st;
+        const unsigned y = __shfl_xor_sync(0xffffffffu, x, k);
+        x = (lane & k) ? ((x & ~mlo[st]) | ((y >> k) & mlo[st])) : ((x & mlo[st]) | ((y << k) & ~mlo[st]));
+    }
+    return x;
+}
 
-__global__ void __launch_bounds__(HY_THREADS) k_hysteresis(const PlaneDesc* __restrict__ planes, int nplanes, const int* __restrict__ tile_base,
-                                                        int ntiles, int* __restrict__ flags, int* __restrict__ ctrl, int* __restrict__ status, int max_rounds) {
+// one tile (32*RPT rows) to local convergence; marks the BIG tiles that can see new border bits
+template <int RPT>
+__device__ __forceinline__ void hyst_process_tile(const PlaneDesc* __restrict__ planes, int nplanes, int tile,
+                                                  int* __restrict__ fl_nxt, int* __restrict__ c_nxt,
+                                                  unsigned (*sS)[HY_SS], int* sPlane, int* sNbr) {
+    constexpr int ROWS = HY_TR * RPT;
+    // warp = one word column (tc), lane = row inside a 32-row block: each warp owns 32x32-px blocks, so a
+    // vertical run can be flooded in one step on the bit-transposed block
+    const int tid = threadIdx.x, tr = tid & 31, tc = tid >> 5;
+    __syncthreads();
+    if (tid == 0) {
+        int p = 0;
+        if (RPT == 1) { while (p + 1 < nplanes && planes[p + 1].hy_base_small <= tile) p++; }
+        else { while (p + 1 < nplanes && planes[p + 1].hy_base_big <= tile) p++; }
+        *sPlane = p; *sNbr = 0;
+    }
+    __syncthreads();
+    const PlaneDesc& P = planes[*sPlane];
+    const int local = tile - (RPT == 1 ? P.hy_base_small : P.hy_base_big);
+    const int ntx = aeaj_cdiv(P.wpr, HY_WW);
+    const int tyi = local / ntx, txi = local - tyi * ntx;
+    const int gy0 = tyi * ROWS, gw0 = txi * HY_WW;
+    for (int i = tid; i < (ROWS + 2) * (HY_WW + 2); i += HY_THREADS) {
+        int ry = i / (HY_WW + 2), rw = i - ry * (HY_WW + 2);
+        int gy = gy0 + ry - 1, gw = gw0 + rw - 1;
+        unsigned v = 0;
+        if (gy >= 0 && gy < P.h && gw >= 0 && gw < P.wpr) v = __ldcg(P.strong + (size_t)gy * P.wpr + gw);
+        sS[ry][rw] = v;
+    }
+    const int gw = gw0 + tc;
+    unsigned wk[RPT], wkT[RPT], s[RPT], s_init[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+        const int gy = gy0 + tr + k * HY_TR;
+        wk[k] = (gy < P.h && gw < P.wpr) ? P.weak[(size_t)gy * P.wpr + gw] : 0u;
+        wkT[k] = HY_VFLOOD ? transpose32(wk[k], tr) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RPT; k++) { s_init[k] = sS[tr + k * HY_TR + 1][tc + 1]; s[k] = s_init[k]; }
+    for (;;) {
+        int ch = 0;
+        unsigned s_new[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; k++) {
+            const int r = tr + k * HY_TR;
+            unsigned n = spread3(sS[r][tc], sS[r][tc + 1], sS[r][tc + 2]) |
+                         spread3(sS[r + 1][tc], s[k], sS[r + 1][tc + 2]) |
+                         spread3(sS[r + 2][tc], sS[r + 2][tc + 1], sS[r + 2][tc + 2]);
+            unsigned add = wk[k] & ~s[k] & n;
+            unsigned t = s[k] | add;
+            while (add) { add = wk[k] & ~t & ((t << 1) | (t >> 1)); t |= add; }   // flood along the row inside the word
+            if (HY_VFLOOD && __any_sync(0xffffffffu, t != s[k])) {
+                // flood along the columns of the 32x32 block: same trick on the transposed block
+                unsigned tt = transpose32(t, tr);
+                unsigned addv = wkT[k] & ~tt & ((tt << 1) | (tt >> 1));
+                while (addv) { tt |= addv; addv = wkT[k] & ~tt & ((tt << 1) | (tt >> 1)); }
+                t = transpose32(tt, tr);
+            }
+            ch |= (t != s[k]);
+            s_new[k] = t;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < RPT; k++) if (s_new[k] != s[k]) { s[k] = s_new[k]; sS[tr + k * HY_TR + 1][tc + 1] = s[k]; }
+        if (!__syncthreads_or(ch)) break;
+    }
+    unsigned nb = 0;
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+        const int r = tr + k * HY_TR, gy = gy0 + r;
+        if (gy < P.h && gw < P.wpr && s[k] != s_init[k]) {
+            P.strong[(size_t)gy * P.wpr + gw] = s[k];
+            // which of the 8 neighbours can see the new bits (bit index = (dy+1)*3 + (dx+1))
+            const unsigned diff = s[k] ^ s_init[k];
+            const bool L = (tc == 0) && (diff & 1u), R = (tc == HY_WW - 1) && (diff >> 31);
+            if (r == 0) nb |= 2u | (L ? 1u : 0u) | (R ? 4u : 0u);
+            if (r == ROWS - 1) nb |= 128u | (L ? 64u : 0u) | (R ? 256u : 0u);
+            if (L) nb |= 8u;
+            if (R) nb |= 32u;
+        }
+    }
+    if (nb) atomicOr(sNbr, (int)nb);
+    __syncthreads();
+    if (tid < 9 && tid != 4 && ((*sNbr >> tid) & 1)) {
+        // neighbour in this tiling -> the big tile that contains its adjacent rows
+        const int dy = tid / 3 - 1, dx = tid % 3 - 1;
+        const int nx = txi + dx;
+        const int row = (dy < 0) ? gy0 - 1 : ((dy > 0) ? gy0 + ROWS : gy0);     // a row of the neighbour (dy == 0: same rows)
+        if (nx >= 0 && nx < ntx && row >= 0 && row < P.h) {
+            const int bty = row / (HY_TR * HY_BIG);
+            fl_nxt[P.hy_base_big + bty * ntx + nx] = 1;
+            atomicAdd(c_nxt, 1);
+        }
+    }
+}
+
+// round 0: every small tile once, plain launch; flags for round 1 go to flags[nbig..2*nbig)
+__global__ void __launch_bounds__(HY_THREADS) k_hysteresis_first(const PlaneDesc* __restrict__ planes, int nplanes, int nbig,
+                                                              int* __restrict__ flags, int* __restrict__ ctrl) {
+    __shared__ unsigned sS[HY_TR + 2][HY_SS];
+    __shared__ int sPlane, sNbr;
+    hyst_process_tile<1>(planes, nplanes, blockIdx.x, flags + nbig, ctrl + 1, sS, &sPlane, &sNbr);
+}
+
+// rounds 1..R: one plain launch per round, one block per tile, early exit when the tile is clean (or when the
+// previous round flagged nothing at all).  Launch latency is far below the cost of a grid-wide barrier here.
+__global__ void __launch_bounds__(HY_THREADS) k_hysteresis_round(const PlaneDesc* __restrict__ planes, int nplanes, int nbig,
+                                                              int* __restrict__ flags, int* __restrict__ ctrl, int round) {
+    __shared__ unsigned sS[HY_TR * HY_BIG + 2][HY_SS];
+    __shared__ int sPlane, sNbr;
+    if (*((volatile int*)(ctrl + round % 3)) == 0) return;          // nothing pending for this round
+    int* fl_cur = flags + (size_t)(round & 1) * nbig;
+    int* fl_nxt = flags + (size_t)((round + 1) & 1) * nbig;
+    const int tile = blockIdx.x;
+    if (tile == 0 && threadIdx.x == 0) ctrl[(round + 2) % 3] = 0;
+    if (__ldcg(fl_cur + tile) == 0) return;
+    __syncthreads();
+    if (threadIdx.x == 0) fl_cur[tile] = 0;
+    hyst_process_tile<HY_BIG>(planes, nplanes, tile, fl_nxt, ctrl + (round + 1) % 3, sS, &sPlane, &sNbr);
+}
+
+// remaining rounds: a cooperative grid loops over the dirty big tiles until no border changed
+__global__ void __launch_bounds__(HY_THREADS) k_hysteresis_rounds(const PlaneDesc* __restrict__ planes, int nplanes, int nbig,
+                                                               int* __restrict__ flags, int* __restrict__ ctrl, int* __restrict__ status,
+                                                               int first_round, int max_rounds) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ unsigned sS[HY_TR + 2][HY_WW + 2];
-    __shared__ int sPlane, sAnyBorder;
-    const int tid = threadIdx.x, tr = tid / HY_WW, tc = tid % HY_WW;
-    int round = 0;
+    __shared__ unsigned sS[HY_TR * HY_BIG + 2][HY_SS];
+    __shared__ int sPlane, sNbr;
+    const int tid = threadIdx.x;
+    int round = first_round;
+    if (*((volatile int*)(ctrl + first_round % 3)) == 0) {   // already converged in the plain rounds
+        if (blockIdx.x == 0 && tid == 0 && status) { status[0] = first_round; status[1] = 1; }
+        return;
+    }
     for (;; round++) {
-        int* fl_cur = flags + (size_t)(round & 1) * ntiles;
-        int* fl_nxt = flags + (size_t)((round + 1) & 1) * ntiles;
+        int* fl_cur = flags + (size_t)(round & 1) * nbig;
+        int* fl_nxt = flags + (size_t)((round + 1) & 1) * nbig;
         int* c_nxt = ctrl + (round + 1) % 3;
         if (blockIdx.x == 0 && tid == 0) ctrl[(round + 2) % 3] = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            if (round > 0 && __ldcg(fl_cur + tile) == 0) continue;   // uniform per block
+        for (int tile = blockIdx.x; tile < nbig; tile += gridDim.x) {
+            if (__ldcg(fl_cur + tile) == 0) continue;  // uniform per block
             __syncthreads();
-            if (tid == 0) {
-                fl_cur[tile] = 0;
-                int p = 0;
-                while (p + 1 < nplanes && tile_base[p + 1] <= tile) p++;
-                sPlane = p; sAnyBorder = 0;
-            }
-            __syncthreads();
-            const PlaneDesc& P = planes[sPlane];
-            const int local = tile - tile_base[sPlane];
-            const int ntx = aeaj_cdiv(P.wpr, HY_WW);
-            const int tyi = local / ntx, txi = local - tyi * ntx;
-            const int gy0 = tyi * HY_TR, gw0 = txi * HY_WW;
-            // load strong words incl. 1-row / 1-word halo
-            for (int i = tid; i < (HY_TR + 2) * (HY_WW + 2); i += HY_THREADS) {
-                int ry = i / (HY_WW + 2), rw = i - ry * (HY_WW + 2);
-                int gy = gy0 + ry - 1, gw = gw0 + rw - 1;
-                unsigned v = 0;
-                if (gy >= 0 && gy < P.h && gw >= 0 && gw < P.wpr) v = __ldcg(P.strong + (size_t)gy * P.wpr + gw);
-                sS[ry][rw] = v;
-            }
-            const int gy = gy0 + tr, gw = gw0 + tc;
-            const bool valid = gy < P.h && gw < P.wpr;
-            const unsigned wk = valid ? P.weak[(size_t)gy * P.wpr + gw] : 0u;
-            __syncthreads();
-            const unsigned s_init = sS[tr + 1][tc + 1];
-            unsigned s = s_init;
-            for (;;) {
-                unsigned n = spread3(sS[tr][tc], sS[tr][tc + 1], sS[tr][tc + 2]) |
-                             spread3(sS[tr + 1][tc], s, sS[tr + 1][tc + 2]) |
-                             spread3(sS[tr + 2][tc], sS[tr + 2][tc + 1], sS[tr + 2][tc + 2]);
-                unsigned add = wk & ~s & n;
-                unsigned s_new = s | add;
-                // flood along the row inside the word
-                while (add) { add = wk & ~s_new & ((s_new << 1) | (s_new >> 1)); s_new |= add; }
-                int ch = (s_new != s);
-                s = s_new;
-                __syncthreads();
-                if (ch) sS[tr + 1][tc + 1] = s;
-                if (!__syncthreads_or(ch)) break;
-            }
-            if (valid && s != s_init) {
-                P.strong[(size_t)gy * P.wpr + gw] = s;
-                unsigned diff = s ^ s_init;
-                bool border = (tr == 0) || (tr == HY_TR - 1) || (gy == P.h - 1) || (tc == 0 && (diff & 1u)) || (tc == HY_WW - 1 && (diff >> 31));
-                if (border) sAnyBorder = 1;
-            }
-            __syncthreads();
-            if (sAnyBorder && tid < 9 && tid != 4) {
-                int dy = tid / 3 - 1, dx = tid % 3 - 1;
-                int nty = aeaj_cdiv(P.h, HY_TR);
-                int ny = tyi + dy, nx = txi + dx;
-                if (ny >= 0 && ny < nty && nx >= 0 && nx < ntx) {
-                    fl_nxt[tile_base[sPlane] + ny * ntx + nx] = 1;
-                    atomicAdd(c_nxt, 1);
-                }
-            }
+            if (tid == 0) { fl_cur[tile] = 0; if (status && round < 30) atomicAdd(&status[2 + round], 1); }
+            hyst_process_tile<HY_BIG>(planes, nplanes, tile, fl_nxt, c_nxt, sS, &sPlane, &sNbr);
         }
         __threadfence();
         grid.sync();
@@ -557,8 +700,8 @@ int launch_clahe_lut(const PlaneDesc* planes_dev, int nplanes, cudaStream_t st) 
     return 0;
 }
 int launch_prefilter(const PlaneDesc* planes_dev, const PlaneDesc* P, int nplanes, int stages, int do_hist, cudaStream_t st) {
-    dim3 grd(aeaj_cdiv(max_dim(P, nplanes, true), PF_TW), aeaj_cdiv(max_dim(P, nplanes, false), PF_TH), nplanes);
-    k_prefilter<<<grd, 256, 0, st>>>(planes_dev, stages, do_hist);
+    const TileMap tm = make_tile_map(P, nplanes, PF_TW, PF_TH);
+    k_prefilter<<<tile_map_total(tm, nplanes), 256, 0, st>>>(planes_dev, tm, stages, do_hist);
     AEAJ_LAUNCH_CHECK();
     return 0;
 }
@@ -579,32 +722,49 @@ int launch_thresholds_from_double(const double* thr_d, int* thr, cudaStream_t st
     return 0;
 }
 int launch_canny_nms(const PlaneDesc* planes_dev, const PlaneDesc* P, int nplanes, cudaStream_t st) {
-    dim3 grd(aeaj_cdiv(max_dim(P, nplanes, true), NM_TW), aeaj_cdiv(max_dim(P, nplanes, false), NM_TH), nplanes);
-    k_canny_nms<<<grd, 256, 0, st>>>(planes_dev);
+    const TileMap tm = make_tile_map(P, nplanes, NM_TW, NM_TH);
+    k_canny_nms<<<tile_map_total(tm, nplanes), 256, 0, st>>>(planes_dev, tm);
     AEAJ_LAUNCH_CHECK();
     return 0;
 }
 
-int hysteresis_tiles(const PlaneDesc* P, int nplanes, int* tile_base_host) {
-    int n = 0;
-    for (int i = 0; i < nplanes; i++) { tile_base_host[i] = n; n += aeaj_cdiv(P[i].wpr, HY_WW) * aeaj_cdiv(P[i].h, HY_TR); }
-    return n;
+// fills hy_base_small / hy_base_big of every plane; returns the number of small tiles, *nbig = big tiles
+int hysteresis_tiles(PlaneDesc* P, int nplanes, int* nbig) {
+    int ns = 0, nb = 0;
+    for (int i = 0; i < nplanes; i++) {
+        P[i].hy_base_small = ns; P[i].hy_base_big = nb;
+        const int ntx = aeaj_cdiv(P[i].wpr, HY_WW);
+        ns += ntx * aeaj_cdiv(P[i].h, HY_TR);
+        nb += ntx * aeaj_cdiv(P[i].h, HY_TR * HY_BIG);
+    }
+    *nbig = nb;
+    return ns;
 }
 
-// flags: int[2*ntiles]; ctrl: int[3]; both zeroed here.  tile_base_dev: int[nplanes]
-int launch_hysteresis(aeaj_handle* h, const PlaneDesc* planes_dev, int nplanes, const int* tile_base_dev, int ntiles,
+// flags: int[2*nbig]; ctrl: int[3]; both zeroed here.
+int launch_hysteresis(aeaj_handle* h, const PlaneDesc* planes_dev, int nplanes, int nsmall, int nbig,
                       int* flags, int* ctrl, int* status, cudaStream_t st) {
-    AEAJ_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 2 * (size_t)ntiles, st));
+    AEAJ_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 2 * (size_t)nbig, st));
     AEAJ_CUDA(cudaMemsetAsync(ctrl, 0, sizeof(int) * 3, st));
+    k_hysteresis_first<<<nsmall, HY_THREADS, 0, st>>>(planes_dev, nplanes, nbig, flags, ctrl);
+    AEAJ_LAUNCH_CHECK();
     static int blocks_per_sm = 0;
     if (!blocks_per_sm) {
-        AEAJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_hysteresis, HY_THREADS, 0));
+        AEAJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_hysteresis_rounds, HY_THREADS, 0));
         if (blocks_per_sm < 1) { aeaj_set_error("hysteresis kernel cannot be resident"); return AEAJ_EINVAL; }
     }
-    int grid = std::min(ntiles, blocks_per_sm * h->sm_count);
-    int max_rounds = 1 << 20;
-    void* args[] = {(void*)&planes_dev, (void*)&nplanes, (void*)&tile_base_dev, (void*)&ntiles, (void*)&flags, (void*)&ctrl, (void*)&status, (void*)&max_rounds};
-    AEAJ_CUDA(cudaLaunchCooperativeKernel((void*)k_hysteresis, dim3(grid), dim3(HY_THREADS), args, 0, st));
+    int plain_rounds = 0;   // measured: per-round cost is the slowest tile's local convergence (~20 us), not the barrier
+    if (const char* e = getenv("AEAJ_HYST_PLAIN")) plain_rounds = std::max(0, atoi(e));
+    for (int r = 1; r <= plain_rounds; r++) {
+        k_hysteresis_round<<<nbig, HY_THREADS, 0, st>>>(planes_dev, nplanes, nbig, flags, ctrl, r);
+        AEAJ_LAUNCH_CHECK();
+    }
+    int bps = std::min(blocks_per_sm, 4);
+    if (const char* e = getenv("AEAJ_HYST_BPS")) bps = std::max(1, std::min(blocks_per_sm, atoi(e)));
+    int grid = std::min(nbig, bps * h->sm_count);
+    int max_rounds = 1 << 20, first_round = plain_rounds + 1;
+    void* args[] = {(void*)&planes_dev, (void*)&nplanes, (void*)&nbig, (void*)&flags, (void*)&ctrl, (void*)&status, (void*)&first_round, (void*)&max_rounds};
+    AEAJ_CUDA(cudaLaunchCooperativeKernel((void*)k_hysteresis_rounds, dim3(grid), dim3(HY_THREADS), args, 0, st));
     return 0;
 }
 

@@ -61,16 +61,16 @@ __device__ __forceinline__ bool cell_has_edge(const uint32_t* __restrict__ bits,
 
 // phase 0: totals per top block.  phase 1: emit states / leaves / class entries.
 // grid: (max top blocks over planes, nplanes)
-__global__ void __launch_bounds__(QT_THREADS) k_qt_blocks(const PlaneDesc* __restrict__ planes, QtParams q, int phase,
+__global__ void __launch_bounds__(QT_THREADS) k_qt_blocks(const PlaneDesc* __restrict__ planes, const __grid_constant__ TileMap tm, QtParams q, int phase,
                                                           ClassEntry* __restrict__ class_lists, int* __restrict__ class_counts,
                                                           const long long* __restrict__ class_offsets) {
-    const PlaneDesc& P = planes[blockIdx.y];
-    const int tb = blockIdx.x;
-    if (tb >= P.ntx * P.nty) return;
+    int plane_i, bx, by;
+    tile_decode(tm, blockIdx.x, plane_i, bx, by);
+    const PlaneDesc& P = planes[plane_i];
+    const int tb = by * P.ntx + bx;
     const int T = P.top, c = q.min_size;
     const int n = T / c;                               // cells per side (power of two, >= 1)
     int L = 0; while ((1 << L) < n) L++;
-    const int bx = tb % P.ntx, by = tb / P.ntx;
     const int X0 = bx * T, Y0 = by * T;
     __shared__ uint8_t occ[QT_OCC_BYTES];
     __shared__ int lvl_off[9];
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_qt_blocks(const PlaneDesc* __res
                     int s = c << l, x = X0 + (k << l) * c, y = Y0 + (j << l) * c;
                     reinterpret_cast<int4*>(P.leaves)[li] = make_int4(x, y, s, co);
                     int r = s_cls_base[l] + atomicAdd(&s_cls[l], 1);
-                    ClassEntry e; e.x = x; e.y = y; e.plane = blockIdx.y; e.coef_off = co;
+                    ClassEntry e; e.x = x; e.y = y; e.plane = plane_i; e.coef_off = co;
                     class_lists[class_offsets[q.lg_min + l] + r] = e;
                 }
             }
@@ -263,15 +263,14 @@ __global__ void __launch_bounds__(256) k_bucket_leaves(const PlaneDesc* __restri
 
 int launch_quadtree(const PlaneDesc* planes_dev, const PlaneDesc* P, int nplanes, int min_size, int max_size,
                     ClassEntry* class_lists, int* class_counts, const long long* class_offsets_dev, cudaStream_t st, int* launches) {
-    int maxtb = 0;
-    for (int i = 0; i < nplanes; i++) maxtb = std::max(maxtb, P[i].ntx * P[i].nty);
     QtParams q; q.min_size = min_size; q.lg_min = ilog2i(min_size); q.max_size = max_size;
-    dim3 grd(maxtb, nplanes);
-    k_qt_blocks<<<grd, QT_THREADS, 0, st>>>(planes_dev, q, 0, class_lists, class_counts, class_offsets_dev);
+    const TileMap tm = make_tile_map(P, nplanes, 0, 0, true);
+    const int grd = tile_map_total(tm, nplanes);
+    k_qt_blocks<<<grd, QT_THREADS, 0, st>>>(planes_dev, tm, q, 0, class_lists, class_counts, class_offsets_dev);
     AEAJ_LAUNCH_CHECK();
     k_qt_scan<<<nplanes, QT_THREADS, 0, st>>>(planes_dev);
     AEAJ_LAUNCH_CHECK();
-    k_qt_blocks<<<grd, QT_THREADS, 0, st>>>(planes_dev, q, 1, class_lists, class_counts, class_offsets_dev);
+    k_qt_blocks<<<grd, QT_THREADS, 0, st>>>(planes_dev, tm, q, 1, class_lists, class_counts, class_offsets_dev);
     AEAJ_LAUNCH_CHECK();
     if (launches) *launches += 3;
     return 0;
