@@ -19,8 +19,19 @@
 
 namespace {
 
+// np.round(block / qmatrix) (jpeg.py:501): the quotient is formed in float64 and rounded half-to-even.
+// A float32 z is never closer than 2^-24 (relative) to a half-integer multiple of q without being exactly on
+// it, so rounding the float64 quotient equals rounding the exact quotient -- which is computed here without any
+// float64: k = rint(z * 1/q) is within one of the answer, the residual z - k*q is exact in one fma, and the
+// comparison of 2r with q (ties to even) fixes k.  Checked against the float64 formula on 20 M values incl. ties.
 __device__ __forceinline__ int quantize(float z, int q) {
-    return __double2int_rn(__ddiv_rn((double)z, (double)q));
+    const float fq = (float)q;
+    float k = rintf(__fmul_rn(z, __frcp_rn(fq)));
+    const float r2 = __fmul_rn(2.0f, __fmaf_rn(-k, fq, z));
+    const bool odd = ((int)k) & 1;
+    if (r2 > fq || (r2 == fq && odd)) k += 1.0f;
+    else if (r2 < -fq || (r2 == -fq && odd)) k -= 1.0f;
+    return (int)k;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -169,12 +180,21 @@ __global__ void __launch_bounds__(256) k_dct_cta(const PlaneDesc* __restrict__ p
     constexpr int T = S / 16;                          // tile edge per thread: 8 (N=128) or 4 (N=64)
     constexpr int RC = T / 4;                          // number of 4-wide chunks along the "4-chunk" axis
     constexpr int CW = T / 2;                          // width of the two mirrored column chunks (forward pass 1)
+    // Bank-conflict avoidance: the odd halves start 16 floats later than a multiple of 32 (the even / odd lanes
+    // of a pair read the same offsets of the two halves), and staging rows are NS = N + 4 floats apart (the
+    // transposed stores walk down a column).
+    constexpr int NS = N + 4, PAD = 16;
     extern __shared__ __align__(16) float smem[];
-    float* sA = smem;                                  // [2][Hh][Hh]
-    float* sB = smem + 2 * Hh * Hh;                    // [N][N]
+    float* sA = smem;                                  // even half matrix [Hh][Hh]
+    float* sAo = sA + Hh * Hh + PAD;                   // odd half matrix
+    float* sB = sAo + Hh * Hh + PAD;                   // staging, first Hh rows  [Hh][NS]
+    float* sBo = sB + Hh * NS + PAD;                   // staging, second Hh rows [Hh][NS]
     const int tid = threadIdx.x, g = tid & 1, p = tid >> 1;
-    for (int i = tid; i < 2 * Hh * Hh / 4; i += 256) reinterpret_cast<float4*>(sA)[i] = __ldg(reinterpret_cast<const float4*>(half_tab) + i);
-    const float* sAg = sA + g * Hh * Hh;
+    for (int i = tid; i < Hh * Hh / 4; i += 256) {
+        reinterpret_cast<float4*>(sA)[i] = __ldg(reinterpret_cast<const float4*>(half_tab) + i);
+        reinterpret_cast<float4*>(sAo)[i] = __ldg(reinterpret_cast<const float4*>(half_tab + Hh * Hh) + i);
+    }
+    const float* sAg = g ? sAo : sA;
     const int count = *count_ptr;
     // pass-1 tile: rows (h of them) in chunks of 4 at stride 32, columns (N of them)
     const int tr = p / 16, tc = p % 16;
@@ -188,13 +208,26 @@ __global__ void __launch_bounds__(256) k_dct_cta(const PlaneDesc* __restrict__ p
             // load X, fold rows: sB[i][j] = X[i][j] + X[N-1-i][j] (i < h), sB[h+i][j] = X[i][j] - X[N-1-i][j]
             const int bh = min(N, P.h - e.y), bw = min(N, P.w - e.x);
             const float mid = P.mid, sc = P.scale;
-            for (int i = tid; i < Hh * N; i += 256) {
-                const int rr = i / N, cc = i - rr * N;
-                const int xx = e.x + pad_reflect(cc, bw);
-                float a = __ldg(P.layer_f32 + (size_t)(e.y + pad_reflect(rr, bh)) * P.w + xx);
-                float b = __ldg(P.layer_f32 + (size_t)(e.y + pad_reflect(N - 1 - rr, bh)) * P.w + xx);
-                a = __fmul_rn(__fsub_rn(a, mid), sc); b = __fmul_rn(__fsub_rn(b, mid), sc);
-                sB[i] = __fadd_rn(a, b); sB[Hh * N + i] = __fsub_rn(a, b);
+            if (bh == N && bw == N && (P.w & 3) == 0) {
+                // full leaf: 128-bit loads of rows rr and N-1-rr
+                for (int i = tid; i < Hh * N / 4; i += 256) {
+                    const int rr = (i * 4) / N, cc = (i * 4) - rr * N;
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(P.layer_f32 + (size_t)(e.y + rr) * P.w + e.x + cc));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(P.layer_f32 + (size_t)(e.y + N - 1 - rr) * P.w + e.x + cc));
+                    const float a0 = __fmul_rn(__fsub_rn(a.x, mid), sc), a1 = __fmul_rn(__fsub_rn(a.y, mid), sc), a2 = __fmul_rn(__fsub_rn(a.z, mid), sc), a3 = __fmul_rn(__fsub_rn(a.w, mid), sc);
+                    const float b0 = __fmul_rn(__fsub_rn(b.x, mid), sc), b1 = __fmul_rn(__fsub_rn(b.y, mid), sc), b2 = __fmul_rn(__fsub_rn(b.z, mid), sc), b3 = __fmul_rn(__fsub_rn(b.w, mid), sc);
+                    *reinterpret_cast<float4*>(sB + rr * NS + cc) = make_float4(__fadd_rn(a0, b0), __fadd_rn(a1, b1), __fadd_rn(a2, b2), __fadd_rn(a3, b3));
+                    *reinterpret_cast<float4*>(sBo + rr * NS + cc) = make_float4(__fsub_rn(a0, b0), __fsub_rn(a1, b1), __fsub_rn(a2, b2), __fsub_rn(a3, b3));
+                }
+            } else {
+                for (int i = tid; i < Hh * N; i += 256) {
+                    const int rr = i / N, cc = i - rr * N;
+                    const int xx = e.x + pad_reflect(cc, bw);
+                    float a = __ldg(P.layer_f32 + (size_t)(e.y + pad_reflect(rr, bh)) * P.w + xx);
+                    float b = __ldg(P.layer_f32 + (size_t)(e.y + pad_reflect(N - 1 - rr, bh)) * P.w + xx);
+                    a = __fmul_rn(__fsub_rn(a, mid), sc); b = __fmul_rn(__fsub_rn(b, mid), sc);
+                    sB[rr * NS + cc] = __fadd_rn(a, b); sBo[rr * NS + cc] = __fsub_rn(a, b);
+                }
             }
         } else {
             // load Z dequantised, rows in split order: even rows first, then odd rows
@@ -203,7 +236,7 @@ __global__ void __launch_bounds__(256) k_dct_cta(const PlaneDesc* __restrict__ p
             for (int i = tid; i < N * N / 4; i += 256) {
                 const int k = (i * 4) / N, l = (i * 4) - k * N;
                 int4 cv = __ldg(reinterpret_cast<const int4*>(cf) + i), qv = __ldg(reinterpret_cast<const int4*>(qt) + i);
-                *reinterpret_cast<float4*>(sB + ((k & 1) * Hh + (k >> 1)) * N + l) =
+                *reinterpret_cast<float4*>(((k & 1) ? sBo : sB) + (k >> 1) * NS + l) =
                     make_float4((float)(cv.x * qv.x), (float)(cv.y * qv.y), (float)(cv.z * qv.z), (float)(cv.w * qv.w));
             }
         }
@@ -213,7 +246,7 @@ __global__ void __launch_bounds__(256) k_dct_cta(const PlaneDesc* __restrict__ p
         for (int a = 0; a < T; a++)
 #pragma unroll
             for (int b = 0; b < T; b++) acc[a][b] = 0.0f;
-        const float* sBg = sB + g * Hh * N;
+        const float* sBg = g ? sBo : sB;
         if (!INVERSE) {
             // pass 1: Vg[m][j] = sum_i Cg[m][i] * Fg[i][j]; sAg[i][m] = Cg[m][i]; columns = two mirrored chunks
             for (int i = 0; i < Hh; i++) {
@@ -221,12 +254,12 @@ __global__ void __launch_bounds__(256) k_dct_cta(const PlaneDesc* __restrict__ p
 #pragma unroll
                 for (int c = 0; c < RC; c++) { float4 t = *reinterpret_cast<const float4*>(sAg + i * Hh + tr * 4 + c * 32); av[4 * c] = t.x; av[4 * c + 1] = t.y; av[4 * c + 2] = t.z; av[4 * c + 3] = t.w; }
                 if (CW == 4) {
-                    float4 t = *reinterpret_cast<const float4*>(sBg + i * N + tc * 4);
-                    float4 u = *reinterpret_cast<const float4*>(sBg + i * N + N - 4 - tc * 4);
+                    float4 t = *reinterpret_cast<const float4*>(sBg + i * NS + tc * 4);
+                    float4 u = *reinterpret_cast<const float4*>(sBg + i * NS + N - 4 - tc * 4);
                     bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w; bv[4] = u.w; bv[5] = u.z; bv[6] = u.y; bv[7] = u.x;
                 } else {
-                    float2 t = *reinterpret_cast<const float2*>(sBg + i * N + tc * 2);
-                    float2 u = *reinterpret_cast<const float2*>(sBg + i * N + N - 2 - tc * 2);
+                    float2 t = *reinterpret_cast<const float2*>(sBg + i * NS + tc * 2);
+                    float2 u = *reinterpret_cast<const float2*>(sBg + i * NS + N - 2 - tc * 2);
                     bv[0] = t.x; bv[1] = t.y; bv[2] = u.y; bv[3] = u.x;
                 }
 #pragma unroll
@@ -247,8 +280,8 @@ __global__ void __launch_bounds__(256) k_dct_cta(const PlaneDesc* __restrict__ p
 #pragma unroll
                     for (int a = 0; a < 4; a++) { pv[a] = __fadd_rn(acc[4 * c + a][b], acc[4 * c + a][b + CW]); qv[a] = __fsub_rn(acc[4 * c + a][b], acc[4 * c + a][b + CW]); }
                     const int kk = g * Hh + tr * 4 + c * 32;
-                    *reinterpret_cast<float4*>(sB + j * N + kk) = make_float4(pv[0], pv[1], pv[2], pv[3]);
-                    *reinterpret_cast<float4*>(sB + (Hh + j) * N + kk) = make_float4(qv[0], qv[1], qv[2], qv[3]);
+                    *reinterpret_cast<float4*>(sB + j * NS + kk) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+                    *reinterpret_cast<float4*>(sBo + j * NS + kk) = make_float4(qv[0], qv[1], qv[2], qv[3]);
                 }
             }
             __syncthreads();
@@ -260,7 +293,7 @@ __global__ void __launch_bounds__(256) k_dct_cta(const PlaneDesc* __restrict__ p
             for (int j = 0; j < Hh; j++) {
                 float av[T], bv[T];
 #pragma unroll
-                for (int c = 0; c < RC; c++) { float4 t = *reinterpret_cast<const float4*>(sBg + j * N + tr2 * 4 + c * 64); av[4 * c] = t.x; av[4 * c + 1] = t.y; av[4 * c + 2] = t.z; av[4 * c + 3] = t.w; }
+                for (int c = 0; c < RC; c++) { float4 t = *reinterpret_cast<const float4*>(sBg + j * NS + tr2 * 4 + c * 64); av[4 * c] = t.x; av[4 * c + 1] = t.y; av[4 * c + 2] = t.z; av[4 * c + 3] = t.w; }
 #pragma unroll
                 for (int c = 0; c < RC; c++) { float4 t = *reinterpret_cast<const float4*>(sAg + j * Hh + tc2 * 4 + c * 32); bv[4 * c] = t.x; bv[4 * c + 1] = t.y; bv[4 * c + 2] = t.z; bv[4 * c + 3] = t.w; }
 #pragma unroll
@@ -294,7 +327,7 @@ __global__ void __launch_bounds__(256) k_dct_cta(const PlaneDesc* __restrict__ p
 #pragma unroll
                 for (int c = 0; c < RC; c++) { float4 t = *reinterpret_cast<const float4*>(sAg + m * Hh + tr * 4 + c * 32); av[4 * c] = t.x; av[4 * c + 1] = t.y; av[4 * c + 2] = t.z; av[4 * c + 3] = t.w; }
 #pragma unroll
-                for (int c = 0; c < RC; c++) { float4 t = *reinterpret_cast<const float4*>(sBg + m * N + tc * 4 + c * 64); bv[4 * c] = t.x; bv[4 * c + 1] = t.y; bv[4 * c + 2] = t.z; bv[4 * c + 3] = t.w; }
+                for (int c = 0; c < RC; c++) { float4 t = *reinterpret_cast<const float4*>(sBg + m * NS + tc * 4 + c * 64); bv[4 * c] = t.x; bv[4 * c + 1] = t.y; bv[4 * c + 2] = t.z; bv[4 * c + 3] = t.w; }
 #pragma unroll
                 for (int a = 0; a < T; a++)
 #pragma unroll
@@ -306,7 +339,7 @@ __global__ void __launch_bounds__(256) k_dct_cta(const PlaneDesc* __restrict__ p
 #pragma unroll
             for (int b = 0; b < T; b++) {
                 const int l = tc * 4 + (b & 3) + (b >> 2) * 64;
-                const int lrow = (l & 1) * Hh + (l >> 1);
+                float* vrow = ((l & 1) ? sBo : sB) + (l >> 1) * NS;
 #pragma unroll
                 for (int c = 0; c < RC; c++) {
                     float v[4];
@@ -317,8 +350,8 @@ __global__ void __launch_bounds__(256) k_dct_cta(const PlaneDesc* __restrict__ p
                         v[a] = g ? __fsub_rn(other, mine) : __fadd_rn(mine, other);     // g=0: E+O ; g=1: E-O
                     }
                     const int i0 = tr * 4 + c * 32;
-                    if (!g) *reinterpret_cast<float4*>(sB + lrow * N + i0) = make_float4(v[0], v[1], v[2], v[3]);
-                    else *reinterpret_cast<float4*>(sB + lrow * N + (N - 4 - i0)) = make_float4(v[3], v[2], v[1], v[0]);
+                    if (!g) *reinterpret_cast<float4*>(vrow + i0) = make_float4(v[0], v[1], v[2], v[3]);
+                    else *reinterpret_cast<float4*>(vrow + (N - 4 - i0)) = make_float4(v[3], v[2], v[1], v[0]);
                 }
             }
             __syncthreads();
@@ -330,7 +363,7 @@ __global__ void __launch_bounds__(256) k_dct_cta(const PlaneDesc* __restrict__ p
             for (int m = 0; m < Hh; m++) {
                 float av[T], bv[T];
 #pragma unroll
-                for (int c = 0; c < RC; c++) { float4 t = *reinterpret_cast<const float4*>(sBg + m * N + tr2 * 4 + c * 64); av[4 * c] = t.x; av[4 * c + 1] = t.y; av[4 * c + 2] = t.z; av[4 * c + 3] = t.w; }
+                for (int c = 0; c < RC; c++) { float4 t = *reinterpret_cast<const float4*>(sBg + m * NS + tr2 * 4 + c * 64); av[4 * c] = t.x; av[4 * c + 1] = t.y; av[4 * c + 2] = t.z; av[4 * c + 3] = t.w; }
 #pragma unroll
                 for (int c = 0; c < RC; c++) { float4 t = *reinterpret_cast<const float4*>(sAg + m * Hh + tc2 * 4 + c * 32); bv[4 * c] = t.x; bv[4 * c + 1] = t.y; bv[4 * c + 2] = t.z; bv[4 * c + 3] = t.w; }
 #pragma unroll
@@ -387,7 +420,7 @@ int launch_rows(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* l
 }
 template <int S, bool INV>
 int launch_cta(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* list, const int* count, int64_t cap, cudaStream_t st) {
-    const size_t smem = (size_t)(S * S + S * S / 2) * sizeof(float);
+    const size_t smem = (size_t)(S * S / 2 + S * (S + 4) + 3 * 16) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         AEAJ_CUDA(cudaFuncSetAttribute(k_dct_cta<S, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
