@@ -50,9 +50,24 @@ def _oracle():
     return O
 
 
-def _frames(n, first_seed):
+def shard_seeds(rank: int, frames_per_rank: int):
+    """frames are sharded by rank: rank r owns seeds r*B .. r*B+B-1 (weak scaling, no data-path collective)"""
+    return list(range(rank * frames_per_rank, (rank + 1) * frames_per_rank))
+
+
+def reduce_max(t, dist):
+    """the only cross-rank exchange of the benchmark: max over ranks of the timings"""
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t
+
+
+def whole_job_mps(world: int, frames_per_rank: int, steps: int, ms: float) -> float:
+    return world * frames_per_rank * (H * W / 1e6) * steps / (ms / 1e3)
+
+
+def _frames(seeds):
     from synth import synth
-    return np.stack([synth(H, W, seed=first_seed + i) for i in range(n)])
+    return np.stack([synth(H, W, seed=s) for s in seeds])
 
 
 def cpu_baseline(frames: np.ndarray, threads: int):
@@ -122,7 +137,7 @@ def run_reference(args):
     O = _oracle()
     cores = os.cpu_count() or 1
     O.set_threads(cores)
-    frames = _frames(1, 0)
+    frames = _frames([0])
     for _ in range(max(args.warmup, 1)):
         O.decode_hot(O.encode_hot(frames[0], SPACE, QRANGE, BRANGE), H, W, SPACE, QRANGE, BRANGE)
     t0 = time.perf_counter()
@@ -168,7 +183,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
     codec = get_codec(local)
-    frames_np = _frames(B, rank * B)
+    frames_np = _frames(shard_seeds(rank, B))
     host_in = torch.from_numpy(frames_np).pin_memory()
     rgb = host_in.to(f"cuda:{local}")
     mp_per_step = B * H * W / 1e6
@@ -229,16 +244,15 @@ def main():
     counts_np = codec._plan(B, H, W, SPACE, BRANGE, QRANGE).out.counts.cpu().numpy()
 
     if world > 1:
-        t = torch.tensor([ms, e2e_ms], device=f"cuda:{local}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = reduce_max(torch.tensor([ms, e2e_ms], device=f"cuda:{local}", dtype=torch.float64), dist)
         ms, e2e_ms = float(t[0]), float(t[1])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    value = world * mp_per_step * args.steps / (ms / 1e3)
-    e2e_value = world * mp_per_step * args.steps / (e2e_ms / 1e3)
+    value = whole_job_mps(world, B, args.steps, ms)
+    e2e_value = whole_job_mps(world, B, args.steps, e2e_ms)
     # roofline: dominant stage of the step
     peaks = {}
     try:
