@@ -64,8 +64,8 @@ class DeviceCodec:
         self.last_launches = 0
 
     # ------------------------------------------------------------------------------------------
-    def _plan(self, B, H, W, space, brange, qrange) -> _Plan:
-        key = (B, H, W, space, tuple(brange))
+    def _plan(self, B, H, W, space, brange, qrange, instance: int = 0) -> _Plan:
+        key = (B, H, W, space, tuple(brange), instance)
         p = self._plans.get(key)
         dev = torch.device("cuda", self.device)
         if p is None:
@@ -100,7 +100,7 @@ class DeviceCodec:
         return self._plan(B, H, W, space, brange, qrange).info
 
     # ------------------------------------------------------------------------------------------
-    def encode(self, rgb: torch.Tensor, space: str, qrange, brange, taps: bool = False) -> EncodedBatch:
+    def encode(self, rgb: torch.Tensor, space: str, qrange, brange, taps: bool = False, instance: int = 0) -> EncodedBatch:
         """rgb: float32 CUDA tensor [B,H,W,3] (or [H,W,3]). Asynchronous on the current stream."""
         if rgb.dim() == 3:
             rgb = rgb.unsqueeze(0)
@@ -108,7 +108,7 @@ class DeviceCodec:
             raise TypeError("encode expects a float32 CUDA tensor of shape [B,H,W,3]")
         rgb = rgb.contiguous()
         B, H, W, _ = rgb.shape
-        p = self._plan(B, H, W, space, brange, qrange)
+        p = self._plan(B, H, W, space, brange, qrange, instance)
         o = p.out
         io = native.EncodeIO()
         io.rgb = rgb.data_ptr()
@@ -129,9 +129,9 @@ class DeviceCodec:
         self.last_launches = self.lib.aeaj_plan_last_launches(p.ptr)
         return o
 
-    def decode(self, coef, leaves, counts, B, H, W, space: str, qrange, brange, taps: bool = False):
+    def decode(self, coef, leaves, counts, B, H, W, space: str, qrange, brange, taps: bool = False, instance: int = 0):
         """coef/leaves: 3 device tensors laid out like EncodedBatch; counts int32 [B,3,4]. Returns rgb [B,H,W,3]."""
-        p = self._plan(B, H, W, space, brange, qrange)
+        p = self._plan(B, H, W, space, brange, qrange, instance)
         io = native.DecodeIO()
         for l in range(3):
             if coef[l].shape[1] != p.info.cap_coef[l] or leaves[l].shape[1] != p.info.cap_leaves[l]:
@@ -168,19 +168,20 @@ class DeviceCodec:
     # ------------------------------------------------------------------------------------------
     # host-buffer path (what a caller holding numpy / pinned host memory uses; bench.py e2e leg)
     # ------------------------------------------------------------------------------------------
-    def _host_staging(self, p: _Plan):
+    def _host_staging(self, p: _Plan, with_rgb: bool = False):
         if not p.keep:
             B = p.info.batch
             st = dict(
-                rgb_in=torch.empty((B, p.info.height, p.info.width, 3), dtype=torch.float32).pin_memory(),
-                rgb_out=torch.empty((B, p.info.height, p.info.width, 3), dtype=torch.float32).pin_memory(),
                 coef=[torch.empty((B, int(p.info.cap_coef[l])), dtype=torch.int32).pin_memory() for l in range(3)],
                 leaves=[torch.empty((B, int(p.info.cap_leaves[l]), 4), dtype=torch.int32).pin_memory() for l in range(3)],
                 states=[torch.empty((B, int(p.info.cap_states[l])), dtype=torch.uint8).pin_memory() for l in range(3)],
                 counts=torch.empty((B, 3, 4), dtype=torch.int32).pin_memory(),
                 rgb_dev=torch.empty((B, p.info.height, p.info.width, 3), dtype=torch.float32, device=p.rgb_out.device))
             p.keep.append(st)
-        return p.keep[0]
+        st = p.keep[0]
+        if with_rgb and "rgb_out" not in st:
+            st["rgb_out"] = torch.empty((p.info.batch, p.info.height, p.info.width, 3), dtype=torch.float32).pin_memory()
+        return st
 
     def host_staging(self, B, H, W, space, brange, qrange):
         return self._host_staging(self._plan(B, H, W, space, brange, qrange))
@@ -190,7 +191,7 @@ class DeviceCodec:
         coefficient / leaf / state buffers into pinned staging.  Returns (staging dict, counts ndarray, bytes h2d, bytes d2h)."""
         B, H, W, _ = rgb_host.shape
         p = self._plan(B, H, W, space, brange, qrange)
-        st = self._host_staging(p)
+        st = self._host_staging(p, with_rgb=True)
         st["rgb_dev"].copy_(rgb_host, non_blocking=True)
         enc = self.encode(st["rgb_dev"], space, qrange, brange)
         st["counts"].copy_(enc.counts, non_blocking=True)
@@ -223,6 +224,85 @@ class DeviceCodec:
         st["rgb_out"].copy_(rgb, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return st["rgb_out"], h2d, st["rgb_out"].numel() * 4
+
+    def roundtrip_host_pipelined(self, host_in: torch.Tensor, host_out: torch.Tensor, space, qrange, brange, slots: int = 8, repeat: int = 1, lag: int = 3):
+        """Host-buffer encode+decode of every frame of `host_in` (pinned float32 [F,H,W,3]) into `host_out`, one frame
+        per job, jobs round-robin over `slots` CUDA streams so that the H2D and D2H copies of different frames overlap
+        each other and the kernels (PCIe is full duplex; the step is copy-bound).  Per frame, in stream order:
+        H2D RGB -> aeaj_encode -> D2H counts -> [host waits for the counts] -> D2H used coefficient / leaf / state ranges ->
+        H2D of the same ranges (what a host-side entropy decoder would hand back) -> aeaj_decode -> D2H RGB.
+        `repeat` > 1 streams the same F frames that many times back to back (a long-running ingest) without draining
+        the pipeline in between.  Returns (h2d_bytes, d2h_bytes) summed over all jobs."""
+        F0, H, W, _ = host_in.shape
+        F = F0 * repeat
+        dev = torch.device("cuda", self.device)
+        if not hasattr(self, "_streams") or len(self._streams) < slots:
+            self._streams = [torch.cuda.Stream(device=dev) for _ in range(slots)]
+        h2d = d2h = 0
+        jobs = []
+        # phase A for every frame: upload + encode + counts
+        for f in range(F):
+            slot = f % slots
+            stream = self._streams[slot]
+            p = self._plan(1, H, W, space, brange, qrange, instance=slot)
+            st = self._host_staging(p)
+            with torch.cuda.stream(stream):
+                if f >= slots:
+                    self._finish_job(jobs[f - slots])              # the slot's previous frame must be done with its buffers
+                st["rgb_dev"].copy_(host_in[f % F0:f % F0 + 1], non_blocking=True)
+                enc = self.encode(st["rgb_dev"], space, qrange, brange, instance=slot)
+                st["counts"].copy_(enc.counts, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+            jobs.append(dict(f=f % F0, slot=slot, p=p, st=st, enc=enc, ev=ev, done=False, phase_b=False))
+            h2d += host_in[0].numel() * 4
+            # phase B of a frame is issued `lag` frames after its phase A (its counts have landed by then), and a slot is
+            # reused only `slots` frames later, so neither host wait normally blocks
+            if f >= lag:
+                a, b_ = self._phase_b(jobs[f - lag], host_out, space, qrange, brange)
+                h2d += a; d2h += b_
+        for j in jobs:
+            if not j["phase_b"]:
+                a, b_ = self._phase_b(j, host_out, space, qrange, brange)
+                h2d += a; d2h += b_
+        for j in jobs:
+            self._finish_job(j)
+        return h2d, d2h
+
+    def _phase_b(self, job, host_out, space, qrange, brange):
+        p, st, enc, slot = job["p"], job["st"], job["enc"], job["slot"]
+        stream = self._streams[slot]
+        job["ev"].synchronize()                                    # counts are on the host now
+        counts = st["counts"].numpy()
+        h2d = d2h = st["counts"].numel() * 4
+        H, W = p.info.height, p.info.width
+        with torch.cuda.stream(stream):
+            for l in range(3):
+                nl, ns, nc = (int(counts[0, l, k]) for k in range(3))
+                st["coef"][l][0, :nc].copy_(enc.coef[l][0, :nc], non_blocking=True)
+                st["leaves"][l][0, :nl].copy_(enc.leaves[l][0, :nl], non_blocking=True)
+                st["states"][l][0, :ns].copy_(enc.states[l][0, :ns], non_blocking=True)
+                d2h += nc * 4 + nl * 16 + ns
+            for l in range(3):
+                nl, nc = int(counts[0, l, 0]), int(counts[0, l, 2])
+                enc.coef[l][0, :nc].copy_(st["coef"][l][0, :nc], non_blocking=True)
+                enc.leaves[l][0, :nl].copy_(st["leaves"][l][0, :nl], non_blocking=True)
+                h2d += nc * 4 + nl * 16
+            enc.counts.copy_(st["counts"], non_blocking=True)
+            rgb = self.decode(enc.coef, enc.leaves, enc.counts, 1, H, W, space, qrange, brange, instance=slot)
+            host_out[job["f"]:job["f"] + 1].copy_(rgb, non_blocking=True)
+            d2h += rgb.numel() * 4
+            job["ev2"] = torch.cuda.Event()
+            job["ev2"].record(stream)
+        job["phase_b"] = True
+        return h2d, d2h
+
+    def _finish_job(self, job):
+        if not job["done"]:
+            if not job["phase_b"]:
+                raise RuntimeError("pipeline order error")
+            job["ev2"].synchronize()
+            job["done"] = True
 
     def decode_encoded(self, enc: EncodedBatch, space, qrange, brange):
         B, H, W = enc.shape

@@ -369,3 +369,17 @@ def test_full_size_properties(codec):
     enc2 = codec.encode(rgb, space, q, b)
     L2 = codec.download(enc2)[0]
     assert chk == [int(L2[i]["coef"].astype(np.int64).sum()) for i in range(3)]
+
+
+def test_host_pipelined_roundtrip_matches_device_path(codec):
+    """the host-buffer API (bench.py's e2e leg) returns the same pixels as the device-resident path"""
+    import torch
+    H, W = 270, 480
+    frames = np.stack([synth(H, W, seed=s) for s in range(5)])
+    space, q, b = "YCbCr", (30, 95), (4, 64)
+    host_in = torch.from_numpy(frames).pin_memory()
+    host_out = torch.empty_like(host_in).pin_memory()
+    h2d, d2h = codec.roundtrip_host_pipelined(host_in, host_out, space, q, b, slots=3, repeat=2, lag=2)
+    dev = codec.decode_encoded(codec.encode(host_in.cuda(), space, q, b), space, q, b).cpu()
+    assert torch.equal(dev, host_out)
+    assert h2d > 2 * frames.nbytes and d2h > 2 * frames.nbytes
