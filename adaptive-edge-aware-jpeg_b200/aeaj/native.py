@@ -20,7 +20,7 @@ EXPORTS = [
     "aeaj_percentile_thresholds", "aeaj_canny_u8", "aeaj_canny", "aeaj_quadtree_caps", "aeaj_quadtree",
     "aeaj_dct_quant", "aeaj_dequant_idct", "aeaj_plan_create", "aeaj_plan_destroy", "aeaj_plan_get_info",
     "aeaj_plan_set_qtables", "aeaj_encode", "aeaj_decode", "aeaj_plan_last_launches",
-    "aeaj_plan_enable_timing", "aeaj_plan_read_timing",
+    "aeaj_plan_enable_timing", "aeaj_plan_read_timing", "aeaj_encode_phase", "aeaj_decode_phase", "aeaj_plan_buffers",
     "aeaj_states_to_leaves_host", "aeaj_pack_states_host",
 ]
 
@@ -45,6 +45,12 @@ class EncodeIO(C.Structure):
 class DecodeIO(C.Structure):
     _fields_ = [("coef", C.c_void_p * 3), ("leaves", C.c_void_p * 3), ("counts", C.c_void_p), ("rgb", C.c_void_p),
                 ("tap_layers", C.c_void_p * 3)]
+
+
+class PlanBuffers(C.Structure):
+    _fields_ = [("layer", C.c_void_p * 3), ("u8a", C.c_void_p * 3), ("u8b", C.c_void_p * 3), ("strong", C.c_void_p * 3),
+                ("weak", C.c_void_p * 3), ("h", C.c_int * 3), ("w", C.c_int * 3), ("wpr", C.c_int * 3),
+                ("clahe_hist", C.c_void_p), ("clahe_hist_bytes", C.c_int64), ("hist", C.c_void_p), ("hist_bytes", C.c_int64)]
 
 
 _lib = None
@@ -94,6 +100,9 @@ def load():
         lib.aeaj_encode.argtypes = [vp, C.POINTER(EncodeIO), vp, vp]
         lib.aeaj_decode.argtypes = [vp, C.POINTER(DecodeIO), vp, vp]
         lib.aeaj_plan_last_launches.argtypes = [vp]
+        lib.aeaj_encode_phase.argtypes = [vp, C.POINTER(EncodeIO), vp, vp, i, i, i]
+        lib.aeaj_decode_phase.argtypes = [vp, C.POINTER(DecodeIO), vp, vp, i, i, i]
+        lib.aeaj_plan_buffers.argtypes = [vp, vp, C.POINTER(PlanBuffers)]
         lib.aeaj_plan_enable_timing.argtypes = [vp, i]
         lib.aeaj_plan_read_timing.argtypes = [vp, C.c_char_p, sz, vp, i, C.POINTER(i)]
         lib.aeaj_states_to_leaves_host.argtypes = [vp, i, i, i, i, vp, C.POINTER(i), C.POINTER(C.c_int64)]

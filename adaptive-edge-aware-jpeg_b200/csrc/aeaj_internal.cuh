@@ -125,6 +125,7 @@ struct aeaj_handle {
 struct PlaneDesc {
     int h, w, wpr, root, top, ntx, nty, layer;
     int hy_base_small, hy_base_big;   // first hysteresis tile of this plane in the small / big tiling
+    int ry0, ry1;                     // rows of this plane the current call works on (halo-split bands); default [0, h)
     float mid, scale;
     float* layer_f32;        // downsampled un-normalised layer
     uint8_t* u8a;            // cast / stage ping
@@ -181,14 +182,14 @@ int aeaj_dct_init(aeaj_handle* h);
 
 int launch_color_forward_planar(aeaj_handle* h, int space, const float* rgb, int B, int H, int W,
                                 const PlaneDesc* planes_dev, const PlaneDesc* planes_host,
-                                float* full_c1, float* full_c2, cudaStream_t st, int* launches);
+                                float* full_c1, float* full_c2, cudaStream_t st, int* launches, int band0 = 0, int band1 = -1);
 int launch_color_pixels(aeaj_handle* h, int space, int inverse, const float* in, float* out, size_t n, cudaStream_t st);
 int launch_normalize(const float* in, float* out, size_t n, float mid, float scale, int inverse, cudaStream_t st);
 int launch_area(const float* src, int H, int W, float* dst, int dh, int dw, uint8_t* u8_out, int planes,
                 size_t src_stride, size_t dst_stride, cudaStream_t st);
 int launch_resize_linear(const float* src, int sh, int sw, float* dst, int H, int W, cudaStream_t st);
 int launch_upsample_color_inverse(aeaj_handle* h, int space, const PlaneDesc* planes_host, int B, int H, int W,
-                                  float* rgb, cudaStream_t st);
+                                  float* rgb, cudaStream_t st, int band0 = 0, int band1 = -1);
 int launch_cast_u8(const float* in, uint8_t* out, size_t n, cudaStream_t st);
 
 int launch_clahe_hist(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, cudaStream_t st);

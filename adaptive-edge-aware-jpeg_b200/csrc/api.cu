@@ -45,6 +45,7 @@ static int64_t cap_coef_of(int h, int w, int top) { return (int64_t)aeaj_cdiv(h,
 
 static void plane_geom(PlaneDesc& P, int h, int w, int mn, int mx) {
     P.h = h; P.w = w; P.wpr = aeaj_cdiv(w, 32);
+    P.ry0 = 0; P.ry1 = h;
     P.root = aeaj_root_size(h, w);
     if (mx > 0) {
         P.top = std::min(mx, P.root);
@@ -553,11 +554,29 @@ static int plan_push_planes(aeaj_plan* p, cudaStream_t st) {
     return 0;
 }
 
-extern "C" int aeaj_encode(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, void* stream) {
+// full-res luma rows [band0, band1) -> rows of every layer (chroma rows scale with the subsampling ratio)
+static int set_band(aeaj_plan* p, int band0, int band1) {
+    const int H = p->info.height;
+    if (band1 < 0) band1 = H;
+    AEAJ_REQUIRE(band0 >= 0 && band0 < band1 && band1 <= H, "bad band");
+    const bool full = (band0 == 0 && band1 == H);
+    for (int i = 0; i < p->nplanes; i++) {
+        PlaneDesc& P = p->planes[i];
+        const int rh = H / P.h;                                    // 1 or 2 (jpeg.py:62-147)
+        if (!full) {
+            AEAJ_REQUIRE(p->info.batch == 1, "halo-split bands need batch 1");
+            AEAJ_REQUIRE(H % P.h == 0 && band0 % (rh * 128) == 0 && (band1 % (rh * 128) == 0 || band1 == H),
+                         "band boundaries must be multiples of 128 rows in every layer");
+        }
+        P.ry0 = band0 / rh; P.ry1 = (band1 == H) ? P.h : band1 / rh;
+    }
+    return 0;
+}
+
+static int encode_impl(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, cudaStream_t st, unsigned phases, int band0, int band1) {
     AEAJ_REQUIRE(p && io && workspace && io->rgb && io->counts, "aeaj_encode: bad arguments");
     AEAJ_REQUIRE(p->qtab_dev, "aeaj_encode: quantisation tables not set (aeaj_plan_set_qtables)");
     aeaj_handle* h = p->h;
-    cudaStream_t st = ST(stream);
     const int B = p->info.batch, NP = p->nplanes;
     int launches = 0;
     size_t s1 = plan_carve(p, workspace);
@@ -576,57 +595,78 @@ extern "C" int aeaj_encode(aeaj_plan* p, const aeaj_encode_io* io, void* workspa
             if (io->tap_edges[l]) { outs[i * 3 + l] = io->tap_edges[l] + (size_t)i * P.h * P.w; any_tap_edge = true; }
         }
     }
-    int rc = plan_push_planes(p, st); if (rc) return rc;
-    // accumulators
-    AEAJ_CUDA(cudaMemsetAsync(p->planes[0].clahe_hist, 0, (size_t)NP * 16 * 256 * sizeof(uint32_t), st));
-    AEAJ_CUDA(cudaMemsetAsync(p->planes[0].hist, 0, (size_t)NP * 256 * sizeof(uint32_t), st));
-    AEAJ_CUDA(cudaMemsetAsync(A.class_counts, 0, 16 * sizeof(int), st));
+    int rc = set_band(p, band0, band1); if (rc) return rc;
+    rc = plan_push_planes(p, st); if (rc) return rc;
     p->ev_n = 0; p->ev_stream = st; p->mark("start");
-    // colour + chroma subsampling + u8 cast
-    rc = launch_color_forward_planar(h, p->info.space, io->rgb, B, p->info.height, p->info.width, p->planes_dev, p->planes.data(),
-                                     A.full_c1, A.full_c2, st, &launches);
-    if (rc) return rc;
-    p->mark("color_forward_planar");
-    // Canny pipeline on all planes of the batch at once
-    rc = launch_clahe_hist(p->planes_dev, p->planes.data(), NP, st); if (rc) return rc;
-    p->mark("clahe_hist");
-    rc = launch_clahe_lut(p->planes_dev, NP, st); if (rc) return rc;
-    p->mark("clahe_lut");
-    rc = launch_prefilter(p->planes_dev, p->planes.data(), NP, 7, 1, st); if (rc) return rc;
-    p->mark("prefilter");
-    rc = launch_thresholds(p->planes_dev, NP, st); if (rc) return rc;
-    p->mark("thresholds");
-    rc = launch_canny_nms(p->planes_dev, p->planes.data(), NP, st); if (rc) return rc;
-    p->mark("canny_nms");
-    rc = launch_hysteresis(h, p->planes_dev, NP, p->ntiles, p->nbig, A.flags, A.ctrl, io->status, st); if (rc) return rc;
-    p->mark("hysteresis");
-    launches += 7;
-    if (any_tap_edge) {
-        AEAJ_CUDA(cudaMemcpyAsync(p->outs_dev, outs.data(), sizeof(uint8_t*) * NP, cudaMemcpyHostToDevice, st));
-        rc = launch_bitmap_to_u8(p->planes_dev, p->planes.data(), NP, p->outs_dev, st); if (rc) return rc;
-        launches++;
+    if (phases & (1u << AEAJ_PHASE_COLOR)) {
+        AEAJ_CUDA(cudaMemsetAsync(p->planes[0].clahe_hist, 0, (size_t)NP * 16 * 256 * sizeof(uint32_t), st));
+        AEAJ_CUDA(cudaMemsetAsync(p->planes[0].hist, 0, (size_t)NP * 256 * sizeof(uint32_t), st));
+        AEAJ_CUDA(cudaMemsetAsync(A.class_counts, 0, 16 * sizeof(int), st));
+        // colour + chroma subsampling + u8 cast
+        rc = launch_color_forward_planar(h, p->info.space, io->rgb, B, p->info.height, p->info.width, p->planes_dev, p->planes.data(),
+                                         A.full_c1, A.full_c2, st, &launches, band0, band1);
+        if (rc) return rc;
+        p->mark("color_forward_planar");
     }
-    for (int l = 0; l < 3; l++)
-        if (io->tap_layers[l])
-            AEAJ_CUDA(cudaMemcpyAsync(io->tap_layers[l], p->planes[l].layer_f32, sizeof(float) * (size_t)B * p->info.layer_h[l] * p->info.layer_w[l],
-                                      cudaMemcpyDeviceToDevice, st));
-    // quadtree + DCT/quantise
-    rc = launch_quadtree(p->planes_dev, p->planes.data(), NP, p->info.block_min, p->info.block_max, A.class_lists, A.class_counts,
-                         p->class_off_dev, st, &launches);
-    if (rc) return rc;
-    p->mark("quadtree");
-    rc = launch_dct_quant(h, p->planes_dev, A.class_lists, A.class_counts, p->cg.off, p->cg.cap, p->lg_min, p->lg_max, st, &launches,
-                          plan_mark_cb, p);
-    if (rc) return rc;
+    // Canny pipeline on all planes of the batch at once
+    if (phases & (1u << AEAJ_PHASE_CLAHE_HIST)) {
+        rc = launch_clahe_hist(p->planes_dev, p->planes.data(), NP, st); if (rc) return rc;
+        launches++;
+        p->mark("clahe_hist");
+    }
+    if (phases & (1u << AEAJ_PHASE_PREFILTER)) {
+        rc = launch_clahe_lut(p->planes_dev, NP, st); if (rc) return rc;
+        p->mark("clahe_lut");
+        rc = launch_prefilter(p->planes_dev, p->planes.data(), NP, 7, 1, st); if (rc) return rc;
+        p->mark("prefilter");
+        launches += 2;
+    }
+    if (phases & (1u << AEAJ_PHASE_NMS)) {
+        rc = launch_thresholds(p->planes_dev, NP, st); if (rc) return rc;
+        p->mark("thresholds");
+        rc = launch_canny_nms(p->planes_dev, p->planes.data(), NP, st); if (rc) return rc;
+        p->mark("canny_nms");
+        launches += 2;
+    }
+    if (phases & (1u << AEAJ_PHASE_TREE)) {
+        rc = launch_hysteresis(h, p->planes_dev, NP, p->ntiles, p->nbig, A.flags, A.ctrl, io->status, st); if (rc) return rc;
+        p->mark("hysteresis");
+        launches += 2;
+        if (any_tap_edge) {
+            AEAJ_CUDA(cudaMemcpyAsync(p->outs_dev, outs.data(), sizeof(uint8_t*) * NP, cudaMemcpyHostToDevice, st));
+            rc = launch_bitmap_to_u8(p->planes_dev, p->planes.data(), NP, p->outs_dev, st); if (rc) return rc;
+            launches++;
+        }
+        for (int l = 0; l < 3; l++)
+            if (io->tap_layers[l])
+                AEAJ_CUDA(cudaMemcpyAsync(io->tap_layers[l], p->planes[l].layer_f32, sizeof(float) * (size_t)B * p->info.layer_h[l] * p->info.layer_w[l],
+                                          cudaMemcpyDeviceToDevice, st));
+        rc = launch_quadtree(p->planes_dev, p->planes.data(), NP, p->info.block_min, p->info.block_max, A.class_lists, A.class_counts,
+                             p->class_off_dev, st, &launches);
+        if (rc) return rc;
+        p->mark("quadtree");
+    }
+    if (phases & (1u << AEAJ_PHASE_DCT)) {
+        rc = launch_dct_quant(h, p->planes_dev, A.class_lists, A.class_counts, p->cg.off, p->cg.cap, p->lg_min, p->lg_max, st, &launches,
+                              plan_mark_cb, p);
+        if (rc) return rc;
+    }
     p->last_launches = launches;
     return 0;
 }
 
-extern "C" int aeaj_decode(aeaj_plan* p, const aeaj_decode_io* io, void* workspace, void* stream) {
+extern "C" int aeaj_encode(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, void* stream) {
+    return encode_impl(p, io, workspace, ST(stream), 0x3fu, 0, -1);
+}
+extern "C" int aeaj_encode_phase(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, void* stream, int phase, int band0, int band1) {
+    AEAJ_REQUIRE(phase >= AEAJ_PHASE_COLOR && phase <= AEAJ_PHASE_DCT, "aeaj_encode_phase: bad phase");
+    return encode_impl(p, io, workspace, ST(stream), 1u << phase, band0, band1);
+}
+
+static int decode_impl(aeaj_plan* p, const aeaj_decode_io* io, void* workspace, cudaStream_t st, unsigned phases, int band0, int band1) {
     AEAJ_REQUIRE(p && io && workspace && io->rgb && io->counts, "aeaj_decode: bad arguments");
     AEAJ_REQUIRE(p->qtab_dev, "aeaj_decode: quantisation tables not set (aeaj_plan_set_qtables)");
     aeaj_handle* h = p->h;
-    cudaStream_t st = ST(stream);
     const int B = p->info.batch, NP = p->nplanes;
     int launches = 0;
     size_t s1 = plan_carve(p, workspace);
@@ -641,23 +681,51 @@ extern "C" int aeaj_decode(aeaj_plan* p, const aeaj_decode_io* io, void* workspa
             P.counts = (int32_t*)io->counts + ((size_t)i * 3 + l) * 4;
         }
     }
-    int rc = plan_push_planes(p, st); if (rc) return rc;
-    AEAJ_CUDA(cudaMemsetAsync(A.class_counts, 0, 16 * sizeof(int), st));
+    int rc = set_band(p, band0, band1); if (rc) return rc;
+    rc = plan_push_planes(p, st); if (rc) return rc;
     p->ev_n = 0; p->ev_stream = st; p->mark("start");
-    rc = launch_bucket_leaves(p->planes_dev, p->planes.data(), NP, A.class_lists, A.class_counts, p->class_off_dev, st); if (rc) return rc;
-    launches++;
-    p->mark("bucket_leaves");
-    rc = launch_dequant_idct(h, p->planes_dev, A.class_lists, A.class_counts, p->cg.off, p->cg.cap, p->lg_min, p->lg_max, st, &launches,
-                             plan_mark_cb, p);
-    if (rc) return rc;
-    for (int l = 0; l < 3; l++)
-        if (io->tap_layers[l])
-            AEAJ_CUDA(cudaMemcpyAsync(io->tap_layers[l], p->planes[l].layer_f32, sizeof(float) * (size_t)B * p->info.layer_h[l] * p->info.layer_w[l],
-                                      cudaMemcpyDeviceToDevice, st));
-    rc = launch_upsample_color_inverse(h, p->info.space, p->planes.data(), B, p->info.height, p->info.width, io->rgb, st); if (rc) return rc;
-    launches++;
-    p->mark("upsample_color_inverse");
+    if (phases & (1u << AEAJ_DPHASE_IDCT)) {
+        AEAJ_CUDA(cudaMemsetAsync(A.class_counts, 0, 16 * sizeof(int), st));
+        rc = launch_bucket_leaves(p->planes_dev, p->planes.data(), NP, A.class_lists, A.class_counts, p->class_off_dev, st); if (rc) return rc;
+        launches++;
+        p->mark("bucket_leaves");
+        rc = launch_dequant_idct(h, p->planes_dev, A.class_lists, A.class_counts, p->cg.off, p->cg.cap, p->lg_min, p->lg_max, st, &launches,
+                                 plan_mark_cb, p);
+        if (rc) return rc;
+        for (int l = 0; l < 3; l++)
+            if (io->tap_layers[l])
+                AEAJ_CUDA(cudaMemcpyAsync(io->tap_layers[l], p->planes[l].layer_f32, sizeof(float) * (size_t)B * p->info.layer_h[l] * p->info.layer_w[l],
+                                          cudaMemcpyDeviceToDevice, st));
+    }
+    if (phases & (1u << AEAJ_DPHASE_COLOR)) {
+        rc = launch_upsample_color_inverse(h, p->info.space, p->planes.data(), B, p->info.height, p->info.width, io->rgb, st, band0, band1);
+        if (rc) return rc;
+        launches++;
+        p->mark("upsample_color_inverse");
+    }
     p->last_launches = launches;
+    return 0;
+}
+extern "C" int aeaj_decode(aeaj_plan* p, const aeaj_decode_io* io, void* workspace, void* stream) {
+    return decode_impl(p, io, workspace, ST(stream), 0x3u, 0, -1);
+}
+extern "C" int aeaj_decode_phase(aeaj_plan* p, const aeaj_decode_io* io, void* workspace, void* stream, int phase, int band0, int band1) {
+    AEAJ_REQUIRE(phase >= AEAJ_DPHASE_IDCT && phase <= AEAJ_DPHASE_COLOR, "aeaj_decode_phase: bad phase");
+    return decode_impl(p, io, workspace, ST(stream), 1u << phase, band0, band1);
+}
+
+// device pointers of the planes a halo-split caller exchanges between phases (batch 1)
+extern "C" int aeaj_plan_buffers(aeaj_plan* p, void* workspace, aeaj_plan_buffers_t* out) {
+    AEAJ_REQUIRE(p && workspace && out, "aeaj_plan_buffers: bad arguments");
+    plan_carve(p, workspace);
+    memset(out, 0, sizeof *out);
+    for (int l = 0; l < 3; l++) {
+        const PlaneDesc& P = p->planes[l];
+        out->layer[l] = P.layer_f32; out->u8a[l] = P.u8a; out->u8b[l] = P.u8b; out->strong[l] = P.strong; out->weak[l] = P.weak;
+        out->h[l] = P.h; out->w[l] = P.w; out->wpr[l] = P.wpr;
+    }
+    out->clahe_hist = p->planes[0].clahe_hist; out->clahe_hist_bytes = (int64_t)p->nplanes * 16 * 256 * 4;
+    out->hist = p->planes[0].hist; out->hist_bytes = (int64_t)p->nplanes * 256 * 4;
     return 0;
 }
 

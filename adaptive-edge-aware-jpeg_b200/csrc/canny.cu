@@ -68,8 +68,12 @@ __global__ void __launch_bounds__(256) k_clahe_hist(const PlaneDesc* __restrict_
     const uint8_t* src = P.u8a;
     unsigned int* my = wh[warp];
     const int cx0 = tx * g.tw, cx1 = cx0 + g.tw;
+    // halo-split bands: this call owns padded rows [ry0, ry1), the band that ends at h also owns the reflected padding
+    const int band_hi = (P.ry1 >= P.h) ? 4 * g.th : P.ry1;
     for (int r = r0 + warp; r < r1; r += 8) {
-        const int sy = reflect101(ty * g.th + r, P.h);
+        const int gy = ty * g.th + r;
+        if (gy < P.ry0 || gy >= band_hi) continue;
+        const int sy = reflect101(gy, P.h);
         const uint8_t* rowp = src + (size_t)sy * P.w;
         const int xa = cx0, xb = min(cx1, P.w);
         if (xa < xb) {
@@ -97,7 +101,6 @@ __global__ void __launch_bounds__(256) k_clahe_lut(const PlaneDesc* __restrict__
     const int tile = blockIdx.x, i = threadIdx.x;
     __shared__ int red[256];
     int hv = (int)P.clahe_hist[tile * 256 + i];
-    P.clahe_hist[tile * 256 + i] = 0;                 // leave the accumulator clean for the next call
     int excess = hv > g.clip ? hv - g.clip : 0;
     hv = hv > g.clip ? g.clip : hv;
     red[i] = excess;
@@ -158,6 +161,7 @@ __global__ void __launch_bounds__(256) k_prefilter(const PlaneDesc* __restrict__
     tile_decode(tm, blockIdx.x, plane_i, txi, tyi);
     const PlaneDesc& P = planes[plane_i];
     const int X0 = txi * PF_TW, Y0 = tyi * PF_TH;
+    if (Y0 < P.ry0 || Y0 >= P.ry1) return;             // halo-split bands are multiples of the tile height
     __shared__ __align__(16) uint8_t sA[PF_TH + 6][PF_AS];     // CLAHE output (or source), halo 3
     __shared__ __align__(16) uint8_t sG[PF_TH + 4][PF_AS];     // Gaussian output, halo 2
     __shared__ __align__(16) uint8_t sLut[16][256];
@@ -331,7 +335,6 @@ __global__ void k_thresholds(const PlaneDesc* __restrict__ planes, int nplanes) 
     double lo = percentile_from_hist(P.hist, n, 10.0 / 100.0), hi = percentile_from_hist(P.hist, n, 30.0 / 100.0);
     if (P.thr_d) { P.thr_d[0] = lo; P.thr_d[1] = hi; }
     canny_prepare_thresholds(lo, hi, P.thr);
-    for (int i = 0; i < 256; i++) P.hist[i] = 0;     // clean accumulator for the next call
 }
 __global__ void k_thresholds_from_double(const double* thr_d, int* thr) { canny_prepare_thresholds(thr_d[0], thr_d[1], thr); }
 
@@ -348,6 +351,7 @@ __global__ void __launch_bounds__(256) k_canny_nms(const PlaneDesc* __restrict__
     tile_decode(tm, blockIdx.x, plane_i, txi, tyi);
     const PlaneDesc& P = planes[plane_i];
     const int X0 = txi * NM_TW, Y0 = tyi * NM_TH;
+    if (Y0 < P.ry0 || Y0 >= P.ry1) return;
     __shared__ __align__(16) uint8_t sS[NM_TH + 4][NM_SS];       // rows Y0-2.., cols X0-4.. (BORDER_REPLICATE)
     __shared__ __align__(16) int sM[NM_TH + 2][NM_MS];           // magnitude, rows Y0-1.., cols X0-1.. (0 outside the image)
     __shared__ __align__(16) int sD[NM_TH + 2][NM_MS];           // dx | dy << 16

@@ -350,9 +350,9 @@ __global__ void __launch_bounds__(256) k_resize_linear(const float* __restrict__
 // (jpeg.py:290-297) -> RGB HWC
 struct UpIn { const float* p[3]; int h[3], w[3]; size_t stride[3]; };
 template <int SPACE>
-__global__ void __launch_bounds__(256) k_upsample_color_inverse(const __grid_constant__ ColorConsts C, UpIn in, int H, int W, float* __restrict__ rgb) {
-    int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y * blockDim.y + threadIdx.y;
-    if (dx >= W || dy >= H) return;
+__global__ void __launch_bounds__(256) k_upsample_color_inverse(const __grid_constant__ ColorConsts C, UpIn in, int H, int W, float* __restrict__ rgb, int y_lo, int y_hi) {
+    int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = y_lo + blockIdx.y * blockDim.y + threadIdx.y;
+    if (dx >= W || dy >= y_hi) return;
     int b = blockIdx.z;
     float v[3];
 #pragma unroll
@@ -384,9 +384,9 @@ __device__ __forceinline__ void up2_coord(int d, int ssize, int& s0, int& s1, fl
     s0 = s; s1 = min(s + 1, ssize - 1); f = fx;
 }
 template <int SPACE>
-__global__ void __launch_bounds__(256) k_upsample2x_color_inverse(const __grid_constant__ ColorConsts C, UpIn in, int H, int W, float* __restrict__ rgb) {
-    const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, dy = blockIdx.y * blockDim.y + threadIdx.y;
-    if (dx0 >= W || dy >= H) return;
+__global__ void __launch_bounds__(256) k_upsample2x_color_inverse(const __grid_constant__ ColorConsts C, UpIn in, int H, int W, float* __restrict__ rgb, int y_lo, int y_hi) {
+    const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, dy = y_lo + blockIdx.y * blockDim.y + threadIdx.y;
+    if (dx0 >= W || dy >= y_hi) return;
     const int b = blockIdx.z;
     const int cw = in.w[1], chh = in.h[1];
     const float4 yv = __ldg(reinterpret_cast<const float4*>(in.p[0] + (size_t)b * in.stride[0] + (size_t)dy * W + dx0));
@@ -496,8 +496,10 @@ int launch_cast_u8(const float* in, uint8_t* out, size_t n, cudaStream_t st) {
 // across the batch (stride = h*w), which is what FwdOut's per-image strides assume.
 int launch_color_forward_planar(aeaj_handle* h, int space, const float* rgb, int B, int H, int W,
                                 const PlaneDesc* planes_dev, const PlaneDesc* P, float* full_c1, float* full_c2,
-                                cudaStream_t st, int* launches) {
+                                cudaStream_t st, int* launches, int band0, int band1) {
     (void)planes_dev;
+    if (band1 < 0) band1 = H;
+    const bool banded = (band0 != 0 || band1 != H);
     const ColorConsts& C = h->colors_host[space];
     const float* lut = h->has_srgb_lut ? h->srgb_lut_dev : nullptr;
     const int ch = P[1].h, cw = P[1].w;
@@ -505,18 +507,30 @@ int launch_color_forward_planar(aeaj_handle* h, int space, const float* rgb, int
     if (ch * 2 == H && cw * 2 == W && (W % 4) == 0) mode = 0;
     else if (ch == H && cw * 4 == W) mode = 1;
     else mode = 2;
+    if (banded) {
+        // a band [band0, band1) of full-res rows is converted as an image of its own; the outputs land at the
+        // band's row offset inside the full-size planes (needs the fused modes: no chroma cell straddles a band)
+        if (mode == 2 || B != 1 || (mode == 0 && ((band0 | band1) & 1))) { aeaj_set_error("banded colour conversion needs batch 1, even band rows and W %% 4 == 0"); return AEAJ_EINVAL; }
+    }
     FwdOut o;
     o.y = P[0].layer_f32; o.y8 = P[0].u8a; o.sy = (size_t)H * W;
     if (mode == 2) { o.c1 = full_c1; o.c2 = full_c2; o.c18 = nullptr; o.c28 = nullptr; o.sc = (size_t)H * W; }
     else { o.c1 = P[1].layer_f32; o.c2 = P[2].layer_f32; o.c18 = P[1].u8a; o.c28 = P[2].u8a; o.sc = (size_t)ch * cw; }
+    int Hk = H;                                         // rows the kernel sees
+    if (banded) {
+        const size_t yo = (size_t)band0 * W, co = (mode == 0) ? (size_t)(band0 / 2) * cw : (size_t)band0 * cw;
+        rgb += yo * 3;
+        o.y += yo; o.y8 += yo; o.c1 += co; o.c2 += co; o.c18 += co; o.c28 += co;
+        Hk = band1 - band0;
+    }
     int rc = dispatch_space(space, [&](auto S) {
         constexpr int SP = decltype(S)::value;
         if (mode == 0) {
-            dim3 blk(32, 8), grd(aeaj_cdiv(W / 4, 32), aeaj_cdiv(H / 2, 8), B);
-            k_color_forward_planar<SP, 0><<<grd, blk, 0, st>>>(C, lut, rgb, H, W, o);
+            dim3 blk(32, 8), grd(aeaj_cdiv(W / 4, 32), aeaj_cdiv(Hk / 2, 8), B);
+            k_color_forward_planar<SP, 0><<<grd, blk, 0, st>>>(C, lut, rgb, Hk, W, o);
         } else if (mode == 1) {
-            dim3 blk(32, 8), grd(aeaj_cdiv(W / 4, 32), aeaj_cdiv(H, 8), B);
-            k_color_forward_planar<SP, 1><<<grd, blk, 0, st>>>(C, lut, rgb, H, W, o);
+            dim3 blk(32, 8), grd(aeaj_cdiv(W / 4, 32), aeaj_cdiv(Hk, 8), B);
+            k_color_forward_planar<SP, 1><<<grd, blk, 0, st>>>(C, lut, rgb, Hk, W, o);
         } else {
             dim3 blk(32, 8), grd(aeaj_cdiv(W, 32), aeaj_cdiv(H, 8), B);
             k_color_forward_planar<SP, 2><<<grd, blk, 0, st>>>(C, lut, rgb, H, W, o);
@@ -536,8 +550,10 @@ int launch_color_forward_planar(aeaj_handle* h, int space, const float* rgb, int
     return 0;
 }
 
-int launch_upsample_color_inverse(aeaj_handle* h, int space, const PlaneDesc* P, int B, int H, int W, float* rgb, cudaStream_t st) {
+int launch_upsample_color_inverse(aeaj_handle* h, int space, const PlaneDesc* P, int B, int H, int W, float* rgb, cudaStream_t st, int band0, int band1) {
     const ColorConsts& C = h->colors_host[space];
+    if (band1 < 0) band1 = H;
+    const int Hb = band1 - band0;
     UpIn in;
     for (int l = 0; l < 3; l++) { in.p[l] = P[l].layer_f32; in.h[l] = P[l].h; in.w[l] = P[l].w; in.stride[l] = (size_t)P[l].h * P[l].w; }
     const bool fast2x = (in.h[1] * 2 == H && in.w[1] * 2 == W && in.h[2] == in.h[1] && in.w[2] == in.w[1] && (W % 4) == 0 &&
@@ -545,11 +561,11 @@ int launch_upsample_color_inverse(aeaj_handle* h, int space, const PlaneDesc* P,
     return dispatch_space(space, [&](auto S) {
         constexpr int SP = decltype(S)::value;
         if (fast2x) {
-            dim3 blk(32, 8), grd(aeaj_cdiv(W / 4, 32), aeaj_cdiv(H, 8), B);
-            k_upsample2x_color_inverse<SP><<<grd, blk, 0, st>>>(C, in, H, W, rgb);
+            dim3 blk(32, 8), grd(aeaj_cdiv(W / 4, 32), aeaj_cdiv(Hb, 8), B);
+            k_upsample2x_color_inverse<SP><<<grd, blk, 0, st>>>(C, in, H, W, rgb, band0, band1);
         } else {
-            dim3 blk(32, 8), grd(aeaj_cdiv(W, 32), aeaj_cdiv(H, 8), B);
-            k_upsample_color_inverse<SP><<<grd, blk, 0, st>>>(C, in, H, W, rgb);
+            dim3 blk(32, 8), grd(aeaj_cdiv(W, 32), aeaj_cdiv(Hb, 8), B);
+            k_upsample_color_inverse<SP><<<grd, blk, 0, st>>>(C, in, H, W, rgb, band0, band1);
         }
         AEAJ_LAUNCH_CHECK();
         return 0;

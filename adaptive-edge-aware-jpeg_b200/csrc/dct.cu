@@ -60,10 +60,11 @@ __global__ void __launch_bounds__(256) k_dct_rows(const PlaneDesc* __restrict__ 
     const int groups = (count + LPW - 1) / LPW;        // warp-sized groups of leaves
     for (int g = blockIdx.x * 8 + warp; g < groups; g += gridDim.x * 8) {
         const int li = g * LPW + sub;
-        const bool act = li < count;
+        bool act = li < count;
         ClassEntry e = {0, 0, 0, 0};
         if (act) e = list[li];
         const PlaneDesc& P = planes[e.plane];
+        act = act && e.y >= P.ry0 && e.y < P.ry1;      // halo-split: only the leaves of this call's band
         float in[S];
         if (act) {
             if (!INVERSE) {
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(256) k_dct_cta(const PlaneDesc* __restrict__ p
     for (int li = blockIdx.x; li < count; li += gridDim.x) {
         const ClassEntry e = list[li];
         const PlaneDesc& P = planes[e.plane];
+        if (e.y < P.ry0 || e.y >= P.ry1) continue;     // halo-split: only the leaves of this call's band (uniform per CTA)
         __syncthreads();                               // previous leaf done with sB
         if (!INVERSE) {
             // load X, fold rows: sB[i][j] = X[i][j] + X[N-1-i][j] (i < h), sB[h+i][j] = X[i][j] - X[N-1-i][j]

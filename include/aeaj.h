@@ -166,6 +166,32 @@ AEAJ_API int aeaj_encode(aeaj_plan* p, const aeaj_encode_io* io, void* workspace
 AEAJ_API int aeaj_decode(aeaj_plan* p, const aeaj_decode_io* io, void* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * halo-split of ONE large image over several GPUs: the same pipeline, one phase
+ * per call, restricted to the band [band0, band1) of full-resolution rows this rank owns (batch 1; band
+ * boundaries multiples of 256 rows, or the image end).  Between phases the caller exchanges the small
+ * planes over NVLink (NCCL): u8 planes and bitmaps are all-gathered, the CLAHE / percentile histograms
+ * all-reduced; hysteresis and the quadtree then run replicated on every rank, colour and DCT stay sharded.
+ * aeaj_encode == all six phases on the full image.  Sequence and collectives: aeaj/tiled.py.
+ * ------------------------------------------------------------------------------------------- */
+enum { AEAJ_PHASE_COLOR = 0,      /* clears accumulators; colour + subsample + u8 cast of the band            */
+       AEAJ_PHASE_CLAHE_HIST = 1, /* CLAHE tile histograms of the band            -> all-reduce clahe_hist    */
+       AEAJ_PHASE_PREFILTER = 2,  /* needs all-gathered u8a; LUTs + CLAHE/Gauss/bilateral of the band         */
+       AEAJ_PHASE_NMS = 3,        /* needs all-gathered u8b, all-reduced hist; thresholds + NMS of the band   */
+       AEAJ_PHASE_TREE = 4,       /* needs all-gathered strong/weak; hysteresis + quadtree, whole image       */
+       AEAJ_PHASE_DCT = 5 };      /* DCT + quantise of the band's leaves (coefficients at global offsets)     */
+enum { AEAJ_DPHASE_IDCT = 0,      /* dequantise + IDCT + merge of the band's leaves                           */
+       AEAJ_DPHASE_COLOR = 1 };   /* needs the neighbouring chroma rows; upsample + inverse colour of the band */
+typedef struct {
+    void* layer[3]; void* u8a[3]; void* u8b[3]; void* strong[3]; void* weak[3];
+    int h[3], w[3], wpr[3];
+    void* clahe_hist; int64_t clahe_hist_bytes;
+    void* hist; int64_t hist_bytes;
+} aeaj_plan_buffers_t;
+AEAJ_API int aeaj_encode_phase(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, void* stream, int phase, int band0, int band1);
+AEAJ_API int aeaj_decode_phase(aeaj_plan* p, const aeaj_decode_io* io, void* workspace, void* stream, int phase, int band0, int band1);
+AEAJ_API int aeaj_plan_buffers(aeaj_plan* p, void* workspace, aeaj_plan_buffers_t* out);
+
+/* ---------------------------------------------------------------------------------------------
  * host-side helpers for the entropy-coding side (plain CPU code, no device work):
  * the 2-bit state stream (jpeg.py:563-571) and its inverse (jpeg.py:768-800 + 428-448).
  * ------------------------------------------------------------------------------------------- */
