@@ -12,7 +12,7 @@ planes are exchanged over NVLink with NCCL:
                                        -> all-reduce SUM  (3 x 256 counters), all-gather filtered u8 planes
     thresholds + Sobel / NMS (band)    -> all-gather      strong / weak bitmaps (2 bit / sample)
     hysteresis + quadtree              replicated on every rank (bit maps only; no exchange rounds needed)
-    DCT + quantise (band's leaves)     -> all-reduce SUM  of the zero-initialised coefficient stream
+    DCT + quantise (band's leaves)     (optional: all-reduce SUM of the zero-initialised coefficient stream)
 
 so every rank ends with the complete, reference-ordered result (leaves, states, coefficients), bit-identical
 to the single-GPU path.  Decode mirrors it: IDCT per band, all-gather of the chroma layers (the bilinear
@@ -82,8 +82,11 @@ class TiledCodec:
         dist.all_reduce(t, group=self.group)
 
     # -- encode ---------------------------------------------------------------------------------
-    def encode(self, rgb: torch.Tensor, H: int, W: int, space: str, qrange, brange) -> EncodedBatch:
-        """rgb: float32 CUDA tensor.  Real multi-rank mode: this rank's band [Hb, W, 3].  Emulation: the whole [H, W, 3]."""
+    def encode(self, rgb: torch.Tensor, H: int, W: int, space: str, qrange, brange, exchange_coef: bool = False) -> EncodedBatch:
+        """rgb: float32 CUDA tensor.  Real multi-rank mode: this rank's band [Hb, W, 3].  Emulation: the whole [H, W, 3].
+        Leaves, states and counts are complete on every rank.  Coefficients: each rank holds the ranges of its own band's
+        leaves (at their global offsets) -- all its decoder phase and its host-side D2H need; `exchange_coef` additionally
+        all-reduces the zero-filled streams so that every rank holds the whole stream (used by the parity check)."""
         c = self.codec
         p = c._plan(1, H, W, space, brange, qrange)
         o = p.out
@@ -125,11 +128,12 @@ class TiledCodec:
                 self._gather_rows(v["strong"][l], p.info.layer_h[l])
                 self._gather_rows(v["weak"][l], p.info.layer_h[l])
         run(PH_TREE, ranks[0])                # whole image, replicated (the band argument is irrelevant for this phase)
-        for l in range(3):
-            o.coef[l].zero_()
+        if multi and exchange_coef:
+            for l in range(3):
+                o.coef[l].zero_()
         for r in ranks:
             run(PH_DCT, r)
-        if multi:
+        if multi and exchange_coef:
             for l in range(3):
                 self._reduce(o.coef[l])
         return o
