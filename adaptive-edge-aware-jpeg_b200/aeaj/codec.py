@@ -41,6 +41,8 @@ class EncodedBatch:
     shape: Tuple[int, int, int]    # B, H, W
     layers: Optional[List[torch.Tensor]] = None   # taps (float32 [B,h,w]) if requested
     edges: Optional[List[torch.Tensor]] = None    # taps (uint8  [B,h,w]) if requested
+    packed_states: Optional[List[torch.Tensor]] = None   # 3 x uint8 [B, (cap_states_l+3)//4] when stream=True
+    zigzag: bool = False                          # coefficient blocks are zigzag-ordered (the .ajpg layout)
 
 
 @dataclass
@@ -100,8 +102,11 @@ class DeviceCodec:
         return self._plan(B, H, W, space, brange, qrange).info
 
     # ------------------------------------------------------------------------------------------
-    def encode(self, rgb: torch.Tensor, space: str, qrange, brange, taps: bool = False, instance: int = 0) -> EncodedBatch:
-        """rgb: float32 CUDA tensor [B,H,W,3] (or [H,W,3]). Asynchronous on the current stream."""
+    def encode(self, rgb: torch.Tensor, space: str, qrange, brange, taps: bool = False, instance: int = 0,
+               stream: bool = False) -> EncodedBatch:
+        """rgb: float32 CUDA tensor [B,H,W,3] (or [H,W,3]). Asynchronous on the current stream.
+        stream=True produces the .ajpg stream layout on the device: zigzag-ordered coefficient blocks and the
+        2-bit packed state stream (what _entropy_encode feeds to zlib / writes, jpeg.py:563-590)."""
         if rgb.dim() == 3:
             rgb = rgb.unsqueeze(0)
         if rgb.dtype != torch.float32 or not rgb.is_cuda or rgb.dim() != 4 or rgb.shape[-1] != 3:
@@ -118,6 +123,13 @@ class DeviceCodec:
             io.states[l] = o.states[l].data_ptr()
         io.counts = o.counts.data_ptr()
         io.status = o.status.data_ptr()
+        native.check(self.lib.aeaj_plan_set_stream_layout(p.ptr, int(stream)), "aeaj_plan_set_stream_layout")
+        o.zigzag = bool(stream)
+        if stream:
+            if o.packed_states is None:
+                o.packed_states = [torch.empty((B, (int(p.info.cap_states[l]) + 3) // 4), dtype=torch.uint8, device=rgb.device) for l in range(3)]
+            for l in range(3):
+                io.packed_states[l] = o.packed_states[l].data_ptr()
         if taps:
             dev = rgb.device
             o.layers = [torch.empty((B, p.info.layer_h[l], p.info.layer_w[l]), dtype=torch.float32, device=dev) for l in range(3)]
@@ -129,9 +141,12 @@ class DeviceCodec:
         self.last_launches = self.lib.aeaj_plan_last_launches(p.ptr)
         return o
 
-    def decode(self, coef, leaves, counts, B, H, W, space: str, qrange, brange, taps: bool = False, instance: int = 0):
-        """coef/leaves: 3 device tensors laid out like EncodedBatch; counts int32 [B,3,4]. Returns rgb [B,H,W,3]."""
+    def decode(self, coef, leaves, counts, B, H, W, space: str, qrange, brange, taps: bool = False, instance: int = 0,
+               zigzag: bool = False):
+        """coef/leaves: 3 device tensors laid out like EncodedBatch; counts int32 [B,3,4]. Returns rgb [B,H,W,3].
+        zigzag=True: the coefficient blocks are in the .ajpg zigzag order."""
         p = self._plan(B, H, W, space, brange, qrange, instance)
+        native.check(self.lib.aeaj_plan_set_stream_layout(p.ptr, int(zigzag)), "aeaj_plan_set_stream_layout")
         io = native.DecodeIO()
         for l in range(3):
             if coef[l].shape[1] != p.info.cap_coef[l] or leaves[l].shape[1] != p.info.cap_leaves[l]:
@@ -306,7 +321,7 @@ class DeviceCodec:
 
     def decode_encoded(self, enc: EncodedBatch, space, qrange, brange):
         B, H, W = enc.shape
-        return self.decode(enc.coef, enc.leaves, enc.counts, B, H, W, space, qrange, brange)
+        return self.decode(enc.coef, enc.leaves, enc.counts, B, H, W, space, qrange, brange, zigzag=enc.zigzag)
 
     # ------------------------------------------------------------------------------------------
     # host <-> device helpers for the reference-facing shim
@@ -322,8 +337,11 @@ class DeviceCodec:
             layers = []
             for l in range(3):
                 nl, ns, nc, root = (int(v) for v in counts[b, l])
-                layers.append(dict(leaves=enc.leaves[l][b, :nl].cpu().numpy(), states=enc.states[l][b, :ns].cpu().numpy(),
-                                   coef=enc.coef[l][b, :nc].cpu().numpy(), root=root))
+                d = dict(leaves=enc.leaves[l][b, :nl].cpu().numpy(), states=enc.states[l][b, :ns].cpu().numpy(),
+                         coef=enc.coef[l][b, :nc].cpu().numpy(), root=root, zigzag=enc.zigzag)
+                if enc.zigzag and enc.packed_states is not None:
+                    d["packed_states"] = enc.packed_states[l][b, :(ns + 3) // 4].cpu().numpy()
+                layers.append(d)
             out.append(layers)
         return out
 
@@ -340,8 +358,8 @@ class DeviceCodec:
                     raise ValueError("stream does not fit the layer geometry (corrupt input?)")
                 counts[b, l, 0] = nl
                 counts[b, l, 2] = nc
-                o.leaves[l][b, :nl].copy_(torch.from_numpy(np.ascontiguousarray(d["leaves"], dtype=np.int32)), non_blocking=False)
-                o.coef[l][b, :nc].copy_(torch.from_numpy(np.ascontiguousarray(d["coef"], dtype=np.int32)), non_blocking=False)
+                o.leaves[l][b, :nl].copy_(torch.from_numpy(np.require(d["leaves"], dtype=np.int32, requirements=["C", "W"])), non_blocking=False)
+                o.coef[l][b, :nc].copy_(torch.from_numpy(np.require(d["coef"], dtype=np.int32, requirements=["C", "W"])), non_blocking=False)
         o.counts.copy_(torch.from_numpy(counts))
         return o.coef, o.leaves, o.counts
 

@@ -21,6 +21,7 @@ EXPORTS = [
     "aeaj_dct_quant", "aeaj_dequant_idct", "aeaj_plan_create", "aeaj_plan_destroy", "aeaj_plan_get_info",
     "aeaj_plan_set_qtables", "aeaj_encode", "aeaj_decode", "aeaj_plan_last_launches",
     "aeaj_plan_enable_timing", "aeaj_plan_read_timing", "aeaj_encode_phase", "aeaj_decode_phase", "aeaj_plan_buffers",
+    "aeaj_plan_set_stream_layout",
     "aeaj_states_to_leaves_host", "aeaj_pack_states_host",
 ]
 
@@ -39,7 +40,8 @@ class PlanInfo(C.Structure):
 
 class EncodeIO(C.Structure):
     _fields_ = [("rgb", C.c_void_p), ("coef", C.c_void_p * 3), ("leaves", C.c_void_p * 3), ("states", C.c_void_p * 3),
-                ("counts", C.c_void_p), ("tap_layers", C.c_void_p * 3), ("tap_edges", C.c_void_p * 3), ("status", C.c_void_p)]
+                ("counts", C.c_void_p), ("tap_layers", C.c_void_p * 3), ("tap_edges", C.c_void_p * 3), ("status", C.c_void_p),
+                ("packed_states", C.c_void_p * 3)]
 
 
 class DecodeIO(C.Structure):
@@ -100,6 +102,7 @@ def load():
         lib.aeaj_encode.argtypes = [vp, C.POINTER(EncodeIO), vp, vp]
         lib.aeaj_decode.argtypes = [vp, C.POINTER(DecodeIO), vp, vp]
         lib.aeaj_plan_last_launches.argtypes = [vp]
+        lib.aeaj_plan_set_stream_layout.argtypes = [vp, i]
         lib.aeaj_encode_phase.argtypes = [vp, C.POINTER(EncodeIO), vp, vp, i, i, i]
         lib.aeaj_decode_phase.argtypes = [vp, C.POINTER(DecodeIO), vp, vp, i, i, i]
         lib.aeaj_plan_buffers.argtypes = [vp, vp, C.POINTER(PlanBuffers)]

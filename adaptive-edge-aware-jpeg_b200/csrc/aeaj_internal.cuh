@@ -114,6 +114,8 @@ struct aeaj_handle {
     float* dct_all_dev;
     float* dct_half_dev[9];       // even/odd half tables for the CTA kernels (sizes 64, 128)
     float* dct_half_all_dev;
+    int32_t* zz_dev[9];           // zigzag tables per log2(size), device
+    int32_t* zz_all_dev;
     // device scratch for single-plane stage calls
     struct PlaneDesc* stage_plane_dev;
     long long* stage_class_off_dev;   // [9]
@@ -145,6 +147,9 @@ struct PlaneDesc {
     int* tb_coef;            // per in-bounds top block: n_coef
     int4* tb_base;           // per in-bounds top block: state base, leaf base, coef base, -
     const int32_t* qtab[9];  // per log2(size)
+    const int32_t* zz[9];    // zigzag order per log2(size): stream index -> row-major index (jpeg.py:726-766)
+    int zigzag;              // 1: coefficient streams are stored zigzag-ordered per block (the .ajpg layout)
+    uint8_t* packed_states;  // optional: 2-bit MSB-first packing of `states` (jpeg.py:563-571)
     int64_t cap_leaves, cap_states, cap_coef;
 };
 
@@ -209,6 +214,7 @@ int launch_u8_to_bitmap(const uint8_t* edge, int h, int w, uint32_t* bits, cudaS
 int launch_quadtree(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, int min_size, int max_size,
                     ClassEntry* class_lists, int* class_counts, const long long* class_offsets_dev, cudaStream_t st,
                     int* launches);
+int launch_pack_states(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, cudaStream_t st);
 int launch_bucket_leaves(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, ClassEntry* class_lists,
                          int* class_counts, const long long* class_offsets_dev, cudaStream_t st);
 int launch_dct_quant(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,

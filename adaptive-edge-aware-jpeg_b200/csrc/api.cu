@@ -127,7 +127,7 @@ extern "C" int aeaj_create(int device, aeaj_handle** out) {
 extern "C" int aeaj_destroy(aeaj_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    cudaFree(h->srgb_lut_dev); cudaFree(h->dct_all_dev); cudaFree(h->dct_half_all_dev); cudaFree(h->stage_plane_dev);
+    cudaFree(h->srgb_lut_dev); cudaFree(h->dct_all_dev); cudaFree(h->dct_half_all_dev); cudaFree(h->zz_all_dev); cudaFree(h->stage_plane_dev);
     cudaFree(h->stage_class_off_dev); cudaFree(h->stage_tile_base_dev); cudaFree(h->stage_outs_dev);
     free(h);
     return 0;
@@ -372,6 +372,7 @@ struct aeaj_plan {
     uint8_t** outs_dev;                  // tap pointers [nplanes]
     int last_launches;
     bool need_full_chroma;
+    int zigzag = 0;
     // optional per-stage CUDA-event timing (bench.py roofline leg)
     bool timing_on = false;
     std::vector<cudaEvent_t> ev;
@@ -505,6 +506,11 @@ extern "C" int aeaj_plan_get_info(const aeaj_plan* p, aeaj_plan_info* info) {
     return 0;
 }
 extern "C" int aeaj_plan_last_launches(const aeaj_plan* p) { return p ? p->last_launches : 0; }
+extern "C" int aeaj_plan_set_stream_layout(aeaj_plan* p, int zigzag) {
+    AEAJ_REQUIRE(p, "aeaj_plan_set_stream_layout: NULL plan");
+    p->zigzag = zigzag != 0;
+    return 0;
+}
 
 extern "C" int aeaj_plan_enable_timing(aeaj_plan* p, int enable) {
     AEAJ_REQUIRE(p, "aeaj_plan_enable_timing: NULL plan");
@@ -550,6 +556,10 @@ extern "C" int aeaj_plan_set_qtables(aeaj_plan* p, const int32_t* tables, size_t
 }
 
 static int plan_push_planes(aeaj_plan* p, cudaStream_t st) {
+    for (auto& P : p->planes) {
+        P.zigzag = p->zigzag;
+        for (int k = 0; k < 9; k++) P.zz[k] = p->h->zz_dev[k];
+    }
     AEAJ_CUDA(cudaMemcpyAsync(p->planes_dev, p->planes.data(), sizeof(PlaneDesc) * p->nplanes, cudaMemcpyHostToDevice, st));
     return 0;
 }
@@ -592,6 +602,7 @@ static int encode_impl(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, 
             P.leaves = io->leaves[l] + (size_t)i * p->info.cap_leaves[l] * 4;
             P.states = io->states[l] + (size_t)i * p->info.cap_states[l];
             P.counts = io->counts + ((size_t)i * 3 + l) * 4;
+            P.packed_states = io->packed_states[l] ? io->packed_states[l] + (size_t)i * ((p->info.cap_states[l] + 3) / 4) : nullptr;
             if (io->tap_edges[l]) { outs[i * 3 + l] = io->tap_edges[l] + (size_t)i * P.h * P.w; any_tap_edge = true; }
         }
     }
@@ -644,6 +655,10 @@ static int encode_impl(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, 
         rc = launch_quadtree(p->planes_dev, p->planes.data(), NP, p->info.block_min, p->info.block_max, A.class_lists, A.class_counts,
                              p->class_off_dev, st, &launches);
         if (rc) return rc;
+        if (io->packed_states[0] || io->packed_states[1] || io->packed_states[2]) {
+            rc = launch_pack_states(p->planes_dev, p->planes.data(), NP, st); if (rc) return rc;
+            launches++;
+        }
         p->mark("quadtree");
     }
     if (phases & (1u << AEAJ_PHASE_DCT)) {
@@ -679,6 +694,7 @@ static int decode_impl(aeaj_plan* p, const aeaj_decode_io* io, void* workspace, 
             P.coef = (int32_t*)io->coef[l] + (size_t)i * p->info.cap_coef[l];
             P.leaves = (int32_t*)io->leaves[l] + (size_t)i * p->info.cap_leaves[l] * 4;
             P.counts = (int32_t*)io->counts + ((size_t)i * 3 + l) * 4;
+            P.packed_states = nullptr;
         }
     }
     int rc = set_band(p, band0, band1); if (rc) return rc;

@@ -327,14 +327,44 @@ __device__ void canny_prepare_thresholds(double lo, double hi, int* thr) {
     if (hi > 0) hi *= hi;
     thr[0] = (int)floor(lo); thr[1] = (int)floor(hi);
 }
-__global__ void k_thresholds(const PlaneDesc* __restrict__ planes, int nplanes) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per plane: lane i owns bins 8i..8i+7; warp-shuffle prefix sums locate the order statistics
+__device__ __forceinline__ int first_bin_above(const unsigned long long* cum8, unsigned long long target, int lane) {
+    // smallest bin whose inclusive cumulative count exceeds `target`
+    const unsigned m = __ballot_sync(0xffffffffu, cum8[7] > target);
+    const int src = __ffs(m) - 1;
+    int bin = 0;
+#pragma unroll
+    for (int k = 7; k >= 0; k--) if (cum8[k] > target) bin = 8 * lane + k;
+    return __shfl_sync(0xffffffffu, bin, src < 0 ? 31 : src);
+}
+__device__ __forceinline__ double percentile_warp(const unsigned long long* cum8, unsigned long long n, double q, int lane) {
+    const double v = (double)(n - 1) * q;
+    const double lo = floor(v), gfrac = v - lo;
+    const unsigned long long ilo = (unsigned long long)lo, ihi = ilo + 1 < n ? ilo + 1 : n - 1;
+    const int a = first_bin_above(cum8, ilo, lane), b = first_bin_above(cum8, ihi, lane);
+    const double d = (double)(b - a);
+    return gfrac < 0.5 ? (double)a + d * gfrac : (double)b - d * (1.0 - gfrac);
+}
+__global__ void __launch_bounds__(128) k_thresholds(const PlaneDesc* __restrict__ planes, int nplanes) {
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (p >= nplanes) return;
     const PlaneDesc& P = planes[p];
-    unsigned long long n = (unsigned long long)P.h * P.w;
-    double lo = percentile_from_hist(P.hist, n, 10.0 / 100.0), hi = percentile_from_hist(P.hist, n, 30.0 / 100.0);
-    if (P.thr_d) { P.thr_d[0] = lo; P.thr_d[1] = hi; }
-    canny_prepare_thresholds(lo, hi, P.thr);
+    unsigned long long cum8[8];
+    unsigned long long run = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { run += P.hist[8 * lane + k]; cum8[k] = run; }
+    unsigned long long inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    const unsigned long long off = inc - run;
+#pragma unroll
+    for (int k = 0; k < 8; k++) cum8[k] += off;
+    const unsigned long long n = (unsigned long long)P.h * P.w;
+    const double lo = percentile_warp(cum8, n, 10.0 / 100.0, lane), hi = percentile_warp(cum8, n, 30.0 / 100.0, lane);
+    if (lane == 0) {
+        if (P.thr_d) { P.thr_d[0] = lo; P.thr_d[1] = hi; }
+        canny_prepare_thresholds(lo, hi, P.thr);
+    }
 }
 __global__ void k_thresholds_from_double(const double* thr_d, int* thr) { canny_prepare_thresholds(thr_d[0], thr_d[1], thr); }
 
@@ -716,7 +746,7 @@ int launch_hist_u8(const uint8_t* src, size_t n, unsigned int* hist, cudaStream_
     return 0;
 }
 int launch_thresholds(const PlaneDesc* planes_dev, int nplanes, cudaStream_t st) {
-    k_thresholds<<<aeaj_cdiv(nplanes, 64), 64, 0, st>>>(planes_dev, nplanes);
+    k_thresholds<<<aeaj_cdiv(nplanes, 4), 128, 0, st>>>(planes_dev, nplanes);
     AEAJ_LAUNCH_CHECK();
     return 0;
 }

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) k_dct_rows(const PlaneDesc* __restrict__ 
                 }
 #pragma unroll
                 for (int j = 0; j < S; j++) in[j] = __fmul_rn(__fsub_rn(in[j], mid), sc);
-            } else {
+            } else if (!P.zigzag) {
                 const int* cf = P.coef + (size_t)e.coef_off + r * S;
                 const int* qt = P.qtab[LG] + r * S;
                 if (S >= 4) {
@@ -101,8 +101,26 @@ __global__ void __launch_bounds__(256) k_dct_rows(const PlaneDesc* __restrict__ 
 #pragma unroll
             for (int j = 0; j < S; j++) in[j] = 0.0f;
         }
-        // pass 1: t[l] = sum_j in[j] * M[l][j]
         float* T = &sT[warp][sub * GS];
+        if (INVERSE && P.zigzag) {
+            // zigzag-ordered stream: coalesced read, scatter through the warp tile into row-major, then dequantise
+            __syncwarp();
+            if (act) {
+                const int* cf = P.coef + (size_t)e.coef_off;
+                const int* qt = P.qtab[LG];
+                const int* zz = P.zz[LG];
+#pragma unroll
+                for (int k = 0; k < S; k++) {
+                    const int idx = r + k * S, nat = __ldg(zz + idx);
+                    T[(nat / S) * TS + (nat % S)] = (float)(__ldg(cf + idx) * __ldg(qt + nat));
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < S; j++) in[j] = act ? T[r * TS + j] : 0.0f;
+            __syncwarp();
+        }
+        // pass 1: t[l] = sum_j in[j] * M[l][j]
 #pragma unroll
         for (int l = 0; l < S; l++) {
             float acc = 0.0f;
@@ -122,7 +140,13 @@ __global__ void __launch_bounds__(256) k_dct_rows(const PlaneDesc* __restrict__ 
         }
         __syncwarp();
         if (act) {
-            if (!INVERSE) {
+            if (!INVERSE && P.zigzag) {
+                // stage the quantised row in the warp tile, then the S lanes of the leaf write the block in zigzag order
+                const int* qt = P.qtab[LG] + r * S;
+                int* Ti = reinterpret_cast<int*>(T);
+#pragma unroll
+                for (int l = 0; l < S; l++) Ti[r * TS + l] = quantize(out[l], __ldg(qt + l));
+            } else if (!INVERSE) {
                 int* cf = P.coef + (size_t)e.coef_off + r * S;
                 const int* qt = P.qtab[LG] + r * S;
                 if (S >= 4) {
@@ -153,6 +177,20 @@ __global__ void __launch_bounds__(256) k_dct_rows(const PlaneDesc* __restrict__ 
                     }
                 }
             }
+        }
+        if (!INVERSE && P.zigzag) {
+            __syncwarp();
+            if (act) {
+                int* cf = P.coef + (size_t)e.coef_off;
+                const int* zz = P.zz[LG];
+                const int* Ti = reinterpret_cast<const int*>(T);
+#pragma unroll
+                for (int k = 0; k < S; k++) {
+                    const int idx = r + k * S, nat = __ldg(zz + idx);
+                    cf[idx] = Ti[(nat / S) * TS + (nat % S)];
+                }
+            }
+            __syncwarp();
         }
     }
 }
@@ -235,11 +273,19 @@ __global__ void __launch_bounds__(256) k_dct_cta(const PlaneDesc* __restrict__ p
             // load Z dequantised, rows in split order: even rows first, then odd rows
             const int* cf = P.coef + (size_t)e.coef_off;
             const int* qt = P.qtab[LG];
-            for (int i = tid; i < N * N / 4; i += 256) {
-                const int k = (i * 4) / N, l = (i * 4) - k * N;
-                int4 cv = __ldg(reinterpret_cast<const int4*>(cf) + i), qv = __ldg(reinterpret_cast<const int4*>(qt) + i);
-                *reinterpret_cast<float4*>(((k & 1) ? sBo : sB) + (k >> 1) * NS + l) =
-                    make_float4((float)(cv.x * qv.x), (float)(cv.y * qv.y), (float)(cv.z * qv.z), (float)(cv.w * qv.w));
+            if (P.zigzag) {
+                const int* zz = P.zz[LG];
+                for (int i = tid; i < N * N; i += 256) {
+                    const int nat = __ldg(zz + i), k = nat / N, l = nat - k * N;
+                    (((k & 1) ? sBo : sB) + (k >> 1) * NS)[l] = (float)(__ldg(cf + i) * __ldg(qt + nat));
+                }
+            } else {
+                for (int i = tid; i < N * N / 4; i += 256) {
+                    const int k = (i * 4) / N, l = (i * 4) - k * N;
+                    int4 cv = __ldg(reinterpret_cast<const int4*>(cf) + i), qv = __ldg(reinterpret_cast<const int4*>(qt) + i);
+                    *reinterpret_cast<float4*>(((k & 1) ? sBo : sB) + (k >> 1) * NS + l) =
+                        make_float4((float)(cv.x * qv.x), (float)(cv.y * qv.y), (float)(cv.z * qv.z), (float)(cv.w * qv.w));
+                }
             }
         }
         __syncthreads();
@@ -306,6 +352,9 @@ __global__ void __launch_bounds__(256) k_dct_cta(const PlaneDesc* __restrict__ p
             // quantise, interleave even/odd columns with the pair lane, store int4
             int* cf = P.coef + (size_t)e.coef_off;
             const int* qt = P.qtab[LG];
+            const bool zig = P.zigzag != 0;
+            int* stage = reinterpret_cast<int*>(sB);              // row-major staging for the zigzag gather (stride N)
+            if (zig) __syncthreads();                              // everyone finished reading sB / sBo in pass 2
 #pragma unroll
             for (int a = 0; a < T; a++) {
                 const int kp = tr2 * 4 + (a & 3) + (a >> 2) * 64;           // split-order row
@@ -319,8 +368,13 @@ __global__ void __launch_bounds__(256) k_dct_cta(const PlaneDesc* __restrict__ p
                     const int x0 = g ? qv[0] : qv[2], x1 = g ? qv[1] : qv[3];
                     const int r0 = __shfl_xor_sync(0xffffffffu, x0, 1), r1 = __shfl_xor_sync(0xffffffffu, x1, 1);
                     const int4 o = g ? make_int4(r0, qv[2], r1, qv[3]) : make_int4(qv[0], r0, qv[1], r1);
-                    *reinterpret_cast<int4*>(cf + k * N + 2 * m0 + 4 * g) = o;
+                    *reinterpret_cast<int4*>((zig ? stage : cf) + k * N + 2 * m0 + 4 * g) = o;
                 }
+            }
+            if (zig) {
+                __syncthreads();
+                const int* zz = P.zz[LG];
+                for (int i = tid; i < N * N; i += 256) cf[i] = stage[__ldg(zz + i)];
             }
         } else {
             // pass 1: Rg[i][l] = sum_m Cg[m][i] * Zg[m][l]; sAg[m][i] = Cg[m][i]; columns l natural in chunks of 4
@@ -518,6 +572,30 @@ int aeaj_dct_init(aeaj_handle* h) {
     }
     AEAJ_CUDA(cudaMemcpy(h->dct_half_all_dev, hh, htotal * sizeof(float), cudaMemcpyHostToDevice));
     free(hh);
+    // zigzag tables: the standard JPEG walk generalised to s x s (jpeg.py:743-766)
+    size_t ztotal = 0;
+    for (int lg = 1; lg <= 7; lg++) ztotal += (size_t)1 << (2 * lg);
+    int32_t* zh = (int32_t*)malloc(ztotal * sizeof(int32_t));
+    if (!zh) return AEAJ_ENOMEM;
+    AEAJ_CUDA(cudaMalloc(&h->zz_all_dev, ztotal * sizeof(int32_t)));
+    size_t zo = 0;
+    for (int k = 0; k < 9; k++) h->zz_dev[k] = nullptr;
+    for (int lg = 1; lg <= 7; lg++) {
+        const int s = 1 << lg;
+        int row = 0, col = 0;
+        for (int i = 0; i < s * s; i++) {
+            zh[zo + i] = row * s + col;
+            if (((row + col) & 1) == 0) {
+                if (col == s - 1) row++; else if (row == 0) col++; else { row--; col++; }
+            } else {
+                if (row == s - 1) col++; else if (col == 0) row++; else { row++; col--; }
+            }
+        }
+        h->zz_dev[lg] = h->zz_all_dev + zo;
+        zo += (size_t)s * s;
+    }
+    AEAJ_CUDA(cudaMemcpy(h->zz_all_dev, zh, ztotal * sizeof(int32_t), cudaMemcpyHostToDevice));
+    free(zh);
     return 0;
 }
 

@@ -259,7 +259,29 @@ __global__ void __launch_bounds__(256) k_bucket_leaves(const PlaneDesc* __restri
     }
 }
 
+// 2 bits per state, MSB first, zero padded (jpeg.py:563-571); grid: (byte chunks, planes)
+__global__ void __launch_bounds__(256) k_pack_states(const PlaneDesc* __restrict__ planes) {
+    const PlaneDesc& P = planes[blockIdx.y];
+    if (!P.packed_states) return;
+    const int n = P.counts[1], nb = (n + 3) >> 2;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < nb; i += gridDim.x * 256) {
+        unsigned v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int idx = 4 * i + k; v = (v << 2) | (idx < n ? (P.states[idx] & 3u) : 0u); }
+        P.packed_states[i] = (uint8_t)v;
+    }
+}
+
 }  // namespace
+
+int launch_pack_states(const PlaneDesc* planes_dev, const PlaneDesc* P, int nplanes, cudaStream_t st) {
+    int64_t maxs = 1;
+    for (int i = 0; i < nplanes; i++) maxs = std::max<int64_t>(maxs, P[i].cap_states);
+    dim3 grd((unsigned)std::min<int64_t>(aeaj_cdiv64(aeaj_cdiv64(maxs, 4), 256), 64), nplanes);
+    k_pack_states<<<grd, 256, 0, st>>>(planes_dev);
+    AEAJ_LAUNCH_CHECK();
+    return 0;
+}
 
 int launch_quadtree(const PlaneDesc* planes_dev, const PlaneDesc* P, int nplanes, int min_size, int max_size,
                     ClassEntry* class_lists, int* class_counts, const long long* class_offsets_dev, cudaStream_t st, int* launches) {

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import json
 import zlib
+from concurrent.futures import ThreadPoolExecutor
 from io import BytesIO
 from typing import List, Optional, Sequence, Tuple
 
@@ -136,7 +137,7 @@ class Jpeg:
             self.extension = imgs[idxs[-1]].extension
             host = np.stack([np.ascontiguousarray(imgs[i].data.reshape(H, W, 3), dtype=np.float32) for i in idxs])
             rgb = torch.from_numpy(host).pin_memory().to(f"cuda:{codec.device}", non_blocking=True)
-            enc = codec.encode(rgb, s.color_space, s.quality_range, s.block_size_range)
+            enc = codec.encode(rgb, s.color_space, s.quality_range, s.block_size_range, stream=True)
             for i, layers in zip(idxs, codec.download(enc)):
                 out[i] = self._entropy_encode(layers, (H, W), imgs[i].extension)
         return out
@@ -150,7 +151,7 @@ class Jpeg:
         codec = get_codec()
         for (H, W, space, q, b), idxs in groups.items():
             coef, leaves, counts = codec.upload_for_decode([parsed[i]["layers"] for i in idxs], len(idxs), H, W, space, q, b)
-            rgb = codec.decode(coef, leaves, counts, len(idxs), H, W, space, q, b).cpu().numpy()
+            rgb = codec.decode(coef, leaves, counts, len(idxs), H, W, space, q, b, zigzag=True).cpu().numpy()
             for k, i in enumerate(idxs):
                 out[i] = Image.from_array(rgb[k].reshape(-1, 3), (H, W, 3), parsed[i]["extension"])
         last = parsed[-1]
@@ -169,15 +170,26 @@ class Jpeg:
         out.write(len(mb).to_bytes(4, byteorder="big"))
         out.write(mb)
         lib = native.load()
-        for L in layers:
+
+        def deflate(L):
+            # zlib releases the GIL: the three layers are compressed concurrently (same bytes as the reference's
+            # sequential zlib.compress(level=9), jpeg.py:590).  With the device-side stream layout the coefficients
+            # already arrive zigzag-ordered.
+            zz = L["coef"] if L.get("zigzag") else _zigzag_stream(L["coef"], L["leaves"][:, 2], self.zigzag_cache, inverse=False)
+            return zlib.compress(zz.tobytes(), level=9)
+
+        with ThreadPoolExecutor(max_workers=len(layers)) as pool:
+            streams = list(pool.map(deflate, layers))
+        for L, z in zip(layers, streams):
             states = np.ascontiguousarray(L["states"], dtype=np.uint8)
-            packed = np.empty((len(states) + 3) // 4, dtype=np.uint8)
-            native.check(lib.aeaj_pack_states_host(states.ctypes.data, len(states), packed.ctypes.data), "aeaj_pack_states_host")
+            if "packed_states" in L:
+                packed = L["packed_states"]
+            else:
+                packed = np.empty((len(states) + 3) // 4, dtype=np.uint8)
+                native.check(lib.aeaj_pack_states_host(states.ctypes.data, len(states), packed.ctypes.data), "aeaj_pack_states_host")
             out.write((2 * len(states)).to_bytes(4, byteorder="big"))
             out.write(int(L["root"]).to_bytes(4, byteorder="big"))
             out.write(packed.tobytes())
-            zz = _zigzag_stream(L["coef"], L["leaves"][:, 2], self.zigzag_cache, inverse=False)
-            z = zlib.compress(zz.tobytes(), level=9)
             out.write(len(z).to_bytes(4, byteorder="big"))
             out.write(z)
         return out.getvalue()
@@ -192,7 +204,6 @@ class Jpeg:
         blocks = (meta["block_size_min"], meta["block_size_max"])
         settings = JpegCompressionSettings(space, quality, blocks)          # raises ValueError on unknown space
         shapes = np.asarray((H, W)) // settings.downsampling_ratios
-        zz_cache = {sz: tables.zigzag_ordering(sz) for sz in tables.block_sizes(blocks)}
         layers = []
         for i in range(meta["num_layers"]):
             nbits = int.from_bytes(s.read(4), byteorder="big")
@@ -204,5 +215,5 @@ class Jpeg:
             coef = np.frombuffer(zlib.decompress(s.read(zl)), dtype=np.int32)
             if coef.size != ncoef:
                 raise ValueError("coefficient stream length does not match the quadtree header")
-            layers.append(dict(leaves=leaves, coef=_zigzag_stream(coef, leaves[:, 2], zz_cache, inverse=True)))
+            layers.append(dict(leaves=leaves, coef=coef))          # still zigzag-ordered: the IDCT kernels undo it on load
         return dict(H=H, W=W, space=space, quality=quality, blocks=blocks, extension=meta["extension"], layers=layers)

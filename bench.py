@@ -283,8 +283,20 @@ def main():
         alg[dom] = ns * 8.0                                            # 4 B in + 4 B out per sample
     alg_bytes = alg.get(dom)
     dom_ms = stage_ms[dom]
+    # measured DRAM traffic of that kernel per launch (dram__bytes_read + write from the committed `ncu --set full`
+    # capture, taken at the default batch of 4 frames); null for other batch sizes / kernels not captured
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        kname = {"prefilter": "k_prefilter", "canny_nms": "k_canny_nms", "color_forward_planar": "k_color_forward_planar<0, 0>",
+                 "dct_quant_128": "k_dct_cta<128, 0>", "dct_quant_64": "k_dct_cta<64, 0>", "hysteresis": "k_hysteresis_rounds"}.get(dom)
+        if B == 4 and kname in tr:
+            traffic = tr[kname]
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": (alg_bytes / 1e9) / (dom_ms / 1e3) if alg_bytes else None, "peak": peak,
-            "unit": "GB/s", "frac": ((alg_bytes / 1e9) / (dom_ms / 1e3) / peak) if alg_bytes else None, "traffic": None,
+            "unit": "GB/s", "frac": ((alg_bytes / 1e9) / (dom_ms / 1e3) / peak) if alg_bytes else None, "traffic": traffic,
+            "algorithmic_bytes": alg_bytes,
             "peak_source": peak_src, "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / sum(stage_ms.values()),
             "pipeline_achieved": (ALG_BYTES_PER_PX * full_px * world / 1e9) / (ms / args.steps / 1e3),
             "pipeline_frac": (ALG_BYTES_PER_PX * full_px / 1e9) / (ms / args.steps / 1e3) / peak,

@@ -151,7 +151,9 @@ typedef struct {
     int32_t* counts;         /* [batch][3][4] n_leaves, n_states, n_coef, root */
     float* tap_layers[3];    /* optional [batch][h_l][w_l]: downsampled un-normalised layers */
     uint8_t* tap_edges[3];   /* optional [batch][h_l][w_l]: edge maps {0,1} */
-    int32_t* status;         /* device int32[2]: hysteresis rounds used, converged flag */
+    int32_t* status;         /* device int32[64]: [0] hysteresis rounds used, [1] converged flag, rest diagnostics */
+    uint8_t* packed_states[3]; /* optional [batch][(cap_states[l]+3)/4]: the state stream packed 2 bits per state,
+                                  MSB first, zero padded -- the bytes _entropy_encode writes (jpeg.py:563-571) */
 } aeaj_encode_io;
 
 typedef struct {
@@ -200,6 +202,12 @@ AEAJ_API int aeaj_states_to_leaves_host(const uint8_t* states_host, int n_states
                                int32_t* leaves_host, int* n_leaves, int64_t* n_coef);
 /* 2 bits per state, MSB first, zero padded; packed_host holds ceil(n_states/4) bytes */
 AEAJ_API int aeaj_pack_states_host(const uint8_t* states_host, int n_states, uint8_t* packed_host);
+
+/* Stream layout.  zigzag = 0 (default): each block of the coefficient stream is row-major,
+ * i.e. the reference's img_quantized blocks.  zigzag = 1: each block is stored in the zigzag order of
+ * Jpeg._zigzag_ordering (jpeg.py:726-766), i.e. the stream is byte-for-byte what _entropy_encode hands to zlib
+ * (jpeg.py:579-590); aeaj_decode then expects that layout. */
+AEAJ_API int aeaj_plan_set_stream_layout(aeaj_plan* p, int zigzag);
 
 /* number of kernel launches issued by the last aeaj_encode / aeaj_decode on this plan */
 AEAJ_API int aeaj_plan_last_launches(const aeaj_plan* p);

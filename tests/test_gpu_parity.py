@@ -404,3 +404,24 @@ def test_halo_split_bands_emulated_on_one_gpu(codec, space, G):
             assert np.array_equal(got[l][k], ref[l][k]), (space, G, l, k)
     dec = t.decode(enc, H, W, space, q, b)
     assert torch.equal(dec, ref_dec)
+
+
+@pytest.mark.parametrize("space,shape,b", [("YCbCr", (200, 328), (4, 128)), ("YCoCg", (135, 241), (2, 32)), ("ICtCp", (96, 160), (8, 64))])
+def test_device_stream_layout_matches_host_packing(codec, space, shape, b):
+    """zigzag-ordered coefficient blocks and the 2-bit state stream produced on the device are
+    byte-identical to the host-side packing of the row-major result; decoding either layout gives the same pixels."""
+    import torch
+    H, W = shape
+    q = (30, 95)
+    rgb = torch.from_numpy(np.stack([synth(H, W, seed=s) for s in (3, 4)])).cuda()
+    nat = codec.download(codec.encode(rgb, space, q, b))
+    dec_nat = codec.decode_encoded(codec._plan(2, H, W, space, b, q).out, space, q, b).clone()
+    enc = codec.encode(rgb, space, q, b, stream=True)
+    zz = codec.download(enc)
+    dec_zz = codec.decode_encoded(enc, space, q, b)
+    assert torch.equal(dec_nat, dec_zz)
+    for k in range(2):
+        for l in range(3):
+            assert np.array_equal(zz[k][l]["coef"], O.zigzag_stream(nat[k][l]["coef"], nat[k][l]["leaves"][:, :3]))
+            assert zz[k][l]["packed_states"].tobytes() == O.pack_states(nat[k][l]["states"])
+            assert np.array_equal(zz[k][l]["states"], nat[k][l]["states"])
