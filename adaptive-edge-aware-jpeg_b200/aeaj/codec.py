@@ -64,6 +64,13 @@ class DeviceCodec:
         self.handle = native.handle(device)
         self._plans: Dict[tuple, _Plan] = {}
         self.last_launches = 0
+        self.tensor_dct = False        # opt-in tcgen05 path for the 128x128 forward DCT
+
+    def tensor_dct_timed_out(self) -> bool:
+        t = (C.c_int * 32)()
+        native.check(self.lib.aeaj_tensor_dct_status(self.handle, C.cast(t, C.POINTER(C.c_int))), "aeaj_tensor_dct_status")
+        self.tensor_dct_phase_cycles = list(t)[1:16]
+        return bool(t[0])
 
     # ------------------------------------------------------------------------------------------
     def _plan(self, B, H, W, space, brange, qrange, instance: int = 0) -> _Plan:
@@ -124,6 +131,7 @@ class DeviceCodec:
         io.counts = o.counts.data_ptr()
         io.status = o.status.data_ptr()
         native.check(self.lib.aeaj_plan_set_stream_layout(p.ptr, int(stream)), "aeaj_plan_set_stream_layout")
+        native.check(self.lib.aeaj_plan_set_tensor_dct(p.ptr, int(self.tensor_dct)), "aeaj_plan_set_tensor_dct")
         o.zigzag = bool(stream)
         if stream:
             if o.packed_states is None:

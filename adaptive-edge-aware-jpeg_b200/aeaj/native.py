@@ -21,7 +21,7 @@ EXPORTS = [
     "aeaj_dct_quant", "aeaj_dequant_idct", "aeaj_plan_create", "aeaj_plan_destroy", "aeaj_plan_get_info",
     "aeaj_plan_set_qtables", "aeaj_encode", "aeaj_decode", "aeaj_plan_last_launches",
     "aeaj_plan_enable_timing", "aeaj_plan_read_timing", "aeaj_encode_phase", "aeaj_decode_phase", "aeaj_plan_buffers",
-    "aeaj_plan_set_stream_layout",
+    "aeaj_plan_set_stream_layout", "aeaj_plan_set_tensor_dct", "aeaj_tensor_dct_status",
     "aeaj_states_to_leaves_host", "aeaj_pack_states_host",
 ]
 
@@ -103,6 +103,8 @@ def load():
         lib.aeaj_decode.argtypes = [vp, C.POINTER(DecodeIO), vp, vp]
         lib.aeaj_plan_last_launches.argtypes = [vp]
         lib.aeaj_plan_set_stream_layout.argtypes = [vp, i]
+        lib.aeaj_plan_set_tensor_dct.argtypes = [vp, i]
+        lib.aeaj_tensor_dct_status.argtypes = [vp, C.POINTER(i)]
         lib.aeaj_encode_phase.argtypes = [vp, C.POINTER(EncodeIO), vp, vp, i, i, i]
         lib.aeaj_decode_phase.argtypes = [vp, C.POINTER(DecodeIO), vp, vp, i, i, i]
         lib.aeaj_plan_buffers.argtypes = [vp, vp, C.POINTER(PlanBuffers)]

@@ -114,6 +114,8 @@ extern "C" int aeaj_create(int device, aeaj_handle** out) {
     if (rc) { free(h); return rc; }
     rc = aeaj_canny_init_constants();
     if (rc) { free(h); return rc; }
+    rc = aeaj_dct_tc_init(h);
+    if (rc) { free(h); return rc; }
     AEAJ_CUDA(cudaMalloc(&h->srgb_lut_dev, 256 * sizeof(float)));
     AEAJ_CUDA(cudaMalloc(&h->stage_plane_dev, sizeof(PlaneDesc)));
     AEAJ_CUDA(cudaMalloc(&h->stage_class_off_dev, 9 * sizeof(long long)));
@@ -127,7 +129,7 @@ extern "C" int aeaj_create(int device, aeaj_handle** out) {
 extern "C" int aeaj_destroy(aeaj_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    cudaFree(h->srgb_lut_dev); cudaFree(h->dct_all_dev); cudaFree(h->dct_half_all_dev); cudaFree(h->zz_all_dev); cudaFree(h->stage_plane_dev);
+    cudaFree(h->srgb_lut_dev); cudaFree(h->dct_all_dev); cudaFree(h->dct_half_all_dev); cudaFree(h->zz_all_dev); cudaFree(h->dct_tc_tiles_dev); cudaFree(h->tc_err_dev); cudaFree(h->stage_plane_dev);
     cudaFree(h->stage_class_off_dev); cudaFree(h->stage_tile_base_dev); cudaFree(h->stage_outs_dev);
     free(h);
     return 0;
@@ -373,6 +375,7 @@ struct aeaj_plan {
     int last_launches;
     bool need_full_chroma;
     int zigzag = 0;
+    int tensor_dct = 0;
     // optional per-stage CUDA-event timing (bench.py roofline leg)
     bool timing_on = false;
     std::vector<cudaEvent_t> ev;
@@ -506,6 +509,16 @@ extern "C" int aeaj_plan_get_info(const aeaj_plan* p, aeaj_plan_info* info) {
     return 0;
 }
 extern "C" int aeaj_plan_last_launches(const aeaj_plan* p) { return p ? p->last_launches : 0; }
+extern "C" int aeaj_plan_set_tensor_dct(aeaj_plan* p, int enable) {
+    AEAJ_REQUIRE(p, "aeaj_plan_set_tensor_dct: NULL plan");
+    p->tensor_dct = enable != 0;
+    return 0;
+}
+extern "C" int aeaj_tensor_dct_status(aeaj_handle* h, int* timed_out) {
+    AEAJ_REQUIRE(h && timed_out, "aeaj_tensor_dct_status: bad arguments");
+    AEAJ_CUDA(cudaMemcpy(timed_out, h->tc_err_dev, 32 * sizeof(int), cudaMemcpyDeviceToHost));   /* [0] flag, [1..] phase cycles of one leaf */
+    return 0;
+}
 extern "C" int aeaj_plan_set_stream_layout(aeaj_plan* p, int zigzag) {
     AEAJ_REQUIRE(p, "aeaj_plan_set_stream_layout: NULL plan");
     p->zigzag = zigzag != 0;
@@ -663,7 +676,7 @@ static int encode_impl(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, 
     }
     if (phases & (1u << AEAJ_PHASE_DCT)) {
         rc = launch_dct_quant(h, p->planes_dev, A.class_lists, A.class_counts, p->cg.off, p->cg.cap, p->lg_min, p->lg_max, st, &launches,
-                              plan_mark_cb, p);
+                              plan_mark_cb, p, p->tensor_dct && !p->zigzag);
         if (rc) return rc;
     }
     p->last_launches = launches;

@@ -19,20 +19,7 @@
 
 namespace {
 
-// np.round(block / qmatrix) (jpeg.py:501): the quotient is formed in float64 and rounded half-to-even.
-// A float32 z is never closer than 2^-24 (relative) to a half-integer multiple of q without being exactly on
-// it, so rounding the float64 quotient equals rounding the exact quotient -- which is computed here without any
-// float64: k = rint(z * 1/q) is within one of the answer, the residual z - k*q is exact in one fma, and the
-// comparison of 2r with q (ties to even) fixes k.  Checked against the float64 formula on 20 M values incl. ties.
-__device__ __forceinline__ int quantize(float z, int q) {
-    const float fq = (float)q;
-    float k = rintf(__fmul_rn(z, __frcp_rn(fq)));
-    const float r2 = __fmul_rn(2.0f, __fmaf_rn(-k, fq, z));
-    const bool odd = ((int)k) & 1;
-    if (r2 > fq || (r2 == fq && odd)) k += 1.0f;
-    else if (r2 < -fq || (r2 == -fq && odd)) k -= 1.0f;
-    return (int)k;
-}
+// quantize(): the exact float32 quantiser, see aeaj_internal.cuh
 
 // ---------------------------------------------------------------------------------------------
 // row kernel, S in {2,4,8,16,32}; block = 256 threads = 8 warps; each warp handles 32/S leaves.
@@ -494,7 +481,7 @@ int launch_cta(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* li
 template <bool INV>
 int launch_all(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,
                const int64_t* off, const int64_t* caps, int lg_min, int lg_max, cudaStream_t st, int* launches,
-               void (*mark)(void*, const char*), void* mark_ctx) {
+               void (*mark)(void*, const char*), void* mark_ctx, int tensor_dct = 0) {
     static const char* fwd_names[9] = {"", "dct_quant_2", "dct_quant_4", "dct_quant_8", "dct_quant_16", "dct_quant_32", "dct_quant_64", "dct_quant_128", ""};
     static const char* inv_names[9] = {"", "dequant_idct_2", "dequant_idct_4", "dequant_idct_8", "dequant_idct_16", "dequant_idct_32", "dequant_idct_64", "dequant_idct_128", ""};
     for (int lg = lg_min; lg <= lg_max; lg++) {
@@ -509,7 +496,8 @@ int launch_all(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* cl
             case 4: rc = launch_rows<16, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
             case 5: rc = launch_rows<32, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
             case 6: rc = launch_cta<64, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
-            case 7: rc = launch_cta<128, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
+            case 7: rc = (!INV && tensor_dct) ? launch_dct_tc128(h, planes_dev, list, cnt, caps[lg], st)
+                                              : launch_cta<128, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
             default: aeaj_set_error("block size %d not supported (2..128)", 1 << lg); return AEAJ_EINVAL;
         }
         if (rc) return rc;
@@ -601,8 +589,8 @@ int aeaj_dct_init(aeaj_handle* h) {
 
 int launch_dct_quant(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,
                      const int64_t* off, const int64_t* caps, int lg_min, int lg_max, cudaStream_t st, int* launches,
-                     void (*mark)(void*, const char*), void* mark_ctx) {
-    return launch_all<false>(h, planes_dev, class_lists, class_counts, off, caps, lg_min, lg_max, st, launches, mark, mark_ctx);
+                     void (*mark)(void*, const char*), void* mark_ctx, int tensor_dct) {
+    return launch_all<false>(h, planes_dev, class_lists, class_counts, off, caps, lg_min, lg_max, st, launches, mark, mark_ctx, tensor_dct);
 }
 int launch_dequant_idct(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,
                         const int64_t* off, const int64_t* caps, int lg_min, int lg_max, cudaStream_t st, int* launches,

@@ -209,6 +209,12 @@ AEAJ_API int aeaj_pack_states_host(const uint8_t* states_host, int n_states, uin
  * (jpeg.py:579-590); aeaj_decode then expects that layout. */
 AEAJ_API int aeaj_plan_set_stream_layout(aeaj_plan* p, int zigzag);
 
+/* Opt-in tensor-core path for the 128x128 forward DCT (tcgen05 kind::tf32, error-compensated 3xTF32, FP32
+ * accumulation in tensor memory).  Off by default: the FP32-FMA kernels define the parity bar.
+ * aeaj_tensor_dct_status reports whether a tensor-core kernel ever gave up on a barrier wait (synchronises). */
+AEAJ_API int aeaj_plan_set_tensor_dct(aeaj_plan* p, int enable);
+AEAJ_API int aeaj_tensor_dct_status(aeaj_handle* h, int* timed_out);
+
 /* number of kernel launches issued by the last aeaj_encode / aeaj_decode on this plan */
 AEAJ_API int aeaj_plan_last_launches(const aeaj_plan* p);
 

@@ -1,0 +1,32 @@
+import sys, torch, numpy as np
+sys.path.insert(0,'adaptive-edge-aware-jpeg_b200'); sys.path.insert(0,'tests'); sys.path.insert(0,'oracle')
+from aeaj.codec import get_codec
+from synth import synth
+c = get_codec(0)
+H,W = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv)>2 else (512,768)
+B = 4
+rgb = torch.from_numpy(np.stack([synth(H,W,s) for s in range(B)])).cuda()
+sp,q,b = 'YCbCr',(30,95),(4,128)
+c.tensor_dct=False
+ref = c.download(c.encode(rgb,sp,q,b))
+c.tensor_dct=True
+enc = c.encode(rgb,sp,q,b); torch.cuda.synchronize()
+print('timed_out', c.tensor_dct_timed_out(), 'phase cycles (load0,issue0,wait0,load1,issue1,wait1,split,issue2,wait2,tmem->smem,sync,quantize+store,final sync):', c.tensor_dct_phase_cycles)
+got = c.download(enc)
+tot=0; bad=0; mx=0; n128=0
+for k in range(B):
+    for l in range(3):
+        a=ref[k][l]['coef'].astype(np.int64); g=got[k][l]['coef'].astype(np.int64)
+        assert np.array_equal(ref[k][l]['leaves'], got[k][l]['leaves'])
+        lv=ref[k][l]['leaves']; n128+=int((lv[:,2]==128).sum())
+        d=np.abs(a-g); tot+=a.size; bad+=int((d!=0).sum()); mx=max(mx,int(d.max()))
+print('leaves128', n128, 'coef total', tot, 'mismatch', bad, 'max', mx)
+args=(B,H,W,sp,b,q)
+for mode in (False, True):
+    c.tensor_dct=mode
+    for _ in range(3): c.encode(rgb,sp,q,b)
+    c.enable_timing(*args, True); t=[]
+    for _ in range(5):
+        c.encode(rgb,sp,q,b); t.append(c.read_timing(*args)['dct_quant_128'])
+    c.enable_timing(*args, False)
+    print('tensor' if mode else 'fp32', 'dct_quant_128 ms', np.mean(t))

@@ -371,6 +371,35 @@ def test_full_size_properties(codec):
     assert chk == [int(L2[i]["coef"].astype(np.int64).sum()) for i in range(3)]
 
 
+def test_tensor_core_dct_parity(codec):
+    """The opt-in tcgen05 (3xTF32, TMEM) 128x128 forward DCT against the oracle and against the default FP32 kernels on a
+    4K frame: the quantiser is exact in both, so the only differences are .5-tie flips of class T-DCT (|d| = 1)."""
+    import torch
+    H, W = 2160, 3840
+    rgb = torch.from_numpy(synth(H, W, seed=5)).cuda()
+    space, q, b = "YCbCr", (30, 95), (4, 128)
+    ref = O.encode_hot(rgb.cpu().numpy(), space, q, b)
+    flips = {}
+    try:
+        for mode in (False, True):
+            codec.tensor_dct = mode
+            L = codec.download(codec.encode(rgb, space, q, b))[0]
+            assert not codec.tensor_dct_timed_out()
+            n = 0
+            for i in range(3):
+                assert np.array_equal(L[i]["leaves"][:, :3], ref[i]["leaves"])
+                d = np.abs(L[i]["coef"].astype(np.int64) - ref[i]["coef"].astype(np.int64))
+                assert d.max() <= 1
+                n += int((d != 0).sum())
+            flips[mode] = n
+    finally:
+        codec.tensor_dct = False
+    n128 = sum(int((ref[i]["leaves"][:, 2] == 128).sum()) for i in range(3))
+    assert n128 > 100                                          # the tensor path actually had work
+    print("T-DCT flips vs oracle: fp32 kernels", flips[False], " tensor-core 128x128", flips[True], " leaves128", n128)
+    assert flips[False] <= 8 and flips[True] <= 8
+
+
 def test_host_pipelined_roundtrip_matches_device_path(codec):
     """the host-buffer API (bench.py's e2e leg) returns the same pixels as the device-resident path"""
     import torch
