@@ -64,7 +64,7 @@ class DeviceCodec:
         self.handle = native.handle(device)
         self._plans: Dict[tuple, _Plan] = {}
         self.last_launches = 0
-        self.tensor_dct = False        # opt-in tcgen05 path for the 128x128 forward DCT
+        self.tensor_dct = True         # tcgen05 / TMEM path for the 128x128 DCT and IDCT (False: FP32-FMA kernels)
 
     def tensor_dct_timed_out(self) -> bool:
         t = (C.c_int * 32)()
@@ -155,6 +155,7 @@ class DeviceCodec:
         zigzag=True: the coefficient blocks are in the .ajpg zigzag order."""
         p = self._plan(B, H, W, space, brange, qrange, instance)
         native.check(self.lib.aeaj_plan_set_stream_layout(p.ptr, int(zigzag)), "aeaj_plan_set_stream_layout")
+        native.check(self.lib.aeaj_plan_set_tensor_dct(p.ptr, int(self.tensor_dct)), "aeaj_plan_set_tensor_dct")
         io = native.DecodeIO()
         for l in range(3):
             if coef[l].shape[1] != p.info.cap_coef[l] or leaves[l].shape[1] != p.info.cap_leaves[l]:

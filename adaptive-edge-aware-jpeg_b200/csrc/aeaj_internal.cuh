@@ -141,6 +141,7 @@ struct aeaj_handle {
     float* dct_half_all_dev;
     int32_t* zz_dev[9];           // zigzag tables per log2(size), device
     int32_t* zz_all_dev;
+    int32_t* tc_izz_dev;          // inverse zigzag permutation for 128x128 (tensor-core IDCT loader)
     float* dct_tc_tiles_dev;      // [Ch | Cl] tiles of the 128x128 DCT matrix for the tcgen05 path
     int* tc_err_dev;              // set by the tcgen05 kernel if a barrier wait timed out
     // device scratch for single-plane stage calls
@@ -248,7 +249,7 @@ int launch_dct_quant(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEnt
                      const int64_t* class_offsets_host, const int64_t* class_caps_host, int lg_min, int lg_max,
                      cudaStream_t st, int* launches, void (*mark)(void*, const char*), void* mark_ctx, int tensor_dct = 0);
 int aeaj_dct_tc_init(aeaj_handle* h);
-int launch_dct_tc128(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* list, const int* count, int64_t cap, cudaStream_t st);
+int launch_dct_tc128(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* list, const int* count, int64_t cap, int inverse, cudaStream_t st);
 int launch_dequant_idct(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,
                         const int64_t* class_offsets_host, const int64_t* class_caps_host, int lg_min, int lg_max,
-                        cudaStream_t st, int* launches, void (*mark)(void*, const char*), void* mark_ctx);
+                        cudaStream_t st, int* launches, void (*mark)(void*, const char*), void* mark_ctx, int tensor_dct);

@@ -129,7 +129,7 @@ extern "C" int aeaj_create(int device, aeaj_handle** out) {
 extern "C" int aeaj_destroy(aeaj_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    cudaFree(h->srgb_lut_dev); cudaFree(h->dct_all_dev); cudaFree(h->dct_half_all_dev); cudaFree(h->zz_all_dev); cudaFree(h->dct_tc_tiles_dev); cudaFree(h->tc_err_dev); cudaFree(h->stage_plane_dev);
+    cudaFree(h->srgb_lut_dev); cudaFree(h->dct_all_dev); cudaFree(h->dct_half_all_dev); cudaFree(h->zz_all_dev); cudaFree(h->dct_tc_tiles_dev); cudaFree(h->tc_izz_dev); cudaFree(h->tc_err_dev); cudaFree(h->stage_plane_dev);
     cudaFree(h->stage_class_off_dev); cudaFree(h->stage_tile_base_dev); cudaFree(h->stage_outs_dev);
     free(h);
     return 0;
@@ -343,7 +343,7 @@ static int stage_blocks(aeaj_handle* hd, bool inverse, float* layer, int h, int 
     AEAJ_CUDA(cudaMemcpyAsync(hd->stage_class_off_dev, off, sizeof off, cudaMemcpyHostToDevice, st));
     AEAJ_CUDA(cudaMemsetAsync(S.class_counts, 0, 16 * sizeof(int), st));
     rc = launch_bucket_leaves(hd->stage_plane_dev, &S.P, 1, S.class_lists, S.class_counts, hd->stage_class_off_dev, st); if (rc) return rc;
-    if (inverse) return launch_dequant_idct(hd, hd->stage_plane_dev, S.class_lists, S.class_counts, S.cg.off, S.cg.cap, ilog2i(mn), ilog2i(mx), st, nullptr, nullptr, nullptr);
+    if (inverse) return launch_dequant_idct(hd, hd->stage_plane_dev, S.class_lists, S.class_counts, S.cg.off, S.cg.cap, ilog2i(mn), ilog2i(mx), st, nullptr, nullptr, nullptr, 0);
     return launch_dct_quant(hd, hd->stage_plane_dev, S.class_lists, S.class_counts, S.cg.off, S.cg.cap, ilog2i(mn), ilog2i(mx), st, nullptr, nullptr, nullptr);
 }
 extern "C" int aeaj_dct_quant(aeaj_handle* hd, const float* layer, int h, int w, float mid, float scale, const int32_t* leaves,
@@ -676,7 +676,7 @@ static int encode_impl(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, 
     }
     if (phases & (1u << AEAJ_PHASE_DCT)) {
         rc = launch_dct_quant(h, p->planes_dev, A.class_lists, A.class_counts, p->cg.off, p->cg.cap, p->lg_min, p->lg_max, st, &launches,
-                              plan_mark_cb, p, p->tensor_dct && !p->zigzag);
+                              plan_mark_cb, p, p->tensor_dct);
         if (rc) return rc;
     }
     p->last_launches = launches;
@@ -719,7 +719,7 @@ static int decode_impl(aeaj_plan* p, const aeaj_decode_io* io, void* workspace, 
         launches++;
         p->mark("bucket_leaves");
         rc = launch_dequant_idct(h, p->planes_dev, A.class_lists, A.class_counts, p->cg.off, p->cg.cap, p->lg_min, p->lg_max, st, &launches,
-                                 plan_mark_cb, p);
+                                 plan_mark_cb, p, p->tensor_dct);
         if (rc) return rc;
         for (int l = 0; l < 3; l++)
             if (io->tap_layers[l])

@@ -496,7 +496,7 @@ int launch_all(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* cl
             case 4: rc = launch_rows<16, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
             case 5: rc = launch_rows<32, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
             case 6: rc = launch_cta<64, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
-            case 7: rc = (!INV && tensor_dct) ? launch_dct_tc128(h, planes_dev, list, cnt, caps[lg], st)
+            case 7: rc = tensor_dct ? launch_dct_tc128(h, planes_dev, list, cnt, caps[lg], INV ? 1 : 0, st)
                                               : launch_cta<128, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
             default: aeaj_set_error("block size %d not supported (2..128)", 1 << lg); return AEAJ_EINVAL;
         }
@@ -594,6 +594,6 @@ int launch_dct_quant(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEnt
 }
 int launch_dequant_idct(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,
                         const int64_t* off, const int64_t* caps, int lg_min, int lg_max, cudaStream_t st, int* launches,
-                        void (*mark)(void*, const char*), void* mark_ctx) {
-    return launch_all<true>(h, planes_dev, class_lists, class_counts, off, caps, lg_min, lg_max, st, launches, mark, mark_ctx);
+                        void (*mark)(void*, const char*), void* mark_ctx, int tensor_dct) {
+    return launch_all<true>(h, planes_dev, class_lists, class_counts, off, caps, lg_min, lg_max, st, launches, mark, mark_ctx, tensor_dct);
 }

@@ -372,18 +372,22 @@ def test_full_size_properties(codec):
 
 
 def test_tensor_core_dct_parity(codec):
-    """The opt-in tcgen05 (3xTF32, TMEM) 128x128 forward DCT against the oracle and against the default FP32 kernels on a
-    4K frame: the quantiser is exact in both, so the only differences are .5-tie flips of class T-DCT (|d| = 1)."""
+    """The tcgen05 (3xTF32, TMEM) 128x128 DCT / IDCT kernels and the FP32-FMA kernels, both against the oracle on a 4K
+    frame: the quantiser is exact in both, so coefficient differences are .5-tie flips of class T-DCT (|d| = 1); decoded
+    samples stay within 1 LSB / 3e-6 of the oracle."""
     import torch
     H, W = 2160, 3840
     rgb = torch.from_numpy(synth(H, W, seed=5)).cuda()
     space, q, b = "YCbCr", (30, 95), (4, 128)
     ref = O.encode_hot(rgb.cpu().numpy(), space, q, b)
-    flips = {}
+    ref_dec = O.decode_hot(ref, H, W, space, q, b)
+    flips, err = {}, {}
+    saved = codec.tensor_dct
     try:
         for mode in (False, True):
             codec.tensor_dct = mode
-            L = codec.download(codec.encode(rgb, space, q, b))[0]
+            enc = codec.encode(rgb, space, q, b)
+            L = codec.download(enc)[0]
             assert not codec.tensor_dct_timed_out()
             n = 0
             for i in range(3):
@@ -392,12 +396,22 @@ def test_tensor_core_dct_parity(codec):
                 assert d.max() <= 1
                 n += int((d != 0).sum())
             flips[mode] = n
+            # decode the ORACLE's coefficients, so that the comparison isolates the inverse path
+            lv4 = [np.concatenate([ref[i]["leaves"], np.concatenate([[0], np.cumsum(ref[i]["leaves"][:, 2].astype(np.int64) ** 2)])[:-1, None]],
+                                  axis=1).astype(np.int32) for i in range(3)]
+            up = codec.upload_for_decode([[dict(leaves=lv4[i], coef=ref[i]["coef"]) for i in range(3)]], 1, H, W, space, q, b)
+            dec = codec.decode(*up, 1, H, W, space, q, b)[0].cpu().numpy()
+            assert not codec.tensor_dct_timed_out()
+            err[mode] = float(np.abs(dec - ref_dec).max())
+            assert np.abs((dec * 255).astype(np.uint8).astype(int) - (ref_dec * 255).astype(np.uint8).astype(int)).max() <= 1
     finally:
-        codec.tensor_dct = False
+        codec.tensor_dct = saved
     n128 = sum(int((ref[i]["leaves"][:, 2] == 128).sum()) for i in range(3))
     assert n128 > 100                                          # the tensor path actually had work
-    print("T-DCT flips vs oracle: fp32 kernels", flips[False], " tensor-core 128x128", flips[True], " leaves128", n128)
+    print("T-DCT flips vs oracle: fp32 kernels", flips[False], " tensor-core 128x128", flips[True], " leaves128", n128,
+          " decode max |err| vs oracle: fp32", err[False], " tensor", err[True])
     assert flips[False] <= 8 and flips[True] <= 8
+    assert err[False] <= 3e-6 and err[True] <= 3e-6
 
 
 def test_host_pipelined_roundtrip_matches_device_path(codec):
