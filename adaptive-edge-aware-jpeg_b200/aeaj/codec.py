@@ -52,6 +52,7 @@ class _Plan:
     workspace: torch.Tensor
     out: EncodedBatch
     rgb_out: torch.Tensor
+    rgb8_out: Optional[torch.Tensor] = None
     qkey: Optional[tuple] = None
     keep: list = field(default_factory=list)
 
@@ -111,19 +112,23 @@ class DeviceCodec:
     # ------------------------------------------------------------------------------------------
     def encode(self, rgb: torch.Tensor, space: str, qrange, brange, taps: bool = False, instance: int = 0,
                stream: bool = False) -> EncodedBatch:
-        """rgb: float32 CUDA tensor [B,H,W,3] (or [H,W,3]). Asynchronous on the current stream.
+        """rgb: float32 CUDA tensor [B,H,W,3] (or [H,W,3]) in [0,1] -- or uint8 pixels, converted on the device exactly
+        as Image.load does (astype(float32) / 255.0, image.py:84).  Asynchronous on the current stream.
         stream=True produces the .ajpg stream layout on the device: zigzag-ordered coefficient blocks and the
         2-bit packed state stream (what _entropy_encode feeds to zlib / writes, jpeg.py:563-590)."""
         if rgb.dim() == 3:
             rgb = rgb.unsqueeze(0)
-        if rgb.dtype != torch.float32 or not rgb.is_cuda or rgb.dim() != 4 or rgb.shape[-1] != 3:
-            raise TypeError("encode expects a float32 CUDA tensor of shape [B,H,W,3]")
+        if rgb.dtype not in (torch.float32, torch.uint8) or not rgb.is_cuda or rgb.dim() != 4 or rgb.shape[-1] != 3:
+            raise TypeError("encode expects a float32 (or uint8) CUDA tensor of shape [B,H,W,3]")
         rgb = rgb.contiguous()
         B, H, W, _ = rgb.shape
         p = self._plan(B, H, W, space, brange, qrange, instance)
         o = p.out
         io = native.EncodeIO()
-        io.rgb = rgb.data_ptr()
+        if rgb.dtype == torch.uint8:
+            io.rgb_u8 = rgb.data_ptr()
+        else:
+            io.rgb = rgb.data_ptr()
         for l in range(3):
             io.coef[l] = o.coef[l].data_ptr()
             io.leaves[l] = o.leaves[l].data_ptr()
@@ -150,9 +155,13 @@ class DeviceCodec:
         return o
 
     def decode(self, coef, leaves, counts, B, H, W, space: str, qrange, brange, taps: bool = False, instance: int = 0,
-               zigzag: bool = False):
+               zigzag: bool = False, out: str = "f32"):
         """coef/leaves: 3 device tensors laid out like EncodedBatch; counts int32 [B,3,4]. Returns rgb [B,H,W,3].
-        zigzag=True: the coefficient blocks are in the .ajpg zigzag order."""
+        zigzag=True: the coefficient blocks are in the .ajpg zigzag order.
+        out: "f32" (Image.data), "u8" (Image.get_uint8(), (data * 255).astype(uint8), written by the same kernel) or "both"
+        (returns the pair)."""
+        if out not in ("f32", "u8", "both"):
+            raise ValueError("out must be 'f32', 'u8' or 'both'")
         p = self._plan(B, H, W, space, brange, qrange, instance)
         native.check(self.lib.aeaj_plan_set_stream_layout(p.ptr, int(zigzag)), "aeaj_plan_set_stream_layout")
         native.check(self.lib.aeaj_plan_set_tensor_dct(p.ptr, int(self.tensor_dct)), "aeaj_plan_set_tensor_dct")
@@ -163,7 +172,12 @@ class DeviceCodec:
             io.coef[l] = coef[l].data_ptr()
             io.leaves[l] = leaves[l].data_ptr()
         io.counts = counts.data_ptr()
-        io.rgb = p.rgb_out.data_ptr()
+        if out != "u8":
+            io.rgb = p.rgb_out.data_ptr()
+        if out != "f32":
+            if p.rgb8_out is None:
+                p.rgb8_out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=p.rgb_out.device)
+            io.rgb_u8 = p.rgb8_out.data_ptr()
         tl = None
         if taps:
             tl = [torch.empty((B, p.info.layer_h[l], p.info.layer_w[l]), dtype=torch.float32, device=p.rgb_out.device) for l in range(3)]
@@ -171,7 +185,8 @@ class DeviceCodec:
                 io.tap_layers[l] = tl[l].data_ptr()
         native.check(self.lib.aeaj_decode(p.ptr, C.byref(io), p.workspace.data_ptr(), _stream()), "aeaj_decode")
         self.last_launches = self.lib.aeaj_plan_last_launches(p.ptr)
-        return (p.rgb_out, tl) if taps else p.rgb_out
+        res = p.rgb_out if out == "f32" else (p.rgb8_out if out == "u8" else (p.rgb_out, p.rgb8_out))
+        return (res, tl) if taps else res
 
     # ------------------------------------------------------------------------------------------
     # measurement support
@@ -200,7 +215,8 @@ class DeviceCodec:
                 leaves=[torch.empty((B, int(p.info.cap_leaves[l]), 4), dtype=torch.int32).pin_memory() for l in range(3)],
                 states=[torch.empty((B, int(p.info.cap_states[l])), dtype=torch.uint8).pin_memory() for l in range(3)],
                 counts=torch.empty((B, 3, 4), dtype=torch.int32).pin_memory(),
-                rgb_dev=torch.empty((B, p.info.height, p.info.width, 3), dtype=torch.float32, device=p.rgb_out.device))
+                rgb_dev=torch.empty((B, p.info.height, p.info.width, 3), dtype=torch.float32, device=p.rgb_out.device),
+                rgb8_dev=torch.empty((B, p.info.height, p.info.width, 3), dtype=torch.uint8, device=p.rgb_out.device))
             p.keep.append(st)
         st = p.keep[0]
         if with_rgb and "rgb_out" not in st:
@@ -250,7 +266,8 @@ class DeviceCodec:
         return st["rgb_out"], h2d, st["rgb_out"].numel() * 4
 
     def roundtrip_host_pipelined(self, host_in: torch.Tensor, host_out: torch.Tensor, space, qrange, brange, slots: int = 8, repeat: int = 1, lag: int = 3):
-        """Host-buffer encode+decode of every frame of `host_in` (pinned float32 [F,H,W,3]) into `host_out`, one frame
+        """Host-buffer encode+decode of every frame of `host_in` (pinned float32 -- or uint8, the 8-bit image flow
+        Image.load -> compress ... decompress -> Image.save -- [F,H,W,3]) into `host_out` (float32 or uint8), one frame
         per job, jobs round-robin over `slots` CUDA streams so that the H2D and D2H copies of different frames overlap
         each other and the kernels (PCIe is full duplex; the step is copy-bound).  Per frame, in stream order:
         H2D RGB -> aeaj_encode -> D2H counts -> [host waits for the counts] -> D2H used coefficient / leaf / state ranges ->
@@ -273,13 +290,14 @@ class DeviceCodec:
             with torch.cuda.stream(stream):
                 if f >= slots:
                     self._finish_job(jobs[f - slots])              # the slot's previous frame must be done with its buffers
-                st["rgb_dev"].copy_(host_in[f % F0:f % F0 + 1], non_blocking=True)
-                enc = self.encode(st["rgb_dev"], space, qrange, brange, instance=slot)
+                src = st["rgb8_dev"] if host_in.dtype == torch.uint8 else st["rgb_dev"]
+                src.copy_(host_in[f % F0:f % F0 + 1], non_blocking=True)
+                enc = self.encode(src, space, qrange, brange, instance=slot)
                 st["counts"].copy_(enc.counts, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(stream)
             jobs.append(dict(f=f % F0, slot=slot, p=p, st=st, enc=enc, ev=ev, done=False, phase_b=False))
-            h2d += host_in[0].numel() * 4
+            h2d += host_in[0].numel() * host_in.element_size()
             # phase B of a frame is issued `lag` frames after its phase A (its counts have landed by then), and a slot is
             # reused only `slots` frames later, so neither host wait normally blocks
             if f >= lag:
@@ -313,9 +331,10 @@ class DeviceCodec:
                 enc.leaves[l][0, :nl].copy_(st["leaves"][l][0, :nl], non_blocking=True)
                 h2d += nc * 4 + nl * 16
             enc.counts.copy_(st["counts"], non_blocking=True)
-            rgb = self.decode(enc.coef, enc.leaves, enc.counts, 1, H, W, space, qrange, brange, instance=slot)
+            rgb = self.decode(enc.coef, enc.leaves, enc.counts, 1, H, W, space, qrange, brange, instance=slot,
+                              out="u8" if host_out.dtype == torch.uint8 else "f32")
             host_out[job["f"]:job["f"] + 1].copy_(rgb, non_blocking=True)
-            d2h += rgb.numel() * 4
+            d2h += rgb.numel() * rgb.element_size()
             job["ev2"] = torch.cuda.Event()
             job["ev2"].record(stream)
         job["phase_b"] = True
@@ -328,9 +347,9 @@ class DeviceCodec:
             job["ev2"].synchronize()
             job["done"] = True
 
-    def decode_encoded(self, enc: EncodedBatch, space, qrange, brange):
+    def decode_encoded(self, enc: EncodedBatch, space, qrange, brange, out: str = "f32"):
         B, H, W = enc.shape
-        return self.decode(enc.coef, enc.leaves, enc.counts, B, H, W, space, qrange, brange, zigzag=enc.zigzag)
+        return self.decode(enc.coef, enc.leaves, enc.counts, B, H, W, space, qrange, brange, zigzag=enc.zigzag, out=out)
 
     # ------------------------------------------------------------------------------------------
     # host <-> device helpers for the reference-facing shim

@@ -41,12 +41,12 @@ class PlanInfo(C.Structure):
 class EncodeIO(C.Structure):
     _fields_ = [("rgb", C.c_void_p), ("coef", C.c_void_p * 3), ("leaves", C.c_void_p * 3), ("states", C.c_void_p * 3),
                 ("counts", C.c_void_p), ("tap_layers", C.c_void_p * 3), ("tap_edges", C.c_void_p * 3), ("status", C.c_void_p),
-                ("packed_states", C.c_void_p * 3)]
+                ("packed_states", C.c_void_p * 3), ("rgb_u8", C.c_void_p)]
 
 
 class DecodeIO(C.Structure):
     _fields_ = [("coef", C.c_void_p * 3), ("leaves", C.c_void_p * 3), ("counts", C.c_void_p), ("rgb", C.c_void_p),
-                ("tap_layers", C.c_void_p * 3)]
+                ("tap_layers", C.c_void_p * 3), ("rgb_u8", C.c_void_p)]
 
 
 class PlanBuffers(C.Structure):

@@ -213,7 +213,7 @@ static inline __device__ void tile_decode(const TileMap& m, int bid, int& plane,
 int aeaj_canny_init_constants();
 int aeaj_dct_init(aeaj_handle* h);
 
-int launch_color_forward_planar(aeaj_handle* h, int space, const float* rgb, int B, int H, int W,
+int launch_color_forward_planar(aeaj_handle* h, int space, const float* rgb, const uint8_t* rgb_u8, int B, int H, int W,
                                 const PlaneDesc* planes_dev, const PlaneDesc* planes_host,
                                 float* full_c1, float* full_c2, cudaStream_t st, int* launches, int band0 = 0, int band1 = -1);
 int launch_color_pixels(aeaj_handle* h, int space, int inverse, const float* in, float* out, size_t n, cudaStream_t st);
@@ -222,7 +222,7 @@ int launch_area(const float* src, int H, int W, float* dst, int dh, int dw, uint
                 size_t src_stride, size_t dst_stride, cudaStream_t st);
 int launch_resize_linear(const float* src, int sh, int sw, float* dst, int H, int W, cudaStream_t st);
 int launch_upsample_color_inverse(aeaj_handle* h, int space, const PlaneDesc* planes_host, int B, int H, int W,
-                                  float* rgb, cudaStream_t st, int band0 = 0, int band1 = -1);
+                                  float* rgb, uint8_t* rgb_u8, cudaStream_t st, int band0 = 0, int band1 = -1);
 int launch_cast_u8(const float* in, uint8_t* out, size_t n, cudaStream_t st);
 
 int launch_clahe_hist(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, cudaStream_t st);

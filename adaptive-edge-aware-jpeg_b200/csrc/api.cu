@@ -597,7 +597,7 @@ static int set_band(aeaj_plan* p, int band0, int band1) {
 }
 
 static int encode_impl(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, cudaStream_t st, unsigned phases, int band0, int band1) {
-    AEAJ_REQUIRE(p && io && workspace && io->rgb && io->counts, "aeaj_encode: bad arguments");
+    AEAJ_REQUIRE(p && io && workspace && (io->rgb || io->rgb_u8) && io->counts, "aeaj_encode: bad arguments (rgb or rgb_u8 required)");
     AEAJ_REQUIRE(p->qtab_dev, "aeaj_encode: quantisation tables not set (aeaj_plan_set_qtables)");
     aeaj_handle* h = p->h;
     const int B = p->info.batch, NP = p->nplanes;
@@ -627,7 +627,7 @@ static int encode_impl(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, 
         AEAJ_CUDA(cudaMemsetAsync(p->planes[0].hist, 0, (size_t)NP * 256 * sizeof(uint32_t), st));
         AEAJ_CUDA(cudaMemsetAsync(A.class_counts, 0, 16 * sizeof(int), st));
         // colour + chroma subsampling + u8 cast
-        rc = launch_color_forward_planar(h, p->info.space, io->rgb, B, p->info.height, p->info.width, p->planes_dev, p->planes.data(),
+        rc = launch_color_forward_planar(h, p->info.space, io->rgb, io->rgb ? nullptr : io->rgb_u8, B, p->info.height, p->info.width, p->planes_dev, p->planes.data(),
                                          A.full_c1, A.full_c2, st, &launches, band0, band1);
         if (rc) return rc;
         p->mark("color_forward_planar");
@@ -692,7 +692,7 @@ extern "C" int aeaj_encode_phase(aeaj_plan* p, const aeaj_encode_io* io, void* w
 }
 
 static int decode_impl(aeaj_plan* p, const aeaj_decode_io* io, void* workspace, cudaStream_t st, unsigned phases, int band0, int band1) {
-    AEAJ_REQUIRE(p && io && workspace && io->rgb && io->counts, "aeaj_decode: bad arguments");
+    AEAJ_REQUIRE(p && io && workspace && (io->rgb || io->rgb_u8) && io->counts, "aeaj_decode: bad arguments (rgb or rgb_u8 required)");
     AEAJ_REQUIRE(p->qtab_dev, "aeaj_decode: quantisation tables not set (aeaj_plan_set_qtables)");
     aeaj_handle* h = p->h;
     const int B = p->info.batch, NP = p->nplanes;
@@ -727,7 +727,7 @@ static int decode_impl(aeaj_plan* p, const aeaj_decode_io* io, void* workspace, 
                                           cudaMemcpyDeviceToDevice, st));
     }
     if (phases & (1u << AEAJ_DPHASE_COLOR)) {
-        rc = launch_upsample_color_inverse(h, p->info.space, p->planes.data(), B, p->info.height, p->info.width, io->rgb, st, band0, band1);
+        rc = launch_upsample_color_inverse(h, p->info.space, p->planes.data(), B, p->info.height, p->info.width, io->rgb, io->rgb_u8, st, band0, band1);
         if (rc) return rc;
         launches++;
         p->mark("upsample_color_inverse");

@@ -218,19 +218,26 @@ struct FwdOut {
     size_t sy, sc;                           // elements per image for luma / chroma outputs
 };
 
-template <int SPACE, int MODE>
+// 8-bit source pixels: Image.load's imread(path).astype(np.float32) / 255.0 (image.py:84), one correctly rounded division
+__device__ __forceinline__ float u8_to_unit(unsigned v) { return __fdiv_rn((float)v, 255.0f); }
+// Image.get_uint8 / Image.save: (data * 255).astype(np.uint8) (image.py:112,127); data is clipped to [0,1] by the inverse colour
+__device__ __forceinline__ unsigned unit_to_u8(float v) { return (unsigned)(int)__fmul_rn(v, 255.0f) & 0xffu; }
+
+template <int SPACE, int MODE, bool U8>
 __global__ void __launch_bounds__(256) k_color_forward_planar(const __grid_constant__ ColorConsts C, const float* __restrict__ lut_g,
-                                                              const float* __restrict__ rgb, int H, int W, FwdOut o) {
+                                                              const void* __restrict__ rgb_any, int H, int W, FwdOut o) {
     __shared__ float lut_s[256];
     const float* lut = (SPACE > AEAJ_YCOCG_R) ? load_lut(lut_g, lut_s) : nullptr;
     const int b = blockIdx.z;
-    const float* img = rgb + (size_t)b * H * W * 3;
+    const float* img = reinterpret_cast<const float*>(rgb_any) + (U8 ? 0 : (size_t)b * H * W * 3);
+    const uint8_t* img8 = reinterpret_cast<const uint8_t*>(rgb_any) + (U8 ? (size_t)b * H * W * 3 : 0);
     if (MODE == 2) {
         int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
         if (x >= W || y >= H) return;
         size_t i = (size_t)y * W + x;
         float v0, v1, v2;
-        color_fwd<SPACE>(C, lut, img[3 * i], img[3 * i + 1], img[3 * i + 2], v0, v1, v2);
+        if (U8) color_fwd<SPACE>(C, lut, u8_to_unit(img8[3 * i]), u8_to_unit(img8[3 * i + 1]), u8_to_unit(img8[3 * i + 2]), v0, v1, v2);
+        else color_fwd<SPACE>(C, lut, img[3 * i], img[3 * i + 1], img[3 * i + 2], v0, v1, v2);
         o.y[b * o.sy + i] = v0; o.y8[b * o.sy + i] = cast_u8(v0);
         o.c1[b * o.sc + i] = v1; o.c2[b * o.sc + i] = v2;     // full-res scratch (sc == H*W here)
         return;
@@ -242,9 +249,21 @@ __global__ void __launch_bounds__(256) k_color_forward_planar(const __grid_const
     float c1v[2][4], c2v[2][4];
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
-        const float4* p = reinterpret_cast<const float4*>(img + ((size_t)(y0 + r) * W + x0) * 3);
-        float4 a = __ldg(p), bq = __ldg(p + 1), c = __ldg(p + 2);
-        float x[12] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w, c.x, c.y, c.z, c.w};
+        float x[12];
+        if (U8) {
+            // 4 px = 12 bytes = three aligned words (W % 4 == 0 in the fused modes)
+            const uint32_t* p8 = reinterpret_cast<const uint32_t*>(img8 + ((size_t)(y0 + r) * W + x0) * 3);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const uint32_t wv = __ldg(p8 + k);
+#pragma unroll
+                for (int j = 0; j < 4; j++) x[4 * k + j] = u8_to_unit((wv >> (8 * j)) & 0xffu);
+            }
+        } else {
+            const float4* p = reinterpret_cast<const float4*>(img + ((size_t)(y0 + r) * W + x0) * 3);
+            float4 a = __ldg(p), bq = __ldg(p + 1), c = __ldg(p + 2);
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = bq.x; x[5] = bq.y; x[6] = bq.z; x[7] = bq.w; x[8] = c.x; x[9] = c.y; x[10] = c.z; x[11] = c.w;
+        }
         float yv[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) color_fwd<SPACE>(C, lut, x[3 * k], x[3 * k + 1], x[3 * k + 2], yv[k], c1v[r][k], c2v[r][k]);
@@ -350,7 +369,8 @@ __global__ void __launch_bounds__(256) k_resize_linear(const float* __restrict__
 // (jpeg.py:290-297) -> RGB HWC
 struct UpIn { const float* p[3]; int h[3], w[3]; size_t stride[3]; };
 template <int SPACE>
-__global__ void __launch_bounds__(256) k_upsample_color_inverse(const __grid_constant__ ColorConsts C, UpIn in, int H, int W, float* __restrict__ rgb, int y_lo, int y_hi) {
+__global__ void __launch_bounds__(256) k_upsample_color_inverse(const __grid_constant__ ColorConsts C, UpIn in, int H, int W, float* __restrict__ rgb,
+                                                                uint8_t* __restrict__ rgb8, int y_lo, int y_hi) {
     int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = y_lo + blockIdx.y * blockDim.y + threadIdx.y;
     if (dx >= W || dy >= y_hi) return;
     int b = blockIdx.z;
@@ -368,8 +388,9 @@ __global__ void __launch_bounds__(256) k_upsample_color_inverse(const __grid_con
     }
     float r, g, bl;
     color_inv<SPACE>(C, v[0], v[1], v[2], r, g, bl);
-    float* o = rgb + ((size_t)b * H * W + (size_t)dy * W + dx) * 3;
-    o[0] = r; o[1] = g; o[2] = bl;
+    const size_t oi = ((size_t)b * H * W + (size_t)dy * W + dx) * 3;
+    if (rgb) { rgb[oi] = r; rgb[oi + 1] = g; rgb[oi + 2] = bl; }
+    if (rgb8) { rgb8[oi] = (uint8_t)unit_to_u8(r); rgb8[oi + 1] = (uint8_t)unit_to_u8(g); rgb8[oi + 2] = (uint8_t)unit_to_u8(bl); }
 }
 
 // 2x2 chroma specialisation (H == 2h, W == 2w, W % 4 == 0): 4 output px per thread, float4 stores.
@@ -384,7 +405,8 @@ __device__ __forceinline__ void up2_coord(int d, int ssize, int& s0, int& s1, fl
     s0 = s; s1 = min(s + 1, ssize - 1); f = fx;
 }
 template <int SPACE>
-__global__ void __launch_bounds__(256) k_upsample2x_color_inverse(const __grid_constant__ ColorConsts C, UpIn in, int H, int W, float* __restrict__ rgb, int y_lo, int y_hi) {
+__global__ void __launch_bounds__(256) k_upsample2x_color_inverse(const __grid_constant__ ColorConsts C, UpIn in, int H, int W, float* __restrict__ rgb,
+                                                                  uint8_t* __restrict__ rgb8, int y_lo, int y_hi) {
     const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, dy = y_lo + blockIdx.y * blockDim.y + threadIdx.y;
     if (dx0 >= W || dy >= y_hi) return;
     const int b = blockIdx.z;
@@ -413,8 +435,17 @@ __global__ void __launch_bounds__(256) k_upsample2x_color_inverse(const __grid_c
     float o[12];
 #pragma unroll
     for (int k = 0; k < 4; k++) color_inv<SPACE>(C, lum[k], cv[0][k], cv[1][k], o[3 * k], o[3 * k + 1], o[3 * k + 2]);
-    float4* out = reinterpret_cast<float4*>(rgb + ((size_t)b * H * W + (size_t)dy * W + dx0) * 3);
-    out[0] = make_float4(o[0], o[1], o[2], o[3]); out[1] = make_float4(o[4], o[5], o[6], o[7]); out[2] = make_float4(o[8], o[9], o[10], o[11]);
+    const size_t oi = ((size_t)b * H * W + (size_t)dy * W + dx0) * 3;
+    if (rgb) {
+        float4* out = reinterpret_cast<float4*>(rgb + oi);
+        out[0] = make_float4(o[0], o[1], o[2], o[3]); out[1] = make_float4(o[4], o[5], o[6], o[7]); out[2] = make_float4(o[8], o[9], o[10], o[11]);
+    }
+    if (rgb8) {
+        uint32_t* out8 = reinterpret_cast<uint32_t*>(rgb8 + oi);          // 12 bytes, word aligned (W % 4 == 0)
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            out8[k] = unit_to_u8(o[4 * k]) | (unit_to_u8(o[4 * k + 1]) << 8) | (unit_to_u8(o[4 * k + 2]) << 16) | (unit_to_u8(o[4 * k + 3]) << 24);
+    }
 }
 
 __global__ void __launch_bounds__(256) k_normalize(const float* __restrict__ in, float* __restrict__ out, size_t n, float mid, float scale, int inverse) {
@@ -494,7 +525,7 @@ int launch_cast_u8(const float* in, uint8_t* out, size_t n, cudaStream_t st) {
 
 // planes_host: [B*3] plane descriptors, plane index = b*3 + layer; layers of one kind are contiguous
 // across the batch (stride = h*w), which is what FwdOut's per-image strides assume.
-int launch_color_forward_planar(aeaj_handle* h, int space, const float* rgb, int B, int H, int W,
+int launch_color_forward_planar(aeaj_handle* h, int space, const float* rgb, const uint8_t* rgb8, int B, int H, int W,
                                 const PlaneDesc* planes_dev, const PlaneDesc* P, float* full_c1, float* full_c2,
                                 cudaStream_t st, int* launches, int band0, int band1) {
     (void)planes_dev;
@@ -519,7 +550,7 @@ int launch_color_forward_planar(aeaj_handle* h, int space, const float* rgb, int
     int Hk = H;                                         // rows the kernel sees
     if (banded) {
         const size_t yo = (size_t)band0 * W, co = (mode == 0) ? (size_t)(band0 / 2) * cw : (size_t)band0 * cw;
-        rgb += yo * 3;
+        if (rgb) rgb += yo * 3; else rgb8 += yo * 3;
         o.y += yo; o.y8 += yo; o.c1 += co; o.c2 += co; o.c18 += co; o.c28 += co;
         Hk = band1 - band0;
     }
@@ -527,13 +558,16 @@ int launch_color_forward_planar(aeaj_handle* h, int space, const float* rgb, int
         constexpr int SP = decltype(S)::value;
         if (mode == 0) {
             dim3 blk(32, 8), grd(aeaj_cdiv(W / 4, 32), aeaj_cdiv(Hk / 2, 8), B);
-            k_color_forward_planar<SP, 0><<<grd, blk, 0, st>>>(C, lut, rgb, Hk, W, o);
+            if (rgb) k_color_forward_planar<SP, 0, false><<<grd, blk, 0, st>>>(C, lut, rgb, Hk, W, o);
+            else k_color_forward_planar<SP, 0, true><<<grd, blk, 0, st>>>(C, lut, rgb8, Hk, W, o);
         } else if (mode == 1) {
             dim3 blk(32, 8), grd(aeaj_cdiv(W / 4, 32), aeaj_cdiv(Hk, 8), B);
-            k_color_forward_planar<SP, 1><<<grd, blk, 0, st>>>(C, lut, rgb, Hk, W, o);
+            if (rgb) k_color_forward_planar<SP, 1, false><<<grd, blk, 0, st>>>(C, lut, rgb, Hk, W, o);
+            else k_color_forward_planar<SP, 1, true><<<grd, blk, 0, st>>>(C, lut, rgb8, Hk, W, o);
         } else {
             dim3 blk(32, 8), grd(aeaj_cdiv(W, 32), aeaj_cdiv(H, 8), B);
-            k_color_forward_planar<SP, 2><<<grd, blk, 0, st>>>(C, lut, rgb, H, W, o);
+            if (rgb) k_color_forward_planar<SP, 2, false><<<grd, blk, 0, st>>>(C, lut, rgb, H, W, o);
+            else k_color_forward_planar<SP, 2, true><<<grd, blk, 0, st>>>(C, lut, rgb8, H, W, o);
         }
         AEAJ_LAUNCH_CHECK();
         return 0;
@@ -550,7 +584,7 @@ int launch_color_forward_planar(aeaj_handle* h, int space, const float* rgb, int
     return 0;
 }
 
-int launch_upsample_color_inverse(aeaj_handle* h, int space, const PlaneDesc* P, int B, int H, int W, float* rgb, cudaStream_t st, int band0, int band1) {
+int launch_upsample_color_inverse(aeaj_handle* h, int space, const PlaneDesc* P, int B, int H, int W, float* rgb, uint8_t* rgb8, cudaStream_t st, int band0, int band1) {
     const ColorConsts& C = h->colors_host[space];
     if (band1 < 0) band1 = H;
     const int Hb = band1 - band0;
@@ -562,10 +596,10 @@ int launch_upsample_color_inverse(aeaj_handle* h, int space, const PlaneDesc* P,
         constexpr int SP = decltype(S)::value;
         if (fast2x) {
             dim3 blk(32, 8), grd(aeaj_cdiv(W / 4, 32), aeaj_cdiv(Hb, 8), B);
-            k_upsample2x_color_inverse<SP><<<grd, blk, 0, st>>>(C, in, H, W, rgb, band0, band1);
+            k_upsample2x_color_inverse<SP><<<grd, blk, 0, st>>>(C, in, H, W, rgb, rgb8, band0, band1);
         } else {
             dim3 blk(32, 8), grd(aeaj_cdiv(W, 32), aeaj_cdiv(Hb, 8), B);
-            k_upsample_color_inverse<SP><<<grd, blk, 0, st>>>(C, in, H, W, rgb, band0, band1);
+            k_upsample_color_inverse<SP><<<grd, blk, 0, st>>>(C, in, H, W, rgb, rgb8, band0, band1);
         }
         AEAJ_LAUNCH_CHECK();
         return 0;

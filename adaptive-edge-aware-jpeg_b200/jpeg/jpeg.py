@@ -111,7 +111,7 @@ class Jpeg:
         """Compress one image to the .ajpg byte stream (jpeg.py:240-272)."""
         if not isinstance(img, Image):
             raise TypeError("Input must be an Image object.")
-        if img.data.ndim != 3:
+        if img.ndim != 3:
             raise ValueError("Input array must be a 3D.")
         return self.compress_batch([img])[0]
 
@@ -124,7 +124,7 @@ class Jpeg:
         for im in imgs:
             if not isinstance(im, Image):
                 raise TypeError("Input must be an Image object.")
-            if im.data.ndim != 3:
+            if im.ndim != 3:
                 raise ValueError("Input array must be a 3D.")
         out: List[Optional[bytes]] = [None] * len(imgs)
         groups = {}
@@ -135,14 +135,23 @@ class Jpeg:
         for (H, W), idxs in groups.items():
             self.update_layer_shapes((H, W))
             self.extension = imgs[idxs[-1]].extension
-            host = np.stack([np.ascontiguousarray(imgs[i].data.reshape(H, W, 3), dtype=np.float32) for i in idxs])
+            if all(imgs[i].uint8_source() is not None for i in idxs):
+                # 8-bit sources: upload the bytes, the device does astype(float32) / 255.0 (image.py:84)
+                host = np.stack([imgs[i].uint8_source().reshape(H, W, 3) for i in idxs])
+            else:
+                host = np.stack([np.ascontiguousarray(imgs[i].data.reshape(H, W, 3), dtype=np.float32) for i in idxs])
             rgb = torch.from_numpy(host).pin_memory().to(f"cuda:{codec.device}", non_blocking=True)
             enc = codec.encode(rgb, s.color_space, s.quality_range, s.block_size_range, stream=True)
             for i, layers in zip(idxs, codec.download(enc)):
                 out[i] = self._entropy_encode(layers, (H, W), imgs[i].extension)
         return out
 
-    def decompress_batch(self, streams: Sequence[bytes]) -> List[Image]:
+    def decompress_uint8(self, img_encoded: bytes) -> np.ndarray:
+        """decompress(...).get_uint8() with the (data * 255).astype(uint8) step (image.py:127) done by the decoding
+        kernel: a quarter of the device-to-host bytes when only 8-bit pixels are wanted (Image.save, previews)."""
+        return self.decompress_batch([img_encoded], as_uint8=True)[0]
+
+    def decompress_batch(self, streams: Sequence[bytes], as_uint8: bool = False) -> List[Image]:
         parsed = [self._entropy_decode(b) for b in streams]
         out: List[Optional[Image]] = [None] * len(streams)
         groups = {}
@@ -151,9 +160,9 @@ class Jpeg:
         codec = get_codec()
         for (H, W, space, q, b), idxs in groups.items():
             coef, leaves, counts = codec.upload_for_decode([parsed[i]["layers"] for i in idxs], len(idxs), H, W, space, q, b)
-            rgb = codec.decode(coef, leaves, counts, len(idxs), H, W, space, q, b, zigzag=True).cpu().numpy()
+            rgb = codec.decode(coef, leaves, counts, len(idxs), H, W, space, q, b, zigzag=True, out="u8" if as_uint8 else "f32").cpu().numpy()
             for k, i in enumerate(idxs):
-                out[i] = Image.from_array(rgb[k].reshape(-1, 3), (H, W, 3), parsed[i]["extension"])
+                out[i] = rgb[k] if as_uint8 else Image.from_array(rgb[k].reshape(-1, 3), (H, W, 3), parsed[i]["extension"])
         last = parsed[-1]
         self.extension = last["extension"]
         self.update_settings(JpegCompressionSettings(last["space"], last["quality"], last["blocks"]), (last["H"], last["W"]))

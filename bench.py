@@ -10,8 +10,10 @@ distinct frames; B*99.5 MB of input per step is larger than the 126 MB L2 (no fl
 Entropy coding / .ajpg framing are host-side and outside the timed region (north_star).
 
   value   : whole-job MP/s with inputs resident in HBM, CUDA events, max over ranks
-  e2e     : the same through the host-buffer API (pinned host RGB in, pinned host RGB out; every
-            host<->device copy inside the timed region)
+  e2e     : the same through the host-buffer API, every host<->device copy inside the timed region, in the reference's
+            own end-to-end flow: 8-bit pixels in (Image.load), coefficient / leaf / state streams to the host and back
+            (where the host-side entropy coder sits), 8-bit pixels out (Image.save / get_uint8).  `e2e.f32` is the same
+            with float32 host buffers on both ends (Image.data in, Image.data out: 4x the pixel bytes over PCIe)
   roofline: the dominant kernel, per-launch algorithmic bytes / its CUDA-event duration
   cpu_baseline: the CPU oracle port on the same frames, on this box's host cores
 
@@ -37,7 +39,7 @@ import numpy as np
 
 H, W = 2160, 3840
 SPACE, QRANGE, BRANGE = "YCbCr", (30, 95), (4, 128)
-WORKLOAD = "C2: synthetic 3840x2160 RGB f32, YCbCr, quality 30-95, blocks 4-128"
+WORKLOAD = "C2: synthetic 3840x2160 RGB (8-bit pixels / 255 as float32, what Image.load yields), YCbCr, quality 30-95, blocks 4-128"
 ALG_BYTES_PER_PX = 36.0          # 12 B RGB in + 6 B coefficients out, both directions
 
 
@@ -65,9 +67,15 @@ def whole_job_mps(world: int, frames_per_rank: int, steps: int, ms: float) -> fl
     return world * frames_per_rank * (H * W / 1e6) * steps / (ms / 1e3)
 
 
-def _frames(seeds):
+def _frames_u8(seeds):
+    """8-bit pixels of the synthetic frames (what an image file holds)"""
     from synth import synth
-    return np.stack([synth(H, W, seed=s) for s in seeds])
+    return np.stack([(synth(H, W, seed=s) * 255).astype(np.uint8) for s in seeds])
+
+
+def _frames(seeds):
+    """the float32 frames the reference works on: Image.load's imread(path).astype(float32) / 255.0 (image.py:84)"""
+    return _frames_u8(seeds).astype(np.float32) / 255.0
 
 
 def cpu_baseline(frames: np.ndarray, threads: int):
@@ -184,8 +192,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
     codec = get_codec(local)
-    frames_np = _frames(shard_seeds(rank, B))
+    frames_u8 = _frames_u8(shard_seeds(rank, B))
+    frames_np = frames_u8.astype(np.float32) / 255.0
     host_in = torch.from_numpy(frames_np).pin_memory()
+    host_in8 = torch.from_numpy(frames_u8).pin_memory()
     rgb = host_in.to(f"cuda:{local}")
     mp_per_step = B * H * W / 1e6
 
@@ -218,16 +228,28 @@ def main():
     # ---- e2e: host buffers in, host buffers out ------------------------------------------------
     # pinned host RGB -> H2D -> encode -> D2H (coefficients, leaves, states) -> H2D -> decode -> D2H pinned host RGB,
     # one frame per job, jobs pipelined over 8 streams so that copies in both directions overlap (PCIe-bound)
-    host_out = torch.empty_like(host_in).pin_memory()
+    out_ref = out.cpu()
+    host_out8 = torch.empty_like(host_in8).pin_memory()
     for _ in range(2):
-        codec.roundtrip_host_pipelined(host_in, host_out, SPACE, QRANGE, BRANGE, repeat=3)   # touches every slot's plan + staging
+        codec.roundtrip_host_pipelined(host_in8, host_out8, SPACE, QRANGE, BRANGE, repeat=3)   # touches every slot's plan + staging
     barrier()
-    e2e_check = float((host_out - out.cpu()).abs().max())            # same pixels as the device-resident path
+    # same pixels as the device-resident float path: (data * 255).astype(uint8) of its output
+    e2e_check = int((host_out8.to(torch.int16) - (out_ref * 255).to(torch.uint8).to(torch.int16)).abs().max())
     t0 = time.perf_counter()
-    h2d, d2h = codec.roundtrip_host_pipelined(host_in, host_out, SPACE, QRANGE, BRANGE, repeat=args.steps)
+    h2d, d2h = codec.roundtrip_host_pipelined(host_in8, host_out8, SPACE, QRANGE, BRANGE, repeat=args.steps)
     h2d, d2h = h2d // args.steps, d2h // args.steps
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
+    # the float32-buffer variant (Image.data in / out)
+    host_out = torch.empty_like(host_in).pin_memory()
+    codec.roundtrip_host_pipelined(host_in, host_out, SPACE, QRANGE, BRANGE, repeat=2)
+    barrier()
+    f32_check = float((host_out - out_ref).abs().max())
+    f32_steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    h2d_f, d2h_f = codec.roundtrip_host_pipelined(host_in, host_out, SPACE, QRANGE, BRANGE, repeat=f32_steps)
+    barrier()
+    e2e_f32_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if sampler else None
 
     # ---- per-stage timing (separate instrumented passes; CUDA events on the launching stream) --
@@ -245,8 +267,8 @@ def main():
     counts_np = codec._plan(B, H, W, SPACE, BRANGE, QRANGE).out.counts.cpu().numpy()
 
     if world > 1:
-        t = reduce_max(torch.tensor([ms, e2e_ms], device=f"cuda:{local}", dtype=torch.float64), dist)
-        ms, e2e_ms = float(t[0]), float(t[1])
+        t = reduce_max(torch.tensor([ms, e2e_ms, e2e_f32_ms], device=f"cuda:{local}", dtype=torch.float64), dist)
+        ms, e2e_ms, e2e_f32_ms = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -315,7 +337,11 @@ def main():
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "l2": "inputs larger than L2 (no flush)",
                        "parallelism": f"batch-sharded x{world}", "hysteresis_rounds": int(status[0]), "hysteresis_converged": int(status[1])},
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps,
-                    "api": "DeviceCodec.roundtrip_host_pipelined (pinned host in/out, 8 streams)", "max_abs_diff_vs_device_path": e2e_check},
+                    "api": "DeviceCodec.roundtrip_host_pipelined (pinned host uint8 pixels in/out, int32 streams to the host and back, 8 CUDA streams)",
+                    "max_abs_diff_vs_device_path": e2e_check,
+                    "f32": {"value": whole_job_mps(world, B, f32_steps, e2e_f32_ms), "unit": "MP/s", "steps": f32_steps,
+                            "h2d_bytes_per_step": int(h2d_f // f32_steps), "d2h_bytes_per_step": int(d2h_f // f32_steps),
+                            "api": "same call with float32 host buffers (Image.data in / out)", "max_abs_diff_vs_device_path": f32_check}},
             "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:

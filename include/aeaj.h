@@ -144,7 +144,7 @@ AEAJ_API int aeaj_plan_get_info(const aeaj_plan* p, aeaj_plan_info* info);
 AEAJ_API int aeaj_plan_set_qtables(aeaj_plan* p, const int32_t* tables_host, size_t n_entries, void* stream);
 
 typedef struct {
-    const float* rgb;        /* [batch][H][W][3] */
+    const float* rgb;        /* [batch][H][W][3] in [0,1]; may be NULL when rgb_u8 is given */
     int32_t* coef[3];        /* [batch][cap_coef[l]]  leaf order, row-major blocks */
     int32_t* leaves[3];      /* [batch][cap_leaves[l]][4] x,y,size,coef offset */
     uint8_t* states[3];      /* [batch][cap_states[l]] */
@@ -154,14 +154,19 @@ typedef struct {
     int32_t* status;         /* device int32[64]: [0] hysteresis rounds used, [1] converged flag, rest diagnostics */
     uint8_t* packed_states[3]; /* optional [batch][(cap_states[l]+3)/4]: the state stream packed 2 bits per state,
                                   MSB first, zero padded -- the bytes _entropy_encode writes (jpeg.py:563-571) */
+    const uint8_t* rgb_u8;   /* alternative input (used when rgb == NULL): 8-bit pixels [batch][H][W][3], converted on the
+                                device as Image.load does, imread(path).astype(float32) / 255.0 (image.py:84) -- a quarter
+                                of the bytes over PCIe / HBM for the same result */
 } aeaj_encode_io;
 
 typedef struct {
     const int32_t* coef[3];
     const int32_t* leaves[3];
     const int32_t* counts;   /* [batch][3][4] (only n_leaves is read) */
-    float* rgb;              /* [batch][H][W][3] */
+    float* rgb;              /* [batch][H][W][3]; may be NULL when only rgb_u8 is wanted */
     float* tap_layers[3];    /* optional [batch][h_l][w_l]: merged + denormalised layers */
+    uint8_t* rgb_u8;         /* optional [batch][H][W][3]: Image.get_uint8() / Image.save(), (data * 255).astype(uint8)
+                                (image.py:112,127), written by the same kernel */
 } aeaj_decode_io;
 
 AEAJ_API int aeaj_encode(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, void* stream);

@@ -468,3 +468,40 @@ def test_device_stream_layout_matches_host_packing(codec, space, shape, b):
             assert np.array_equal(zz[k][l]["coef"], O.zigzag_stream(nat[k][l]["coef"], nat[k][l]["leaves"][:, :3]))
             assert zz[k][l]["packed_states"].tobytes() == O.pack_states(nat[k][l]["states"])
             assert np.array_equal(zz[k][l]["states"], nat[k][l]["states"])
+
+
+@pytest.mark.parametrize("space,shape,b", [("YCbCr", (144, 256), (4, 128)), ("ICtCp", (96, 160), (4, 64)), ("YCoCg", (135, 241), (4, 64)),
+                                             ("JzAzBz", (100, 100), (4, 128))])
+def test_uint8_io_bit_exact(codec, space, shape, b):
+    """8-bit pixels in (Image.load: astype(float32) / 255.0, image.py:84) and out (Image.get_uint8: (data * 255).astype(uint8),
+    image.py:127): the u8 entry points give exactly what the float path gives on the converted data."""
+    import torch
+    H, W = shape
+    q = (30, 95)
+    px = np.stack([(synth(H, W, seed=s) * 255).astype(np.uint8) for s in (4, 9)])
+    as_float = px.astype(np.float32) / 255.0
+    ref = codec.download(codec.encode(torch.from_numpy(as_float).cuda(), space, q, b))
+    enc = codec.encode(torch.from_numpy(px).cuda(), space, q, b)
+    got = codec.download(enc)
+    for k in range(2):
+        for i in range(3):
+            for key in ("coef", "leaves", "states"):
+                assert np.array_equal(got[k][i][key], ref[k][i][key]), (k, i, key)
+    f32, u8 = codec.decode_encoded(enc, space, q, b, out="both")
+    f32, u8 = f32.cpu().numpy(), u8.cpu().numpy()
+    assert np.array_equal(u8, (f32 * 255).astype(np.uint8))
+    only = codec.decode_encoded(enc, space, q, b, out="u8").cpu().numpy()
+    assert np.array_equal(only, u8)
+    # the shim: an Image made from 8-bit pixels compresses to the same bytes as its float twin, decompress_uint8 == get_uint8
+    from image import Image
+    from jpeg import Jpeg, JpegCompressionSettings
+    j = Jpeg(JpegCompressionSettings(space, q, b))
+    img8 = Image.from_uint8(px[0], ".png")
+    assert img8.uint8_source() is not None
+    a = j.compress(img8)
+    bb = j.compress(Image.from_array(as_float[0].copy(), None, ".png"))
+    assert a == bb
+    dec = Jpeg(JpegCompressionSettings()).decompress(a)
+    assert np.array_equal(Jpeg(JpegCompressionSettings()).decompress_uint8(a), dec.get_uint8())
+    _ = img8.data                                              # handing the floats out drops the shortcut
+    assert img8.uint8_source() is None and np.array_equal(img8.data, as_float[0])
