@@ -150,46 +150,69 @@ __device__ __forceinline__ uint8_t clahe_apply_px(const uint8_t (*lut)[256], con
 // Gaussian is symmetric; the bilateral is evaluated at in-image pixels only).
 // stages: bit0 CLAHE apply, bit1 Gaussian, bit2 bilateral.   grid: (tiles x, tiles y, planes)
 // ---------------------------------------------------------------------------------------------
-constexpr int PF_TW = 64, PF_TH = 32;
+constexpr int PF_TW = 128, PF_TH = 64;
+constexpr int PF_CG = PF_TW / 4;                     // 4-px groups per output row (stage C)
+constexpr int PF_CR = 2 * (256 / PF_CG);             // output rows per stage-C pass
 constexpr int PF_AS = PF_TW + 8;                     // row stride of both staging tiles (4-byte aligned rows)
+constexpr int PF_AG = PF_AS / 4;                     // 4-column groups per staging row
 // tap k of the 13-tap bilateral window in raster order -> (dy, dx, weight class r^2 in {0,1,2,4} -> 0..3)
-#define BIL_TAPS(X) X(0,-2,0,3) X(1,-1,-1,2) X(2,-1,0,1) X(3,-1,1,2) X(4,0,-2,3) X(5,0,-1,1) X(6,0,0,0) X(7,0,1,1) X(8,0,2,3) \
-                    X(9,1,-1,2) X(10,1,0,1) X(11,1,1,2) X(12,2,0,3)
+#define BIL_TAPS_UP(X) X(0,-2,0,3) X(1,-1,-1,2) X(2,-1,0,1) X(3,-1,1,2) X(4,0,-2,3) X(5,0,-1,1)
+#define BIL_TAPS_DN(X) X(7,0,1,1) X(8,0,2,3) X(9,1,-1,2) X(10,1,0,1) X(11,1,1,2) X(12,2,0,3)
 
-__global__ void __launch_bounds__(256) k_prefilter(const PlaneDesc* __restrict__ planes, const __grid_constant__ TileMap tm, int stages, int do_hist) {
+// Instruction budget (the kernel is issue bound, ~250 -> ~200 thread instructions per sample):
+//  * stage A works on 4-column groups (one 16-byte read of the folded coordinates / weights, one word store) and, when
+//    the whole tile interpolates between the same four CLAHE tiles (all but the tiles that straddle a CLAHE tile centre
+//    line), reads the four LUT bytes of a pixel with ONE shared load from a per-block table of packed quadruples;
+//  * stage B stores 4 x the Gaussian result as u16, so that |a - b| of two window elements IS the byte offset into the
+//    float weight table (no shift / LEA per tap); the sums are carried scaled by 4, which commutes with every rounding
+//    (sum4 = 4 sum exactly, (4 s) / w = 4 (s / w)), and the centre tap needs no table lookup;
+//  * stage C gives a thread 4 px of two ADJACENT rows: the 6 x 8 window is extracted / converted once for 8 px.
+__global__ void __launch_bounds__(256, 4) k_prefilter(const PlaneDesc* __restrict__ planes, const __grid_constant__ TileMap tm, int stages, int do_hist) {
     int plane_i, txi, tyi;
     tile_decode(tm, blockIdx.x, plane_i, txi, tyi);
     const PlaneDesc& P = planes[plane_i];
     const int X0 = txi * PF_TW, Y0 = tyi * PF_TH;
     if (Y0 < P.ry0 || Y0 >= P.ry1) return;             // halo-split bands are multiples of the tile height
     __shared__ __align__(16) uint8_t sA[PF_TH + 6][PF_AS];     // CLAHE output (or source), halo 3
-    __shared__ __align__(16) uint8_t sG[PF_TH + 4][PF_AS];     // Gaussian output, halo 2
-    __shared__ __align__(16) uint8_t sLut[16][256];
+    __shared__ __align__(16) uint16_t sG[PF_TH + 4][PF_AS];    // 4 x Gaussian output, halo 2
+    __shared__ __align__(16) uint8_t sLut[16][256];            // general path only
+    __shared__ uint32_t sQuad[256];                            // uniform path: the four LUT bytes of value v in one word
     __shared__ float sW[4][256];                               // space weight (r^2 = 0,1,2,4) x colour weight, rounded product
     __shared__ unsigned int sHist[256];
-    __shared__ float sXa[PF_AS], sYa[PF_TH + 6];               // CLAHE interpolation weights per tile column / row
+    __shared__ __align__(16) float sXa[PF_AS];                 // CLAHE interpolation weights per tile column / row
+    __shared__ float sYa[PF_TH + 6];
     __shared__ uint8_t sTx[PF_AS][2], sTy[PF_TH + 6][2];       // CLAHE tile indices per tile column / row
-    __shared__ int sFx[PF_AS], sFy[PF_TH + 6];                 // REFLECT_101-folded source coordinates
+    __shared__ __align__(16) int sFx[PF_AS];                   // REFLECT_101-folded source coordinates
+    __shared__ int sFy[PF_TH + 6];
     const int tid = threadIdx.x;
     const ClaheGeom g = clahe_geom(P.h, P.w);
+    auto tile_of = [](int coord, float inv, float& frac, int& t_lo, int& t_hi) {
+        const float tf = __fsub_rn(__fmul_rn((float)coord, inv), 0.5f);
+        const int t1 = (int)floorf(tf);
+        frac = __fsub_rn(tf, (float)t1);
+        t_lo = max(t1, 0); t_hi = min(t1 + 1, 3);
+    };
+    int same = 1;                                              // does this column / row use the tiles of column / row 0?
     if (tid < PF_AS) {
         const int x = reflect101(X0 + tid - 3, P.w);
         sFx[tid] = x;
-        const float txf = __fsub_rn(__fmul_rn((float)x, g.inv_tw), 0.5f);
-        const int t1 = (int)floorf(txf);
-        sXa[tid] = __fsub_rn(txf, (float)t1);
-        sTx[tid][0] = (uint8_t)max(t1, 0); sTx[tid][1] = (uint8_t)min(t1 + 1, 3);
-    } else if (tid >= 128 && tid < 128 + PF_TH + 6) {
-        const int r = tid - 128;
+        float fr, fr0; int lo, hi, lo0, hi0;
+        tile_of(x, g.inv_tw, fr, lo, hi);
+        tile_of(reflect101(X0 - 3, P.w), g.inv_tw, fr0, lo0, hi0);
+        sXa[tid] = fr;
+        sTx[tid][0] = (uint8_t)lo; sTx[tid][1] = (uint8_t)hi;
+        same = (lo == lo0 && hi == hi0);
+    } else if (tid >= PF_AS && tid < PF_AS + PF_TH + 6) {
+        const int r = tid - PF_AS;
         const int y = reflect101(Y0 + r - 3, P.h);
         sFy[r] = y;
-        const float tyf = __fsub_rn(__fmul_rn((float)y, g.inv_th), 0.5f);
-        const int t1 = (int)floorf(tyf);
-        sYa[r] = __fsub_rn(tyf, (float)t1);
-        sTy[r][0] = (uint8_t)(max(t1, 0) * 4); sTy[r][1] = (uint8_t)(min(t1 + 1, 3) * 4);
+        float fr, fr0; int lo, hi, lo0, hi0;
+        tile_of(y, g.inv_th, fr, lo, hi);
+        tile_of(reflect101(Y0 - 3, P.h), g.inv_th, fr0, lo0, hi0);
+        sYa[r] = fr;
+        sTy[r][0] = (uint8_t)(lo * 4); sTy[r][1] = (uint8_t)(hi * 4);
+        same = (lo == lo0 && hi == hi0);
     }
-    if (stages & 1)
-        for (int i = tid; i < 16 * 256 / 4; i += 256) reinterpret_cast<uint32_t*>(&sLut[0][0])[i] = reinterpret_cast<const uint32_t*>(P.clahe_lut)[i];
     {
         float cw = c_bil_color[tid];
         sW[0][tid] = cw;                                       // centre tap: space weight exp(0) = 1
@@ -198,15 +221,50 @@ __global__ void __launch_bounds__(256) k_prefilter(const PlaneDesc* __restrict__
         sW[3][tid] = __fmul_rn(c_bil_space[0], cw);            // r^2 = 4
         sHist[tid] = 0;
     }
-    __syncthreads();
+    const bool uniform = __syncthreads_and(same) != 0;         // (also publishes the tables above)
+    const bool clahe = (stages & 1) != 0;
+    if (clahe) {
+        if (uniform) {
+            const uint8_t* l = P.clahe_lut;
+            const int r0 = sTy[0][0] * 256, r1 = sTy[0][1] * 256, c0 = sTx[0][0] * 256, c1 = sTx[0][1] * 256;
+            sQuad[tid] = (uint32_t)l[r0 + c0 + tid] | ((uint32_t)l[r0 + c1 + tid] << 8) | ((uint32_t)l[r1 + c0 + tid] << 16) | ((uint32_t)l[r1 + c1 + tid] << 24);
+        } else {
+            for (int i = tid; i < 16 * 256 / 4; i += 256) reinterpret_cast<uint32_t*>(&sLut[0][0])[i] = reinterpret_cast<const uint32_t*>(P.clahe_lut)[i];
+        }
+        __syncthreads();
+    }
     const uint8_t* src = P.u8a;
-    // stage A: source (folded coordinates) -> CLAHE; the staging region is 38 rows x 72 columns (2 spare
+    // stage A: source (folded coordinates) -> CLAHE; the staging region is PF_TH + 6 rows x 72 columns (2 spare
     // columns keep the index arithmetic to shifts; they hold valid folded pixels and are never read)
-    for (int i = tid; i < (PF_TH + 6) * PF_AS; i += 256) {
-        const int ry = i / PF_AS, rx = i - ry * PF_AS;
-        const int v = src[(size_t)sFy[ry] * P.w + sFx[rx]];
-        int outv = v;
-        if (stages & 1) {
+    if (!clahe || uniform) {
+        for (int it = tid; it < (PF_TH + 6) * PF_AG; it += 256) {
+            const int ry = it / PF_AG, gx = (it - ry * PF_AG) * 4;
+            const uint8_t* srow = src + (size_t)sFy[ry] * P.w;
+            const int4 fx = *reinterpret_cast<const int4*>(&sFx[gx]);
+            const int v[4] = {srow[fx.x], srow[fx.y], srow[fx.z], srow[fx.w]};
+            uint32_t packed = 0;
+            if (clahe) {
+                const float4 xa4 = *reinterpret_cast<const float4*>(&sXa[gx]);
+                const float xav[4] = {xa4.x, xa4.y, xa4.z, xa4.w};
+                const float ya = sYa[ry], ya1 = __fsub_rn(1.0f, ya);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t q = sQuad[v[k]];
+                    const float xa = xav[k], xa1 = __fsub_rn(1.0f, xa);
+                    const float a = __fmul_rn((float)(q & 0xffu), xa1), b = __fmul_rn((float)((q >> 8) & 0xffu), xa);
+                    const float c = __fmul_rn((float)((q >> 16) & 0xffu), xa1), d = __fmul_rn((float)(q >> 24), xa);
+                    const float r = __fadd_rn(__fmul_rn(__fadd_rn(a, b), ya1), __fmul_rn(__fadd_rn(c, d), ya));
+                    packed |= (uint32_t)min(max(__float2int_rn(r), 0), 255) << (8 * k);
+                }
+            } else {
+                packed = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+            }
+            *reinterpret_cast<uint32_t*>(&sA[ry][gx]) = packed;
+        }
+    } else {
+        for (int i = tid; i < (PF_TH + 6) * PF_AS; i += 256) {
+            const int ry = i / PF_AS, rx = i - ry * PF_AS;
+            const int v = src[(size_t)sFy[ry] * P.w + sFx[rx]];
             const float xa = sXa[rx], xa1 = __fsub_rn(1.0f, xa), ya = sYa[ry], ya1 = __fsub_rn(1.0f, ya);
             const uint8_t* l0 = &sLut[sTy[ry][0]][v];
             const uint8_t* l1 = &sLut[sTy[ry][1]][v];
@@ -214,79 +272,94 @@ __global__ void __launch_bounds__(256) k_prefilter(const PlaneDesc* __restrict__
             const float a = __fmul_rn((float)l0[c0], xa1), b = __fmul_rn((float)l0[c1], xa);
             const float c = __fmul_rn((float)l1[c0], xa1), d = __fmul_rn((float)l1[c1], xa);
             const float r = __fadd_rn(__fmul_rn(__fadd_rn(a, b), ya1), __fmul_rn(__fadd_rn(c, d), ya));
-            outv = min(max(__float2int_rn(r), 0), 255);
+            sA[ry][rx] = (uint8_t)min(max(__float2int_rn(r), 0), 255);
         }
-        sA[ry][rx] = (uint8_t)outv;
     }
     __syncthreads();
-    // stage B: Gaussian [1 2 1]x[1 2 1], 4 outputs per thread sharing the 6 column sums
-    for (int i = tid; i < (PF_TH + 4) * 17; i += 256) {
-        const int ry = i / 17, gx = (i - ry * 17) * 4;            // output cells (ry, gx..gx+3) of the halo-2 region
-        uchar4 o;
+    // stage B: Gaussian [1 2 1]x[1 2 1], 4 outputs per thread sharing the 6 column sums; stored as 4 * value (u16)
+    for (int i = tid; i < (PF_TH + 4) * (PF_CG + 1); i += 256) {
+        const int ry = i / (PF_CG + 1), gx = (i - ry * (PF_CG + 1)) * 4;            // output cells (ry, gx..gx+3) of the halo-2 region
+        int o[4];
         if (stages & 2) {
             int cs[6];
 #pragma unroll
             for (int j = 0; j < 6; j++) cs[j] = sA[ry][gx + j] + 2 * sA[ry + 1][gx + j] + sA[ry + 2][gx + j];
-            o.x = (uint8_t)((cs[0] + 2 * cs[1] + cs[2] + 8) >> 4); o.y = (uint8_t)((cs[1] + 2 * cs[2] + cs[3] + 8) >> 4);
-            o.z = (uint8_t)((cs[2] + 2 * cs[3] + cs[4] + 8) >> 4); o.w = (uint8_t)((cs[3] + 2 * cs[4] + cs[5] + 8) >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; k++) o[k] = (cs[k] + 2 * cs[k + 1] + cs[k + 2] + 8) >> 4;
         } else {
-            o = make_uchar4(sA[ry + 1][gx + 1], sA[ry + 1][gx + 2], sA[ry + 1][gx + 3], sA[ry + 1][gx + 4]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) o[k] = sA[ry + 1][gx + 1 + k];
         }
-        *reinterpret_cast<uchar4*>(&sG[ry][gx]) = o;
+        *reinterpret_cast<uint2*>(&sG[ry][gx]) = make_uint2((uint32_t)(o[0] << 2) | ((uint32_t)(o[1] << 2) << 16), (uint32_t)(o[2] << 2) | ((uint32_t)(o[3] << 2) << 16));
     }
     __syncthreads();
-    // stage C: bilateral, thread -> 4 consecutive px in rows (tid/16) and (tid/16 + 16)
+    // stage C: bilateral, thread -> 4 consecutive px in rows 2*(tid/16) and 2*(tid/16) + 1 of each 32-row half of the tile
     uint8_t* dst = P.u8b;
-    const int tx = (tid & 15) * 4;
+    const int tx = (tid % PF_CG) * 4;
+#pragma unroll 1
+    for (int half = 0; half < PF_TH / PF_CR; half++) {
+    const int ty0 = (tid / PF_CG) * 2 + PF_CR * half;
+    uint32_t outw[2] = {0, 0};
+    {
+        // 6 rows x 8 elements window: rows ty0..ty0+5, cols tx..tx+7 of sG (each element = 4 * pixel)
+        int wi[6][8];
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
-        const int ty = (tid >> 4) + half * 16;
-        const int y = Y0 + ty;
-        if (y >= P.h) continue;
-        uint8_t outv[4];
+        for (int r = 0; r < 6; r++) {
+            const uint2 a = *reinterpret_cast<const uint2*>(&sG[ty0 + r][tx]);
+            const uint2 b = *reinterpret_cast<const uint2*>(&sG[ty0 + r][tx + 4]);
+            wi[r][0] = a.x & 0xffffu; wi[r][1] = a.x >> 16; wi[r][2] = a.y & 0xffffu; wi[r][3] = a.y >> 16;
+            wi[r][4] = b.x & 0xffffu; wi[r][5] = b.x >> 16; wi[r][6] = b.y & 0xffffu; wi[r][7] = b.y >> 16;
+        }
         if (stages & 4) {
-            // 5 rows x 8 bytes window: rows ty..ty+4, cols tx..tx+7 of sG
-            int win[5][8];
+            const float w_c = sW[0][0];
+            const char* wbase = reinterpret_cast<const char*>(&sW[0][0]);
 #pragma unroll
-            for (int r = 0; r < 5; r++) {
-                const uchar4 a = *reinterpret_cast<const uchar4*>(&sG[ty + r][tx]);
-                const uchar4 b = *reinterpret_cast<const uchar4*>(&sG[ty + r][tx + 4]);
-                win[r][0] = a.x; win[r][1] = a.y; win[r][2] = a.z; win[r][3] = a.w;
-                win[r][4] = b.x; win[r][5] = b.y; win[r][6] = b.z; win[r][7] = b.w;
-            }
+            for (int rr = 0; rr < 2; rr++)
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int v0 = win[2][k + 2];
-                float sum = 0.0f, wsum = 0.0f;
-#define BIL_ONE(idx, dy, dx, cls) { const int v = win[2 + (dy)][k + 2 + (dx)]; const float wgt = sW[cls][__sad(v, v0, 0u)]; \
+                for (int k = 0; k < 4; k++) {
+                    const int v0 = wi[rr + 2][k + 2];
+                    float sum = 0.0f, wsum = 0.0f;
+#define BIL_ONE(idx, dy, dx, cls) { const int v = wi[rr + 2 + (dy)][k + 2 + (dx)]; \
+                                    const float wgt = *reinterpret_cast<const float*>(wbase + (cls) * 1024 + __sad(v, v0, 0u)); \
                                     sum = __fmaf_rn((float)v, wgt, sum); wsum = __fadd_rn(wsum, wgt); }
-                BIL_TAPS(BIL_ONE)
+                    BIL_TAPS_UP(BIL_ONE)
+                    sum = __fmaf_rn((float)v0, w_c, sum); wsum = __fadd_rn(wsum, w_c);
+                    BIL_TAPS_DN(BIL_ONE)
 #undef BIL_ONE
-                const int res = __float2int_rn(__fdiv_rn(sum, wsum));
-                outv[k] = (uint8_t)min(max(res, 0), 255);
-            }
+                    const int res = __float2int_rn(__fmul_rn(__fdiv_rn(sum, wsum), 0.25f));
+                    outw[rr] |= (uint32_t)min(max(res, 0), 255) << (8 * k);
+                }
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; k++) outv[k] = sG[ty + 2][tx + k + 2];
+            for (int rr = 0; rr < 2; rr++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) outw[rr] |= (uint32_t)(wi[rr + 2][k + 2] >> 2) << (8 * k);
         }
-        const int x = X0 + tx;
+    }
+    const int x = X0 + tx;
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+        const int y = Y0 + ty0 + rr;
+        if (y >= P.h) continue;
         uint8_t* drow = dst + (size_t)y * P.w;
-        if (x + 3 < P.w && ((P.w & 3) == 0)) *reinterpret_cast<uchar4*>(drow + x) = make_uchar4(outv[0], outv[1], outv[2], outv[3]);
+        if (x + 3 < P.w && ((P.w & 3) == 0)) *reinterpret_cast<uint32_t*>(drow + x) = outw[rr];
         else {
 #pragma unroll
-            for (int k = 0; k < 4; k++) if (x + k < P.w) drow[x + k] = outv[k];
+            for (int k = 0; k < 4; k++) if (x + k < P.w) drow[x + k] = (uint8_t)(outw[rr] >> (8 * k));
         }
         if (do_hist) {
             int prev = -1, cnt = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 if (x + k < P.w) {
-                    if (outv[k] == prev) cnt++;
-                    else { if (cnt) atomicAdd(&sHist[prev], (unsigned)cnt); prev = outv[k]; cnt = 1; }
+                    const int ov = (outw[rr] >> (8 * k)) & 0xff;
+                    if (ov == prev) cnt++;
+                    else { if (cnt) atomicAdd(&sHist[prev], (unsigned)cnt); prev = ov; cnt = 1; }
                 }
             }
             if (cnt) atomicAdd(&sHist[prev], (unsigned)cnt);
         }
+    }
     }
     if (do_hist) {
         __syncthreads();
