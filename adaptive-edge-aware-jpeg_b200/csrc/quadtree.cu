@@ -84,11 +84,12 @@ __global__ void __launch_bounds__(QT_THREADS) k_qt_blocks(const PlaneDesc* __res
     // (cell row, bitmap word) pair and splits the word into 32/c cell flags.
     if (c <= 32) {
         const int cpw = 32 / c;                                    // cells per word
-        const int wpt = (T + 31) / 32;                             // words per top-block row
+        const int wpt = (T + 31) / 32;                             // words per top-block row (a power of two)
+        const int lg_wpt = 31 - __clz(wpt);
         const int w0 = X0 >> 5;                                    // X0 is a multiple of T; if T < 32, bits are offset
         const int bit0 = X0 & 31;
         for (int i = tid; i < n * wpt; i += QT_THREADS) {
-            const int cy = i / wpt, wi = i - cy * wpt;
+            const int cy = i >> lg_wpt, wi = i & (wpt - 1);
             const int y0 = Y0 + cy * c, y1 = min(y0 + c, P.h);
             unsigned acc = 0;
             if (w0 + wi < P.wpr)
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_qt_blocks(const PlaneDesc* __res
         }
     } else {
         for (int i = tid; i < n * n; i += QT_THREADS) {
-            int cy = i / n, cx = i - cy * n;
+            int cy = i >> L, cx = i & (n - 1);
             occ[i] = cell_has_edge(P.strong, P.wpr, P.h, P.w, X0 + cx * c, Y0 + cy * c, c);
         }
     }
@@ -110,70 +111,71 @@ __global__ void __launch_bounds__(QT_THREADS) k_qt_blocks(const PlaneDesc* __res
         const uint8_t* prev = occ + lvl_off[l - 1];
         uint8_t* cur = occ + lvl_off[l];
         for (int i = tid; i < nl * nl; i += QT_THREADS) {
-            int j = i / nl, k = i - j * nl;
+            int j = i >> (L - l), k = i & (nl - 1);
             cur[i] = prev[(2 * j) * np + 2 * k] | prev[(2 * j) * np + 2 * k + 1] | prev[(2 * j + 1) * np + 2 * k] | prev[(2 * j + 1) * np + 2 * k + 1];
         }
         __syncthreads();
     }
     // node predicates ---------------------------------------------------------------------------
-    auto node_split = [&](int l, int j, int k) -> bool { return l > 0 && occ[lvl_off[l] + j * (n >> l) + k]; };
+    auto node_split = [&](int l, int j, int k) -> bool { return l > 0 && occ[lvl_off[l] + (j << (L - l)) + k]; };
     auto node_exists = [&](int l, int j, int k) -> bool { return l == L ? true : node_split(l + 1, j >> 1, k >> 1); };
     auto node_inb = [&](int l, int j, int k) -> bool { return (X0 + (k << l) * c) < P.w && (Y0 + (j << l) * c) < P.h; };
 
-    if (phase == 1) {
-        // per-class leaf counts for this block -> reserve ranges in the global class lists
-        int tot_nodes = lvl_off[L] + 1;
-        for (int i = tid; i < tot_nodes; i += QT_THREADS) {
-            int l = 0; while (l < L && i >= lvl_off[l + 1]) l++;
-            int r = i - lvl_off[l], nl = n >> l, j = r / nl, k = r - j * nl;
-            if (node_exists(l, j, k) && node_inb(l, j, k) && !node_split(l, j, k)) atomicAdd(&s_cls[l], 1);
-        }
-        __syncthreads();
-        if (tid <= L && s_cls[tid] > 0) s_cls_base[tid] = atomicAdd(&class_counts[q.lg_min + tid], s_cls[tid]);
-        __syncthreads();
-        if (tid < 9) s_cls[tid] = 0;
-        __syncthreads();
-    }
-    const int4 base = (phase == 1) ? P.tb_base[tb] : make_int4(0, 0, 0, 0);
-    Scan3 carry = {0, 0, 0};
+    // Every thread owns `per` consecutive Morton positions (a 2x2 quad of cells for the usual 32x32 block), so one
+    // block scan serves the whole top block; a node of level l starts at z iff z has 2l trailing zero bits.
     const int ncell = n * n;
-    for (int z0 = 0; z0 < ncell; z0 += QT_THREADS) {
-        const int z = z0 + tid;
-        Scan3 cnt = {0, 0, 0};
-        int cx = 0, cy = 0;
-        if (z < ncell) {
-            cx = (int)compact1by1((uint32_t)z); cy = (int)compact1by1((uint32_t)z >> 1);
-            for (int l = L; l >= 0; l--) {
-                if (z & ((1 << (2 * l)) - 1)) continue;
-                int j = cy >> l, k = cx >> l;
-                if (!node_exists(l, j, k)) continue;
-                cnt.a++;
-                if (node_inb(l, j, k) && !node_split(l, j, k)) { cnt.b++; int s = c << l; cnt.c += s * s; }
+    const int per = (ncell + QT_THREADS - 1) / QT_THREADS;
+    const int zb = tid * per;
+    Scan3 cnt = {0, 0, 0};
+    for (int t = 0; t < per; t++) {
+        const int z = zb + t;
+        if (z >= ncell) break;
+        const int cx = (int)compact1by1((uint32_t)z), cy = (int)compact1by1((uint32_t)z >> 1);
+        const int lmax = z ? min(L, (__ffs(z) - 1) >> 1) : L;
+        for (int l = lmax; l >= 0; l--) {
+            const int j = cy >> l, k = cx >> l;
+            if (!node_exists(l, j, k)) continue;
+            cnt.a++;
+            if (node_inb(l, j, k) && !node_split(l, j, k)) {
+                cnt.b++; const int sz = c << l; cnt.c += sz * sz;
+                if (phase == 1) atomicAdd(&s_cls[l], 1);           // per-class leaf counts of this block
             }
         }
-        Scan3 tot;
-        Scan3 ex = block_excl_scan3(cnt, tot, s_scan);
-        if (phase == 1 && z < ncell && cnt.a) {
-            int spos = base.x + carry.a + ex.a;
-            for (int l = L; l >= 0; l--) {
-                if (z & ((1 << (2 * l)) - 1)) continue;
-                int j = cy >> l, k = cx >> l;
-                if (!node_exists(l, j, k)) continue;
-                bool inb = node_inb(l, j, k), sp = node_split(l, j, k);
-                P.states[spos++] = inb ? (sp ? 1 : 0) : 2;
-                if (inb && !sp) {
-                    int li = base.y + carry.b + ex.b, co = base.z + carry.c + ex.c;
-                    int s = c << l, x = X0 + (k << l) * c, y = Y0 + (j << l) * c;
-                    reinterpret_cast<int4*>(P.leaves)[li] = make_int4(x, y, s, co);
-                    int r = s_cls_base[l] + atomicAdd(&s_cls[l], 1);
-                    ClassEntry e; e.x = x; e.y = y; e.plane = plane_i; e.coef_off = co;
-                    class_lists[class_offsets[q.lg_min + l] + r] = e;
-                }
-            }
-        }
-        carry.a += tot.a; carry.b += tot.b; carry.c += tot.c;
     }
-    if (phase == 0 && tid == 0) { P.tb_tot[tb] = make_int2(carry.a, carry.b); P.tb_coef[tb] = carry.c; }
+    Scan3 tot;
+    const Scan3 ex = block_excl_scan3(cnt, tot, s_scan);
+    if (phase == 0) {
+        if (tid == 0) { P.tb_tot[tb] = make_int2(tot.a, tot.b); P.tb_coef[tb] = tot.c; }
+        return;
+    }
+    // phase 1: reserve this block's ranges in the global class lists, then emit in Morton order
+    __syncthreads();
+    if (tid <= L && s_cls[tid] > 0) s_cls_base[tid] = atomicAdd(&class_counts[q.lg_min + tid], s_cls[tid]);
+    __syncthreads();
+    if (tid < 9) s_cls[tid] = 0;
+    __syncthreads();
+    const int4 base = P.tb_base[tb];
+    int spos = base.x + ex.a, li = base.y + ex.b, co = base.z + ex.c;
+    for (int t = 0; t < per; t++) {
+        const int z = zb + t;
+        if (z >= ncell) break;
+        const int cx = (int)compact1by1((uint32_t)z), cy = (int)compact1by1((uint32_t)z >> 1);
+        const int lmax = z ? min(L, (__ffs(z) - 1) >> 1) : L;
+        for (int l = lmax; l >= 0; l--) {
+            const int j = cy >> l, k = cx >> l;
+            if (!node_exists(l, j, k)) continue;
+            const bool inb = node_inb(l, j, k), sp = node_split(l, j, k);
+            P.states[spos++] = inb ? (sp ? 1 : 0) : 2;
+            if (inb && !sp) {
+                const int sz = c << l, x = X0 + (k << l) * c, y = Y0 + (j << l) * c;
+                reinterpret_cast<int4*>(P.leaves)[li] = make_int4(x, y, sz, co);
+                const int r = s_cls_base[l] + atomicAdd(&s_cls[l], 1);
+                ClassEntry e; e.x = x; e.y = y; e.plane = plane_i; e.coef_off = co;
+                class_lists[class_offsets[q.lg_min + l] + r] = e;
+                li++; co += sz * sz;
+            }
+        }
+    }
 }
 
 // one block per plane: Morton-order scan over all (root/T)^2 top positions, emitting the states of

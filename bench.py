@@ -168,7 +168,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=4, help="frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=8, help="frames per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=2, help="frames in the bounded cpu_baseline sample (0 = skip)")
     args = ap.parse_args()
