@@ -188,6 +188,34 @@ class DeviceCodec:
         res = p.rgb_out if out == "f32" else (p.rgb8_out if out == "u8" else (p.rgb_out, p.rgb8_out))
         return (res, tl) if taps else res
 
+    def roundtrip_device(self, rgb: torch.Tensor, space: str, qrange, brange, streams: int = 2, out: str = "f32"):
+        """encode + decode of a device-resident batch, split into `streams` sub-batches that run concurrently on their
+        own CUDA streams (and plan instances): the latency-bound stages of one sub-batch (hysteresis rounds, quadtree
+        scans) overlap the throughput-bound stages of the other.  Fork / join around the current stream, so to the
+        caller it behaves like one asynchronous call.  Returns the list of per-sub-batch results (views of plan buffers)."""
+        B = rgb.shape[0]
+        n = max(1, min(streams, B))
+        if not hasattr(self, "_rt_streams") or len(self._rt_streams) < n:
+            self._rt_streams = [torch.cuda.Stream(device=rgb.device) for _ in range(n)]
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        H, W = rgb.shape[1], rgb.shape[2]
+        outs, launches = [], 0
+        for i, part in enumerate(rgb.chunk(n)):
+            s = self._rt_streams[i]
+            s.wait_event(fork)
+            with torch.cuda.stream(s):
+                enc = self.encode(part, space, qrange, brange, instance=1000 + i)
+                launches += self.last_launches
+                outs.append(self.decode(enc.coef, enc.leaves, enc.counts, part.shape[0], H, W, space, qrange, brange, instance=1000 + i, out=out))
+                launches += self.last_launches
+            join = torch.cuda.Event()
+            join.record(s)
+            main.wait_event(join)
+        self.last_launches = launches
+        return outs
+
     # ------------------------------------------------------------------------------------------
     # measurement support
     # ------------------------------------------------------------------------------------------

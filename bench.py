@@ -168,7 +168,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=8, help="frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=16, help="frames per step per GPU")
+    ap.add_argument("--streams", type=int, default=2, help="CUDA streams the batch of a step is spread over (sub-batches run concurrently)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=2, help="frames in the bounded cpu_baseline sample (0 = skip)")
     args = ap.parse_args()
@@ -200,8 +201,8 @@ def main():
     mp_per_step = B * H * W / 1e6
 
     def step():
-        enc = codec.encode(rgb, SPACE, QRANGE, BRANGE)
-        return codec.decode_encoded(enc, SPACE, QRANGE, BRANGE)
+        # encode + decode of the batch; two half-batches on two CUDA streams (fork / join around the current stream)
+        return codec.roundtrip_device(rgb, SPACE, QRANGE, BRANGE, streams=args.streams)
 
     def barrier():
         if world > 1:
@@ -219,11 +220,10 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches_per_step = 0
-    codec.encode(rgb, SPACE, QRANGE, BRANGE); launches_per_step += codec.last_launches
-    codec.decode_encoded(codec._plan(B, H, W, SPACE, BRANGE, QRANGE).out, SPACE, QRANGE, BRANGE); launches_per_step += codec.last_launches
+    out = torch.cat(out)
+    launches_per_step = codec.last_launches
     torch.cuda.synchronize()
-    status = codec._plan(B, H, W, SPACE, BRANGE, QRANGE).out.status.cpu().numpy()
+    status = codec._plan(rgb.chunk(args.streams)[0].shape[0], H, W, SPACE, BRANGE, QRANGE, instance=1000).out.status.cpu().numpy()
 
     # ---- e2e: host buffers in, host buffers out ------------------------------------------------
     # pinned host RGB -> H2D -> encode -> D2H (coefficients, leaves, states) -> H2D -> decode -> D2H pinned host RGB,
@@ -252,19 +252,21 @@ def main():
     e2e_f32_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if sampler else None
 
-    # ---- per-stage timing (separate instrumented passes; CUDA events on the launching stream) --
-    codec.enable_timing(B, H, W, SPACE, BRANGE, QRANGE, True)
+    # ---- per-stage timing (separate instrumented single-stream passes over one sub-batch; CUDA events on the launching stream)
+    Bs = rgb.chunk(args.streams)[0].shape[0]                        # frames per launch (sub-batch)
+    sub = rgb[:Bs]
+    codec.enable_timing(Bs, H, W, SPACE, BRANGE, QRANGE, True)
     stage_ms = {}
     reps = max(3, min(args.steps, 10))
     for _ in range(reps):
-        enc = codec.encode(rgb, SPACE, QRANGE, BRANGE)
-        for k, v in codec.read_timing(B, H, W, SPACE, BRANGE, QRANGE).items():
+        enc = codec.encode(sub, SPACE, QRANGE, BRANGE)
+        for k, v in codec.read_timing(Bs, H, W, SPACE, BRANGE, QRANGE).items():
             stage_ms[k] = stage_ms.get(k, 0.0) + v / reps
         codec.decode_encoded(enc, SPACE, QRANGE, BRANGE)
-        for k, v in codec.read_timing(B, H, W, SPACE, BRANGE, QRANGE).items():
+        for k, v in codec.read_timing(Bs, H, W, SPACE, BRANGE, QRANGE).items():
             stage_ms[k] = stage_ms.get(k, 0.0) + v / reps
-    codec.enable_timing(B, H, W, SPACE, BRANGE, QRANGE, False)
-    counts_np = codec._plan(B, H, W, SPACE, BRANGE, QRANGE).out.counts.cpu().numpy()
+    codec.enable_timing(Bs, H, W, SPACE, BRANGE, QRANGE, False)
+    counts_np = codec._plan(Bs, H, W, SPACE, BRANGE, QRANGE).out.counts.cpu().numpy()
 
     if world > 1:
         t = reduce_max(torch.tensor([ms, e2e_ms, e2e_f32_ms], device=f"cuda:{local}", dtype=torch.float64), dist)
@@ -286,7 +288,7 @@ def main():
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     dom = max(stage_ms, key=stage_ms.get)
     n_samples = float(counts_np[:, :, 2].sum())                       # coefficients = samples incl. padding, whole batch
-    full_px = B * H * W
+    full_px = Bs * H * W                                              # pixels one launch processes
     alg = {  # algorithmic bytes per launch of each stage (DESIGN.md "kernels")
         "color_forward_planar": full_px * (12 + 6 + 1.5), "upsample_color_inverse": full_px * (6 + 12),
         "prefilter": full_px * 1.5 * 2, "clahe_hist": full_px * 1.5, "canny_nms": full_px * 1.5 * (1 + 0.25),
@@ -295,24 +297,24 @@ def main():
         s = int(dom.rsplit("_", 1)[1])
         lg = int(np.log2(s))
         # samples of this size class: recount from the leaf lists
-        plan = codec._plan(B, H, W, SPACE, BRANGE, QRANGE)
+        plan = codec._plan(Bs, H, W, SPACE, BRANGE, QRANGE)
         ns = 0
         for l in range(3):
             lv = plan.out.leaves[l].cpu().numpy()
-            for b in range(B):
+            for b in range(Bs):
                 sz = lv[b, : counts_np[b, l, 0], 2]
                 ns += int((sz == s).sum()) * s * s
         alg[dom] = ns * 8.0                                            # 4 B in + 4 B out per sample
     alg_bytes = alg.get(dom)
     dom_ms = stage_ms[dom]
     # measured DRAM traffic of that kernel per launch (dram__bytes_read + write from the committed `ncu --set full`
-    # capture, taken at the default batch of 4 frames); null for other batch sizes / kernels not captured
+    # capture of one 8-frame launch, tests/_prof_step.py); null for other sub-batch sizes / kernels not captured
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        kname = {"prefilter": "k_prefilter", "canny_nms": "k_canny_nms", "color_forward_planar": "k_color_forward_planar<0, 0>",
-                 "dct_quant_128": "k_dct_cta<128, 0>", "dct_quant_64": "k_dct_cta<64, 0>", "hysteresis": "k_hysteresis_rounds"}.get(dom)
-        if B == 4 and kname in tr:
+        kname = {"prefilter": "k_prefilter", "canny_nms": "k_canny_nms", "color_forward_planar": "k_color_forward_planar<0, 0, 0>",
+                 "dct_quant_128": "k_dct_tc128<0>", "dequant_idct_128": "k_dct_tc128<1>", "upsample_color_inverse": "k_upsample2x_color_inverse<0>", "dct_quant_64": "k_dct_cta<64, 0>", "hysteresis": "k_hysteresis_rounds"}.get(dom)
+        if Bs == 8 and kname in tr:
             traffic = tr[kname]
     except Exception:
         pass
@@ -320,8 +322,9 @@ def main():
             "unit": "GB/s", "frac": ((alg_bytes / 1e9) / (dom_ms / 1e3) / peak) if alg_bytes else None, "traffic": traffic,
             "algorithmic_bytes": alg_bytes,
             "peak_source": peak_src, "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / sum(stage_ms.values()),
-            "pipeline_achieved": (ALG_BYTES_PER_PX * full_px * world / 1e9) / (ms / args.steps / 1e3),
-            "pipeline_frac": (ALG_BYTES_PER_PX * full_px / 1e9) / (ms / args.steps / 1e3) / peak,
+            "frames_per_launch": Bs,
+            "pipeline_achieved": (ALG_BYTES_PER_PX * B * H * W * world / 1e9) / (ms / args.steps / 1e3),
+            "pipeline_frac": (ALG_BYTES_PER_PX * B * H * W / 1e9) / (ms / args.steps / 1e3) / peak,
             "stage_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])}}
 
     cpu = None
@@ -335,7 +338,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "l2": "inputs larger than L2 (no flush)",
-                       "parallelism": f"batch-sharded x{world}", "hysteresis_rounds": int(status[0]), "hysteresis_converged": int(status[1])},
+                       "streams_per_step": args.streams, "parallelism": f"batch-sharded x{world}", "hysteresis_rounds": int(status[0]), "hysteresis_converged": int(status[1])},
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps,
                     "api": "DeviceCodec.roundtrip_host_pipelined (pinned host uint8 pixels in/out, int32 streams to the host and back, 8 CUDA streams)",
                     "max_abs_diff_vs_device_path": e2e_check,
