@@ -375,7 +375,7 @@ struct aeaj_plan {
     int last_launches;
     bool need_full_chroma;
     int zigzag = 0;
-    int tensor_dct = 0;
+    int tensor_dct = 1;           // tcgen05 kernels for 128x128 leaves (aeaj_plan_set_tensor_dct)
     // optional per-stage CUDA-event timing (bench.py roofline leg)
     bool timing_on = false;
     std::vector<cudaEvent_t> ev;

@@ -3,9 +3,9 @@
 // (hi = top 11 mantissa bits, exactly representable in TF32) and  P.Q ~= Ph.Qh + Ph.Ql + Pl.Qh  accumulated in
 // FP32 in tensor memory.
 //
-// OPT-IN (aeaj_plan_set_tensor_dct): the parity bar for the forward DCT is the quantiser (tie class T-DCT) and for
-// the inverse the <= 1 LSB / 3e-6 bound of the decoded samples; the FP32-FMA kernels in dct.cu are the default,
-// tests/test_gpu_parity.py::test_tensor_core_dct_parity compares both against the oracle.
+// Default path for 128x128 leaves (aeaj_plan_set_tensor_dct(plan, 0) selects the FP32-FMA kernels of dct.cu): the
+// parity bar for the forward DCT is the quantiser (tie class T-DCT) and for the inverse the <= 1 LSB / 3e-6 bound of
+// the decoded samples; tests/test_gpu_parity.py::test_tensor_core_dct_parity compares both paths against the oracle.
 //
 // One CTA (256 threads) per 128x128 leaf, persistent over the size-128 work list:
 //   GEMM1  W = A . X      A tile (smem, K-major, hi/lo)         B = X^T (smem, K-major, hi/lo; four 32-row K chunks)

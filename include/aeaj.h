@@ -214,9 +214,11 @@ AEAJ_API int aeaj_pack_states_host(const uint8_t* states_host, int n_states, uin
  * (jpeg.py:579-590); aeaj_decode then expects that layout. */
 AEAJ_API int aeaj_plan_set_stream_layout(aeaj_plan* p, int zigzag);
 
-/* Opt-in tensor-core path for the 128x128 forward DCT (tcgen05 kind::tf32, error-compensated 3xTF32, FP32
- * accumulation in tensor memory).  Off by default: the FP32-FMA kernels define the parity bar.
- * aeaj_tensor_dct_status reports whether a tensor-core kernel ever gave up on a barrier wait (synchronises). */
+/* Tensor-core path for the 128x128 DCT (cv.dct, jpeg.py:471) and IDCT (cv.idct, jpeg.py:483): tcgen05 kind::tf32,
+ * error-compensated 3xTF32, FP32 accumulation in tensor memory.  On by default; enable = 0 selects the FP32-FMA
+ * kernels (same parity class -- the quantiser is exact in both, DESIGN.md section 4 -- at half the speed).
+ * aeaj_tensor_dct_status: timed_out must point to int[32]; [0] is set if a tensor-core kernel ever gave up on a
+ * barrier wait, [1..] hold the phase clocks of one leaf (diagnostics).  Synchronises the device. */
 AEAJ_API int aeaj_plan_set_tensor_dct(aeaj_plan* p, int enable);
 AEAJ_API int aeaj_tensor_dct_status(aeaj_handle* h, int* timed_out);
 
