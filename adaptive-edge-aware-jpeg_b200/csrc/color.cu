@@ -416,21 +416,32 @@ __global__ void __launch_bounds__(256) k_upsample2x_color_inverse(const __grid_c
     int y0, y1; float fy;
     up2_coord(dy, chh, y0, y1, fy);
     const float b0 = __fsub_rn(1.0f, fy);
+    // The 4 px of a thread (dx0 = 4m) read chroma columns 2m-1 .. 2m+2: px0 = (2m-1, 2m; .75), px1 = (2m, 2m+1; .25),
+    // px2 = (2m, 2m+1; .75), px3 = (2m+1, 2m+2; .25), with up2_coord's clamps at the two borders (t = 0).  Same operands
+    // and the same a*(1-t) + b*t expressions as the per-pixel form, with 3 loads per row instead of 8.
+    const int m2 = dx0 >> 1;
+    const bool first = (m2 == 0), last = (m2 + 1 >= cw - 1);
+    const float f0 = first ? 0.0f : 0.75f, f3 = last ? 0.0f : 0.25f;
+    const float a0 = __fsub_rn(1.0f, f0), a3 = __fsub_rn(1.0f, f3);
     float cv[2][4];
 #pragma unroll
     for (int l = 1; l <= 2; l++) {
         const float* p = in.p[l] + (size_t)b * in.stride[l];
-        const float* r0 = p + (size_t)y0 * cw;
-        const float* r1 = p + (size_t)y1 * cw;
+        float t[2][4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int x0, x1; float fx;
-            up2_coord(dx0 + k, cw, x0, x1, fx);
-            const float a0 = __fsub_rn(1.0f, fx);
-            float t0 = __fadd_rn(__fmul_rn(__ldg(r0 + x0), a0), __fmul_rn(__ldg(r0 + x1), fx));
-            float t1 = __fadd_rn(__fmul_rn(__ldg(r1 + x0), a0), __fmul_rn(__ldg(r1 + x1), fx));
-            cv[l - 1][k] = __fadd_rn(__fmul_rn(t0, b0), __fmul_rn(t1, fy));
+        for (int r = 0; r < 2; r++) {
+            const float* row = p + (size_t)(r ? y1 : y0) * cw;
+            const float2 mid = __ldg(reinterpret_cast<const float2*>(row + m2));
+            const float vm = __ldg(row + max(m2 - 1, 0)), vp = __ldg(row + min(m2 + 2, cw - 1));
+            const float p0a = first ? mid.x : vm, p0b = first ? mid.y : mid.x;        // (x0, x1) of px0
+            const float p3b = last ? mid.y : vp;                                       // x1 of px3 (x0 = 2m+1)
+            t[r][0] = __fadd_rn(__fmul_rn(p0a, a0), __fmul_rn(p0b, f0));
+            t[r][1] = __fadd_rn(__fmul_rn(mid.x, 0.75f), __fmul_rn(mid.y, 0.25f));
+            t[r][2] = __fadd_rn(__fmul_rn(mid.x, 0.25f), __fmul_rn(mid.y, 0.75f));
+            t[r][3] = __fadd_rn(__fmul_rn(mid.y, a3), __fmul_rn(p3b, f3));
         }
+#pragma unroll
+        for (int k = 0; k < 4; k++) cv[l - 1][k] = __fadd_rn(__fmul_rn(t[0][k], b0), __fmul_rn(t[1][k], fy));
     }
     float o[12];
 #pragma unroll

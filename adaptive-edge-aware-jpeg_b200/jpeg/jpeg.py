@@ -9,6 +9,7 @@ Entropy coding (zigzag gather, state packing, zlib level 9) stays on the host, a
 from __future__ import annotations
 
 import json
+import os
 import zlib
 from concurrent.futures import ThreadPoolExecutor
 from io import BytesIO
@@ -142,8 +143,15 @@ class Jpeg:
                 host = np.stack([np.ascontiguousarray(imgs[i].data.reshape(H, W, 3), dtype=np.float32) for i in idxs])
             rgb = torch.from_numpy(host).pin_memory().to(f"cuda:{codec.device}", non_blocking=True)
             enc = codec.encode(rgb, s.color_space, s.quality_range, s.block_size_range, stream=True)
-            for i, layers in zip(idxs, codec.download(enc)):
-                out[i] = self._entropy_encode(layers, (H, W), imgs[i].extension)
+            downloaded = codec.download(enc)
+            # zlib level 9 is the end-to-end bottleneck once the hot path is on the GPU: deflate every layer of
+            # every image of the group concurrently (zlib releases the GIL; same bytes as the sequential reference loop)
+            jobs = [(i, l) for i in range(len(idxs)) for l in range(len(downloaded[i]))]
+            with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+                deflated = list(pool.map(lambda il: self._deflate_layer(downloaded[il[0]][il[1]]), jobs))
+            for k, i in enumerate(idxs):
+                streams = [deflated[j] for j, (ii, _) in enumerate(jobs) if ii == k]
+                out[i] = self._entropy_encode(downloaded[k], (H, W), imgs[i].extension, streams)
         return out
 
     def decompress_uint8(self, img_encoded: bytes) -> np.ndarray:
@@ -169,7 +177,12 @@ class Jpeg:
         return out
 
     # -- host-side entropy coding (byte-compatible with jpeg.py:531-674) -------------------------
-    def _entropy_encode(self, layers, layer_shape, extension) -> bytes:
+    def _deflate_layer(self, L) -> bytes:
+        # With the device-side stream layout the coefficients already arrive zigzag-ordered (jpeg.py:579-590).
+        zz = L["coef"] if L.get("zigzag") else _zigzag_stream(L["coef"], L["leaves"][:, 2], self.zigzag_cache, inverse=False)
+        return zlib.compress(zz.tobytes(), level=9)
+
+    def _entropy_encode(self, layers, layer_shape, extension, streams=None) -> bytes:
         s = self.settings
         out = BytesIO()
         meta = {"height": int(layer_shape[0]), "width": int(layer_shape[1]), "num_layers": len(layers),
@@ -180,15 +193,9 @@ class Jpeg:
         out.write(mb)
         lib = native.load()
 
-        def deflate(L):
-            # zlib releases the GIL: the three layers are compressed concurrently (same bytes as the reference's
-            # sequential zlib.compress(level=9), jpeg.py:590).  With the device-side stream layout the coefficients
-            # already arrive zigzag-ordered.
-            zz = L["coef"] if L.get("zigzag") else _zigzag_stream(L["coef"], L["leaves"][:, 2], self.zigzag_cache, inverse=False)
-            return zlib.compress(zz.tobytes(), level=9)
-
-        with ThreadPoolExecutor(max_workers=len(layers)) as pool:
-            streams = list(pool.map(deflate, layers))
+        if streams is None:
+            with ThreadPoolExecutor(max_workers=len(layers)) as pool:
+                streams = list(pool.map(self._deflate_layer, layers))
         for L, z in zip(layers, streams):
             states = np.ascontiguousarray(L["states"], dtype=np.uint8)
             if "packed_states" in L:
