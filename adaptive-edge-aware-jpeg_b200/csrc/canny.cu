@@ -446,7 +446,7 @@ __global__ void k_thresholds_from_double(const double* thr_d, int* thr) { canny_
 // tile 64x32, 8 warps; each warp classifies 32 consecutive pixels of a row and ballots them into
 // one bitmap word.   grid: (tiles x, tiles y, planes)
 // ---------------------------------------------------------------------------------------------
-constexpr int NM_TW = 64, NM_TH = 32;
+constexpr int NM_TW = 64, NM_TH = 64;
 constexpr int NM_SS = NM_TW + 8;                      // source tile: 72 columns starting at X0-4 (4-byte aligned)
 constexpr int NM_MS = NM_TW + 4;                      // magnitude tile: 68 columns starting at X0-1
 __global__ void __launch_bounds__(256) k_canny_nms(const PlaneDesc* __restrict__ planes, const __grid_constant__ TileMap tm) {
@@ -510,8 +510,8 @@ __global__ void __launch_bounds__(256) k_canny_nms(const PlaneDesc* __restrict__
     const int low = P.thr[0], high = P.thr[1];
     const int lane = tid & 31;
     const int gx4 = (tid & 15) * 4;                                // first of the 4 px inside the tile row
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
+#pragma unroll 2
+    for (int half = 0; half < NM_TH / 16; half++) {
         const int ty = (tid >> 4) + half * 16;
         const int y = Y0 + ty;
         // magnitude rows ty, ty+1, ty+2 of sM (pixel rows y-1, y, y+1), columns gx4 .. gx4+5 (pixel x-1 .. x+4)
