@@ -222,6 +222,20 @@ def main():
     ms = e0.elapsed_time(e1)
     out = torch.cat(out)
     launches_per_step = codec.last_launches
+    # the same step with 8-bit pixels resident in HBM on both ends (18 instead of 36 compulsory B/px)
+    rgb8 = host_in8.to(f"cuda:{local}")
+    for _ in range(2):
+        codec.roundtrip_device(rgb8, SPACE, QRANGE, BRANGE, streams=args.streams, out="u8")
+    barrier()
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u0.record()
+    for _ in range(args.steps):
+        out8 = codec.roundtrip_device(rgb8, SPACE, QRANGE, BRANGE, streams=args.streams, out="u8")
+    u1.record()
+    barrier()
+    ms_u8 = u0.elapsed_time(u1)
+    u8_check = int((torch.cat(out8).to(torch.int16) - (out * 255).to(torch.uint8).to(torch.int16)).abs().max())
+    del rgb8
     torch.cuda.synchronize()
     status = codec._plan(rgb.chunk(args.streams)[0].shape[0], H, W, SPACE, BRANGE, QRANGE, instance=1000).out.status.cpu().numpy()
 
@@ -269,8 +283,8 @@ def main():
     counts_np = codec._plan(Bs, H, W, SPACE, BRANGE, QRANGE).out.counts.cpu().numpy()
 
     if world > 1:
-        t = reduce_max(torch.tensor([ms, e2e_ms, e2e_f32_ms], device=f"cuda:{local}", dtype=torch.float64), dist)
-        ms, e2e_ms, e2e_f32_ms = float(t[0]), float(t[1]), float(t[2])
+        t = reduce_max(torch.tensor([ms, e2e_ms, e2e_f32_ms, ms_u8], device=f"cuda:{local}", dtype=torch.float64), dist)
+        ms, e2e_ms, e2e_f32_ms, ms_u8 = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -345,6 +359,9 @@ def main():
                     "f32": {"value": whole_job_mps(world, B, f32_steps, e2e_f32_ms), "unit": "MP/s", "steps": f32_steps,
                             "h2d_bytes_per_step": int(h2d_f // f32_steps), "d2h_bytes_per_step": int(d2h_f // f32_steps),
                             "api": "same call with float32 host buffers (Image.data in / out)", "max_abs_diff_vs_device_path": f32_check}},
+            "value_u8_io": {"value": whole_job_mps(world, B, args.steps, ms_u8), "unit": "MP/s", "ms_per_step": ms_u8 / args.steps,
+                            "note": "same step, uint8 pixels resident in HBM in and out (Image.load / Image.get_uint8 conversions on the device)",
+                            "max_abs_diff_vs_f32_path_u8_view": u8_check},
             "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
