@@ -41,9 +41,24 @@ __global__ void __launch_bounds__(256) k_dct_rows(const PlaneDesc* __restrict__ 
     const int count = *count_ptr;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sub = lane / S, r = lane % S;            // leaf slot in warp, row in leaf
-    float mrow[S];                                     // M[r][*] for pass 2
+    // S >= 16 uses the even / odd symmetry of the DCT matrix, C[k][S-1-i] = (-1)^k C[k][i], in both passes: half the FMAs
+    // and half the shared-memory reads of the matrix (the passes are bound by shared-memory latency, not by HBM).
+    constexpr bool EO = (S >= 16);
+    constexpr int Hh = S / 2;
+    // pass-2 coefficients of this lane.  plain: M[r][i], i < S.  EO forward (lane = frequency k): C[k][i], i < S/2.
+    // EO inverse (lane pair i, S-1-i; the low lane sums the even k, the high lane the odd k): C[2kk+par][min(i, S-1-i)].
+    float mrow[EO ? Hh : S];
+    if (!EO) {
 #pragma unroll
-    for (int i = 0; i < S; i++) mrow[i] = sMt[i * S + r];
+        for (int i = 0; i < S; i++) mrow[i] = sMt[i * S + r];
+    } else if (!INVERSE) {
+#pragma unroll
+        for (int i = 0; i < Hh; i++) mrow[i] = sMt[i * S + r];
+    } else {
+        const int rlo = min(r, S - 1 - r), par = (r < Hh) ? 0 : 1;
+#pragma unroll
+        for (int kk = 0; kk < Hh; kk++) mrow[kk] = sMt[(2 * kk + par) * S + rlo];
+    }
     const int groups = (count + LPW - 1) / LPW;        // warp-sized groups of leaves
     for (int g = blockIdx.x * 8 + warp; g < groups; g += gridDim.x * 8) {
         const int li = g * LPW + sub;
@@ -107,23 +122,86 @@ __global__ void __launch_bounds__(256) k_dct_rows(const PlaneDesc* __restrict__ 
             for (int j = 0; j < S; j++) in[j] = act ? T[r * TS + j] : 0.0f;
             __syncwarp();
         }
-        // pass 1: t[l] = sum_j in[j] * M[l][j]
-#pragma unroll
-        for (int l = 0; l < S; l++) {
-            float acc = 0.0f;
-#pragma unroll
-            for (int j = 0; j < S; j++) acc = __fmaf_rn(in[j], sM[l * S + j], acc);
-            T[r * TS + l] = acc;
-        }
-        __syncwarp();
-        // pass 2: out[l] = sum_i M[r][i] * T[i][l]
         float out[S];
+        if (!EO) {
+            // pass 1: t[l] = sum_j in[j] * M[l][j]
 #pragma unroll
-        for (int l = 0; l < S; l++) out[l] = 0.0f;
+            for (int l = 0; l < S; l++) {
+                float acc = 0.0f;
 #pragma unroll
-        for (int i = 0; i < S; i++) {
+                for (int j = 0; j < S; j++) acc = __fmaf_rn(in[j], sM[l * S + j], acc);
+                T[r * TS + l] = acc;
+            }
+            __syncwarp();
+            // pass 2: out[l] = sum_i M[r][i] * T[i][l]
 #pragma unroll
-            for (int l = 0; l < S; l++) out[l] = __fmaf_rn(mrow[i], T[i * TS + l], out[l]);
+            for (int l = 0; l < S; l++) out[l] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < S; i++) {
+#pragma unroll
+                for (int l = 0; l < S; l++) out[l] = __fmaf_rn(mrow[i], T[i * TS + l], out[l]);
+            }
+        } else if (!INVERSE) {
+            // pass 1 (rows): fold the input, t[2m] = sum_{j<h} (x[j] + x[S-1-j]) C[2m][j], t[2m+1] = sum_{j<h} (x[j] - x[S-1-j]) C[2m+1][j]
+            float u[Hh], d[Hh];
+#pragma unroll
+            for (int j = 0; j < Hh; j++) { u[j] = __fadd_rn(in[j], in[S - 1 - j]); d[j] = __fsub_rn(in[j], in[S - 1 - j]); }
+#pragma unroll
+            for (int m = 0; m < Hh; m++) {
+                float ae = 0.0f, ao = 0.0f;
+#pragma unroll
+                for (int j = 0; j < Hh; j++) { ae = __fmaf_rn(u[j], sM[(2 * m) * S + j], ae); ao = __fmaf_rn(d[j], sM[(2 * m + 1) * S + j], ao); }
+                T[r * TS + 2 * m] = ae; T[r * TS + 2 * m + 1] = ao;
+            }
+            __syncwarp();
+            // fold the rows of the intermediate in place: row i <- T[i] + T[S-1-i], row S-1-i <- T[i] - T[S-1-i]; the two lanes
+            // of a row pair take half the columns each
+            {
+                const int rlo = min(r, S - 1 - r), rhi = S - 1 - rlo, c0 = (r < Hh) ? 0 : Hh;
+#pragma unroll
+                for (int l = 0; l < Hh; l += 4) {
+                    float4 a = *reinterpret_cast<const float4*>(T + rlo * TS + c0 + l), b = *reinterpret_cast<const float4*>(T + rhi * TS + c0 + l);
+                    *reinterpret_cast<float4*>(T + rlo * TS + c0 + l) = make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
+                    *reinterpret_cast<float4*>(T + rhi * TS + c0 + l) = make_float4(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z), __fsub_rn(a.w, b.w));
+                }
+            }
+            __syncwarp();
+            // pass 2 (columns): lane = frequency k; even k reads the sum rows (0 .. h-1), odd k the difference rows (S-1 .. h)
+            const float* Tb = (r & 1) ? (T + (S - 1) * TS) : T;
+            const int step = (r & 1) ? -TS : TS;
+#pragma unroll
+            for (int l = 0; l < S; l++) out[l] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < Hh; i++) {
+#pragma unroll
+                for (int l = 0; l < S; l++) out[l] = __fmaf_rn(mrow[i], Tb[i * step + l], out[l]);
+            }
+        } else {
+            // pass 1 (rows): E[l] = sum_{j even} z[j] C[j][l], O[l] = sum_{j odd} z[j] C[j][l] (l < h); t[l] = E + O, t[S-1-l] = E - O
+#pragma unroll
+            for (int l = 0; l < Hh; l++) {
+                float ae = 0.0f, ao = 0.0f;
+#pragma unroll
+                for (int j = 0; j < S; j += 2) { ae = __fmaf_rn(in[j], sM[l * S + j], ae); ao = __fmaf_rn(in[j + 1], sM[l * S + j + 1], ao); }
+                T[r * TS + l] = __fadd_rn(ae, ao); T[r * TS + S - 1 - l] = __fsub_rn(ae, ao);
+            }
+            __syncwarp();
+            // pass 2 (columns): the lane pair (i, S-1-i) shares the work -- the low lane sums the even k, the high lane the odd k
+            const int par = (r < Hh) ? 0 : 1;
+            float acc[S];
+#pragma unroll
+            for (int l = 0; l < S; l++) acc[l] = 0.0f;
+#pragma unroll
+            for (int kk = 0; kk < Hh; kk++) {
+                const float* Tk = T + (2 * kk) * TS + par * TS;
+#pragma unroll
+                for (int l = 0; l < S; l++) acc[l] = __fmaf_rn(mrow[kk], Tk[l], acc[l]);
+            }
+#pragma unroll
+            for (int l = 0; l < S; l++) {
+                const float other = __shfl_xor_sync(0xffffffffu, acc[l], S - 1);
+                out[l] = par ? __fsub_rn(other, acc[l]) : __fadd_rn(acc[l], other);     // row i: E + O, row S-1-i: E - O
+            }
         }
         __syncwarp();
         if (act) {
