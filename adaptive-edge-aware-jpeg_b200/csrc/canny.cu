@@ -175,8 +175,10 @@ __global__ void __launch_bounds__(256, 4) k_prefilter(const PlaneDesc* __restric
     if (Y0 < P.ry0 || Y0 >= P.ry1) return;             // halo-split bands are multiples of the tile height
     __shared__ __align__(16) uint8_t sA[PF_TH + 6][PF_AS];     // CLAHE output (or source), halo 3
     __shared__ __align__(16) uint16_t sG[PF_TH + 4][PF_AS];    // 4 x Gaussian output, halo 2
-    __shared__ __align__(16) uint8_t sLut[16][256];            // general path only
-    __shared__ uint32_t sQuad[256];                            // uniform path: the four LUT bytes of value v in one word
+    __shared__ __align__(16) uint8_t sLut[16][256];            // general path only (tiny planes: > 2 CLAHE tile pairs per axis)
+    __shared__ uint32_t sQuad[4][256];                         // packed path: the four LUT bytes of value v in one word, per
+                                                               // (row regime, column regime); a tile straddles at most one CLAHE
+                                                               // tile-centre line per axis unless the plane is tiny
     __shared__ float sW[4][256];                               // space weight (r^2 = 0,1,2,4) x colour weight, rounded product
     __shared__ unsigned int sHist[256];
     __shared__ __align__(16) float sXa[PF_AS];                 // CLAHE interpolation weights per tile column / row
@@ -184,6 +186,8 @@ __global__ void __launch_bounds__(256, 4) k_prefilter(const PlaneDesc* __restric
     __shared__ uint8_t sTx[PF_AS][2], sTy[PF_TH + 6][2];       // CLAHE tile indices per tile column / row
     __shared__ __align__(16) int sFx[PF_AS];                   // REFLECT_101-folded source coordinates
     __shared__ int sFy[PF_TH + 6];
+    __shared__ __align__(16) int sCo[PF_AS];                   // byte offset of the column's regime table inside sQuad (0 / 1024)
+    __shared__ int sRo[PF_TH + 6];                             // same for the row regime (0 / 2048)
     const int tid = threadIdx.x;
     const ClaheGeom g = clahe_geom(P.h, P.w);
     auto tile_of = [](int coord, float inv, float& frac, int& t_lo, int& t_hi) {
@@ -192,26 +196,33 @@ __global__ void __launch_bounds__(256, 4) k_prefilter(const PlaneDesc* __restric
         frac = __fsub_rn(tf, (float)t1);
         t_lo = max(t1, 0); t_hi = min(t1 + 1, 3);
     };
-    int same = 1;                                              // does this column / row use the tiles of column / row 0?
+    // regime 0 = the tile pair of column / row 0, regime 1 = the pair of the last column / row; anything else -> general path
+    int two_ok = 1;
     if (tid < PF_AS) {
         const int x = reflect101(X0 + tid - 3, P.w);
         sFx[tid] = x;
-        float fr, fr0; int lo, hi, lo0, hi0;
+        float fr, fr0; int lo, hi, lo0, hi0, loL, hiL;
         tile_of(x, g.inv_tw, fr, lo, hi);
         tile_of(reflect101(X0 - 3, P.w), g.inv_tw, fr0, lo0, hi0);
+        tile_of(reflect101(X0 + PF_AS - 4, P.w), g.inv_tw, fr0, loL, hiL);
         sXa[tid] = fr;
         sTx[tid][0] = (uint8_t)lo; sTx[tid][1] = (uint8_t)hi;
-        same = (lo == lo0 && hi == hi0);
+        const bool r0 = (lo == lo0 && hi == hi0), r1 = (lo == loL && hi == hiL);
+        sCo[tid] = r0 ? 0 : 1024;
+        two_ok = r0 || r1;
     } else if (tid >= PF_AS && tid < PF_AS + PF_TH + 6) {
         const int r = tid - PF_AS;
         const int y = reflect101(Y0 + r - 3, P.h);
         sFy[r] = y;
-        float fr, fr0; int lo, hi, lo0, hi0;
+        float fr, fr0; int lo, hi, lo0, hi0, loL, hiL;
         tile_of(y, g.inv_th, fr, lo, hi);
         tile_of(reflect101(Y0 - 3, P.h), g.inv_th, fr0, lo0, hi0);
+        tile_of(reflect101(Y0 + PF_TH + 2, P.h), g.inv_th, fr0, loL, hiL);
         sYa[r] = fr;
         sTy[r][0] = (uint8_t)(lo * 4); sTy[r][1] = (uint8_t)(hi * 4);
-        same = (lo == lo0 && hi == hi0);
+        const bool r0 = (lo == lo0 && hi == hi0), r1 = (lo == loL && hi == hiL);
+        sRo[r] = r0 ? 0 : 2048;
+        two_ok = r0 || r1;
     }
     {
         float cw = c_bil_color[tid];
@@ -221,13 +232,18 @@ __global__ void __launch_bounds__(256, 4) k_prefilter(const PlaneDesc* __restric
         sW[3][tid] = __fmul_rn(c_bil_space[0], cw);            // r^2 = 4
         sHist[tid] = 0;
     }
-    const bool uniform = __syncthreads_and(same) != 0;         // (also publishes the tables above)
+    const bool uniform = __syncthreads_and(two_ok) != 0;       // packed path usable (also publishes the tables above)
     const bool clahe = (stages & 1) != 0;
     if (clahe) {
         if (uniform) {
             const uint8_t* l = P.clahe_lut;
-            const int r0 = sTy[0][0] * 256, r1 = sTy[0][1] * 256, c0 = sTx[0][0] * 256, c1 = sTx[0][1] * 256;
-            sQuad[tid] = (uint32_t)l[r0 + c0 + tid] | ((uint32_t)l[r0 + c1 + tid] << 8) | ((uint32_t)l[r1 + c0 + tid] << 16) | ((uint32_t)l[r1 + c1 + tid] << 24);
+            const int rr[2] = {sTy[0][0] * 256, sTy[PF_TH + 5][0] * 256}, rh[2] = {sTy[0][1] * 256, sTy[PF_TH + 5][1] * 256};
+            const int cl[2] = {sTx[0][0] * 256, sTx[PF_AS - 1][0] * 256}, ch[2] = {sTx[0][1] * 256, sTx[PF_AS - 1][1] * 256};
+            const int nry = (sRo[PF_TH + 5] != 0) ? 2 : 1, ncx = (sCo[PF_AS - 1] != 0) ? 2 : 1;
+            for (int ry = 0; ry < nry; ry++)
+                for (int cx = 0; cx < ncx; cx++)
+                    sQuad[ry * 2 + cx][tid] = (uint32_t)l[rr[ry] + cl[cx] + tid] | ((uint32_t)l[rr[ry] + ch[cx] + tid] << 8) |
+                                              ((uint32_t)l[rh[ry] + cl[cx] + tid] << 16) | ((uint32_t)l[rh[ry] + ch[cx] + tid] << 24);
         } else {
             for (int i = tid; i < 16 * 256 / 4; i += 256) reinterpret_cast<uint32_t*>(&sLut[0][0])[i] = reinterpret_cast<const uint32_t*>(P.clahe_lut)[i];
         }
@@ -247,9 +263,13 @@ __global__ void __launch_bounds__(256, 4) k_prefilter(const PlaneDesc* __restric
                 const float4 xa4 = *reinterpret_cast<const float4*>(&sXa[gx]);
                 const float xav[4] = {xa4.x, xa4.y, xa4.z, xa4.w};
                 const float ya = sYa[ry], ya1 = __fsub_rn(1.0f, ya);
+                const int4 co4 = *reinterpret_cast<const int4*>(&sCo[gx]);
+                const int ro = sRo[ry];
+                const int cov[4] = {co4.x + ro, co4.y + ro, co4.z + ro, co4.w + ro};
+                const char* qbase = reinterpret_cast<const char*>(&sQuad[0][0]);
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    const uint32_t q = sQuad[v[k]];
+                    const uint32_t q = *reinterpret_cast<const uint32_t*>(qbase + cov[k] + v[k] * 4);
                     const float xa = xav[k], xa1 = __fsub_rn(1.0f, xa);
                     const float a = __fmul_rn((float)(q & 0xffu), xa1), b = __fmul_rn((float)((q >> 8) & 0xffu), xa);
                     const float c = __fmul_rn((float)((q >> 16) & 0xffu), xa1), d = __fmul_rn((float)(q >> 24), xa);
@@ -279,18 +299,29 @@ __global__ void __launch_bounds__(256, 4) k_prefilter(const PlaneDesc* __restric
     // stage B: Gaussian [1 2 1]x[1 2 1], 4 outputs per thread sharing the 6 column sums; stored as 4 * value (u16)
     for (int i = tid; i < (PF_TH + 4) * (PF_CG + 1); i += 256) {
         const int ry = i / (PF_CG + 1), gx = (i - ry * (PF_CG + 1)) * 4;            // output cells (ry, gx..gx+3) of the halo-2 region
-        int o[4];
         if (stages & 2) {
-            int cs[6];
+            // two 16-bit lanes per register: (c0,c1), (c2,c3), (c4,c5) of each of the three rows -> column sums -> row sums
+            uint32_t cs[3];
+            {
+                uint32_t p[3][3];
 #pragma unroll
-            for (int j = 0; j < 6; j++) cs[j] = sA[ry][gx + j] + 2 * sA[ry + 1][gx + j] + sA[ry + 2][gx + j];
+                for (int r = 0; r < 3; r++) {
+                    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(&sA[ry + r][gx]), w1 = *reinterpret_cast<const uint32_t*>(&sA[ry + r][gx + 4]);
+                    p[r][0] = __byte_perm(w0, 0, 0x4140); p[r][1] = __byte_perm(w0, 0, 0x4342); p[r][2] = __byte_perm(w1, 0, 0x4140);
+                }
 #pragma unroll
-            for (int k = 0; k < 4; k++) o[k] = (cs[k] + 2 * cs[k + 1] + cs[k + 2] + 8) >> 4;
+                for (int j = 0; j < 3; j++) cs[j] = p[0][j] + 2 * p[1][j] + p[2][j];          // <= 1020 per lane
+            }
+            const uint32_t s1 = __byte_perm(cs[0], cs[1], 0x5432), s3 = __byte_perm(cs[1], cs[2], 0x5432);   // (c1,c2), (c3,c4)
+            const uint32_t o01 = cs[0] + cs[1] + 0x00080008u + 2 * s1, o23 = cs[1] + cs[2] + 0x00080008u + 2 * s3;   // sum + 8, <= 4088
+            // ((x >> 4) << 2) per lane: the two bits that cross the lane boundary are masked away
+            *reinterpret_cast<uint2*>(&sG[ry][gx]) = make_uint2((o01 >> 2) & 0x03fc03fcu, (o23 >> 2) & 0x03fc03fcu);
         } else {
+            int o[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) o[k] = sA[ry + 1][gx + 1 + k];
+            *reinterpret_cast<uint2*>(&sG[ry][gx]) = make_uint2((uint32_t)(o[0] << 2) | ((uint32_t)(o[1] << 2) << 16), (uint32_t)(o[2] << 2) | ((uint32_t)(o[3] << 2) << 16));
         }
-        *reinterpret_cast<uint2*>(&sG[ry][gx]) = make_uint2((uint32_t)(o[0] << 2) | ((uint32_t)(o[1] << 2) << 16), (uint32_t)(o[2] << 2) | ((uint32_t)(o[3] << 2) << 16));
     }
     __syncthreads();
     // stage C: bilateral, thread -> 4 consecutive px in rows 2*(tid/16) and 2*(tid/16) + 1 of each 32-row half of the tile
@@ -326,7 +357,14 @@ __global__ void __launch_bounds__(256, 4) k_prefilter(const PlaneDesc* __restric
                     sum = __fmaf_rn((float)v0, w_c, sum); wsum = __fadd_rn(wsum, w_c);
                     BIL_TAPS_DN(BIL_ONE)
 #undef BIL_ONE
-                    const int res = __float2int_rn(__fmul_rn(__fdiv_rn(sum, wsum), 0.25f));
+                    // cvRound(sum / wsum): an approximate quotient decides unless it is within 1e-3 of a .5 tie (its error is
+                    // < 1e-4 on values <= 255), where the correctly rounded division is taken
+                    float rw;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rw) : "f"(wsum));
+                    const float q0 = __fmul_rn(__fmul_rn(sum, rw), 0.25f);
+                    const float kf = rintf(q0);
+                    int res = (int)kf;
+                    if (fabsf(__fsub_rn(q0, kf)) > 0.499f) res = __float2int_rn(__fmul_rn(__fdiv_rn(sum, wsum), 0.25f));
                     outw[rr] |= (uint32_t)min(max(res, 0), 255) << (8 * k);
                 }
         } else {
