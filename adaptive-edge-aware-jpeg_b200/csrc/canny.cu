@@ -386,16 +386,15 @@ __global__ void __launch_bounds__(256, 4) k_prefilter(const PlaneDesc* __restric
             for (int k = 0; k < 4; k++) if (x + k < P.w) drow[x + k] = (uint8_t)(outw[rr] >> (8 * k));
         }
         if (do_hist) {
-            int prev = -1, cnt = 0;
+            // shared-memory atomics; four equal px (flat areas, where same-address conflicts would serialise) -> one add of 4
+            const uint32_t w = outw[rr], b0 = w & 0xffu;
+            if ((x + 3 < P.w) && (w == b0 * 0x01010101u)) {
+                atomicAdd(&sHist[b0], 4u);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (x + k < P.w) {
-                    const int ov = (outw[rr] >> (8 * k)) & 0xff;
-                    if (ov == prev) cnt++;
-                    else { if (cnt) atomicAdd(&sHist[prev], (unsigned)cnt); prev = ov; cnt = 1; }
-                }
+                for (int k = 0; k < 4; k++)
+                    if (x + k < P.w) atomicAdd(&sHist[(w >> (8 * k)) & 0xffu], 1u);
             }
-            if (cnt) atomicAdd(&sHist[prev], (unsigned)cnt);
         }
     }
     }
