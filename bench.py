@@ -322,7 +322,7 @@ def main():
     alg_bytes = alg.get(dom)
     dom_ms = stage_ms[dom]
     # measured DRAM traffic of that kernel per launch (dram__bytes_read + write from the committed `ncu --set full`
-    # capture of one 8-frame launch, tests/_prof_step.py); null for other sub-batch sizes / kernels not captured
+    # capture of one 8-frame launch, tools/prof_step.py); null for other sub-batch sizes / kernels not captured
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))

@@ -1,4 +1,4 @@
-"""scratch tool: leaf-size census of the C2 bench frames"""
+"""measurement tool: leaf-size census of the C2 bench frames"""
 import sys, torch, numpy as np
 sys.path.insert(0,'adaptive-edge-aware-jpeg_b200'); sys.path.insert(0,'tests')
 from aeaj.codec import get_codec

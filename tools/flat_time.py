@@ -1,4 +1,4 @@
-"""scratch: prefilter time on flat / noisy inputs (histogram atomics worst cases)"""
+"""measurement tool: prefilter time on flat / noisy inputs (histogram atomics worst cases)"""
 import sys, torch, numpy as np
 sys.path.insert(0,'adaptive-edge-aware-jpeg_b200'); sys.path.insert(0,'tests')
 from aeaj.codec import get_codec

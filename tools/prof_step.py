@@ -1,4 +1,4 @@
-"""scratch tool for ncu: two device-resident steps (encode+decode) of the C2 workload; usage: python tests/_prof_step.py [B]"""
+"""measurement tool for ncu: two device-resident steps (encode+decode) of the C2 workload; usage: python tools/prof_step.py [B]"""
 import sys, torch, numpy as np
 sys.path.insert(0,'adaptive-edge-aware-jpeg_b200'); sys.path.insert(0,'tests')
 from aeaj.codec import get_codec

@@ -1,4 +1,4 @@
-"""scratch tool: per-stage device times (ms) of the C2 workload; usage: python tests/_stage_times.py [B] [tensor]"""
+"""measurement tool: per-stage device times (ms) of the C2 workload; usage: python tools/stage_times.py [B] [tensor]"""
 import sys, torch, numpy as np
 sys.path.insert(0,'adaptive-edge-aware-jpeg_b200'); sys.path.insert(0,'tests')
 from aeaj.codec import get_codec

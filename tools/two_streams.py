@@ -1,4 +1,4 @@
-"""scratch: does running two half-batches on two CUDA streams hide the latency-bound stages?"""
+"""measurement tool: does running two half-batches on two CUDA streams hide the latency-bound stages?"""
 import sys, torch, numpy as np
 sys.path.insert(0,'adaptive-edge-aware-jpeg_b200'); sys.path.insert(0,'tests')
 from aeaj.codec import get_codec
