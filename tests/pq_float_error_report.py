@@ -1,3 +1,4 @@
+"""checker-side report (uses the oracle, hence under tests/): decoded float error of the PQ spaces for both DCT paths; run from the repo root on a GPU box"""
 import sys, torch, numpy as np
 sys.path.insert(0,'adaptive-edge-aware-jpeg_b200'); sys.path.insert(0,'tests'); sys.path.insert(0,'oracle')
 import oracle as O

@@ -1,3 +1,4 @@
+"""measurement tool: hysteresis round / dirty-tile statistics of the bench frames"""
 import sys, os, torch, numpy as np
 sys.path.insert(0,'adaptive-edge-aware-jpeg_b200'); sys.path.insert(0,'tests')
 from aeaj.codec import get_codec

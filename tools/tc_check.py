@@ -1,5 +1,6 @@
+"""measurement tool: tensor-core vs FP32 128x128 DCT / IDCT (mismatch counts, phase clocks, stage times); usage: python tools/tc_check.py H W"""
 import sys, torch, numpy as np
-sys.path.insert(0,'adaptive-edge-aware-jpeg_b200'); sys.path.insert(0,'tests'); sys.path.insert(0,'oracle')
+sys.path.insert(0,'adaptive-edge-aware-jpeg_b200'); sys.path.insert(0,'tests')
 from aeaj.codec import get_codec
 from synth import synth
 c = get_codec(0)
