@@ -486,6 +486,13 @@ __global__ void k_thresholds_from_double(const double* thr_d, int* thr) { canny_
 constexpr int NM_TW = 64, NM_TH = 64;
 constexpr int NM_SS = NM_TW + 8;                      // source tile: 72 columns starting at X0-4 (4-byte aligned)
 constexpr int NM_MS = NM_TW + 4;                      // magnitude tile: 68 columns starting at X0-1
+// unsigned bytes of a . signed bytes of b + c
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 __global__ void __launch_bounds__(256) k_canny_nms(const PlaneDesc* __restrict__ planes, const __grid_constant__ TileMap tm) {
     int plane_i, txi, tyi;
     tile_decode(tm, blockIdx.x, plane_i, txi, tyi);
@@ -516,24 +523,24 @@ __global__ void __launch_bounds__(256) k_canny_nms(const PlaneDesc* __restrict__
     // its 3x3 window starts at source tile row ry, column c+2
     for (int i = tid; i < (NM_TH + 2) * (NM_MS / 4); i += 256) {
         const int ry = i / (NM_MS / 4), c0 = (i - ry * (NM_MS / 4)) * 4;
-        int r[3][6];
+        // columns c0 .. c0+7 of the three source rows as two aligned words each; cell k reads bytes k+2 .. k+4.  The Sobel
+        // sums are byte dot products (dp4a, unsigned pixels x signed taps): gx = rows (1,2,1) x (-1,0,1), gy = (bottom - top) x (1,2,1)
+        uint32_t wa[3], wb[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            // columns c0+2 .. c0+7 of the source tile: two aligned words starting at c0 (c0 % 4 == 0)
-            const uchar4 a = *reinterpret_cast<const uchar4*>(&sS[ry + k][c0]);
-            const uchar4 b = *reinterpret_cast<const uchar4*>(&sS[ry + k][c0 + 4]);
-            r[k][0] = a.z; r[k][1] = a.w; r[k][2] = b.x; r[k][3] = b.y; r[k][4] = b.z; r[k][5] = b.w;
+            wa[k] = *reinterpret_cast<const uint32_t*>(&sS[ry + k][c0]);
+            wb[k] = *reinterpret_cast<const uint32_t*>(&sS[ry + k][c0 + 4]);
         }
-        int cs[6], cd[6];
-#pragma unroll
-        for (int j = 0; j < 6; j++) { cs[j] = r[0][j] + 2 * r[1][j] + r[2][j]; cd[j] = r[2][j] - r[0][j]; }
         int m[4], d[4];
         const int y = Y0 - 1 + ry;
         const bool yin = (y >= 0 && y < P.h);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
+            constexpr unsigned sel[4] = {0x5432u, 0x6543u, 0x7654u, 0x7765u};
+            const uint32_t t = __byte_perm(wa[0], wb[0], sel[k]), c = __byte_perm(wa[1], wb[1], sel[k]), b = __byte_perm(wa[2], wb[2], sel[k]);
+            int gx = dp4a_us(b, 0x000100ffu, dp4a_us(c, 0x000200feu, dp4a_us(t, 0x000100ffu, 0)));
+            int gy = dp4a_us(b, 0x00010201u, dp4a_us(t, 0x00fffeffu, 0));
             const int x = X0 - 1 + c0 + k;
-            int gx = cs[k + 2] - cs[k], gy = cd[k] + 2 * cd[k + 1] + cd[k + 2];
             const bool in = yin && x >= 0 && x < P.w;
             gx = in ? gx : 0; gy = in ? gy : 0;
             m[k] = gx * gx + gy * gy;
