@@ -511,3 +511,20 @@ def test_uint8_io_bit_exact(codec, space, shape, b):
     assert np.array_equal(Jpeg(JpegCompressionSettings()).decompress_uint8(a), dec.get_uint8())
     _ = img8.data                                              # handing the floats out drops the shortcut
     assert img8.uint8_source() is None and np.array_equal(img8.data, as_float[0])
+
+
+def test_two_stream_roundtrip_equals_single_stream(codec):
+    """DeviceCodec.roundtrip_device spreads a batch over two CUDA streams (two plans): same bits as one plan, one stream."""
+    import torch
+    H, W = 272, 480
+    space, q, b = "YCbCr", (30, 95), (4, 128)
+    batch = torch.from_numpy(np.stack([synth(H, W, seed=s) for s in range(6)])).cuda()
+    one = codec.decode_encoded(codec.encode(batch, space, q, b), space, q, b).clone()
+    for n in (2, 3):
+        parts = codec.roundtrip_device(batch, space, q, b, streams=n)
+        torch.cuda.synchronize()
+        assert torch.equal(torch.cat(parts), one)
+    parts8 = codec.roundtrip_device((batch * 255).to(torch.uint8), space, q, b, streams=2, out="u8")
+    ref8 = codec.decode_encoded(codec.encode((batch * 255).to(torch.uint8), space, q, b), space, q, b, out="u8")
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat(parts8), ref8)
