@@ -141,6 +141,8 @@ struct aeaj_handle {
     float* dct_half_all_dev;
     int32_t* zz_dev[9];           // zigzag tables per log2(size), device
     int32_t* zz_all_dev;
+    int32_t* izz256_dev;          // inverse zigzag permutation for 256x256
+    float* dct256_scratch;        // per-CTA intermediate tiles of k_dct256 (allocated on first use)
     int32_t* tc_izz_dev;          // inverse zigzag permutation for 128x128 (tensor-core IDCT loader)
     float* dct_tc_tiles_dev;      // [Ch | Cl] tiles of the 128x128 DCT matrix for the tcgen05 path
     int* tc_err_dev;              // set by the tcgen05 kernel if a barrier wait timed out

@@ -129,7 +129,7 @@ extern "C" int aeaj_create(int device, aeaj_handle** out) {
 extern "C" int aeaj_destroy(aeaj_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    cudaFree(h->srgb_lut_dev); cudaFree(h->dct_all_dev); cudaFree(h->dct_half_all_dev); cudaFree(h->zz_all_dev); cudaFree(h->dct_tc_tiles_dev); cudaFree(h->tc_izz_dev); cudaFree(h->tc_err_dev); cudaFree(h->stage_plane_dev);
+    cudaFree(h->srgb_lut_dev); cudaFree(h->dct_all_dev); cudaFree(h->dct_half_all_dev); cudaFree(h->zz_all_dev); cudaFree(h->izz256_dev); cudaFree(h->dct256_scratch); cudaFree(h->dct_tc_tiles_dev); cudaFree(h->tc_izz_dev); cudaFree(h->tc_err_dev); cudaFree(h->stage_plane_dev);
     cudaFree(h->stage_class_off_dev); cudaFree(h->stage_tile_base_dev); cudaFree(h->stage_outs_dev);
     free(h);
     return 0;
@@ -311,7 +311,7 @@ extern "C" int aeaj_quadtree_caps(int h, int w, int mn, int mx, int64_t* cl, int
 }
 static int check_blocks(int h, int w, int mn, int mx) {
     AEAJ_REQUIRE(mn >= 2 && mx >= mn && !(mn & (mn - 1)) && !(mx & (mx - 1)), "block sizes must be powers of two with 2 <= min <= max");
-    AEAJ_REQUIRE(mx <= 128, "block sizes above 128 are not supported by this build");
+    AEAJ_REQUIRE(mx <= 256, "block sizes above 256 are not supported");
     AEAJ_REQUIRE(aeaj_root_size(h, w) >= mn, "image smaller than the minimum block size");
     AEAJ_REQUIRE(std::min(mx, aeaj_root_size(h, w)) / mn <= 128, "max/min block ratio above 128 is not supported");
     return 0;

@@ -556,12 +556,110 @@ int launch_cta(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* li
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// 256 x 256 leaves.  Only the reference's GUI sliders reach this size (gui/main_frame.py:44-45), so this is a plain,
+// untuned kernel: one CTA per leaf, two tiled FP32 GEMMs (64 x 64 output tiles, K chunks of 16) through a per-CTA
+// global scratch tile; sequential-k FMA accumulation like the other FP32 kernels, the same fused load / store epilogues.
+// ---------------------------------------------------------------------------------------------
+constexpr int D256_CTAS = 64;
+template <class FA, class FB, class FS>
+__device__ __forceinline__ void gemm256(FA a_of, FB b_of, FS store) {           // Out[r][c] = sum_k A(r,k) * B(k,c), all 256 x 256
+    constexpr int N = 256, TM = 64, TK = 16;
+    __shared__ float sAt[TK][TM + 4];                                             // A tile transposed: [k][r]
+    __shared__ float sBt[TK][TM + 4];                                             // B tile: [k][c]
+    const int tid = threadIdx.x, tr = tid >> 4, tc = tid & 15;                    // 16 x 16 threads, 4 x 4 outputs each
+    for (int r0 = 0; r0 < N; r0 += TM)
+        for (int c0 = 0; c0 < N; c0 += TM) {
+            float acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+            for (int k0 = 0; k0 < N; k0 += TK) {
+                __syncthreads();
+                for (int i = tid; i < TM * TK; i += 256) {
+                    const int rr = i / TK, kk = i - rr * TK;                      // A: consecutive threads walk k (row-major A)
+                    sAt[kk][rr] = a_of(r0 + rr, k0 + kk);
+                    const int k2 = i / TM, cc = i - k2 * TM;                      // B: consecutive threads walk c
+                    sBt[k2][cc] = b_of(k0 + k2, c0 + cc);
+                }
+                __syncthreads();
+#pragma unroll
+                for (int kk = 0; kk < TK; kk++) {
+                    const float4 av = *reinterpret_cast<const float4*>(&sAt[kk][tr * 4]);
+                    const float4 bv = *reinterpret_cast<const float4*>(&sBt[kk][tc * 4]);
+                    const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) acc[i][j] = __fmaf_rn(a[i], b[j], acc[i][j]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) store(r0 + tr * 4 + i, c0 + tc * 4 + j, acc[i][j]);
+        }
+}
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(256) k_dct256(const PlaneDesc* __restrict__ planes, const ClassEntry* __restrict__ list, const int* __restrict__ count_ptr,
+                                                const float* __restrict__ Cm, const float* __restrict__ Ct, const int* __restrict__ izz,
+                                                float* __restrict__ scratch) {
+    constexpr int N = 256;
+    float* Wt = scratch + (size_t)blockIdx.x * N * N;
+    const int count = *count_ptr;
+    for (int li = blockIdx.x; li < count; li += gridDim.x) {
+        const ClassEntry e = list[li];
+        const PlaneDesc& P = planes[e.plane];
+        if (e.y < P.ry0 || e.y >= P.ry1) continue;
+        const int bh = min(N, P.h - e.y), bw = min(N, P.w - e.x);
+        const float mid = P.mid, sc = P.scale;
+        int* cf = P.coef + (size_t)e.coef_off;
+        const int* qt = P.qtab[8];
+        const bool zig = P.zigzag != 0;
+        float* lay = P.layer_f32 + (size_t)e.y * P.w + e.x;
+        const int w = P.w;
+        if (!INVERSE) {
+            // W = C . X   (X: normalised, reflect-padded samples)
+            gemm256([&](int r, int k) { return __ldg(Cm + r * N + k); },
+                    [&](int k, int c) { return __fmul_rn(__fsub_rn(__ldg(lay + (size_t)pad_reflect(k, bh) * w + pad_reflect(c, bw)), mid), sc); },
+                    [&](int r, int c, float v) { Wt[r * N + c] = v; });
+            __syncthreads();
+            // Out = W . C^T, quantised
+            gemm256([&](int r, int k) { return Wt[r * N + k]; },
+                    [&](int k, int c) { return __ldg(Ct + k * N + c); },
+                    [&](int r, int c, float v) { const int nat = r * N + c; cf[zig ? __ldg(izz + nat) : nat] = quantize(v, __ldg(qt + nat)); });
+        } else {
+            // V = C^T . Z   (Z: dequantised coefficients, jpeg.py:524)
+            gemm256([&](int r, int k) { return __ldg(Ct + r * N + k); },
+                    [&](int k, int c) { const int nat = k * N + c; return (float)(__ldg(cf + (zig ? __ldg(izz + nat) : nat)) * __ldg(qt + nat)); },
+                    [&](int r, int c, float v) { Wt[r * N + c] = v; });
+            __syncthreads();
+            // X = V . C, de-normalised and cropped
+            gemm256([&](int r, int k) { return Wt[r * N + k]; },
+                    [&](int k, int c) { return __ldg(Cm + k * N + c); },
+                    [&](int r, int c, float v) { if (r < bh && c < bw) lay[(size_t)r * w + c] = __fadd_rn(__fdiv_rn(v, sc), mid); });
+        }
+        __syncthreads();
+    }
+}
+
+template <bool INV>
+int launch_256(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* list, const int* count, int64_t cap, cudaStream_t st) {
+    if (!h->dct256_scratch) AEAJ_CUDA(cudaMalloc(&h->dct256_scratch, (size_t)D256_CTAS * 256 * 256 * sizeof(float)));
+    const int blocks = (int)std::min<int64_t>(std::max<int64_t>(cap, 1), D256_CTAS);
+    k_dct256<INV><<<blocks, 256, 0, st>>>(planes_dev, list, count, h->dct_dev[8], h->dct_dev[8] + 256 * 256, h->izz256_dev, h->dct256_scratch);
+    AEAJ_LAUNCH_CHECK();
+    return 0;
+}
+
 template <bool INV>
 int launch_all(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,
                const int64_t* off, const int64_t* caps, int lg_min, int lg_max, cudaStream_t st, int* launches,
                void (*mark)(void*, const char*), void* mark_ctx, int tensor_dct = 0) {
-    static const char* fwd_names[9] = {"", "dct_quant_2", "dct_quant_4", "dct_quant_8", "dct_quant_16", "dct_quant_32", "dct_quant_64", "dct_quant_128", ""};
-    static const char* inv_names[9] = {"", "dequant_idct_2", "dequant_idct_4", "dequant_idct_8", "dequant_idct_16", "dequant_idct_32", "dequant_idct_64", "dequant_idct_128", ""};
+    static const char* fwd_names[9] = {"", "dct_quant_2", "dct_quant_4", "dct_quant_8", "dct_quant_16", "dct_quant_32", "dct_quant_64", "dct_quant_128", "dct_quant_256"};
+    static const char* inv_names[9] = {"", "dequant_idct_2", "dequant_idct_4", "dequant_idct_8", "dequant_idct_16", "dequant_idct_32", "dequant_idct_64", "dequant_idct_128", "dequant_idct_256"};
     for (int lg = lg_min; lg <= lg_max; lg++) {
         if (caps[lg] <= 0) continue;
         const ClassEntry* list = class_lists + off[lg];
@@ -576,7 +674,8 @@ int launch_all(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* cl
             case 6: rc = launch_cta<64, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
             case 7: rc = tensor_dct ? launch_dct_tc128(h, planes_dev, list, cnt, caps[lg], INV ? 1 : 0, st)
                                               : launch_cta<128, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
-            default: aeaj_set_error("block size %d not supported (2..128)", 1 << lg); return AEAJ_EINVAL;
+            case 8: rc = launch_256<INV>(h, planes_dev, list, cnt, caps[lg], st); break;
+            default: aeaj_set_error("block size %d not supported (2..256)", 1 << lg); return AEAJ_EINVAL;
         }
         if (rc) return rc;
         if (launches) (*launches)++;
@@ -591,12 +690,12 @@ int launch_all(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* cl
 // layout [C (s*s)][C^T (s*s)].
 int aeaj_dct_init(aeaj_handle* h) {
     size_t total = 0;
-    for (int lg = 1; lg <= 7; lg++) total += 2 * ((size_t)1 << (2 * lg));
+    for (int lg = 1; lg <= 8; lg++) total += 2 * ((size_t)1 << (2 * lg));
     float* host = (float*)malloc(total * sizeof(float));
     if (!host) return AEAJ_ENOMEM;
     AEAJ_CUDA(cudaMalloc(&h->dct_all_dev, total * sizeof(float)));
     size_t o = 0;
-    for (int lg = 1; lg <= 7; lg++) {
+    for (int lg = 1; lg <= 8; lg++) {
         const int s = 1 << lg;
         for (int k = 0; k < s; k++)
             for (int i = 0; i < s; i++) {
@@ -608,7 +707,7 @@ int aeaj_dct_init(aeaj_handle* h) {
         h->dct_dev[lg] = h->dct_all_dev + o;
         o += 2 * (size_t)s * s;
     }
-    h->dct_dev[0] = nullptr; h->dct_dev[8] = nullptr;
+    h->dct_dev[0] = nullptr;
     AEAJ_CUDA(cudaMemcpy(h->dct_all_dev, host, total * sizeof(float), cudaMemcpyHostToDevice));
     free(host);
     // half tables for the even/odd CTA kernels (sizes 64, 128):
@@ -640,13 +739,13 @@ int aeaj_dct_init(aeaj_handle* h) {
     free(hh);
     // zigzag tables: the standard JPEG walk generalised to s x s (jpeg.py:743-766)
     size_t ztotal = 0;
-    for (int lg = 1; lg <= 7; lg++) ztotal += (size_t)1 << (2 * lg);
+    for (int lg = 1; lg <= 8; lg++) ztotal += (size_t)1 << (2 * lg);
     int32_t* zh = (int32_t*)malloc(ztotal * sizeof(int32_t));
     if (!zh) return AEAJ_ENOMEM;
     AEAJ_CUDA(cudaMalloc(&h->zz_all_dev, ztotal * sizeof(int32_t)));
     size_t zo = 0;
     for (int k = 0; k < 9; k++) h->zz_dev[k] = nullptr;
-    for (int lg = 1; lg <= 7; lg++) {
+    for (int lg = 1; lg <= 8; lg++) {
         const int s = 1 << lg;
         int row = 0, col = 0;
         for (int i = 0; i < s * s; i++) {
@@ -659,6 +758,14 @@ int aeaj_dct_init(aeaj_handle* h) {
         }
         h->zz_dev[lg] = h->zz_all_dev + zo;
         zo += (size_t)s * s;
+    }
+    {   // inverse permutation for 256 x 256 (row-major index -> stream position), used by k_dct256
+        const int n = 256 * 256;
+        const int32_t* z256 = zh + (h->zz_dev[8] - h->zz_all_dev);
+        std::vector<int32_t> inv((size_t)n);
+        for (int i = 0; i < n; i++) inv[z256[i]] = i;
+        AEAJ_CUDA(cudaMalloc(&h->izz256_dev, (size_t)n * sizeof(int32_t)));
+        AEAJ_CUDA(cudaMemcpy(h->izz256_dev, inv.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
     AEAJ_CUDA(cudaMemcpy(h->zz_all_dev, zh, ztotal * sizeof(int32_t), cudaMemcpyHostToDevice));
     free(zh);
