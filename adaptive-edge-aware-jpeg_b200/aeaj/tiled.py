@@ -36,10 +36,11 @@ DPH_IDCT, DPH_COLOR = range(2)
 BAND_ALIGN = 256
 
 
-def band_of(rank: int, world: int, H: int):
-    """rows [lo, hi) of the full-resolution image owned by `rank`"""
-    if H % (world * BAND_ALIGN) != 0:
-        raise ValueError(f"halo-split needs the image height ({H}) to be a multiple of {BAND_ALIGN} x world size ({world})")
+def band_of(rank: int, world: int, H: int, block_max: int = 128):
+    """rows [lo, hi) of the full-resolution image owned by `rank` (bands are multiples of 2 x max(128, block_max) rows)"""
+    align = max(BAND_ALIGN, 2 * block_max)
+    if H % (world * align) != 0:
+        raise ValueError(f"halo-split needs the image height ({H}) to be a multiple of {align} x world size ({world})")
     hb = H // world
     return rank * hb, (rank + 1) * hb
 
@@ -100,7 +101,7 @@ class TiledCodec:
         rgb = rgb.contiguous()
 
         def run(phase, r):
-            lo, hi = band_of(r, G, H)
+            lo, hi = band_of(r, G, H, brange[1])
             # the kernel indexes rows from the top of the full image: hand it the (virtual) address of row 0
             io.rgb = rgb.data_ptr() - (0 if self.emulate else lo * W * 12)
             native.check(self.lib.aeaj_encode_phase(p.ptr, C.byref(io), ws, _stream(), phase, lo, hi), f"aeaj_encode_phase({phase})")
@@ -153,7 +154,7 @@ class TiledCodec:
         multi = not self.emulate and self.world > 1
 
         def run(phase, r):
-            lo, hi = band_of(r, G, H)
+            lo, hi = band_of(r, G, H, brange[1])
             native.check(self.lib.aeaj_decode_phase(p.ptr, C.byref(io), ws, _stream(), phase, lo, hi), f"aeaj_decode_phase({phase})")
 
         for r in ranks:

@@ -588,8 +588,9 @@ static int set_band(aeaj_plan* p, int band0, int band1) {
         const int rh = H / P.h;                                    // 1 or 2 (jpeg.py:62-147)
         if (!full) {
             AEAJ_REQUIRE(p->info.batch == 1, "halo-split bands need batch 1");
-            AEAJ_REQUIRE(H % P.h == 0 && band0 % (rh * 128) == 0 && (band1 % (rh * 128) == 0 || band1 == H),
-                         "band boundaries must be multiples of 128 rows in every layer");
+            const int align = rh * std::max(128, p->info.block_max);  // no leaf, filter tile or chroma cell may straddle a band
+            AEAJ_REQUIRE(H % P.h == 0 && band0 % align == 0 && (band1 % align == 0 || band1 == H),
+                         "band boundaries must be multiples of max(128, block_max) rows in every layer");
         }
         P.ry0 = band0 / rh; P.ry1 = (band1 == H) ? P.h : band1 / rh;
     }
