@@ -64,3 +64,35 @@ def test_state_stream_parse_rejects_truncated_coefficients():
     blob = len(mb).to_bytes(4, "big") + mb + body + len(coef).to_bytes(4, "big") + coef
     with pytest.raises(ValueError):
         Jpeg(JpegCompressionSettings())._entropy_decode(blob)
+
+
+def test_evaluation_metrics_surface_and_known_answers():
+    """EvaluationMetrics(original, compressed).psnr() / .ssim() / .ms_ssim() (evaluation_metrics.py:31-110): piq's published
+    formulas restated with torch; known answers that do not need piq."""
+    import torch
+    from image import EvaluationMetrics
+    from image.evaluation_metrics import rgb_to_gray_u8
+    rng = np.random.default_rng(0)
+    a = rng.random((200, 240, 3), dtype=np.float32)
+    img_a, img_same = Image.from_array(a.copy()), Image.from_array(a.copy())
+    ev = EvaluationMetrics(img_a, img_same)
+    assert isinstance(ev.psnr(), torch.Tensor) and abs(float(ev.psnr()) - 80.0) < 1e-3        # -10 log10(0 + 1e-8)
+    assert abs(float(ev.ssim()) - 1.0) < 1e-6 and abs(float(ev.ms_ssim()) - 1.0) < 1e-5
+    b = np.clip(a * 0.0 + 0.5, 0, 1).astype(np.float32)
+    c = (b + 0.1).astype(np.float32)                                                          # mse = 0.01 -> 20 dB
+    assert abs(float(EvaluationMetrics(Image.from_array(b), Image.from_array(c)).psnr()) - 20.0) < 1e-3
+    noisy = np.clip(a + rng.normal(0, 0.1, a.shape).astype(np.float32), 0, 1)
+    s1 = float(EvaluationMetrics(img_a, Image.from_array(noisy)).ssim())
+    s2 = float(EvaluationMetrics(Image.from_array(noisy), img_a).ssim())
+    assert 0.0 < s1 < 0.99 and abs(s1 - s2) < 1e-6                                            # symmetric, penalises noise
+    m = float(EvaluationMetrics(img_a, Image.from_array(noisy)).ms_ssim())
+    assert 0.0 < m < 1.0
+    with pytest.raises(ValueError):
+        EvaluationMetrics(Image.from_array(a[:100, :100].copy()), Image.from_array(a[:100, :100].copy())).ms_ssim()
+    with pytest.raises(NotImplementedError):
+        ev.lpips()
+    with pytest.raises(TypeError):
+        EvaluationMetrics._image_to_tensor([1, 2, 3])
+    cv2 = pytest.importorskip("cv2")
+    px = rng.integers(0, 256, (64, 48, 3), dtype=np.uint8)
+    assert np.array_equal(rgb_to_gray_u8(px), cv2.cvtColor(px, cv2.COLOR_RGB2GRAY))           # the reference's grey conversion
