@@ -332,9 +332,14 @@ def main():
             traffic = tr[kname]
     except Exception:
         pass
+    ncu_stats = None                                                   # what actually limits that kernel (same ncu capture)
+    try:
+        ncu_stats = json.load(open(os.path.join(ROOT, "profiles", "r1_kernel_stats.json"))).get(kname)
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": (alg_bytes / 1e9) / (dom_ms / 1e3) if alg_bytes else None, "peak": peak,
             "unit": "GB/s", "frac": ((alg_bytes / 1e9) / (dom_ms / 1e3) / peak) if alg_bytes else None, "traffic": traffic,
-            "algorithmic_bytes": alg_bytes,
+            "algorithmic_bytes": alg_bytes, "ncu": ncu_stats,
             "peak_source": peak_src, "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / sum(stage_ms.values()),
             "frames_per_launch": Bs,
             "pipeline_achieved": (ALG_BYTES_PER_PX * B * H * W * world / 1e9) / (ms / args.steps / 1e3),

@@ -61,6 +61,7 @@ def kernels(rep, tag):
     hdr, units = r[0], r[1]
     out = [f"# {tag}: `ncu --set full --clock-control none` of the top kernels (one launch each)\n"]
     traffic = {}
+    stats = {}
     seen = set()
     for row in r[2:]:
         name = short(row[hdr.index("Kernel Name")])
@@ -81,9 +82,18 @@ def kernels(rep, tag):
                     wr = float(row[i]) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}.get(units[i], 1)
         if rd is not None and wr is not None:
             traffic[name] = rd + wr
+        st = {}
+        for k, label in (("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
+                         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct_of_peak"),
+                         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_pct"),
+                         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct")):
+            if k in hdr and row[hdr.index(k)] not in ("", "n/a"):
+                st[label] = float(row[hdr.index(k)])
+        stats[name] = st
         out.append("")
     open(os.path.join(HERE, f"{tag}_kernels.md"), "w").write("\n".join(out) + "\n")
     json.dump(traffic, open(os.path.join(HERE, f"{tag}_traffic.json"), "w"), indent=1, sort_keys=True)
+    json.dump(stats, open(os.path.join(HERE, f"{tag}_kernel_stats.json"), "w"), indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":
