@@ -127,22 +127,6 @@ __global__ void __launch_bounds__(256) k_clahe_lut(const PlaneDesc* __restrict__
     P.clahe_lut[tile * 256 + i] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
-__device__ __forceinline__ uint8_t clahe_apply_px(const uint8_t (*lut)[256], const ClaheGeom& g, int y, int x, int v) {
-    float tyf = __fsub_rn(__fmul_rn((float)y, g.inv_th), 0.5f);
-    int ty1 = (int)floorf(tyf), ty2 = ty1 + 1;
-    float ya = __fsub_rn(tyf, (float)ty1), ya1 = __fsub_rn(1.0f, ya);
-    ty1 = max(ty1, 0); ty2 = min(ty2, 3);
-    float txf = __fsub_rn(__fmul_rn((float)x, g.inv_tw), 0.5f);
-    int tx1 = (int)floorf(txf), tx2 = tx1 + 1;
-    float xa = __fsub_rn(txf, (float)tx1), xa1 = __fsub_rn(1.0f, xa);
-    tx1 = max(tx1, 0); tx2 = min(tx2, 3);
-    float a = __fmul_rn((float)lut[ty1 * 4 + tx1][v], xa1), b = __fmul_rn((float)lut[ty1 * 4 + tx2][v], xa);
-    float c = __fmul_rn((float)lut[ty2 * 4 + tx1][v], xa1), d = __fmul_rn((float)lut[ty2 * 4 + tx2][v], xa);
-    float r = __fadd_rn(__fmul_rn(__fadd_rn(a, b), ya1), __fmul_rn(__fadd_rn(c, d), ya));
-    int iv = __float2int_rn(r);
-    return (uint8_t)(iv < 0 ? 0 : (iv > 255 ? 255 : iv));
-}
-
 // ---------------------------------------------------------------------------------------------
 // fused pre-filter: [CLAHE apply] -> [Gaussian 3x3] -> [bilateral d=5] on a 64x32 tile.
 // Halo cells hold the value at the REFLECT_101-folded coordinate, so each stage sees exactly the
@@ -415,21 +399,7 @@ __global__ void __launch_bounds__(256) k_hist_u8(const uint8_t* __restrict__ src
 }
 
 // np.percentile(img, 10 / 30) (method 'linear') from the histogram, then cv.Canny's threshold prep
-// (imgproc/canny.cpp: L2gradient -> squared, clamped to 32767, floor).  One thread per plane.
-__device__ double percentile_from_hist(const unsigned int* hist, unsigned long long n, double q) {
-    double v = (double)(n - 1) * q;
-    double lo = floor(v), gfrac = v - lo;
-    unsigned long long ilo = (unsigned long long)lo, ihi = ilo + 1 < n ? ilo + 1 : n - 1;
-    int a = 0, b = 0, fa = 0;
-    unsigned long long c = 0;
-    for (int i = 0; i < 256; i++) {
-        c += hist[i];
-        if (!fa && c > ilo) { a = i; fa = 1; }
-        if (c > ihi) { b = i; break; }
-    }
-    double d = (double)(b - a);
-    return gfrac < 0.5 ? (double)a + d * gfrac : (double)b - d * (1.0 - gfrac);
-}
+// (imgproc/canny.cpp: L2gradient -> squared, clamped to 32767, floor); the order statistics are located in k_thresholds.
 __device__ void canny_prepare_thresholds(double lo, double hi, int* thr) {
     if (lo > hi) { double t = lo; lo = hi; hi = t; }
     lo = fmin(32767.0, lo); hi = fmin(32767.0, hi);

@@ -16,8 +16,7 @@
 namespace {
 
 constexpr int QT_THREADS = 256;
-constexpr int QT_MAX_CELLS = 128;                    // T / min_size <= 128 (e.g. 256 / 2)
-constexpr int QT_OCC_BYTES = 22016;                  // sum_{l} (128 >> l)^2 = 21845, padded
+constexpr int QT_OCC_BYTES = 22016;                  // T / min_size <= 128 cells per side: sum_{l} (128 >> l)^2 = 21845, padded
 
 struct QtParams { int min_size, lg_min, max_size; };
 
