@@ -1,0 +1,85 @@
+"""Randomised differential check of the fused CUDA path against the oracle (checker-side tool, not collected by pytest):
+
+    python tests/fuzz_vs_oracle.py [n_cases] [seed]
+
+Random shapes (1 .. 700 px per side, incl. degenerate ones), spaces, block ranges (2 .. 256) and quality ranges; batch of 2.
+Linear spaces: edge maps, states, leaves bit-exact, coefficients within the T-DCT budget; all spaces: decode <= 1 LSB
+against the oracle's decode of the same coefficients (T-NAN pixels excluded as in test_gpu_parity.py)."""
+import sys
+import numpy as np
+import torch
+
+sys.path.insert(0, "adaptive-edge-aware-jpeg_b200"); sys.path.insert(0, "tests"); sys.path.insert(0, "oracle")
+import oracle as O
+from aeaj.codec import get_codec
+from synth import synth
+
+SPACES = ["YCbCr", "YCoCg", "YCoCg-R", "OKLAB", "ICaCb", "ICtCp", "JzAzBz"]
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    codec = get_codec(0)
+    bad = 0
+    for case in range(n):
+        space = SPACES[rng.integers(len(SPACES))]
+        H = int(rng.choice([1, 2, 3, 5, 17, 64, 100, 129, 255, 256, 300, 511, 640, 700]))
+        W = int(rng.choice([1, 2, 4, 7, 33, 64, 96, 130, 256, 257, 320, 512, 520, 700]))
+        if min(min(sh) for sh in O.layer_shapes(H, W, space)) < 1:   # a chroma layer would be empty: the reference's cv.resize raises too
+            continue
+        lo = int(2 ** rng.integers(1, 6)); hi = int(lo * 2 ** rng.integers(0, 8))
+        hi = min(hi, 256)
+        if O.root_size(max(H // 2, 1), max(W // 4, 1)) < lo:      # smallest layer must hold one minimum block
+            lo = 2
+        if min(hi, O.root_size(H, W)) // lo > 128:
+            hi = lo * 128
+        q0 = int(rng.integers(1, 99)); q = (q0, int(rng.integers(q0, 100)))
+        b = (lo, max(lo, hi))
+        kind = rng.integers(3)
+        imgs = []
+        for s in range(2):
+            if kind == 0:
+                im = synth(H, W, seed=int(rng.integers(1 << 20)))
+            elif kind == 1:
+                im = (rng.integers(0, 256, (H, W, 3)).astype(np.float32) / 255.0).astype(np.float32)
+            else:
+                im = np.full((H, W, 3), float(rng.random()), np.float32)
+            imgs.append(im.astype(np.float32))
+        batch = np.stack(imgs)
+        tag = f"case {case}: {space} {H}x{W} q{q} b{b} kind {kind}"
+        try:
+            enc = codec.encode(torch.from_numpy(batch).cuda(), space, q, b, taps=True)
+            got = codec.download(enc)
+            edges = [e.cpu().numpy() for e in enc.edges]
+            dec = codec.decode_encoded(enc, space, q, b).cpu().numpy()
+        except Exception as ex:                                   # settings the library rejects must be rejected by the oracle too
+            print(tag, "-> library raised", type(ex).__name__, str(ex)[:80]); bad += 1
+            continue
+        exact = space in ("YCbCr", "YCoCg", "YCoCg-R")
+        for k in range(2):
+            ref = O.encode_hot(batch[k], space, q, b)
+            same_edges = all(np.array_equal(edges[i][k], ref[i]["edge"].astype(np.uint8)) for i in range(3))
+            if exact and not same_edges:
+                print(tag, "edge maps differ"); bad += 1
+            if same_edges:
+                for i in range(3):
+                    if not (np.array_equal(got[k][i]["states"], ref[i]["states"]) and np.array_equal(got[k][i]["leaves"][:, :3], ref[i]["leaves"])):
+                        print(tag, f"quadtree differs (layer {i})"); bad += 1
+                        break
+                    d = np.abs(got[k][i]["coef"].astype(np.int64) - ref[i]["coef"].astype(np.int64))
+                    if d.size and (d.max() > 1 or (d != 0).sum() > (4 if exact else 200)):
+                        print(tag, f"coefficients: max {d.max()} n {(d != 0).sum()} (layer {i})"); bad += 1
+            ref_dec = O.decode_hot([dict(leaves=got[k][i]["leaves"][:, :3], coef=got[k][i]["coef"]) for i in range(3)], H, W, space, q, b)
+            lsb = np.abs((dec[k] * 255).astype(np.uint8).astype(int) - (ref_dec * 255).astype(np.uint8).astype(int))
+            if space in ("ICaCb", "ICtCp", "JzAzBz"):
+                nan_class = np.all(dec[k] == 1.0, axis=-1) | np.all(ref_dec == 1.0, axis=-1)
+                lsb[nan_class] = 0
+            if lsb.max() > 1:
+                print(tag, "decode LSB", lsb.max()); bad += 1
+    print(f"{n} cases, {bad} problems")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
