@@ -57,6 +57,25 @@ def main():
             print(tag, "-> library raised", type(ex).__name__, str(ex)[:80]); bad += 1
             continue
         exact = space in ("YCbCr", "YCoCg", "YCoCg-R")
+        # the device-side .ajpg stream layout (zigzag blocks) must be the natural layout permuted, and decode back identically
+        from aeaj import tables
+        encz = codec.encode(torch.from_numpy(batch).cuda(), space, q, b, stream=True)
+        gotz = codec.download(encz)
+        decz = codec.decode_encoded(encz, space, q, b).cpu().numpy()
+        if not np.array_equal(decz, dec):
+            print(tag, "zigzag-layout decode differs"); bad += 1
+        for k in range(2):
+            for i in range(3):
+                sizes = got[k][i]["leaves"][:, 2].astype(np.int64)
+                offs = np.concatenate([[0], np.cumsum(sizes * sizes)])
+                nat, zz = got[k][i]["coef"], gotz[k][i]["coef"]
+                okz = len(nat) == len(zz)
+                for j in np.random.default_rng(case).choice(len(sizes), size=min(len(sizes), 40), replace=False) if okz and len(sizes) else []:
+                    sz = int(sizes[j]); blk = nat[offs[j]:offs[j + 1]]
+                    if not np.array_equal(zz[offs[j]:offs[j + 1]], blk[tables.zigzag_ordering(sz)]):
+                        okz = False; break
+                if not okz:
+                    print(tag, f"zigzag stream mismatch (image {k}, layer {i})"); bad += 1
         for k in range(2):
             ref = O.encode_hot(batch[k], space, q, b)
             same_edges = all(np.array_equal(edges[i][k], ref[i]["edge"].astype(np.uint8)) for i in range(3))
