@@ -12,6 +12,7 @@ Everything is asynchronous on the current torch CUDA stream; nothing falls back 
 from __future__ import annotations
 
 import ctypes as C
+from collections import OrderedDict
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -37,7 +38,7 @@ class EncodedBatch:
     leaves: List[torch.Tensor]     # 3 x int32 [B, cap_leaves_l, 4]  (x, y, size, coef offset)
     states: List[torch.Tensor]     # 3 x uint8 [B, cap_states_l]
     counts: torch.Tensor           # int32 [B, 3, 4]  n_leaves, n_states, n_coef, root
-    status: torch.Tensor           # int32 [2]        hysteresis rounds, converged
+    status: torch.Tensor           # int32 [64]       [0] hysteresis re-visits, [1] converged, [2] tensor-DCT timeout flag
     shape: Tuple[int, int, int]    # B, H, W
     layers: Optional[List[torch.Tensor]] = None   # taps (float32 [B,h,w]) if requested
     edges: Optional[List[torch.Tensor]] = None    # taps (uint8  [B,h,w]) if requested
@@ -55,15 +56,20 @@ class _Plan:
     rgb8_out: Optional[torch.Tensor] = None
     qkey: Optional[tuple] = None
     keep: list = field(default_factory=list)
+    dec_status: Optional[torch.Tensor] = None     # int32 [64]: [2] tensor-IDCT timeout flag, [3] leaves rejected by the device guard
+    nbytes: int = 0
 
 
 class DeviceCodec:
+    MAX_PLANS = 48                      # plans (geometry + workspace + output buffers) kept per device, least recently used first out
+    MAX_PLAN_BYTES = 96 << 30           # ... and the device memory they may hold together
+
     def __init__(self, device: int = 0):
         _require_cuda()
         self.device = device
         self.lib = native.load()
         self.handle = native.handle(device)
-        self._plans: Dict[tuple, _Plan] = {}
+        self._plans: "OrderedDict[tuple, _Plan]" = OrderedDict()
         self.last_launches = 0
         self.tensor_dct = True         # tcgen05 / TMEM path for the 128x128 DCT and IDCT (False: FP32-FMA kernels)
 
@@ -78,6 +84,8 @@ class DeviceCodec:
         key = (B, H, W, space, tuple(brange), instance)
         p = self._plans.get(key)
         dev = torch.device("cuda", self.device)
+        if p is not None:
+            self._plans.move_to_end(key)
         if p is None:
             if space not in tables.CODEC_SPACES:
                 raise ValueError(f"Unsupported color space: {space}")
@@ -94,8 +102,10 @@ class DeviceCodec:
                 counts=torch.zeros((B, 3, 4), dtype=torch.int32, device=dev),
                 status=torch.zeros(64, dtype=torch.int32, device=dev), shape=(B, H, W))
             rgb_out = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
-            p = _Plan(ptr, info, ws, out, rgb_out)
+            p = _Plan(ptr, info, ws, out, rgb_out, dec_status=torch.zeros(64, dtype=torch.int32, device=dev))
+            p.nbytes = ws.numel() + rgb_out.numel() * 4 + sum(t.numel() * t.element_size() for t in out.coef + out.leaves + out.states)
             self._plans[key] = p
+            self._evict(keep=key)
         qkey = tuple(qrange)
         if p.qkey != qkey:
             cache = tables.quantization_cache(qrange, brange)
@@ -105,6 +115,35 @@ class DeviceCodec:
             torch.cuda.current_stream().synchronize()     # `flat` is pageable host memory
             p.qkey = qkey
         return p
+
+    def _evict(self, keep=None):
+        """Bound the plan cache (a dataset of mixed image sizes would otherwise hold a workspace per distinct shape until OOM)."""
+        def total():
+            return sum(q.nbytes for q in self._plans.values())
+        while len(self._plans) > 1 and (len(self._plans) > self.MAX_PLANS or total() > self.MAX_PLAN_BYTES):
+            key = next(k for k in self._plans if k != keep)
+            old = self._plans.pop(key)
+            torch.cuda.synchronize(self.device)          # nothing in flight may still read the plan's device tables
+            native.check(self.lib.aeaj_plan_destroy(old.ptr), "aeaj_plan_destroy")
+            old.ptr = None
+
+    def close(self):
+        """Destroy every cached plan (their tensors are freed by torch once unreferenced)."""
+        torch.cuda.synchronize(self.device)
+        while self._plans:
+            _, old = self._plans.popitem(last=False)
+            native.check(self.lib.aeaj_plan_destroy(old.ptr), "aeaj_plan_destroy")
+            old.ptr = None
+
+    def check_status(self, status: torch.Tensor, what: str = "encode"):
+        """Raise if the device reported a problem for the call that wrote `status` (synchronises the stream)."""
+        s = status[:4].cpu().numpy()
+        if what == "encode" and int(s[1]) != 1:
+            raise native.AeajError("hysteresis did not converge")
+        if int(s[2]) != 0:
+            raise native.AeajError("the tensor-core DCT kernel timed out on a barrier wait; its coefficients are invalid")
+        if what == "decode" and int(s[3]) != 0:
+            raise ValueError(f"{int(s[3])} leaves do not fit the layer geometry / block range (corrupt stream)")
 
     def plan_info(self, B, H, W, space, brange, qrange=(40, 80)) -> native.PlanInfo:
         return self._plan(B, H, W, space, brange, qrange).info
@@ -178,6 +217,8 @@ class DeviceCodec:
             if p.rgb8_out is None:
                 p.rgb8_out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=p.rgb_out.device)
             io.rgb_u8 = p.rgb8_out.data_ptr()
+        io.status = p.dec_status.data_ptr()
+        self.last_decode_status = p.dec_status
         tl = None
         if taps:
             tl = [torch.empty((B, p.info.layer_h[l], p.info.layer_w[l]), dtype=torch.float32, device=p.rgb_out.device) for l in range(3)]
@@ -385,8 +426,7 @@ class DeviceCodec:
     def download(self, enc: EncodedBatch):
         """D2H of exactly the used parts. Returns per image a list of 3 dicts(leaves, states, coef, root)."""
         counts = enc.counts.cpu().numpy()                  # synchronises the stream
-        if int(enc.status[1].item()) != 1:
-            raise native.AeajError("hysteresis did not converge")
+        self.check_status(enc.status, "encode")
         B = enc.shape[0]
         out = []
         for b in range(B):

@@ -46,7 +46,7 @@ class EncodeIO(C.Structure):
 
 class DecodeIO(C.Structure):
     _fields_ = [("coef", C.c_void_p * 3), ("leaves", C.c_void_p * 3), ("counts", C.c_void_p), ("rgb", C.c_void_p),
-                ("tap_layers", C.c_void_p * 3), ("rgb_u8", C.c_void_p)]
+                ("tap_layers", C.c_void_p * 3), ("rgb_u8", C.c_void_p), ("status", C.c_void_p)]
 
 
 class PlanBuffers(C.Structure):
@@ -110,7 +110,7 @@ def load():
         lib.aeaj_plan_buffers.argtypes = [vp, vp, C.POINTER(PlanBuffers)]
         lib.aeaj_plan_enable_timing.argtypes = [vp, i]
         lib.aeaj_plan_read_timing.argtypes = [vp, C.c_char_p, sz, vp, i, C.POINTER(i)]
-        lib.aeaj_states_to_leaves_host.argtypes = [vp, i, i, i, i, vp, C.POINTER(i), C.POINTER(C.c_int64)]
+        lib.aeaj_states_to_leaves_host.argtypes = [vp, i, i, i, i, i, i, vp, C.POINTER(i), C.POINTER(C.c_int64)]
         lib.aeaj_pack_states_host.argtypes = [vp, i, vp]
         _lib = lib
         return lib
@@ -145,14 +145,18 @@ def handle(device: int = 0):
     return h
 
 
-def states_to_leaves(states: np.ndarray, root: int, h: int, w: int):
+def states_to_leaves(states: np.ndarray, root: int, h: int, w: int, block_range=(0, 0)):
     """Host-side inverse of the state stream (jpeg.py:768-800 + 428-448): DFS pre-order 2-bit states
-    -> (x, y, size, coefficient offset) per leaf.  Part of the entropy-decode side, runs on the host."""
+    -> (x, y, size, coefficient offset) per leaf.  Part of the entropy-decode side, runs on the host.
+    The stream is untrusted: a root / leaf that does not fit the (h, w) layer or `block_range` raises ValueError."""
     lib = load()
     states = np.ascontiguousarray(states, dtype=np.uint8)
     leaves = np.empty((max(len(states), 1), 4), dtype=np.int32)
     n = C.c_int()
     ncoef = C.c_int64()
-    check(lib.aeaj_states_to_leaves_host(states.ctypes.data, len(states), root, h, w, leaves.ctypes.data, C.byref(n), C.byref(ncoef)),
-          "aeaj_states_to_leaves_host")
+    rc = lib.aeaj_states_to_leaves_host(states.ctypes.data, len(states), int(root), int(h), int(w), int(block_range[0]), int(block_range[1]),
+                                        leaves.ctypes.data, C.byref(n), C.byref(ncoef))
+    if rc == -1:
+        raise ValueError("corrupt quadtree header: " + lib.aeaj_last_error().decode("utf-8", "replace"))
+    check(rc, "aeaj_states_to_leaves_host")
     return leaves[: n.value], int(ncoef.value)

@@ -131,6 +131,7 @@ static inline __host__ __device__ uint32_t part1by1(uint32_t v) {
 struct aeaj_handle {
     int device;
     int sm_count;
+    int hyst_blocks_per_sm;       // occupancy of k_hysteresis on this device (aeaj_canny_init)
     ColorConsts colors_host[8];
     ColorConsts* colors_dev;      // [8]
     float* srgb_lut_dev;          // 256 floats, 0 until aeaj_set_srgb_lut
@@ -142,7 +143,6 @@ struct aeaj_handle {
     int32_t* zz_dev[9];           // zigzag tables per log2(size), device
     int32_t* zz_all_dev;
     int32_t* izz256_dev;          // inverse zigzag permutation for 256x256
-    float* dct256_scratch;        // per-CTA intermediate tiles of k_dct256 (allocated on first use)
     int32_t* tc_izz_dev;          // inverse zigzag permutation for 128x128 (tensor-core IDCT loader)
     float* dct_tc_tiles_dev;      // [Ch | Cl] tiles of the 128x128 DCT matrix for the tcgen05 path
     int* tc_err_dev;              // set by the tcgen05 kernel if a barrier wait timed out
@@ -156,7 +156,7 @@ struct aeaj_handle {
 // device-side description of every plane of a batch; lives in the plan's device memory
 struct PlaneDesc {
     int h, w, wpr, root, top, ntx, nty, layer;
-    int hy_base_small, hy_base_big;   // first hysteresis tile of this plane in the small / big tiling
+    int hy_base;                      // first hysteresis tile of this plane (tiles of all planes form one index space)
     int ry0, ry1;                     // rows of this plane the current call works on (halo-split bands); default [0, h)
     float mid, scale;
     float* layer_f32;        // downsampled un-normalised layer
@@ -184,6 +184,7 @@ struct PlaneDesc {
 };
 
 struct ClassEntry { int x, y, plane, coef_off; };
+struct ClassCaps { long long cap[9]; };
 
 // exact 1-D grids over the tiles of all planes of a batch (no empty blocks for the smaller chroma planes):
 // planes are ordered image-major with `nl` layers per image and identical geometry per layer.
@@ -212,7 +213,7 @@ static inline __device__ void tile_decode(const TileMap& m, int bid, int& plane,
 }
 
 // kernels' host launchers (defined in the .cu files)
-int aeaj_canny_init_constants();
+int aeaj_canny_init(aeaj_handle* h);
 int aeaj_dct_init(aeaj_handle* h);
 
 int launch_color_forward_planar(aeaj_handle* h, int space, const float* rgb, const uint8_t* rgb_u8, int B, int H, int W,
@@ -234,9 +235,9 @@ int launch_hist_u8(const uint8_t* src, size_t n, unsigned int* hist, cudaStream_
 int launch_thresholds(const PlaneDesc* planes_dev, int nplanes, cudaStream_t st);
 int launch_thresholds_from_double(const double* thr_d, int* thr, cudaStream_t st);
 int launch_canny_nms(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, cudaStream_t st);
-int hysteresis_tiles(PlaneDesc* planes_host, int nplanes, int* nbig);
-int launch_hysteresis(aeaj_handle* h, const PlaneDesc* planes_dev, int nplanes, int nsmall, int nbig,
-                      int* flags, int* ctrl, int* status, cudaStream_t st);
+int hysteresis_tiles(PlaneDesc* planes_host, int nplanes, int* ring_cap);
+int launch_hysteresis(aeaj_handle* h, const PlaneDesc* planes_dev, int nplanes, int ntiles, int ring_cap,
+                      int* flags, int* ring, int* ctrl, int* status, cudaStream_t st);
 int launch_bitmap_to_u8(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes,
                         uint8_t* const* outs_dev, cudaStream_t st);
 int launch_u8_to_bitmap(const uint8_t* edge, int h, int w, uint32_t* bits, cudaStream_t st);
@@ -246,12 +247,14 @@ int launch_quadtree(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, i
                     int* launches);
 int launch_pack_states(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, cudaStream_t st);
 int launch_bucket_leaves(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, ClassEntry* class_lists,
-                         int* class_counts, const long long* class_offsets_dev, cudaStream_t st);
+                         int* class_counts, const long long* class_offsets_dev, int lg_min, int lg_max, const int64_t* class_caps_host,
+                         cudaStream_t st);
 int launch_dct_quant(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,
                      const int64_t* class_offsets_host, const int64_t* class_caps_host, int lg_min, int lg_max,
-                     cudaStream_t st, int* launches, void (*mark)(void*, const char*), void* mark_ctx, int tensor_dct = 0);
+                     cudaStream_t st, int* launches, void (*mark)(void*, const char*), void* mark_ctx, int tensor_dct, float* scratch256);
+size_t aeaj_dct256_scratch_floats();
 int aeaj_dct_tc_init(aeaj_handle* h);
 int launch_dct_tc128(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* list, const int* count, int64_t cap, int inverse, cudaStream_t st);
 int launch_dequant_idct(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,
                         const int64_t* class_offsets_host, const int64_t* class_caps_host, int lg_min, int lg_max,
-                        cudaStream_t st, int* launches, void (*mark)(void*, const char*), void* mark_ctx, int tensor_dct);
+                        cudaStream_t st, int* launches, void (*mark)(void*, const char*), void* mark_ctx, int tensor_dct, float* scratch256);

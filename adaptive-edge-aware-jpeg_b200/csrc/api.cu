@@ -112,7 +112,7 @@ extern "C" int aeaj_create(int device, aeaj_handle** out) {
     h->sm_count = prop.multiProcessorCount;
     int rc = aeaj_dct_init(h);
     if (rc) { free(h); return rc; }
-    rc = aeaj_canny_init_constants();
+    rc = aeaj_canny_init(h);
     if (rc) { free(h); return rc; }
     rc = aeaj_dct_tc_init(h);
     if (rc) { free(h); return rc; }
@@ -129,7 +129,7 @@ extern "C" int aeaj_create(int device, aeaj_handle** out) {
 extern "C" int aeaj_destroy(aeaj_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    cudaFree(h->srgb_lut_dev); cudaFree(h->dct_all_dev); cudaFree(h->dct_half_all_dev); cudaFree(h->zz_all_dev); cudaFree(h->izz256_dev); cudaFree(h->dct256_scratch); cudaFree(h->dct_tc_tiles_dev); cudaFree(h->tc_izz_dev); cudaFree(h->tc_err_dev); cudaFree(h->stage_plane_dev);
+    cudaFree(h->srgb_lut_dev); cudaFree(h->dct_all_dev); cudaFree(h->dct_half_all_dev); cudaFree(h->zz_all_dev); cudaFree(h->izz256_dev); cudaFree(h->dct_tc_tiles_dev); cudaFree(h->tc_izz_dev); cudaFree(h->tc_err_dev); cudaFree(h->stage_plane_dev);
     cudaFree(h->stage_class_off_dev); cudaFree(h->stage_tile_base_dev); cudaFree(h->stage_outs_dev);
     free(h);
     return 0;
@@ -196,10 +196,11 @@ extern "C" int aeaj_cast_u8(aeaj_handle* h, const float* layer, uint8_t* out, si
 struct StageWs {
     PlaneDesc P;
     uint8_t* u8a; uint8_t* u8b;
-    int* flags; int* ctrl; int* status;
+    int* flags; int* ring; int* ctrl; int* status;
     ClassEntry* class_lists; int* class_counts;
+    float* scratch256;
     ClassGeom cg;
-    int ntiles, nbig;
+    int ntiles, ring_cap;
     size_t bytes;
 };
 static void stage_ws(void* ws, int h, int w, int mn, int mx, StageWs& S) {
@@ -209,14 +210,16 @@ static void stage_ws(void* ws, int h, int w, int mn, int mx, StageWs& S) {
     carve_plane_scratch(b, S.P, true, mx > 0);
     S.u8a = b.take<uint8_t>((size_t)h * w);
     S.u8b = b.take<uint8_t>((size_t)h * w);
-    S.ntiles = hysteresis_tiles(&S.P, 1, &S.nbig);
-    S.flags = b.take<int>(2 * (size_t)S.nbig);
-    S.ctrl = b.take<int>(4);
-    S.status = b.take<int>(2);
+    S.ntiles = hysteresis_tiles(&S.P, 1, &S.ring_cap);
+    S.flags = b.take<int>((size_t)S.ntiles);
+    S.ring = b.take<int>((size_t)S.ring_cap);
+    S.ctrl = b.take<int>(8);
+    S.status = b.take<int>(4);
     S.class_counts = b.take<int>(16);
     if (mx > 0) {
         class_geom(&S.P, 1, ilog2i(mn), ilog2i(mx), S.cg);
         S.class_lists = b.take<ClassEntry>((size_t)S.cg.total);
+        if (mx >= 256) S.scratch256 = b.take<float>(aeaj_dct256_scratch_floats());
     }
     S.bytes = b.used();
 }
@@ -272,7 +275,7 @@ extern "C" int aeaj_percentile_thresholds(aeaj_handle* hd, const uint8_t* src, i
 
 static int run_nms_hysteresis(aeaj_handle* hd, StageWs& S, uint8_t* edge, cudaStream_t st) {
     int rc = launch_canny_nms(hd->stage_plane_dev, &S.P, 1, st); if (rc) return rc;
-    rc = launch_hysteresis(hd, hd->stage_plane_dev, 1, S.ntiles, S.nbig, S.flags, S.ctrl, S.status, st);
+    rc = launch_hysteresis(hd, hd->stage_plane_dev, 1, S.ntiles, S.ring_cap, S.flags, S.ring, S.ctrl, S.status, st);
     if (rc) return rc;
     if (edge) {
         AEAJ_CUDA(cudaMemcpyAsync(hd->stage_outs_dev, &edge, sizeof(uint8_t*), cudaMemcpyHostToDevice, st));
@@ -342,9 +345,11 @@ static int stage_blocks(aeaj_handle* hd, bool inverse, float* layer, int h, int 
     long long off[9]; for (int k = 0; k < 9; k++) off[k] = S.cg.off[k];
     AEAJ_CUDA(cudaMemcpyAsync(hd->stage_class_off_dev, off, sizeof off, cudaMemcpyHostToDevice, st));
     AEAJ_CUDA(cudaMemsetAsync(S.class_counts, 0, 16 * sizeof(int), st));
-    rc = launch_bucket_leaves(hd->stage_plane_dev, &S.P, 1, S.class_lists, S.class_counts, hd->stage_class_off_dev, st); if (rc) return rc;
-    if (inverse) return launch_dequant_idct(hd, hd->stage_plane_dev, S.class_lists, S.class_counts, S.cg.off, S.cg.cap, ilog2i(mn), ilog2i(mx), st, nullptr, nullptr, nullptr, 0);
-    return launch_dct_quant(hd, hd->stage_plane_dev, S.class_lists, S.class_counts, S.cg.off, S.cg.cap, ilog2i(mn), ilog2i(mx), st, nullptr, nullptr, nullptr);
+    S.P.cap_leaves = INT32_MAX;                        // the stage API trusts counts[0] (the caller sized the leaf list)
+    rc = push_stage_plane(hd, S.P, st); if (rc) return rc;
+    rc = launch_bucket_leaves(hd->stage_plane_dev, &S.P, 1, S.class_lists, S.class_counts, hd->stage_class_off_dev, ilog2i(mn), ilog2i(mx), S.cg.cap, st); if (rc) return rc;
+    if (inverse) return launch_dequant_idct(hd, hd->stage_plane_dev, S.class_lists, S.class_counts, S.cg.off, S.cg.cap, ilog2i(mn), ilog2i(mx), st, nullptr, nullptr, nullptr, 0, S.scratch256);
+    return launch_dct_quant(hd, hd->stage_plane_dev, S.class_lists, S.class_counts, S.cg.off, S.cg.cap, ilog2i(mn), ilog2i(mx), st, nullptr, nullptr, nullptr, 0, S.scratch256);
 }
 extern "C" int aeaj_dct_quant(aeaj_handle* hd, const float* layer, int h, int w, float mid, float scale, const int32_t* leaves,
                               const int32_t* counts, int mn, int mx, const int32_t* const* qtab, int32_t* coef, void* ws, void* stream) {
@@ -366,7 +371,7 @@ struct aeaj_plan {
     int nplanes, lg_min, lg_max;
     std::vector<PlaneDesc> planes;       // host copy, index b*3 + l
     PlaneDesc* planes_dev;
-    int ntiles, nbig;
+    int ntiles, ring_cap;
     long long* class_off_dev;
     ClassGeom cg;
     int32_t* qtab_dev; size_t qtab_entries;
@@ -434,16 +439,19 @@ static size_t plan_carve(aeaj_plan* p, void* ws) {
     return b.off;
 }
 
-struct PlanAux { float* full_c1; float* full_c2; int* flags; int* ctrl; int* class_counts; ClassEntry* class_lists; };
+struct PlanAux { float* full_c1; float* full_c2; int* flags; int* ring; int* ctrl; int* class_counts; ClassEntry* class_lists; float* scratch256; };
 static size_t plan_carve_aux(aeaj_plan* p, void* ws, size_t start, PlanAux& A) {
     Bump b(ws); b.off = start;
     const size_t HW = (size_t)p->info.height * p->info.width;
     if (p->need_full_chroma) { A.full_c1 = b.take<float>(HW * p->info.batch); A.full_c2 = b.take<float>(HW * p->info.batch); }
     else { A.full_c1 = A.full_c2 = nullptr; }
-    A.flags = b.take<int>(2 * (size_t)p->nbig);
-    A.ctrl = b.take<int>(4);
+    A.flags = b.take<int>((size_t)p->ntiles);
+    A.ring = b.take<int>((size_t)p->ring_cap);
+    A.ctrl = b.take<int>(8);
     A.class_counts = b.take<int>(16);
     A.class_lists = b.take<ClassEntry>((size_t)p->cg.total);
+    // the 256 x 256 kernel's intermediate tiles belong to the call (plans run concurrently on several streams)
+    A.scratch256 = (p->lg_max >= 8) ? b.take<float>(aeaj_dct256_scratch_floats()) : nullptr;
     return b.used();
 }
 
@@ -480,7 +488,7 @@ extern "C" int aeaj_plan_create(aeaj_handle* h, int batch, int height, int width
     const int ch = p->info.layer_h[1], cw = p->info.layer_w[1];
     p->need_full_chroma = !((ch * 2 == height && cw * 2 == width && (width % 4) == 0) || (ch == height && cw * 4 == width));
     class_geom(p->planes.data(), p->nplanes, p->lg_min, p->lg_max, p->cg);
-    p->ntiles = hysteresis_tiles(p->planes.data(), p->nplanes, &p->nbig);
+    p->ntiles = hysteresis_tiles(p->planes.data(), p->nplanes, &p->ring_cap);
     size_t s1 = plan_carve(p, nullptr);
     PlanAux A;
     p->info.workspace_bytes = (int64_t)plan_carve_aux(p, nullptr, s1, A) + 256;
@@ -654,9 +662,9 @@ static int encode_impl(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, 
         launches += 2;
     }
     if (phases & (1u << AEAJ_PHASE_TREE)) {
-        rc = launch_hysteresis(h, p->planes_dev, NP, p->ntiles, p->nbig, A.flags, A.ctrl, io->status, st); if (rc) return rc;
+        rc = launch_hysteresis(h, p->planes_dev, NP, p->ntiles, p->ring_cap, A.flags, A.ring, A.ctrl, io->status, st); if (rc) return rc;
         p->mark("hysteresis");
-        launches += 2;
+        launches += 1;
         if (any_tap_edge) {
             AEAJ_CUDA(cudaMemcpyAsync(p->outs_dev, outs.data(), sizeof(uint8_t*) * NP, cudaMemcpyHostToDevice, st));
             rc = launch_bitmap_to_u8(p->planes_dev, p->planes.data(), NP, p->outs_dev, st); if (rc) return rc;
@@ -677,8 +685,9 @@ static int encode_impl(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, 
     }
     if (phases & (1u << AEAJ_PHASE_DCT)) {
         rc = launch_dct_quant(h, p->planes_dev, A.class_lists, A.class_counts, p->cg.off, p->cg.cap, p->lg_min, p->lg_max, st, &launches,
-                              plan_mark_cb, p, p->tensor_dct);
+                              plan_mark_cb, p, p->tensor_dct, A.scratch256);
         if (rc) return rc;
+        if (io->status) AEAJ_CUDA(cudaMemcpyAsync(io->status + 2, h->tc_err_dev, sizeof(int), cudaMemcpyDeviceToDevice, st));
     }
     p->last_launches = launches;
     return 0;
@@ -716,12 +725,18 @@ static int decode_impl(aeaj_plan* p, const aeaj_decode_io* io, void* workspace, 
     p->ev_n = 0; p->ev_stream = st; p->mark("start");
     if (phases & (1u << AEAJ_DPHASE_IDCT)) {
         AEAJ_CUDA(cudaMemsetAsync(A.class_counts, 0, 16 * sizeof(int), st));
-        rc = launch_bucket_leaves(p->planes_dev, p->planes.data(), NP, A.class_lists, A.class_counts, p->class_off_dev, st); if (rc) return rc;
+        rc = launch_bucket_leaves(p->planes_dev, p->planes.data(), NP, A.class_lists, A.class_counts, p->class_off_dev, p->lg_min, p->lg_max,
+                                  p->cg.cap, st);
+        if (rc) return rc;
         launches++;
         p->mark("bucket_leaves");
         rc = launch_dequant_idct(h, p->planes_dev, A.class_lists, A.class_counts, p->cg.off, p->cg.cap, p->lg_min, p->lg_max, st, &launches,
-                                 plan_mark_cb, p, p->tensor_dct);
+                                 plan_mark_cb, p, p->tensor_dct, A.scratch256);
         if (rc) return rc;
+        if (io->status) {
+            AEAJ_CUDA(cudaMemcpyAsync(io->status + 2, h->tc_err_dev, sizeof(int), cudaMemcpyDeviceToDevice, st));
+            AEAJ_CUDA(cudaMemcpyAsync(io->status + 3, A.class_counts + 15, sizeof(int), cudaMemcpyDeviceToDevice, st));
+        }
         for (int l = 0; l < 3; l++)
             if (io->tap_layers[l])
                 AEAJ_CUDA(cudaMemcpyAsync(io->tap_layers[l], p->planes[l].layer_f32, sizeof(float) * (size_t)B * p->info.layer_h[l] * p->info.layer_w[l],
@@ -762,10 +777,14 @@ extern "C" int aeaj_plan_buffers(aeaj_plan* p, void* workspace, aeaj_plan_buffer
 // ---------------------------------------------------------------------------------------------
 // host-side helpers (entropy-coding side; CPU only)
 // ---------------------------------------------------------------------------------------------
-extern "C" int aeaj_states_to_leaves_host(const uint8_t* states, int n_states, int root, int h, int w, int32_t* leaves,
-                                          int* n_leaves, int64_t* n_coef) {
-    AEAJ_REQUIRE(states && leaves && n_leaves && n_states >= 0 && root > 0, "aeaj_states_to_leaves_host: bad arguments");
-    (void)h; (void)w;
+// The state stream comes from a file: nothing in it is trusted.  Rejected (AEAJ_EINVAL, the shim raises ValueError where the
+// reference dies with a KeyError on zigzag_cache[size], jpeg.py:665): a root that is not the layer's root, a split below
+// size 2, a leaf outside [block_min, block_max] (0 = unchecked) or outside the layer.  State 3 splits like the reference's
+// `else` branch (jpeg.py:793); a truncated stream yields the leaves seen so far, as jpeg.py:784 does.
+extern "C" int aeaj_states_to_leaves_host(const uint8_t* states, int n_states, int root, int h, int w, int block_min, int block_max,
+                                          int32_t* leaves, int* n_leaves, int64_t* n_coef) {
+    AEAJ_REQUIRE(states && leaves && n_leaves && n_states >= 0 && root > 0 && h > 0 && w > 0, "aeaj_states_to_leaves_host: bad arguments");
+    AEAJ_REQUIRE(root == aeaj_root_size(h, w), "state stream: root size does not match the layer shape");
     struct Node { int x, y, s; };
     std::vector<Node> st;
     st.push_back({0, 0, root});
@@ -775,9 +794,13 @@ extern "C" int aeaj_states_to_leaves_host(const uint8_t* states, int n_states, i
         Node nd = st.back(); st.pop_back();
         int s = states[si++];
         if (s == 0) {
+            AEAJ_REQUIRE(nd.x < w && nd.y < h, "state stream: leaf outside the layer");
+            AEAJ_REQUIRE(nd.s >= 2 && (block_max <= 0 || (nd.s >= block_min && nd.s <= block_max)), "state stream: leaf size outside the block range");
+            AEAJ_REQUIRE(off + (int64_t)nd.s * nd.s < ((int64_t)1 << 31), "state stream: coefficient offsets overflow");
             leaves[4 * nl] = nd.x; leaves[4 * nl + 1] = nd.y; leaves[4 * nl + 2] = nd.s; leaves[4 * nl + 3] = (int32_t)off;
             off += (int64_t)nd.s * nd.s; nl++;
-        } else if (s == 1) {
+        } else if (s != 2) {
+            AEAJ_REQUIRE(nd.s >= 4 && (block_min <= 0 || nd.s > block_min), "state stream: split below the minimum block size");
             int hs = nd.s / 2;
             st.push_back({nd.x + hs, nd.y + hs, hs});
             st.push_back({nd.x, nd.y + hs, hs});

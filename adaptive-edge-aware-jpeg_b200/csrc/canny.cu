@@ -3,15 +3,12 @@
 //   u8 cast (color.cu) -> CLAHE tile histograms -> CLAHE LUTs -> [CLAHE apply + Gaussian 3x3 +
 //   bilateral 5x5] fused, shared-memory tiled with halo staging -> 256-bin histogram -> percentile
 //   thresholds -> Sobel/magnitude/NMS/double threshold -> bit-packed strong/weak maps (warp ballot)
-//   -> hysteresis by iterative bitmap frontier propagation (cooperative grid, tile-local convergence
-//   in shared memory, border exchange through global bitmaps between rounds).
+//   -> hysteresis by bitmap frontier propagation (persistent CTAs, tile-local convergence in shared
+//   memory, dirty neighbour tiles re-queued through a global work queue; no grid-wide barriers).
 //
 // All of it is integer / u8 work bounded by HBM (or L2) bandwidth and launch latency, not by math.
 // Arithmetic follows SURVEY.md App. A3 as validated by the CPU oracle against the reference.
-#include <cooperative_groups.h>
 #include "aeaj_internal.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -579,188 +576,150 @@ __global__ void __launch_bounds__(256) k_canny_nms(const PlaneDesc* __restrict__
 
 // ---------------------------------------------------------------------------------------------
 // hysteresis: strong |= weak pixels 8-connected (through weak pixels) to a strong pixel.
-// Bit-packed frontier propagation.  A block owns a tile of 8 words x 32 rows (256 x 32 px), one
-// word per thread; it iterates to local convergence in shared memory.  A cooperative grid loop
-// repeats until no tile's border changed; tiles whose neighbours did not change are skipped.
+// Bit-packed frontier propagation without grid-wide barriers.  A tile is 8 words x 32 rows (256 x 32 px), one
+// word per thread; a CTA takes a tile to local convergence in shared memory (word-parallel 3x3 spread + in-word
+// flood), ORs the new bits into the global bitmap and -- if bits on the tile's border changed -- pushes the (up to
+// 8) neighbour tiles that can see them onto a global work queue.  One persistent kernel: every CTA first walks
+// its static share of the tiles (each tile needs one pass anyway), then pulls re-visits from the queue until the
+// outstanding-work counter drops to zero.  The result is the fixed point reach(strong) through weak pixels, which
+// does not depend on the order of the passes (reach(S u T) = reach(S) u reach(T), bits are only ever set, stores
+// are atomic ORs), so asynchronous propagation is bit-identical to the round-synchronous version it replaces.
+//
+// queue: ring of tile ids (-1 = empty slot), capacity >= 2 x tiles; a tile is in the ring at most once (flags[]);
+// ctrl: [0] head  [1] tail  [2] pending re-visits (queued or running)  [3] first passes finished  [4] abort
 // ---------------------------------------------------------------------------------------------
-// Two tilings of every plane's bitmap, both 8 words (256 px) wide, one word-row per thread-row:
-//   small tiles: 32 rows  (round 0: every tile once, one block per tile, maximal parallelism)
-//   big tiles  : 128 rows (rounds 1..: only dirty tiles, 4 rows per thread; a chain advances 128 rows
-//                per round instead of 32, so the number of grid-wide rounds drops ~4x)
-// Dirty flags always refer to the big tiling.
-constexpr int HY_WW = 8, HY_TR = 32, HY_BIG = 1;
+constexpr int HY_WW = 8, HY_TR = 32;
 constexpr int HY_THREADS = HY_WW * HY_TR;
-constexpr bool HY_VFLOOD = false;                   // bit-transposed column flood: measured slower on the 4K workload
-
 constexpr int HY_SS = HY_WW + 3;                      // smem row stride (odd: lanes that differ in the row hit different banks)
+constexpr long long HY_SPIN_LIMIT = 4000000;          // x >= 200 ns: a lost wake-up must not hang the GPU
+
+struct HystQueue { int* flags; int* ring; int* ctrl; int ring_mask; int ntiles; };
+
 __device__ __forceinline__ unsigned spread3(unsigned L, unsigned Cw, unsigned R) {
     return Cw | (Cw << 1) | (Cw >> 1) | (L >> 31) | (R << 31);
 }
-// 32x32 bit-matrix transpose inside a warp: lane i holds row i, returns column i (5 shuffle stages)
-__device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
-    const unsigned mlo[5] = {0x0000ffffu, 0x00ff00ffu, 0x0f0f0f0fu, 0x33333333u, 0x55555555u};
-#pragma unroll
-    for (int st = 0; st < 5; st++) {
-        const int k = 16 >> st;
-        const unsigned y = __shfl_xor_sync(0xffffffffu, x, k);
-        x = (lane & k) ? ((x & ~mlo[st]) | ((y >> k) & mlo[st])) : ((x & mlo[st]) | ((y << k) & ~mlo[st]));
-    }
-    return x;
-}
+__device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
-// one tile (32*RPT rows) to local convergence; marks the BIG tiles that can see new border bits
-template <int RPT>
-__device__ __forceinline__ void hyst_process_tile(const PlaneDesc* __restrict__ planes, int nplanes, int tile,
-                                                  int* __restrict__ fl_nxt, int* __restrict__ c_nxt,
+// one pass over one tile: local convergence, atomic write-back, neighbour pushes
+__device__ __forceinline__ void hyst_process_tile(const PlaneDesc* __restrict__ planes, int nplanes, int tile, const HystQueue& q,
                                                   unsigned (*sS)[HY_SS], int* sPlane, int* sNbr) {
-    constexpr int ROWS = HY_TR * RPT;
-    // warp = one word column (tc), lane = row inside a 32-row block: each warp owns 32x32-px blocks, so a
-    // vertical run can be flooded in one step on the bit-transposed block
-    const int tid = threadIdx.x, tr = tid & 31, tc = tid >> 5;
+    const int tid = threadIdx.x, tr = tid & 31, tc = tid >> 5;     // warp = word column, lane = row
     __syncthreads();
     if (tid == 0) {
         int p = 0;
-        if (RPT == 1) { while (p + 1 < nplanes && planes[p + 1].hy_base_small <= tile) p++; }
-        else { while (p + 1 < nplanes && planes[p + 1].hy_base_big <= tile) p++; }
+        while (p + 1 < nplanes && planes[p + 1].hy_base <= tile) p++;
         *sPlane = p; *sNbr = 0;
     }
     __syncthreads();
     const PlaneDesc& P = planes[*sPlane];
-    const int local = tile - (RPT == 1 ? P.hy_base_small : P.hy_base_big);
+    const int local = tile - P.hy_base;
     const int ntx = aeaj_cdiv(P.wpr, HY_WW);
     const int tyi = local / ntx, txi = local - tyi * ntx;
-    const int gy0 = tyi * ROWS, gw0 = txi * HY_WW;
-    for (int i = tid; i < (ROWS + 2) * (HY_WW + 2); i += HY_THREADS) {
-        int ry = i / (HY_WW + 2), rw = i - ry * (HY_WW + 2);
-        int gy = gy0 + ry - 1, gw = gw0 + rw - 1;
+    const int gy0 = tyi * HY_TR, gw0 = txi * HY_WW;
+    for (int i = tid; i < (HY_TR + 2) * (HY_WW + 2); i += HY_THREADS) {
+        const int ry = i / (HY_WW + 2), rw = i - ry * (HY_WW + 2);
+        const int gy = gy0 + ry - 1, gw = gw0 + rw - 1;
         unsigned v = 0;
         if (gy >= 0 && gy < P.h && gw >= 0 && gw < P.wpr) v = __ldcg(P.strong + (size_t)gy * P.wpr + gw);
         sS[ry][rw] = v;
     }
-    const int gw = gw0 + tc;
-    unsigned wk[RPT], wkT[RPT], s[RPT], s_init[RPT];
-#pragma unroll
-    for (int k = 0; k < RPT; k++) {
-        const int gy = gy0 + tr + k * HY_TR;
-        wk[k] = (gy < P.h && gw < P.wpr) ? P.weak[(size_t)gy * P.wpr + gw] : 0u;
-        wkT[k] = HY_VFLOOD ? transpose32(wk[k], tr) : 0u;
-    }
+    const int gw = gw0 + tc, gy = gy0 + tr;
+    const bool inb = (gy < P.h && gw < P.wpr);
+    const unsigned wk = inb ? __ldg(P.weak + (size_t)gy * P.wpr + gw) : 0u;
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < RPT; k++) { s_init[k] = sS[tr + k * HY_TR + 1][tc + 1]; s[k] = s_init[k]; }
+    const unsigned s_init = sS[tr + 1][tc + 1];
+    unsigned s = s_init;
     for (;;) {
-        int ch = 0;
-        unsigned s_new[RPT];
-#pragma unroll
-        for (int k = 0; k < RPT; k++) {
-            const int r = tr + k * HY_TR;
-            unsigned n = spread3(sS[r][tc], sS[r][tc + 1], sS[r][tc + 2]) |
-                         spread3(sS[r + 1][tc], s[k], sS[r + 1][tc + 2]) |
-                         spread3(sS[r + 2][tc], sS[r + 2][tc + 1], sS[r + 2][tc + 2]);
-            unsigned add = wk[k] & ~s[k] & n;
-            unsigned t = s[k] | add;
-            while (add) { add = wk[k] & ~t & ((t << 1) | (t >> 1)); t |= add; }   // flood along the row inside the word
-            if (HY_VFLOOD && __any_sync(0xffffffffu, t != s[k])) {
-                // flood along the columns of the 32x32 block: same trick on the transposed block
-                unsigned tt = transpose32(t, tr);
-                unsigned addv = wkT[k] & ~tt & ((tt << 1) | (tt >> 1));
-                while (addv) { tt |= addv; addv = wkT[k] & ~tt & ((tt << 1) | (tt >> 1)); }
-                t = transpose32(tt, tr);
-            }
-            ch |= (t != s[k]);
-            s_new[k] = t;
-        }
+        const unsigned n = spread3(sS[tr][tc], sS[tr][tc + 1], sS[tr][tc + 2]) |
+                           spread3(sS[tr + 1][tc], s, sS[tr + 1][tc + 2]) |
+                           spread3(sS[tr + 2][tc], sS[tr + 2][tc + 1], sS[tr + 2][tc + 2]);
+        unsigned add = wk & ~s & n;
+        unsigned t = s | add;
+        while (add) { add = wk & ~t & ((t << 1) | (t >> 1)); t |= add; }       // flood along the row inside the word
+        const int ch = (t != s);
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < RPT; k++) if (s_new[k] != s[k]) { s[k] = s_new[k]; sS[tr + k * HY_TR + 1][tc + 1] = s[k]; }
+        if (ch) { s = t; sS[tr + 1][tc + 1] = s; }
         if (!__syncthreads_or(ch)) break;
     }
     unsigned nb = 0;
-#pragma unroll
-    for (int k = 0; k < RPT; k++) {
-        const int r = tr + k * HY_TR, gy = gy0 + r;
-        if (gy < P.h && gw < P.wpr && s[k] != s_init[k]) {
-            P.strong[(size_t)gy * P.wpr + gw] = s[k];
-            // which of the 8 neighbours can see the new bits (bit index = (dy+1)*3 + (dx+1))
-            const unsigned diff = s[k] ^ s_init[k];
-            const bool L = (tc == 0) && (diff & 1u), R = (tc == HY_WW - 1) && (diff >> 31);
-            if (r == 0) nb |= 2u | (L ? 1u : 0u) | (R ? 4u : 0u);
-            if (r == ROWS - 1) nb |= 128u | (L ? 64u : 0u) | (R ? 256u : 0u);
-            if (L) nb |= 8u;
-            if (R) nb |= 32u;
-        }
+    if (inb && s != s_init) {
+        atomicOr(P.strong + (size_t)gy * P.wpr + gw, s);
+        __threadfence();                                                       // the new bits are visible before any push below
+        // which of the 8 neighbours can see the new bits (bit index = (dy+1)*3 + (dx+1))
+        const unsigned diff = s ^ s_init;
+        const bool L = (tc == 0) && (diff & 1u), R = (tc == HY_WW - 1) && (diff >> 31);
+        if (tr == 0) nb |= 2u | (L ? 1u : 0u) | (R ? 4u : 0u);
+        if (tr == HY_TR - 1) nb |= 128u | (L ? 64u : 0u) | (R ? 256u : 0u);
+        if (L) nb |= 8u;
+        if (R) nb |= 32u;
     }
     if (nb) atomicOr(sNbr, (int)nb);
     __syncthreads();
     if (tid < 9 && tid != 4 && ((*sNbr >> tid) & 1)) {
-        // neighbour in this tiling -> the big tile that contains its adjacent rows
         const int dy = tid / 3 - 1, dx = tid % 3 - 1;
-        const int nx = txi + dx;
-        const int row = (dy < 0) ? gy0 - 1 : ((dy > 0) ? gy0 + ROWS : gy0);     // a row of the neighbour (dy == 0: same rows)
-        if (nx >= 0 && nx < ntx && row >= 0 && row < P.h) {
-            const int bty = row / (HY_TR * HY_BIG);
-            fl_nxt[P.hy_base_big + bty * ntx + nx] = 1;
-            atomicAdd(c_nxt, 1);
+        const int nx = txi + dx, ny = tyi + dy;
+        if (nx >= 0 && nx < ntx && ny >= 0 && ny * HY_TR < P.h) {
+            const int nt = P.hy_base + ny * ntx + nx;
+            if (atomicExch(&q.flags[nt], 1) == 0) {                            // not queued yet (a queued tile will load after our store)
+                atomicAdd(&q.ctrl[2], 1);
+                const int slot = atomicAdd(&q.ctrl[1], 1) & q.ring_mask;
+                long long spins = 0;
+                while (atomicCAS(&q.ring[slot], -1, nt) != -1)                 // the slot's previous ticket has not been read yet
+                    if (++spins > HY_SPIN_LIMIT) { atomicExch(&q.ctrl[4], 1); break; }
+            }
         }
     }
-}
-
-// round 0: every small tile once, plain launch; flags for round 1 go to flags[nbig..2*nbig)
-__global__ void __launch_bounds__(HY_THREADS) k_hysteresis_first(const PlaneDesc* __restrict__ planes, int nplanes, int nbig,
-                                                              int* __restrict__ flags, int* __restrict__ ctrl) {
-    __shared__ unsigned sS[HY_TR + 2][HY_SS];
-    __shared__ int sPlane, sNbr;
-    hyst_process_tile<1>(planes, nplanes, blockIdx.x, flags + nbig, ctrl + 1, sS, &sPlane, &sNbr);
-}
-
-// rounds 1..R: one plain launch per round, one block per tile, early exit when the tile is clean (or when the
-// previous round flagged nothing at all).  Launch latency is far below the cost of a grid-wide barrier here.
-__global__ void __launch_bounds__(HY_THREADS) k_hysteresis_round(const PlaneDesc* __restrict__ planes, int nplanes, int nbig,
-                                                              int* __restrict__ flags, int* __restrict__ ctrl, int round) {
-    __shared__ unsigned sS[HY_TR * HY_BIG + 2][HY_SS];
-    __shared__ int sPlane, sNbr;
-    if (*((volatile int*)(ctrl + round % 3)) == 0) return;          // nothing pending for this round
-    int* fl_cur = flags + (size_t)(round & 1) * nbig;
-    int* fl_nxt = flags + (size_t)((round + 1) & 1) * nbig;
-    const int tile = blockIdx.x;
-    if (tile == 0 && threadIdx.x == 0) ctrl[(round + 2) % 3] = 0;
-    if (__ldcg(fl_cur + tile) == 0) return;
     __syncthreads();
-    if (threadIdx.x == 0) fl_cur[tile] = 0;
-    hyst_process_tile<HY_BIG>(planes, nplanes, tile, fl_nxt, ctrl + (round + 1) % 3, sS, &sPlane, &sNbr);
 }
 
-// remaining rounds: a cooperative grid loops over the dirty big tiles until no border changed
-__global__ void __launch_bounds__(HY_THREADS) k_hysteresis_rounds(const PlaneDesc* __restrict__ planes, int nplanes, int nbig,
-                                                               int* __restrict__ flags, int* __restrict__ ctrl, int* __restrict__ status,
-                                                               int first_round, int max_rounds) {
-    cg::grid_group grid = cg::this_grid();
-    __shared__ unsigned sS[HY_TR * HY_BIG + 2][HY_SS];
-    __shared__ int sPlane, sNbr;
+__global__ void __launch_bounds__(HY_THREADS) k_hysteresis(const PlaneDesc* __restrict__ planes, int nplanes, HystQueue q, int* __restrict__ status) {
+    __shared__ unsigned sS[HY_TR + 2][HY_SS];
+    __shared__ int sPlane, sNbr, sTile;
     const int tid = threadIdx.x;
-    int round = first_round;
-    if (*((volatile int*)(ctrl + first_round % 3)) == 0) {   // already converged in the plain rounds
-        if (blockIdx.x == 0 && tid == 0 && status) { status[0] = first_round; status[1] = 1; }
-        return;
+    // first pass: a static share of the tiles
+    for (int tile = blockIdx.x; tile < q.ntiles; tile += gridDim.x) {
+        if (tid == 0) { atomicExch(&q.flags[tile], 0); __threadfence(); }
+        hyst_process_tile(planes, nplanes, tile, q, sS, &sPlane, &sNbr);
+        if (tid == 0) { __threadfence(); atomicAdd(&q.ctrl[3], 1); }
     }
-    for (;; round++) {
-        int* fl_cur = flags + (size_t)(round & 1) * nbig;
-        int* fl_nxt = flags + (size_t)((round + 1) & 1) * nbig;
-        int* c_nxt = ctrl + (round + 1) % 3;
-        if (blockIdx.x == 0 && tid == 0) ctrl[(round + 2) % 3] = 0;
-        for (int tile = blockIdx.x; tile < nbig; tile += gridDim.x) {
-            if (__ldcg(fl_cur + tile) == 0) continue;  // uniform per block
-            __syncthreads();
-            if (tid == 0) { fl_cur[tile] = 0; if (status && round < 30) atomicAdd(&status[2 + round], 1); }
-            hyst_process_tile<HY_BIG>(planes, nplanes, tile, fl_nxt, c_nxt, sS, &sPlane, &sNbr);
+    // re-visits from the queue until nothing is queued or running anywhere
+    for (;;) {
+        if (tid == 0) {
+            int t = -2;
+            long long spins = 0;
+            for (;;) {
+                const int hd = ld_volatile(&q.ctrl[0]), tl = ld_volatile(&q.ctrl[1]);
+                if (hd < tl) {
+                    if (atomicCAS(&q.ctrl[0], hd, hd + 1) != hd) continue;
+                    const int slot = hd & q.ring_mask;
+                    int v;
+                    long long sp2 = 0;
+                    while ((v = ld_volatile(&q.ring[slot])) == -1)
+                        if (++sp2 > HY_SPIN_LIMIT) { atomicExch(&q.ctrl[4], 1); break; }
+                    if (v >= 0) atomicExch(&q.ring[slot], -1);
+                    t = v >= 0 ? v : -2;
+                    break;
+                }
+                if (ld_volatile(&q.ctrl[4])) break;
+                if (ld_volatile(&q.ctrl[3]) >= q.ntiles) {                     // every first pass (and its pushes) is counted ...
+                    __threadfence();
+                    if (ld_volatile(&q.ctrl[2]) == 0) break;                   // ... and no re-visit is queued or running
+                }
+                if (++spins > HY_SPIN_LIMIT) { atomicExch(&q.ctrl[4], 1); break; }
+                __nanosleep(200);
+            }
+            sTile = t;
         }
-        __threadfence();
-        grid.sync();
-        int pending = *((volatile int*)c_nxt);
-        if (pending == 0 || round + 1 >= max_rounds) {
-            if (blockIdx.x == 0 && tid == 0 && status) { status[0] = round + 1; status[1] = (pending == 0); }
-            break;
-        }
+        __syncthreads();
+        const int tile = sTile;
+        if (tile < 0) break;
+        if (tid == 0) { atomicExch(&q.flags[tile], 0); __threadfence(); }
+        hyst_process_tile(planes, nplanes, tile, q, sS, &sPlane, &sNbr);
+        if (tid == 0) { __threadfence(); atomicSub(&q.ctrl[2], 1); }
+    }
+    if (tid == 0 && status) {                                                  // every CTA reports the same final values
+        status[0] = ld_volatile(&q.ctrl[1]);                                   // tile re-visits in total
+        status[1] = ld_volatile(&q.ctrl[4]) ? 0 : 1;                           // converged
     }
 }
 
@@ -849,43 +808,37 @@ int launch_canny_nms(const PlaneDesc* planes_dev, const PlaneDesc* P, int nplane
     return 0;
 }
 
-// fills hy_base_small / hy_base_big of every plane; returns the number of small tiles, *nbig = big tiles
-int hysteresis_tiles(PlaneDesc* P, int nplanes, int* nbig) {
-    int ns = 0, nb = 0;
+// fills hy_base of every plane; returns the number of hysteresis tiles
+int hysteresis_tiles(PlaneDesc* P, int nplanes, int* ring_cap) {
+    int ns = 0;
     for (int i = 0; i < nplanes; i++) {
-        P[i].hy_base_small = ns; P[i].hy_base_big = nb;
-        const int ntx = aeaj_cdiv(P[i].wpr, HY_WW);
-        ns += ntx * aeaj_cdiv(P[i].h, HY_TR);
-        nb += ntx * aeaj_cdiv(P[i].h, HY_TR * HY_BIG);
+        P[i].hy_base = ns;
+        ns += aeaj_cdiv(P[i].wpr, HY_WW) * aeaj_cdiv(P[i].h, HY_TR);
     }
-    *nbig = nb;
+    int cap = 64;
+    while (cap < 2 * ns) cap *= 2;
+    *ring_cap = cap;
     return ns;
 }
 
-// flags: int[2*nbig]; ctrl: int[3]; both zeroed here.
-int launch_hysteresis(aeaj_handle* h, const PlaneDesc* planes_dev, int nplanes, int nsmall, int nbig,
-                      int* flags, int* ctrl, int* status, cudaStream_t st) {
-    AEAJ_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 2 * (size_t)nbig, st));
-    AEAJ_CUDA(cudaMemsetAsync(ctrl, 0, sizeof(int) * 3, st));
-    k_hysteresis_first<<<nsmall, HY_THREADS, 0, st>>>(planes_dev, nplanes, nbig, flags, ctrl);
+int aeaj_canny_init(aeaj_handle* h) {
+    int rc = aeaj_canny_init_constants(); if (rc) return rc;
+    AEAJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->hyst_blocks_per_sm, k_hysteresis, HY_THREADS, 0));
+    if (h->hyst_blocks_per_sm < 1) { aeaj_set_error("hysteresis kernel cannot be resident"); return AEAJ_EINVAL; }
+    return 0;
+}
+
+// flags: int[ntiles] (set = queued; the first pass counts as queued); ring: int[ring_cap]; ctrl: int[8]
+int launch_hysteresis(aeaj_handle* h, const PlaneDesc* planes_dev, int nplanes, int ntiles, int ring_cap,
+                      int* flags, int* ring, int* ctrl, int* status, cudaStream_t st) {
+    AEAJ_CUDA(cudaMemsetAsync(flags, 1, sizeof(int) * (size_t)ntiles, st));
+    AEAJ_CUDA(cudaMemsetAsync(ring, 0xff, sizeof(int) * (size_t)ring_cap, st));
+    AEAJ_CUDA(cudaMemsetAsync(ctrl, 0, sizeof(int) * 8, st));
+    HystQueue q;
+    q.flags = flags; q.ring = ring; q.ctrl = ctrl; q.ring_mask = ring_cap - 1; q.ntiles = ntiles;
+    const int grid = std::max(1, std::min(ntiles, std::min(h->hyst_blocks_per_sm, 6) * h->sm_count));
+    k_hysteresis<<<grid, HY_THREADS, 0, st>>>(planes_dev, nplanes, q, status);
     AEAJ_LAUNCH_CHECK();
-    static int blocks_per_sm = 0;
-    if (!blocks_per_sm) {
-        AEAJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_hysteresis_rounds, HY_THREADS, 0));
-        if (blocks_per_sm < 1) { aeaj_set_error("hysteresis kernel cannot be resident"); return AEAJ_EINVAL; }
-    }
-    int plain_rounds = 0;   // measured: per-round cost is the slowest tile's local convergence (~20 us), not the barrier
-    if (const char* e = getenv("AEAJ_HYST_PLAIN")) plain_rounds = std::max(0, atoi(e));
-    for (int r = 1; r <= plain_rounds; r++) {
-        k_hysteresis_round<<<nbig, HY_THREADS, 0, st>>>(planes_dev, nplanes, nbig, flags, ctrl, r);
-        AEAJ_LAUNCH_CHECK();
-    }
-    int bps = std::min(blocks_per_sm, 4);
-    if (const char* e = getenv("AEAJ_HYST_BPS")) bps = std::max(1, std::min(blocks_per_sm, atoi(e)));
-    int grid = std::min(nbig, bps * h->sm_count);
-    int max_rounds = 1 << 20, first_round = plain_rounds + 1;
-    void* args[] = {(void*)&planes_dev, (void*)&nplanes, (void*)&nbig, (void*)&flags, (void*)&ctrl, (void*)&status, (void*)&first_round, (void*)&max_rounds};
-    AEAJ_CUDA(cudaLaunchCooperativeKernel((void*)k_hysteresis_rounds, dim3(grid), dim3(HY_THREADS), args, 0, st));
     return 0;
 }
 

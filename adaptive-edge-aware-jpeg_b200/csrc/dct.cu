@@ -5,8 +5,9 @@
 // product  Out = M . In . M^T  with M = C (forward, cv.dct) or M = C^T (inverse, cv.idct), where
 // C[k][i] = sqrt(2/s) cos(pi (2i+1) k / 2s), row 0 scaled by 1/sqrt 2, evaluated in f64 on the host
 // and stored as f32.  FP32 FMA accumulation: SURVEY.md App. A5 measured 0 quantiser flips against
-// cv.dct for an f32 matrix DCT (tie class T-DCT), which is the parity bar; tensor-core (tf32) tiles do
-// not hold that bar without error compensation and are not used here.
+// cv.dct for an f32 matrix DCT (tie class T-DCT), which is the parity bar.  Plain TF32 tensor-core tiles do
+// not hold that bar; the error-compensated 3xTF32 tcgen05 kernels that do are in dct_tc.cu (the default for the
+// size classes they cover) and the kernels of this file serve the small classes and the FP32 reference path.
 //
 //   s <= 32 : "row" kernel -- s lanes per leaf, lane r owns row r; pass 1 in registers against
 //             broadcast reads of M from shared memory, exchange through a per-warp shared tile,
@@ -539,14 +540,11 @@ int launch_rows(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* l
     AEAJ_LAUNCH_CHECK();
     return 0;
 }
+constexpr size_t cta_smem_bytes(int S) { return (size_t)(S * S / 2 + S * (S + 4) + 3 * 16) * sizeof(float); }
+
 template <int S, bool INV>
 int launch_cta(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* list, const int* count, int64_t cap, cudaStream_t st) {
-    const size_t smem = (size_t)(S * S / 2 + S * (S + 4) + 3 * 16) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        AEAJ_CUDA(cudaFuncSetAttribute(k_dct_cta<S, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    const size_t smem = cta_smem_bytes(S);             // opted in per device by aeaj_dct_init
     int per_sm = (smem > 110 * 1024) ? 1 : ((smem > 56 * 1024) ? 2 : 4);
     int blocks = (int)std::min<int64_t>(std::max<int64_t>(cap, 1), (int64_t)h->sm_count * per_sm);
     const int lg = ilog2i(S);
@@ -646,10 +644,10 @@ __global__ void __launch_bounds__(256) k_dct256(const PlaneDesc* __restrict__ pl
 }
 
 template <bool INV>
-int launch_256(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* list, const int* count, int64_t cap, cudaStream_t st) {
-    if (!h->dct256_scratch) AEAJ_CUDA(cudaMalloc(&h->dct256_scratch, (size_t)D256_CTAS * 256 * 256 * sizeof(float)));
+int launch_256(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* list, const int* count, int64_t cap, float* scratch, cudaStream_t st) {
+    AEAJ_REQUIRE(scratch, "256 x 256 leaves need the per-call scratch tiles (aeaj_dct256_scratch_floats)");
     const int blocks = (int)std::min<int64_t>(std::max<int64_t>(cap, 1), D256_CTAS);
-    k_dct256<INV><<<blocks, 256, 0, st>>>(planes_dev, list, count, h->dct_dev[8], h->dct_dev[8] + 256 * 256, h->izz256_dev, h->dct256_scratch);
+    k_dct256<INV><<<blocks, 256, 0, st>>>(planes_dev, list, count, h->dct_dev[8], h->dct_dev[8] + 256 * 256, h->izz256_dev, scratch);
     AEAJ_LAUNCH_CHECK();
     return 0;
 }
@@ -657,7 +655,7 @@ int launch_256(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* li
 template <bool INV>
 int launch_all(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,
                const int64_t* off, const int64_t* caps, int lg_min, int lg_max, cudaStream_t st, int* launches,
-               void (*mark)(void*, const char*), void* mark_ctx, int tensor_dct = 0) {
+               void (*mark)(void*, const char*), void* mark_ctx, int tensor_dct, float* scratch256) {
     static const char* fwd_names[9] = {"", "dct_quant_2", "dct_quant_4", "dct_quant_8", "dct_quant_16", "dct_quant_32", "dct_quant_64", "dct_quant_128", "dct_quant_256"};
     static const char* inv_names[9] = {"", "dequant_idct_2", "dequant_idct_4", "dequant_idct_8", "dequant_idct_16", "dequant_idct_32", "dequant_idct_64", "dequant_idct_128", "dequant_idct_256"};
     for (int lg = lg_min; lg <= lg_max; lg++) {
@@ -674,7 +672,7 @@ int launch_all(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* cl
             case 6: rc = launch_cta<64, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
             case 7: rc = tensor_dct ? launch_dct_tc128(h, planes_dev, list, cnt, caps[lg], INV ? 1 : 0, st)
                                               : launch_cta<128, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
-            case 8: rc = launch_256<INV>(h, planes_dev, list, cnt, caps[lg], st); break;
+            case 8: rc = launch_256<INV>(h, planes_dev, list, cnt, caps[lg], scratch256, st); break;
             default: aeaj_set_error("block size %d not supported (2..256)", 1 << lg); return AEAJ_EINVAL;
         }
         if (rc) return rc;
@@ -688,7 +686,14 @@ int launch_all(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* cl
 
 // DCT-II matrices C and C^T per size, f64 on the host, stored f32: table for size s at dct_dev[log2 s],
 // layout [C (s*s)][C^T (s*s)].
+size_t aeaj_dct256_scratch_floats() { return (size_t)D256_CTAS * 256 * 256; }
+
 int aeaj_dct_init(aeaj_handle* h) {
+    // function attributes are per device: set them for the device of every new handle (aeaj_create selected it)
+    AEAJ_CUDA(cudaFuncSetAttribute(k_dct_cta<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem_bytes(64)));
+    AEAJ_CUDA(cudaFuncSetAttribute(k_dct_cta<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem_bytes(64)));
+    AEAJ_CUDA(cudaFuncSetAttribute(k_dct_cta<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem_bytes(128)));
+    AEAJ_CUDA(cudaFuncSetAttribute(k_dct_cta<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem_bytes(128)));
     size_t total = 0;
     for (int lg = 1; lg <= 8; lg++) total += 2 * ((size_t)1 << (2 * lg));
     float* host = (float*)malloc(total * sizeof(float));
@@ -774,11 +779,11 @@ int aeaj_dct_init(aeaj_handle* h) {
 
 int launch_dct_quant(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,
                      const int64_t* off, const int64_t* caps, int lg_min, int lg_max, cudaStream_t st, int* launches,
-                     void (*mark)(void*, const char*), void* mark_ctx, int tensor_dct) {
-    return launch_all<false>(h, planes_dev, class_lists, class_counts, off, caps, lg_min, lg_max, st, launches, mark, mark_ctx, tensor_dct);
+                     void (*mark)(void*, const char*), void* mark_ctx, int tensor_dct, float* scratch256) {
+    return launch_all<false>(h, planes_dev, class_lists, class_counts, off, caps, lg_min, lg_max, st, launches, mark, mark_ctx, tensor_dct, scratch256);
 }
 int launch_dequant_idct(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,
                         const int64_t* off, const int64_t* caps, int lg_min, int lg_max, cudaStream_t st, int* launches,
-                        void (*mark)(void*, const char*), void* mark_ctx, int tensor_dct) {
-    return launch_all<true>(h, planes_dev, class_lists, class_counts, off, caps, lg_min, lg_max, st, launches, mark, mark_ctx, tensor_dct);
+                        void (*mark)(void*, const char*), void* mark_ctx, int tensor_dct, float* scratch256) {
+    return launch_all<true>(h, planes_dev, class_lists, class_counts, off, caps, lg_min, lg_max, st, launches, mark, mark_ctx, tensor_dct, scratch256);
 }

@@ -20,6 +20,7 @@
 namespace {
 
 constexpr int TC_N = 128;
+constexpr size_t TC_SMEM_BYTES = (size_t)(2 * TC_N * TC_N + 2 * TC_N * 64) * sizeof(float);
 constexpr uint32_t TC_IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);   // F32 accum, TF32 x TF32, K-major, M=128
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -371,6 +372,8 @@ __global__ void __launch_bounds__(256, 1) k_dct_tc128(const PlaneDesc* __restric
 // forward tile element (r, k) = C[r][k], inverse tile element (r, k) = C[k][r]
 int aeaj_dct_tc_init(aeaj_handle* h) {
     const int N = TC_N;
+    AEAJ_CUDA(cudaFuncSetAttribute(k_dct_tc128<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    AEAJ_CUDA(cudaFuncSetAttribute(k_dct_tc128<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
     std::vector<float> host(4 * (size_t)N * N);
     for (int inv = 0; inv < 2; inv++)
         for (int r = 0; r < N; r++)
@@ -398,13 +401,7 @@ int aeaj_dct_tc_init(aeaj_handle* h) {
 }
 
 int launch_dct_tc128(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* list, const int* count, int64_t cap, int inverse, cudaStream_t st) {
-    const size_t smem = (size_t)(2 * TC_N * TC_N + 2 * TC_N * 64) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        AEAJ_CUDA(cudaFuncSetAttribute(k_dct_tc128<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        AEAJ_CUDA(cudaFuncSetAttribute(k_dct_tc128<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    const size_t smem = TC_SMEM_BYTES;                  // opted in per device by aeaj_dct_tc_init
     int blocks = (int)std::min<int64_t>(std::max<int64_t>(cap, 1), (int64_t)h->sm_count);
     if (inverse) k_dct_tc128<true><<<blocks, 256, smem, st>>>(planes_dev, list, count, h->dct_tc_tiles_dev + 2 * TC_N * TC_N, h->tc_izz_dev, h->tc_err_dev);
     else k_dct_tc128<false><<<blocks, 256, smem, st>>>(planes_dev, list, count, h->dct_tc_tiles_dev, h->tc_izz_dev, h->tc_err_dev);

@@ -236,10 +236,14 @@ __global__ void __launch_bounds__(QT_THREADS) k_qt_scan(const PlaneDesc* __restr
 }
 
 // decode side: leaves (x,y,size,coef_off) -> per-size-class work lists
+// A leaf list that did not come from aeaj_quadtree / aeaj_states_to_leaves_host is not trusted: leaves whose size is not a
+// power of two inside [2^lg_min, 2^lg_max], whose origin lies outside the layer or whose coefficient block leaves the
+// plane's buffer are skipped and counted in class_counts[15] (reported through aeaj_decode_io.status).
 __global__ void __launch_bounds__(256) k_bucket_leaves(const PlaneDesc* __restrict__ planes, ClassEntry* __restrict__ class_lists,
-                                                       int* __restrict__ class_counts, const long long* __restrict__ class_offsets) {
+                                                       int* __restrict__ class_counts, const long long* __restrict__ class_offsets,
+                                                       int lg_min, int lg_max, const ClassCaps caps) {
     const PlaneDesc& P = planes[blockIdx.y];
-    const int nl = P.counts[0];
+    const int nl = (int)min((long long)max(P.counts[0], 0), (long long)P.cap_leaves);
     __shared__ int s_cls[9], s_base[9];
     if (threadIdx.x < 9) s_cls[threadIdx.x] = 0;
     __syncthreads();
@@ -248,15 +252,20 @@ __global__ void __launch_bounds__(256) k_bucket_leaves(const PlaneDesc* __restri
     int lg = -1, rank = 0;
     if (i < nl) {
         lf = reinterpret_cast<const int4*>(P.leaves)[i];
-        lg = 31 - __clz(lf.z);
-        rank = atomicAdd(&s_cls[lg], 1);
+        lg = lf.z > 0 ? 31 - __clz(lf.z) : -1;
+        const bool ok = lg >= lg_min && lg <= lg_max && lf.z == (1 << lg) && lf.x >= 0 && lf.y >= 0 && lf.x < P.w && lf.y < P.h &&
+                        lf.w >= 0 && (long long)lf.w + (long long)lf.z * lf.z <= (long long)P.cap_coef;
+        if (ok) rank = atomicAdd(&s_cls[lg], 1);
+        else { lg = -1; atomicAdd(&class_counts[15], 1); }
     }
     __syncthreads();
     if (threadIdx.x < 9 && s_cls[threadIdx.x] > 0) s_base[threadIdx.x] = atomicAdd(&class_counts[threadIdx.x], s_cls[threadIdx.x]);
     __syncthreads();
-    if (i < nl) {
+    if (i < nl && lg >= 0) {
         ClassEntry e; e.x = lf.x; e.y = lf.y; e.plane = blockIdx.y; e.coef_off = lf.w;
-        class_lists[class_offsets[lg] + s_base[lg] + rank] = e;
+        const long long slot = (long long)s_base[lg] + rank;
+        if (slot < caps.cap[lg]) class_lists[class_offsets[lg] + slot] = e;      // more leaves of a size than can tile the planes: overlapping leaves
+        else atomicAdd(&class_counts[15], 1);
     }
 }
 
@@ -300,11 +309,14 @@ int launch_quadtree(const PlaneDesc* planes_dev, const PlaneDesc* P, int nplanes
 }
 
 int launch_bucket_leaves(const PlaneDesc* planes_dev, const PlaneDesc* P, int nplanes, ClassEntry* class_lists,
-                         int* class_counts, const long long* class_offsets_dev, cudaStream_t st) {
+                         int* class_counts, const long long* class_offsets_dev, int lg_min, int lg_max, const int64_t* class_caps_host,
+                         cudaStream_t st) {
     int64_t maxl = 1;
     for (int i = 0; i < nplanes; i++) maxl = std::max<int64_t>(maxl, P[i].cap_leaves);
     dim3 grd((unsigned)aeaj_cdiv64(maxl, 256), nplanes);
-    k_bucket_leaves<<<grd, 256, 0, st>>>(planes_dev, class_lists, class_counts, class_offsets_dev);
+    ClassCaps caps;
+    for (int k = 0; k < 9; k++) caps.cap[k] = class_caps_host[k];
+    k_bucket_leaves<<<grd, 256, 0, st>>>(planes_dev, class_lists, class_counts, class_offsets_dev, lg_min, lg_max, caps);
     AEAJ_LAUNCH_CHECK();
     return 0;
 }

@@ -169,6 +169,7 @@ class Jpeg:
         for (H, W, space, q, b), idxs in groups.items():
             coef, leaves, counts = codec.upload_for_decode([parsed[i]["layers"] for i in idxs], len(idxs), H, W, space, q, b)
             rgb = codec.decode(coef, leaves, counts, len(idxs), H, W, space, q, b, zigzag=True, out="u8" if as_uint8 else "f32").cpu().numpy()
+            codec.check_status(codec.last_decode_status, "decode")
             for k, i in enumerate(idxs):
                 out[i] = rgb[k] if as_uint8 else Image.from_array(rgb[k].reshape(-1, 3), (H, W, 3), parsed[i]["extension"])
         last = parsed[-1]
@@ -226,7 +227,7 @@ class Jpeg:
             root = int.from_bytes(s.read(4), byteorder="big")
             raw = np.frombuffer(s.read((nbits + 7) // 8), dtype=np.uint8)
             states = np.stack([(raw >> 6) & 3, (raw >> 4) & 3, (raw >> 2) & 3, raw & 3], axis=1).reshape(-1)[: nbits // 2]
-            leaves, ncoef = native.states_to_leaves(states.astype(np.uint8), root, int(shapes[i][0]), int(shapes[i][1]))
+            leaves, ncoef = native.states_to_leaves(states.astype(np.uint8), root, int(shapes[i][0]), int(shapes[i][1]), blocks)
             zl = int.from_bytes(s.read(4), byteorder="big")
             coef = np.frombuffer(zlib.decompress(s.read(zl)), dtype=np.int32)
             if coef.size != ncoef:

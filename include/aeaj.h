@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AEAJ_VERSION 1
+#define AEAJ_VERSION 2
 
 #if defined(__GNUC__)
 #define AEAJ_API __attribute__((visibility("default")))
@@ -151,7 +151,8 @@ typedef struct {
     int32_t* counts;         /* [batch][3][4] n_leaves, n_states, n_coef, root */
     float* tap_layers[3];    /* optional [batch][h_l][w_l]: downsampled un-normalised layers */
     uint8_t* tap_edges[3];   /* optional [batch][h_l][w_l]: edge maps {0,1} */
-    int32_t* status;         /* device int32[64]: [0] hysteresis rounds used, [1] converged flag, rest diagnostics */
+    int32_t* status;         /* device int32[64]: [0] hysteresis tile re-visits, [1] hysteresis converged (1 = ok),
+                                [2] a tensor-core DCT kernel gave up on a barrier wait (0 = ok), rest diagnostics */
     uint8_t* packed_states[3]; /* optional [batch][(cap_states[l]+3)/4]: the state stream packed 2 bits per state,
                                   MSB first, zero padded -- the bytes _entropy_encode writes (jpeg.py:563-571) */
     const uint8_t* rgb_u8;   /* alternative input (used when rgb == NULL): 8-bit pixels [batch][H][W][3], converted on the
@@ -167,6 +168,8 @@ typedef struct {
     float* tap_layers[3];    /* optional [batch][h_l][w_l]: merged + denormalised layers */
     uint8_t* rgb_u8;         /* optional [batch][H][W][3]: Image.get_uint8() / Image.save(), (data * 255).astype(uint8)
                                 (image.py:112,127), written by the same kernel */
+    int32_t* status;         /* optional device int32[64]: [2] tensor-core IDCT barrier timeout (0 = ok), [3] number of leaves
+                                that were skipped because they do not fit the plan (bad size / position / offset; 0 = ok) */
 } aeaj_decode_io;
 
 AEAJ_API int aeaj_encode(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, void* stream);
@@ -202,9 +205,11 @@ AEAJ_API int aeaj_plan_buffers(aeaj_plan* p, void* workspace, aeaj_plan_buffers_
  * host-side helpers for the entropy-coding side (plain CPU code, no device work):
  * the 2-bit state stream (jpeg.py:563-571) and its inverse (jpeg.py:768-800 + 428-448).
  * ------------------------------------------------------------------------------------------- */
-/* states (0 leaf, 1 split, 2 absent; DFS pre-order) -> leaves_host[n][4] = x, y, size, coef offset */
+/* states (0 leaf, 1 split, 2 absent; DFS pre-order) -> leaves_host[n][4] = x, y, size, coef offset.
+ * The stream is untrusted input: AEAJ_EINVAL if `root` is not the root size of an (h, w) layer, if a leaf lies outside
+ * the layer or outside [block_min, block_max] (pass 0, 0 to skip the range check), or if a node is split below size 2. */
 AEAJ_API int aeaj_states_to_leaves_host(const uint8_t* states_host, int n_states, int root, int h, int w,
-                               int32_t* leaves_host, int* n_leaves, int64_t* n_coef);
+                               int block_min, int block_max, int32_t* leaves_host, int* n_leaves, int64_t* n_coef);
 /* 2 bits per state, MSB first, zero padded; packed_host holds ceil(n_states/4) bytes */
 AEAJ_API int aeaj_pack_states_host(const uint8_t* states_host, int n_states, uint8_t* packed_host);
 

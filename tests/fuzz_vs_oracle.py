@@ -1,15 +1,20 @@
-"""Randomised differential check of the fused CUDA path against the oracle (checker-side tool, not collected by pytest):
+"""Randomised differential check of the fused CUDA path against the oracle.  Collected by pytest through
+tests/test_gpu_fuzz.py (30 cases, -m gpu); also a command-line tool for longer runs:
 
     python tests/fuzz_vs_oracle.py [n_cases] [seed]
 
 Random shapes (1 .. 700 px per side, incl. degenerate ones), spaces, block ranges (2 .. 256) and quality ranges; batch of 2.
 Linear spaces: edge maps, states, leaves bit-exact, coefficients within the T-DCT budget; all spaces: decode <= 1 LSB
 against the oracle's decode of the same coefficients (T-NAN pixels excluded as in test_gpu_parity.py)."""
+import os
 import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, "adaptive-edge-aware-jpeg_b200"); sys.path.insert(0, "tests"); sys.path.insert(0, "oracle")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in ("adaptive-edge-aware-jpeg_b200", "tests", "oracle"):
+    if os.path.join(_ROOT, _p) not in sys.path:
+        sys.path.insert(0, os.path.join(_ROOT, _p))
 import oracle as O
 from aeaj.codec import get_codec
 from synth import synth
@@ -17,11 +22,16 @@ from synth import synth
 SPACES = ["YCbCr", "YCoCg", "YCoCg-R", "OKLAB", "ICaCb", "ICtCp", "JzAzBz"]
 
 
-def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
-    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+def run_cases(n: int, seed: int = 0, verbose: bool = True):
+    """-> list of problem descriptions (empty = clean)"""
+    rng = np.random.default_rng(seed)
     codec = get_codec(0)
-    bad = 0
+    problems = []
+
+    def report(*a):
+        problems.append(" ".join(str(x) for x in a))
+        if verbose:
+            print(problems[-1])
     for case in range(n):
         space = SPACES[rng.integers(len(SPACES))]
         H = int(rng.choice([1, 2, 3, 5, 17, 64, 100, 129, 255, 256, 300, 511, 640, 700]))
@@ -54,7 +64,7 @@ def main():
             edges = [e.cpu().numpy() for e in enc.edges]
             dec = codec.decode_encoded(enc, space, q, b).cpu().numpy()
         except Exception as ex:                                   # settings the library rejects must be rejected by the oracle too
-            print(tag, "-> library raised", type(ex).__name__, str(ex)[:80]); bad += 1
+            report(tag, "-> library raised", type(ex).__name__, str(ex)[:80])
             continue
         exact = space in ("YCbCr", "YCoCg", "YCoCg-R")
         # the device-side .ajpg stream layout (zigzag blocks) must be the natural layout permuted, and decode back identically
@@ -63,7 +73,7 @@ def main():
         gotz = codec.download(encz)
         decz = codec.decode_encoded(encz, space, q, b).cpu().numpy()
         if not np.array_equal(decz, dec):
-            print(tag, "zigzag-layout decode differs"); bad += 1
+            report(tag, "zigzag-layout decode differs")
         for k in range(2):
             for i in range(3):
                 sizes = got[k][i]["leaves"][:, 2].astype(np.int64)
@@ -75,29 +85,35 @@ def main():
                     if not np.array_equal(zz[offs[j]:offs[j + 1]], blk[tables.zigzag_ordering(sz)]):
                         okz = False; break
                 if not okz:
-                    print(tag, f"zigzag stream mismatch (image {k}, layer {i})"); bad += 1
+                    report(tag, f"zigzag stream mismatch (image {k}, layer {i})")
         for k in range(2):
             ref = O.encode_hot(batch[k], space, q, b)
             same_edges = all(np.array_equal(edges[i][k], ref[i]["edge"].astype(np.uint8)) for i in range(3))
             if exact and not same_edges:
-                print(tag, "edge maps differ"); bad += 1
+                report(tag, "edge maps differ")
             if same_edges:
                 for i in range(3):
                     if not (np.array_equal(got[k][i]["states"], ref[i]["states"]) and np.array_equal(got[k][i]["leaves"][:, :3], ref[i]["leaves"])):
-                        print(tag, f"quadtree differs (layer {i})"); bad += 1
+                        report(tag, f"quadtree differs (layer {i})")
                         break
                     d = np.abs(got[k][i]["coef"].astype(np.int64) - ref[i]["coef"].astype(np.int64))
                     if d.size and (d.max() > 1 or (d != 0).sum() > (4 if exact else 200)):
-                        print(tag, f"coefficients: max {d.max()} n {(d != 0).sum()} (layer {i})"); bad += 1
+                        report(tag, f"coefficients: max {d.max()} n {(d != 0).sum()} (layer {i})")
             ref_dec = O.decode_hot([dict(leaves=got[k][i]["leaves"][:, :3], coef=got[k][i]["coef"]) for i in range(3)], H, W, space, q, b)
             lsb = np.abs((dec[k] * 255).astype(np.uint8).astype(int) - (ref_dec * 255).astype(np.uint8).astype(int))
             if space in ("ICaCb", "ICtCp", "JzAzBz"):
                 nan_class = np.all(dec[k] == 1.0, axis=-1) | np.all(ref_dec == 1.0, axis=-1)
                 lsb[nan_class] = 0
             if lsb.max() > 1:
-                print(tag, "decode LSB", lsb.max()); bad += 1
-    print(f"{n} cases, {bad} problems")
-    return 1 if bad else 0
+                report(tag, "decode LSB", lsb.max())
+    if verbose:
+        print(f"{n} cases, {len(problems)} problems")
+    return problems
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    return 1 if run_cases(n, int(sys.argv[2]) if len(sys.argv) > 2 else 0) else 0
 
 
 if __name__ == "__main__":

@@ -24,7 +24,7 @@ from synth import synth
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    os.environ["NCCL_DEBUG"] = os.environ.get("AEAJ_NCCL_DEBUG", "NONE")
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     H, W = (int(a) for a in (sys.argv[1:3] if len(sys.argv) > 2 else (2048, 2048)))

@@ -214,13 +214,22 @@ def test_dct_quant_and_inverse(st, brange):
 # ------------------------------------------------------------------------------------------------
 # fused batch path + reference-facing shim
 # ------------------------------------------------------------------------------------------------
+def _check_layer(got_layer, ref_layer, coef_budget, tag):
+    assert np.array_equal(got_layer["states"], ref_layer["states"]), f"{tag} states"
+    assert np.array_equal(got_layer["leaves"][:, :3], ref_layer["leaves"]), f"{tag} leaves"
+    assert got_layer["root"] == ref_layer["root"]
+    d = np.abs(got_layer["coef"].astype(np.int64) - ref_layer["coef"].astype(np.int64))
+    assert d.max() <= 1 and int((d != 0).sum()) <= coef_budget, (tag, int((d != 0).sum()))
+    return int((d != 0).sum())
+
+
 def _check_encode(layers, ref, coef_budget=2):
     for i in range(3):
-        assert np.array_equal(layers[i]["states"], ref[i]["states"]), f"layer {i} states"
-        assert np.array_equal(layers[i]["leaves"][:, :3], ref[i]["leaves"]), f"layer {i} leaves"
-        assert layers[i]["root"] == ref[i]["root"]
-        d = np.abs(layers[i]["coef"].astype(np.int64) - ref[i]["coef"].astype(np.int64))
-        assert d.max() <= 1 and int((d != 0).sum()) <= coef_budget, (i, int((d != 0).sum()))
+        _check_layer(layers[i], ref[i], coef_budget, f"layer {i}")
+
+
+EDGE_BUDGET_PX = 4        # per layer, PQ / cube-root spaces only (class T-POW: a 1-ULP colour difference flips a u8 truncation);
+                          # the same budget test_oracle_golden.py gives the oracle against the reference
 
 
 @pytest.mark.parametrize("space,shape,q,b", [("YCbCr", (144, 256), (30, 95), (4, 128)), ("YCoCg", (135, 241), (1, 99), (4, 64)),
@@ -229,10 +238,13 @@ def _check_encode(layers, ref, coef_budget=2):
                                              ("YCoCg-R", (270, 480), (40, 80), (8, 64)),
                                              # BASELINE configs C5 (1080p, reference defaults, extreme quality) and C4's spaces at 2K
                                              ("YCoCg", (1080, 1920), (1, 99), (4, 64)), ("ICtCp", (1024, 2048), (30, 95), (4, 128)),
-                                             ("JzAzBz", (1024, 1536), (30, 95), (4, 128)),
+                                             ("JzAzBz", (1024, 1536), (30, 95), (4, 128)), ("OKLAB", (768, 1024), (30, 95), (4, 128)),
                                              # GUI-reachable extremes (main_frame.py:44-45): blocks 2 .. 256
                                              ("YCbCr", (300, 520), (30, 95), (2, 256)), ("YCoCg", (520, 300), (50, 90), (8, 256))])
 def test_fused_encode_decode_vs_oracle(codec, space, shape, q, b):
+    """Fused batch path against the oracle, layer by layer.  Linear spaces: layers and edge maps bit-exact, every quadtree
+    equal.  PQ / cube-root spaces: at most EDGE_BUDGET_PX edge pixels may differ per layer (counted, never skipped), and
+    every layer whose edge map matches must have the oracle's quadtree and coefficients."""
     import torch
     H, W = shape
     batch = np.stack([synth(H, W, seed=s) for s in (1, 2, 3)])
@@ -241,17 +253,22 @@ def test_fused_encode_decode_vs_oracle(codec, space, shape, q, b):
     edges = [e.cpu().numpy() for e in enc.edges]
     lays = [l.cpu().numpy() for l in enc.layers]
     dec = codec.decode_encoded(enc, space, q, b).cpu().numpy()
+    exact_color = space in ("YCbCr", "YCoCg", "YCoCg-R")
+    n_layers = n_struct_equal = edge_px_total = coef_flips = 0
     for k in range(3):
         ref = O.encode_hot(batch[k], space, q, b)
-        exact_color = space in ("YCbCr", "YCoCg", "YCoCg-R")
         for i in range(3):
             if exact_color:
                 assert bits_differ(lays[i][k], ref[i]["layer"]) == 0, "colour + downsample"
-            assert np.array_equal(edges[i][k], ref[i]["edge"].astype(np.uint8)) or not exact_color, "edge map"
-        if all(np.array_equal(edges[i][k], ref[i]["edge"].astype(np.uint8)) for i in range(3)):
-            _check_encode(got[k], ref, coef_budget=2 if exact_color else 50)
-        else:
-            assert not exact_color      # T-POW: a 1-ULP colour difference may flip a u8 truncation
+            else:
+                assert np.abs(lays[i][k] - ref[i]["layer"]).max() <= 4e-7 * max(1.0, float(np.abs(ref[i]["layer"]).max()))
+            mism = int((edges[i][k] != ref[i]["edge"].astype(np.uint8)).sum())
+            assert mism <= (0 if exact_color else EDGE_BUDGET_PX), (space, k, i, "edge map mismatches", mism)
+            n_layers += 1
+            edge_px_total += mism
+            if mism == 0:
+                coef_flips += _check_layer(got[k][i], ref[i], 2 if exact_color else 50, f"{space} image {k} layer {i}")
+                n_struct_equal += 1
         ref_dec = O.decode_hot([dict(leaves=got[k][i]["leaves"][:, :3], coef=got[k][i]["coef"]) for i in range(3)], H, W, space, q, b)
         lsb = np.abs((dec[k] * 255).astype(np.uint8).astype(int) - (ref_dec * 255).astype(np.uint8).astype(int))
         diff = np.abs(dec[k] - ref_dec)
@@ -268,29 +285,158 @@ def test_fused_encode_decode_vs_oracle(codec, space, shape, q, b):
         # black and amplifies the last-bit differences of an f32 IDCT (both the FP32 and the tensor-core kernels; the oracle
         # accumulates in f64) up to ~3e-5 on megapixel images -- the 8-bit bar above (<= 1 LSB) is the one that matters there
         assert diff.max() <= (5e-5 if space in ("ICaCb", "ICtCp", "JzAzBz", "OKLAB") else 3e-6)
+    print(f"[parity] {space} {H}x{W}: quadtree+coefficients equal to the oracle's on {n_struct_equal}/{n_layers} layers, "
+          f"{edge_px_total} edge px differ in total, {coef_flips} coefficient ties flipped")
+    assert n_struct_equal >= n_layers - (0 if exact_color else 2)
 
 
-def test_golden_reference_streams(golden):
-    """Jpeg.compress / decompress of the shim against the reference's own .ajpg streams (mode S)."""
+def _golden_names():
+    import json, os
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    names = []
+    for f in ("golden.json", "golden_natural.json"):
+        with open(os.path.join(d, f)) as fh:
+            names += [k for k, v in json.load(fh)["cases"].items() if v.get("mode") != "D"]
+    return sorted(names)
+
+
+@pytest.mark.parametrize("name", _golden_names())
+def test_golden_reference_stream(golden, codec, name):
+    """Jpeg.compress / decompress of the shim against the reference's own .ajpg stream (mode S), ONE named case at a time:
+    byte identity where tests/golden/expected_parity.json pins it for the CUDA path, otherwise no more tie-class differences
+    (edge pixels, coefficient flips) than pinned; lena, the synthetic cases, and the natural images of configuration C3
+    (six odd-sized LIVE images + baboon + peppers in OKLAB) and one LIVE image per PQ space."""
+    import parity_report as PR
+    from pin_expected_parity import gpu_case
+    from jpeg import Jpeg, JpegCompressionSettings
+    c = golden.case(name)
+    rgb = golden.input_f32(name)
+    got = gpu_case(golden, name, codec)
+    expected = PR.load_expected()
+    exact = c["space"] in ("YCbCr", "YCoCg", "YCoCg-R")
+    print(f"[parity] {name}: {'byte-identical' if got['byte_identical'] else 'differs'}", [(l["edge_px"], l["tree_equal"], l["coef_diffs"]) for l in got["layers"]])
+    for i, l in enumerate(got["layers"]):
+        assert l["edge_px"] <= (0 if exact else EDGE_BUDGET_PX), (name, i, "edge map")
+        if l["edge_px"] == 0:
+            assert l["tree_equal"], (name, i, "quadtree differs although the edge map matches")
+        if l["tree_equal"]:
+            assert l["coef_max_abs"] <= 1 and l["coef_diffs"] <= 8, (name, i, l)             # T-DCT: exact .5 ties only
+    if "gpu" in expected:
+        PR.check_against_expected("gpu", name, got, expected)
+    ref_bytes = golden.get(name, "ajpg").tobytes()
+    dec = Jpeg(JpegCompressionSettings()).decompress(ref_bytes)
+    assert dec.data.shape == rgb.shape and dec.data.dtype == np.float32
+    ref_u8 = golden.get(name, "decoded_u8_s3")
+    assert np.abs(ref_u8.astype(int) - dec.get_uint8()[::3, ::3].astype(int)).max() <= 1, name
+
+
+def test_pinned_gpu_identity_rate():
+    import parity_report as PR
+    exp = PR.load_expected()
+    if "gpu" not in exp:
+        pytest.skip("CUDA-path expectations not pinned yet (tests/golden/pin_expected_parity.py --gpu)")
+    ident = [n for n, r in exp["gpu"].items() if r["byte_identical"]]
+    print(f"[parity] {len(ident)} of {len(exp['gpu'])} reference streams reproduced byte for byte by the CUDA path")
+    assert len(exp["gpu"]) == len(_golden_names()) and len(ident) >= 0.8 * len(exp["gpu"])
+
+
+def test_corrupt_streams_raise(codec):
+    """Crafted .ajpg headers: wrong root, leaves outside the block range, and -- through the C ABI directly -- leaf
+    lists that do not fit the plan must be rejected / skipped, never written through."""
+    import io, json, torch
     from image import Image
     from jpeg import Jpeg, JpegCompressionSettings
-    identical = 0
-    names = [k for k, v in golden.meta["cases"].items() if v.get("mode") != "D"]
-    for name in names:
-        c = golden.case(name)
-        rgb = golden.input_f32(name)
-        ref_bytes = golden.get(name, "ajpg").tobytes()
-        j = Jpeg(JpegCompressionSettings(c["space"], tuple(c["quality"]), tuple(c["blocks"])))
-        mine = j.compress(Image.from_array(rgb, None, ".png"))
-        identical += mine == ref_bytes
-        exact = c["space"] in ("YCbCr", "YCoCg", "YCoCg-R")
-        if exact:
-            assert abs(len(mine) - len(ref_bytes)) <= 16, name       # at most a few T-DCT ties
-        dec = Jpeg(JpegCompressionSettings()).decompress(ref_bytes)
-        assert dec.data.shape == rgb.shape and dec.data.dtype == np.float32
-        ref_u8 = golden.get(name, "decoded_u8_s3")
-        assert np.abs(ref_u8.astype(int) - dec.get_uint8()[::3, ::3].astype(int)).max() <= 1, name
-    assert identical >= 0.6 * len(names), identical
+    rgb = synth(96, 160, seed=4)
+    j = Jpeg(JpegCompressionSettings("YCbCr", (40, 80), (4, 64)))
+    good = j.compress(Image.from_array(rgb, None, ".png"))
+    ml = int.from_bytes(good[:4], "big")
+    meta = json.loads(good[4:4 + ml])
+    body = good[4 + ml:]
+    def with_meta(**kw):
+        m = dict(meta); m.update(kw)
+        mb = json.dumps(m).encode()
+        return len(mb).to_bytes(4, "big") + mb + body
+    for bad in (with_meta(block_size_max=16),          # leaves of 32 / 64 are now outside the declared range
+                with_meta(height=48, width=80),         # root no longer matches the layer
+                with_meta(block_size_min=8)):           # 4 x 4 leaves below the declared minimum
+        with pytest.raises(ValueError):
+            Jpeg(JpegCompressionSettings()).decompress(bad)
+    # root patched in the first layer header: bits_len(4) root(4)
+    patched = bytearray(good)
+    patched[4 + ml + 4:4 + ml + 8] = (1024).to_bytes(4, "big")
+    with pytest.raises(ValueError):
+        Jpeg(JpegCompressionSettings()).decompress(bytes(patched))
+    # C ABI: a hostile leaf list (sizes 0, 3, 512, negative / far positions, wild offsets) is skipped and counted
+    H, W, space, q, b = 96, 160, "YCbCr", (40, 80), (4, 64)
+    enc = codec.encode(torch.from_numpy(rgb).cuda(), space, q, b)
+    lv = enc.leaves[0].clone()
+    n = int(enc.counts[0, 0, 0])
+    evil = torch.tensor([[0, 0, 0, 0], [4, 4, 3, 16], [0, 0, 512, 0], [-8, 0, 8, 0], [100000, 0, 8, 0], [0, 0, 8, 2 ** 30], [0, 0, 128, 0]],
+                        dtype=torch.int32, device=lv.device)
+    lv[0, :evil.shape[0]] = evil
+    out = codec.decode([enc.coef[0], enc.coef[1], enc.coef[2]], [lv, enc.leaves[1], enc.leaves[2]], enc.counts, 1, H, W, space, q, b)
+    torch.cuda.synchronize()
+    assert int(codec.last_decode_status[3]) == evil.shape[0] and n > evil.shape[0]
+    with pytest.raises(ValueError):
+        codec.check_status(codec.last_decode_status, "decode")
+    assert torch.isfinite(out).all()
+
+
+def test_plan_cache_is_bounded():
+    from aeaj.codec import DeviceCodec
+    import torch
+    c = DeviceCodec(0)
+    c.MAX_PLANS = 3
+    for k in range(6):
+        H, W = 64 + 16 * k, 96
+        enc = c.encode(torch.from_numpy(synth(H, W, seed=k)).cuda(), "YCbCr", (40, 80), (4, 64))
+        dec = c.decode_encoded(enc, "YCbCr", (40, 80), (4, 64))
+        assert dec.shape == (1, H, W, 3)
+    assert len(c._plans) == 3
+    c.close()
+    assert len(c._plans) == 0
+
+
+def test_two_streams_with_256_leaves(codec):
+    """the 256 x 256 kernel's intermediate tiles belong to the call -- two plans running concurrently on two
+    streams (roundtrip_device) must not share them."""
+    import torch
+    H, W = 520, 784
+    space, q, b = "YCbCr", (30, 95), (8, 256)
+    frames = []
+    for s in range(4):                                         # flat upper part (edge-free 256 x 256 blocks), textured lower part
+        f = np.full((H, W, 3), np.float32(round((0.2 + 0.15 * s) * 255) / 255), np.float32)
+        f[300:] = synth(H, W, seed=s)[300:]
+        frames.append(f)
+    batch = torch.from_numpy(np.stack(frames)).cuda()
+    enc = codec.encode(batch, space, q, b)
+    n256 = int(sum((codec.download(enc)[k][0]["leaves"][:, 2] == 256).sum() for k in range(4)))
+    assert n256 >= 4                                           # the 256 class has work in every image
+    one = codec.decode_encoded(enc, space, q, b).clone()
+    for _ in range(3):
+        parts = codec.roundtrip_device(batch, space, q, b, streams=2)
+        torch.cuda.synchronize()
+        assert torch.equal(torch.cat(parts), one)
+
+
+def test_two_devices_one_process():
+    """function attributes and occupancy are per device -- a second handle on another GPU in the same process."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from aeaj.codec import get_codec
+    rgb = synth(272, 480, seed=3)
+    outs = []
+    for d in (0, 1):
+        with torch.cuda.device(d):
+            c = get_codec(d)
+            enc = c.encode(torch.from_numpy(rgb).to(f"cuda:{d}"), "YCbCr", (30, 95), (4, 128))
+            L = c.download(enc)[0]
+            outs.append((L, c.decode_encoded(enc, "YCbCr", (30, 95), (4, 128)).cpu()))
+    for i in range(3):
+        for key in ("coef", "leaves", "states"):
+            assert np.array_equal(outs[0][0][i][key], outs[1][0][i][key])
+    assert torch.equal(outs[0][1], outs[1][1])
 
 
 def test_shim_api_surface_and_errors():

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/aeaj.h but not exported"
     assert sorted(native.EXPORTS) == declared
-    assert lib.aeaj_version() == 1
+    assert lib.aeaj_version() == 2
 
 
 def test_no_cpu_fallback_without_cuda():
@@ -100,3 +100,32 @@ def test_host_state_helpers_round_trip():
         packed = np.empty((len(states) + 3) // 4, dtype=np.uint8)
         assert lib.aeaj_pack_states_host(states.ctypes.data, len(states), packed.ctypes.data) == 0
         assert packed.tobytes() == O.pack_states(states)
+
+
+def test_corrupt_state_streams_are_rejected():
+    """The state stream of an .ajpg file is untrusted input: a wrong root, a leaf outside the block range or the
+    layer, or a split below size 2 must raise instead of reaching the device (the reference dies with a KeyError there)."""
+    import oracle as O
+    from aeaj import native
+    rng = np.random.default_rng(1)
+    shape, (mn, mx) = (130, 257), (4, 64)
+    edge = (rng.random(shape) < 0.01).astype(np.float32)
+    leaves, states, root = O.quadtree(edge, mx, mn)
+    got, _ = native.states_to_leaves(states, root, *shape, (mn, mx))
+    assert np.array_equal(got[:, :3], leaves)
+    with pytest.raises(ValueError):                                    # root taken "straight from the stream"
+        native.states_to_leaves(states, root * 2, *shape, (mn, mx))
+    with pytest.raises(ValueError):                                    # a leaf of the root's size (512 > block_max)
+        native.states_to_leaves(np.array([0], np.uint8), root, *shape, (mn, mx))
+    with pytest.raises(ValueError):                                    # splits all the way down: size 1, then 0
+        native.states_to_leaves(np.ones(64, np.uint8), 4, 3, 3, (2, 2))
+    with pytest.raises(ValueError):                                    # leaves below block_min
+        native.states_to_leaves(np.array([1, 1, 0, 0, 0, 0, 0, 0, 0], np.uint8), 8, 8, 8, (4, 8))
+    bad = states.copy()
+    k = int(np.nonzero(bad == 2)[0][0])                                # an out-of-bounds node declared a leaf
+    bad[k] = 0
+    with pytest.raises(ValueError):
+        native.states_to_leaves(bad, root, *shape, (mn, mx))
+    # a truncated stream yields the leaves seen so far (jpeg.py:784 stops the same way); the caller's length check catches it
+    part, _ = native.states_to_leaves(states[: len(states) // 2], root, *shape, (mn, mx))
+    assert 0 < len(part) < len(leaves)
