@@ -47,6 +47,15 @@ class EncodedBatch:
 
 
 @dataclass
+class PackedBatch:
+    """Packed coefficient streams of one batch (include/aeaj.h, aeaj_pack_coefficients): per plane a non-zero bit mask and the
+    non-zero values as int16 -- what travels over PCIe to the host-side entropy coder instead of the int32 streams."""
+    mask: List[torch.Tensor]       # 3 x int32 [B, cap_coef_l // 32 + 1]   (uint32 words)
+    vals: List[torch.Tensor]       # 3 x int16 [B, cap_coef_l]
+    counts: torch.Tensor           # int32 [B, 3, 4]  nnz, n_coef, overflow flag, mask words
+
+
+@dataclass
 class _Plan:
     ptr: C.c_void_p
     info: native.PlanInfo
@@ -57,6 +66,7 @@ class _Plan:
     qkey: Optional[tuple] = None
     keep: list = field(default_factory=list)
     dec_status: Optional[torch.Tensor] = None     # int32 [64]: [2] tensor-IDCT timeout flag, [3] leaves rejected by the device guard
+    packed: Optional[PackedBatch] = None
     nbytes: int = 0
 
 
@@ -229,6 +239,64 @@ class DeviceCodec:
         res = p.rgb_out if out == "f32" else (p.rgb8_out if out == "u8" else (p.rgb_out, p.rgb8_out))
         return (res, tl) if taps else res
 
+    # ------------------------------------------------------------------------------------------
+    # packed coefficient streams (PCIe form)
+    # ------------------------------------------------------------------------------------------
+    def _packed(self, p: _Plan) -> PackedBatch:
+        if p.packed is None:
+            B, dev = p.info.batch, p.rgb_out.device
+            p.packed = PackedBatch(mask=[torch.empty((B, int(p.info.cap_coef[l]) // 32 + 1), dtype=torch.int32, device=dev) for l in range(3)],
+                                   vals=[torch.empty((B, int(p.info.cap_coef[l])), dtype=torch.int16, device=dev) for l in range(3)],
+                                   counts=torch.zeros((B, 3, 4), dtype=torch.int32, device=dev))
+            p.nbytes += sum(t.numel() * t.element_size() for t in p.packed.mask + p.packed.vals)
+        return p.packed
+
+    def pack(self, enc: EncodedBatch, space, qrange, brange, instance: int = 0) -> PackedBatch:
+        """Lossless packed form of enc.coef (bit mask + int16 non-zeros) in the plan's packed buffers; asynchronous."""
+        B, H, W = enc.shape
+        p = self._plan(B, H, W, space, brange, qrange, instance)
+        pk = self._packed(p)
+        io = native.PackedIO()
+        coef = (C.c_void_p * 3)(*[enc.coef[l].data_ptr() for l in range(3)])
+        for l in range(3):
+            io.mask[l], io.vals[l] = pk.mask[l].data_ptr(), pk.vals[l].data_ptr()
+        io.counts = pk.counts.data_ptr()
+        native.check(self.lib.aeaj_pack_coefficients(p.ptr, coef, enc.counts.data_ptr(), C.byref(io), p.workspace.data_ptr(), _stream()),
+                     "aeaj_pack_coefficients")
+        return pk
+
+    def unpack(self, pk: PackedBatch, B, H, W, space, qrange, brange, instance: int = 0) -> List[torch.Tensor]:
+        """Inverse of pack(): expands into the plan's int32 coefficient buffers (returned); asynchronous."""
+        p = self._plan(B, H, W, space, brange, qrange, instance)
+        io = native.PackedIO()
+        coef = (C.c_void_p * 3)(*[p.out.coef[l].data_ptr() for l in range(3)])
+        for l in range(3):
+            io.mask[l], io.vals[l] = pk.mask[l].data_ptr(), pk.vals[l].data_ptr()
+        io.counts = pk.counts.data_ptr()
+        native.check(self.lib.aeaj_unpack_coefficients(p.ptr, C.byref(io), coef, p.workspace.data_ptr(), _stream()), "aeaj_unpack_coefficients")
+        return p.out.coef
+
+    def capture_roundtrip(self, rgb: torch.Tensor, space, qrange, brange, out: str = "f32"):
+        """CUDA-graph capture of encode + decode of `rgb` (the per-call launches -- ~25 kernels and a few memsets -- become one
+        graph launch; for single-image latency).  Steady-state calls issue no host-to-device copy, so they are capturable after
+        one eager warm-up call.  Returns (graph, result tensor); replay with graph.replay()."""
+        if rgb.dim() == 3:
+            rgb = rgb.unsqueeze(0)
+        B, H, W, _ = rgb.shape
+        side = torch.cuda.Stream(device=rgb.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):                                     # warm-up on the capture stream: tables, plane descriptors
+                enc = self.encode(rgb, space, qrange, brange, instance=2000)
+                res = self.decode(enc.coef, enc.leaves, enc.counts, B, H, W, space, qrange, brange, instance=2000, out=out)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(rgb.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            enc = self.encode(rgb, space, qrange, brange, instance=2000)
+            res = self.decode(enc.coef, enc.leaves, enc.counts, B, H, W, space, qrange, brange, instance=2000, out=out)
+        return g, res
+
     def roundtrip_device(self, rgb: torch.Tensor, space: str, qrange, brange, streams: int = 2, out: str = "f32"):
         """encode + decode of a device-resident batch, split into `streams` sub-batches that run concurrently on their
         own CUDA streams (and plan instances): the latency-bound stages of one sub-batch (hysteresis rounds, quadtree
@@ -284,6 +352,9 @@ class DeviceCodec:
                 leaves=[torch.empty((B, int(p.info.cap_leaves[l]), 4), dtype=torch.int32).pin_memory() for l in range(3)],
                 states=[torch.empty((B, int(p.info.cap_states[l])), dtype=torch.uint8).pin_memory() for l in range(3)],
                 counts=torch.empty((B, 3, 4), dtype=torch.int32).pin_memory(),
+                pk_counts=torch.empty((B, 3, 4), dtype=torch.int32).pin_memory(),
+                mask=[torch.empty((B, int(p.info.cap_coef[l]) // 32 + 1), dtype=torch.int32).pin_memory() for l in range(3)],
+                vals=[torch.empty((B, int(p.info.cap_coef[l])), dtype=torch.int16).pin_memory() for l in range(3)],
                 rgb_dev=torch.empty((B, p.info.height, p.info.width, 3), dtype=torch.float32, device=p.rgb_out.device),
                 rgb8_dev=torch.empty((B, p.info.height, p.info.width, 3), dtype=torch.uint8, device=p.rgb_out.device))
             p.keep.append(st)
@@ -334,7 +405,8 @@ class DeviceCodec:
         torch.cuda.current_stream().synchronize()
         return st["rgb_out"], h2d, st["rgb_out"].numel() * 4
 
-    def roundtrip_host_pipelined(self, host_in: torch.Tensor, host_out: torch.Tensor, space, qrange, brange, slots: int = 8, repeat: int = 1, lag: int = 3):
+    def roundtrip_host_pipelined(self, host_in: torch.Tensor, host_out: torch.Tensor, space, qrange, brange, slots: int = 8, repeat: int = 1, lag: int = 3,
+                                 packed: bool = True):
         """Host-buffer encode+decode of every frame of `host_in` (pinned float32 -- or uint8, the 8-bit image flow
         Image.load -> compress ... decompress -> Image.save -- [F,H,W,3]) into `host_out` (float32 or uint8), one frame
         per job, jobs round-robin over `slots` CUDA streams so that the H2D and D2H copies of different frames overlap
@@ -342,7 +414,9 @@ class DeviceCodec:
         H2D RGB -> aeaj_encode -> D2H counts -> [host waits for the counts] -> D2H used coefficient / leaf / state ranges ->
         H2D of the same ranges (what a host-side entropy decoder would hand back) -> aeaj_decode -> D2H RGB.
         `repeat` > 1 streams the same F frames that many times back to back (a long-running ingest) without draining
-        the pipeline in between.  Returns (h2d_bytes, d2h_bytes) summed over all jobs."""
+        the pipeline in between.  packed=True moves the coefficient streams in their packed form (bit mask + int16 non-zeros,
+        aeaj_pack_coefficients after the encode, aeaj_unpack_coefficients before the decode; a plane whose overflow flag is
+        set travels as int32).  Returns (h2d_bytes, d2h_bytes) summed over all jobs."""
         F0, H, W, _ = host_in.shape
         F = F0 * repeat
         dev = torch.device("cuda", self.device)
@@ -363,9 +437,12 @@ class DeviceCodec:
                 src.copy_(host_in[f % F0:f % F0 + 1], non_blocking=True)
                 enc = self.encode(src, space, qrange, brange, instance=slot)
                 st["counts"].copy_(enc.counts, non_blocking=True)
+                if packed:
+                    pk = self.pack(enc, space, qrange, brange, instance=slot)
+                    st["pk_counts"].copy_(pk.counts, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(stream)
-            jobs.append(dict(f=f % F0, slot=slot, p=p, st=st, enc=enc, ev=ev, done=False, phase_b=False))
+            jobs.append(dict(f=f % F0, slot=slot, p=p, st=st, enc=enc, ev=ev, done=False, phase_b=False, packed=packed))
             h2d += host_in[0].numel() * host_in.element_size()
             # phase B of a frame is issued `lag` frames after its phase A (its counts have landed by then), and a slot is
             # reused only `slots` frames later, so neither host wait normally blocks
@@ -387,19 +464,47 @@ class DeviceCodec:
         counts = st["counts"].numpy()
         h2d = d2h = st["counts"].numel() * 4
         H, W = p.info.height, p.info.width
+        pk = p.packed if job.get("packed") else None
+        pkc = st["pk_counts"].numpy() if pk is not None else None
         with torch.cuda.stream(stream):
             for l in range(3):
                 nl, ns, nc = (int(counts[0, l, k]) for k in range(3))
-                st["coef"][l][0, :nc].copy_(enc.coef[l][0, :nc], non_blocking=True)
+                if pk is not None and pkc[0, l, 2] == 0:             # packed: mask words + int16 non-zeros
+                    nnz, nw = int(pkc[0, l, 0]), int(pkc[0, l, 3])
+                    st["mask"][l][0, :nw].copy_(pk.mask[l][0, :nw], non_blocking=True)
+                    st["vals"][l][0, :nnz].copy_(pk.vals[l][0, :nnz], non_blocking=True)
+                    d2h += nw * 4 + nnz * 2
+                else:
+                    st["coef"][l][0, :nc].copy_(enc.coef[l][0, :nc], non_blocking=True)
+                    d2h += nc * 4
                 st["leaves"][l][0, :nl].copy_(enc.leaves[l][0, :nl], non_blocking=True)
                 st["states"][l][0, :ns].copy_(enc.states[l][0, :ns], non_blocking=True)
-                d2h += nc * 4 + nl * 16 + ns
+                d2h += nl * 16 + ns
+            any_packed = False
             for l in range(3):
                 nl, nc = int(counts[0, l, 0]), int(counts[0, l, 2])
-                enc.coef[l][0, :nc].copy_(st["coef"][l][0, :nc], non_blocking=True)
+                if pk is not None and pkc[0, l, 2] == 0:
+                    nnz, nw = int(pkc[0, l, 0]), int(pkc[0, l, 3])
+                    pk.mask[l][0, :nw].copy_(st["mask"][l][0, :nw], non_blocking=True)
+                    pk.vals[l][0, :nnz].copy_(st["vals"][l][0, :nnz], non_blocking=True)
+                    h2d += nw * 4 + nnz * 2
+                    any_packed = True
+                else:
+                    enc.coef[l][0, :nc].copy_(st["coef"][l][0, :nc], non_blocking=True)
+                    h2d += nc * 4
                 enc.leaves[l][0, :nl].copy_(st["leaves"][l][0, :nl], non_blocking=True)
-                h2d += nc * 4 + nl * 16
+                h2d += nl * 16
             enc.counts.copy_(st["counts"], non_blocking=True)
+            if any_packed:
+                if any(pkc[0, l, 2] != 0 for l in range(3)):         # mixed: keep the int32 planes, expand the others around them
+                    keep = [enc.coef[l][0].clone() if pkc[0, l, 2] != 0 else None for l in range(3)]
+                pk.counts.copy_(st["pk_counts"], non_blocking=True)
+                h2d += st["pk_counts"].numel() * 4
+                self.unpack(pk, 1, H, W, space, qrange, brange, instance=slot)
+                if any(pkc[0, l, 2] != 0 for l in range(3)):
+                    for l in range(3):
+                        if keep[l] is not None:
+                            enc.coef[l][0].copy_(keep[l])
             rgb = self.decode(enc.coef, enc.leaves, enc.counts, 1, H, W, space, qrange, brange, instance=slot,
                               out="u8" if host_out.dtype == torch.uint8 else "f32")
             host_out[job["f"]:job["f"] + 1].copy_(rgb, non_blocking=True)

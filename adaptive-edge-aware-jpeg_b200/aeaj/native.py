@@ -23,6 +23,7 @@ EXPORTS = [
     "aeaj_plan_enable_timing", "aeaj_plan_read_timing", "aeaj_encode_phase", "aeaj_decode_phase", "aeaj_plan_buffers",
     "aeaj_plan_set_stream_layout", "aeaj_plan_set_tensor_dct", "aeaj_tensor_dct_status",
     "aeaj_states_to_leaves_host", "aeaj_pack_states_host",
+    "aeaj_pack_coefficients", "aeaj_unpack_coefficients", "aeaj_pack_coefficients_host", "aeaj_unpack_coefficients_host",
 ]
 
 
@@ -47,6 +48,10 @@ class EncodeIO(C.Structure):
 class DecodeIO(C.Structure):
     _fields_ = [("coef", C.c_void_p * 3), ("leaves", C.c_void_p * 3), ("counts", C.c_void_p), ("rgb", C.c_void_p),
                 ("tap_layers", C.c_void_p * 3), ("rgb_u8", C.c_void_p), ("status", C.c_void_p)]
+
+
+class PackedIO(C.Structure):
+    _fields_ = [("mask", C.c_void_p * 3), ("vals", C.c_void_p * 3), ("counts", C.c_void_p)]
 
 
 class PlanBuffers(C.Structure):
@@ -112,6 +117,10 @@ def load():
         lib.aeaj_plan_read_timing.argtypes = [vp, C.c_char_p, sz, vp, i, C.POINTER(i)]
         lib.aeaj_states_to_leaves_host.argtypes = [vp, i, i, i, i, i, i, vp, C.POINTER(i), C.POINTER(C.c_int64)]
         lib.aeaj_pack_states_host.argtypes = [vp, i, vp]
+        lib.aeaj_pack_coefficients.argtypes = [vp, C.POINTER(vp), vp, C.POINTER(PackedIO), vp, vp]
+        lib.aeaj_unpack_coefficients.argtypes = [vp, C.POINTER(PackedIO), C.POINTER(vp), vp, vp]
+        lib.aeaj_pack_coefficients_host.argtypes = [vp, C.c_int64, vp, vp, C.POINTER(C.c_int64), C.POINTER(i)]
+        lib.aeaj_unpack_coefficients_host.argtypes = [vp, vp, C.c_int64, C.c_int64, vp]
         _lib = lib
         return lib
 
@@ -160,3 +169,30 @@ def states_to_leaves(states: np.ndarray, root: int, h: int, w: int, block_range=
         raise ValueError("corrupt quadtree header: " + lib.aeaj_last_error().decode("utf-8", "replace"))
     check(rc, "aeaj_states_to_leaves_host")
     return leaves[: n.value], int(ncoef.value)
+
+
+def pack_coefficients_host(coef: np.ndarray):
+    """int32 stream -> (mask uint32[ceil(n/32)], vals int16[nnz], overflow flag): the packed form of include/aeaj.h, on the CPU"""
+    lib = load()
+    coef = np.ascontiguousarray(coef, dtype=np.int32)
+    mask = np.empty((coef.size + 31) // 32, dtype=np.uint32)
+    vals = np.empty(max(coef.size, 1), dtype=np.int16)
+    nnz, ovf = C.c_int64(), C.c_int()
+    check(lib.aeaj_pack_coefficients_host(coef.ctypes.data, coef.size, mask.ctypes.data, vals.ctypes.data, C.byref(nnz), C.byref(ovf)),
+          "aeaj_pack_coefficients_host")
+    return mask, vals[: nnz.value], bool(ovf.value)
+
+
+def unpack_coefficients_host(mask: np.ndarray, vals: np.ndarray, n_coef: int) -> np.ndarray:
+    """inverse of the packed form: -> int32 stream of n_coef coefficients (what the .ajpg container stores, jpeg.py:590)"""
+    lib = load()
+    mask = np.ascontiguousarray(mask, dtype=np.uint32)
+    vals = np.ascontiguousarray(vals, dtype=np.int16)
+    if mask.size < (n_coef + 31) // 32:
+        raise ValueError("packed stream: mask too short")
+    out = np.empty(n_coef, dtype=np.int32)
+    rc = lib.aeaj_unpack_coefficients_host(mask.ctypes.data, vals.ctypes.data, n_coef, vals.size, out.ctypes.data)
+    if rc == -1:
+        raise ValueError(lib.aeaj_last_error().decode("utf-8", "replace"))
+    check(rc, "aeaj_unpack_coefficients_host")
+    return out

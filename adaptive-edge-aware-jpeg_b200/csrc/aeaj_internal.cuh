@@ -148,7 +148,7 @@ struct aeaj_handle {
     int* tc_err_dev;              // set by the tcgen05 kernel if a barrier wait timed out
     // device scratch for single-plane stage calls
     struct PlaneDesc* stage_plane_dev;
-    long long* stage_class_off_dev;   // [9]
+    long long* stage_class_off_dev;   // [18]: offsets, capacities
     int* stage_tile_base_dev;         // [1]
     uint8_t** stage_outs_dev;         // [1]
 };
@@ -156,7 +156,6 @@ struct aeaj_handle {
 // device-side description of every plane of a batch; lives in the plan's device memory
 struct PlaneDesc {
     int h, w, wpr, root, top, ntx, nty, layer;
-    int hy_base;                      // first hysteresis tile of this plane (tiles of all planes form one index space)
     int ry0, ry1;                     // rows of this plane the current call works on (halo-split bands); default [0, h)
     float mid, scale;
     float* layer_f32;        // downsampled un-normalised layer
@@ -184,7 +183,6 @@ struct PlaneDesc {
 };
 
 struct ClassEntry { int x, y, plane, coef_off; };
-struct ClassCaps { long long cap[9]; };
 
 // exact 1-D grids over the tiles of all planes of a batch (no empty blocks for the smaller chroma planes):
 // planes are ordered image-major with `nl` layers per image and identical geometry per layer.
@@ -212,6 +210,19 @@ static inline __device__ void tile_decode(const TileMap& m, int bid, int& plane,
     plane = b * m.nl + l;
 }
 
+// one plane's coefficient stream in packed form (pack.cu)
+struct PackPlane {
+    const int32_t* coef;      // pack: in, unpack: out
+    uint32_t* mask;           // [ceil(n / 32)]
+    int16_t* vals;            // [nnz]
+    const int32_t* n_coef;    // device: number of coefficients of this plane
+    int32_t* pk_counts;       // device int32[4]: nnz, n_coef, overflow flag, mask words
+    int* chunk_sums;          // scratch: per-chunk nnz, then exclusive offsets
+    int64_t cap_coef;         // capacity of the stream buffers
+};
+size_t aeaj_pack_scratch_ints(int64_t cap_coef);
+int launch_pack(const PackPlane* planes_host, PackPlane* planes_dev, int nplanes, int64_t max_cap_coef, int unpack, cudaStream_t st);
+
 // kernels' host launchers (defined in the .cu files)
 int aeaj_canny_init(aeaj_handle* h);
 int aeaj_dct_init(aeaj_handle* h);
@@ -236,7 +247,8 @@ int launch_thresholds(const PlaneDesc* planes_dev, int nplanes, cudaStream_t st)
 int launch_thresholds_from_double(const double* thr_d, int* thr, cudaStream_t st);
 int launch_canny_nms(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, cudaStream_t st);
 int hysteresis_tiles(PlaneDesc* planes_host, int nplanes, int* ring_cap);
-int launch_hysteresis(aeaj_handle* h, const PlaneDesc* planes_dev, int nplanes, int ntiles, int ring_cap,
+int hysteresis_ctrl_ints();
+int launch_hysteresis(aeaj_handle* h, const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, int ntiles, int ring_cap,
                       int* flags, int* ring, int* ctrl, int* status, cudaStream_t st);
 int launch_bitmap_to_u8(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes,
                         uint8_t* const* outs_dev, cudaStream_t st);
@@ -247,8 +259,7 @@ int launch_quadtree(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, i
                     int* launches);
 int launch_pack_states(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, cudaStream_t st);
 int launch_bucket_leaves(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, ClassEntry* class_lists,
-                         int* class_counts, const long long* class_offsets_dev, int lg_min, int lg_max, const int64_t* class_caps_host,
-                         cudaStream_t st);
+                         int* class_counts, const long long* class_offsets_dev, int lg_min, int lg_max, cudaStream_t st);
 int launch_dct_quant(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,
                      const int64_t* class_offsets_host, const int64_t* class_caps_host, int lg_min, int lg_max,
                      cudaStream_t st, int* launches, void (*mark)(void*, const char*), void* mark_ctx, int tensor_dct, float* scratch256);

@@ -118,7 +118,7 @@ extern "C" int aeaj_create(int device, aeaj_handle** out) {
     if (rc) { free(h); return rc; }
     AEAJ_CUDA(cudaMalloc(&h->srgb_lut_dev, 256 * sizeof(float)));
     AEAJ_CUDA(cudaMalloc(&h->stage_plane_dev, sizeof(PlaneDesc)));
-    AEAJ_CUDA(cudaMalloc(&h->stage_class_off_dev, 9 * sizeof(long long)));
+    AEAJ_CUDA(cudaMalloc(&h->stage_class_off_dev, 18 * sizeof(long long)));
     AEAJ_CUDA(cudaMalloc(&h->stage_tile_base_dev, sizeof(int)));
     AEAJ_CUDA(cudaMalloc(&h->stage_outs_dev, sizeof(uint8_t*)));
     AEAJ_CUDA(cudaMemset(h->stage_tile_base_dev, 0, sizeof(int)));
@@ -213,7 +213,7 @@ static void stage_ws(void* ws, int h, int w, int mn, int mx, StageWs& S) {
     S.ntiles = hysteresis_tiles(&S.P, 1, &S.ring_cap);
     S.flags = b.take<int>((size_t)S.ntiles);
     S.ring = b.take<int>((size_t)S.ring_cap);
-    S.ctrl = b.take<int>(8);
+    S.ctrl = b.take<int>(hysteresis_ctrl_ints());
     S.status = b.take<int>(4);
     S.class_counts = b.take<int>(16);
     if (mx > 0) {
@@ -275,7 +275,7 @@ extern "C" int aeaj_percentile_thresholds(aeaj_handle* hd, const uint8_t* src, i
 
 static int run_nms_hysteresis(aeaj_handle* hd, StageWs& S, uint8_t* edge, cudaStream_t st) {
     int rc = launch_canny_nms(hd->stage_plane_dev, &S.P, 1, st); if (rc) return rc;
-    rc = launch_hysteresis(hd, hd->stage_plane_dev, 1, S.ntiles, S.ring_cap, S.flags, S.ring, S.ctrl, S.status, st);
+    rc = launch_hysteresis(hd, hd->stage_plane_dev, &S.P, 1, S.ntiles, S.ring_cap, S.flags, S.ring, S.ctrl, S.status, st);
     if (rc) return rc;
     if (edge) {
         AEAJ_CUDA(cudaMemcpyAsync(hd->stage_outs_dev, &edge, sizeof(uint8_t*), cudaMemcpyHostToDevice, st));
@@ -327,7 +327,7 @@ extern "C" int aeaj_quadtree(aeaj_handle* hd, const uint8_t* edge, int h, int w,
     S.P.leaves = leaves; S.P.states = states; S.P.counts = counts;
     cudaStream_t st = ST(stream);
     rc = push_stage_plane(hd, S.P, st); if (rc) return rc;
-    long long off[9]; for (int k = 0; k < 9; k++) off[k] = S.cg.off[k];
+    long long off[18]; for (int k = 0; k < 9; k++) { off[k] = S.cg.off[k]; off[9 + k] = S.cg.cap[k]; }
     AEAJ_CUDA(cudaMemcpyAsync(hd->stage_class_off_dev, off, sizeof off, cudaMemcpyHostToDevice, st));
     AEAJ_CUDA(cudaMemsetAsync(S.class_counts, 0, 16 * sizeof(int), st));
     rc = launch_u8_to_bitmap(edge, h, w, S.P.strong, st); if (rc) return rc;
@@ -342,12 +342,12 @@ static int stage_blocks(aeaj_handle* hd, bool inverse, float* layer, int h, int 
     S.P.leaves = (int32_t*)leaves; S.P.counts = (int32_t*)counts; S.P.coef = coef;
     for (int k = 0; k < 9; k++) S.P.qtab[k] = qtab[k];
     rc = push_stage_plane(hd, S.P, st); if (rc) return rc;
-    long long off[9]; for (int k = 0; k < 9; k++) off[k] = S.cg.off[k];
+    long long off[18]; for (int k = 0; k < 9; k++) { off[k] = S.cg.off[k]; off[9 + k] = S.cg.cap[k]; }
     AEAJ_CUDA(cudaMemcpyAsync(hd->stage_class_off_dev, off, sizeof off, cudaMemcpyHostToDevice, st));
     AEAJ_CUDA(cudaMemsetAsync(S.class_counts, 0, 16 * sizeof(int), st));
     S.P.cap_leaves = INT32_MAX;                        // the stage API trusts counts[0] (the caller sized the leaf list)
     rc = push_stage_plane(hd, S.P, st); if (rc) return rc;
-    rc = launch_bucket_leaves(hd->stage_plane_dev, &S.P, 1, S.class_lists, S.class_counts, hd->stage_class_off_dev, ilog2i(mn), ilog2i(mx), S.cg.cap, st); if (rc) return rc;
+    rc = launch_bucket_leaves(hd->stage_plane_dev, &S.P, 1, S.class_lists, S.class_counts, hd->stage_class_off_dev, ilog2i(mn), ilog2i(mx), st); if (rc) return rc;
     if (inverse) return launch_dequant_idct(hd, hd->stage_plane_dev, S.class_lists, S.class_counts, S.cg.off, S.cg.cap, ilog2i(mn), ilog2i(mx), st, nullptr, nullptr, nullptr, 0, S.scratch256);
     return launch_dct_quant(hd, hd->stage_plane_dev, S.class_lists, S.class_counts, S.cg.off, S.cg.cap, ilog2i(mn), ilog2i(mx), st, nullptr, nullptr, nullptr, 0, S.scratch256);
 }
@@ -370,13 +370,18 @@ struct aeaj_plan {
     aeaj_plan_info info;
     int nplanes, lg_min, lg_max;
     std::vector<PlaneDesc> planes;       // host copy, index b*3 + l
+    std::vector<PlaneDesc> planes_pushed; // what planes_dev holds (the upload is skipped while nothing changed: steady-state
+                                         // calls issue no host-to-device copy at all, which also makes them CUDA-graph capturable)
     PlaneDesc* planes_dev;
+    cudaStream_t pushed_stream = 0;
     int ntiles, ring_cap;
     long long* class_off_dev;
     ClassGeom cg;
     int32_t* qtab_dev; size_t qtab_entries;
     const int32_t* qtab_ptr[2][9];       // device pointers per table (0 luma, 1 chroma) and log2 size
     uint8_t** outs_dev;                  // tap pointers [nplanes]
+    std::vector<PackPlane> pack_planes;  // host copy of the packing descriptors
+    PackPlane* pack_planes_dev;
     int last_launches;
     bool need_full_chroma;
     int zigzag = 0;
@@ -439,7 +444,8 @@ static size_t plan_carve(aeaj_plan* p, void* ws) {
     return b.off;
 }
 
-struct PlanAux { float* full_c1; float* full_c2; int* flags; int* ring; int* ctrl; int* class_counts; ClassEntry* class_lists; float* scratch256; };
+struct PlanAux { float* full_c1; float* full_c2; int* flags; int* ring; int* ctrl; int* class_counts; ClassEntry* class_lists; float* scratch256;
+                 int* pack_sums[3]; };
 static size_t plan_carve_aux(aeaj_plan* p, void* ws, size_t start, PlanAux& A) {
     Bump b(ws); b.off = start;
     const size_t HW = (size_t)p->info.height * p->info.width;
@@ -447,11 +453,12 @@ static size_t plan_carve_aux(aeaj_plan* p, void* ws, size_t start, PlanAux& A) {
     else { A.full_c1 = A.full_c2 = nullptr; }
     A.flags = b.take<int>((size_t)p->ntiles);
     A.ring = b.take<int>((size_t)p->ring_cap);
-    A.ctrl = b.take<int>(8);
+    A.ctrl = b.take<int>(hysteresis_ctrl_ints());
     A.class_counts = b.take<int>(16);
     A.class_lists = b.take<ClassEntry>((size_t)p->cg.total);
     // the 256 x 256 kernel's intermediate tiles belong to the call (plans run concurrently on several streams)
     A.scratch256 = (p->lg_max >= 8) ? b.take<float>(aeaj_dct256_scratch_floats()) : nullptr;
+    for (int l = 0; l < 3; l++) A.pack_sums[l] = b.take<int>(aeaj_pack_scratch_ints(p->info.cap_coef[l]) * p->info.batch);
     return b.used();
 }
 
@@ -493,9 +500,11 @@ extern "C" int aeaj_plan_create(aeaj_handle* h, int batch, int height, int width
     PlanAux A;
     p->info.workspace_bytes = (int64_t)plan_carve_aux(p, nullptr, s1, A) + 256;
     AEAJ_CUDA(cudaMalloc(&p->planes_dev, sizeof(PlaneDesc) * p->nplanes));
-    AEAJ_CUDA(cudaMalloc(&p->class_off_dev, sizeof(long long) * 9));
+    AEAJ_CUDA(cudaMalloc(&p->class_off_dev, sizeof(long long) * 18));
     AEAJ_CUDA(cudaMalloc(&p->outs_dev, sizeof(uint8_t*) * p->nplanes));
-    long long off[9]; for (int k = 0; k < 9; k++) off[k] = p->cg.off[k];
+    p->pack_planes.resize(p->nplanes);
+    AEAJ_CUDA(cudaMalloc(&p->pack_planes_dev, sizeof(PackPlane) * p->nplanes));
+    long long off[18]; for (int k = 0; k < 9; k++) { off[k] = p->cg.off[k]; off[9 + k] = p->cg.cap[k]; }
     AEAJ_CUDA(cudaMemcpy(p->class_off_dev, off, sizeof off, cudaMemcpyHostToDevice));
     p->qtab_dev = nullptr; p->qtab_entries = 0;
     memset(p->qtab_ptr, 0, sizeof p->qtab_ptr);
@@ -507,7 +516,7 @@ extern "C" int aeaj_plan_create(aeaj_handle* h, int batch, int height, int width
 extern "C" int aeaj_plan_destroy(aeaj_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->h->device);
-    cudaFree(p->planes_dev); cudaFree(p->class_off_dev); cudaFree(p->outs_dev); cudaFree(p->qtab_dev);
+    cudaFree(p->planes_dev); cudaFree(p->class_off_dev); cudaFree(p->outs_dev); cudaFree(p->qtab_dev); cudaFree(p->pack_planes_dev);
     delete p;
     return 0;
 }
@@ -581,7 +590,11 @@ static int plan_push_planes(aeaj_plan* p, cudaStream_t st) {
         P.zigzag = p->zigzag;
         for (int k = 0; k < 9; k++) P.zz[k] = p->h->zz_dev[k];
     }
+    if (p->pushed_stream == st && p->planes_pushed.size() == p->planes.size() &&
+        memcmp(p->planes_pushed.data(), p->planes.data(), sizeof(PlaneDesc) * p->planes.size()) == 0) return 0;
     AEAJ_CUDA(cudaMemcpyAsync(p->planes_dev, p->planes.data(), sizeof(PlaneDesc) * p->nplanes, cudaMemcpyHostToDevice, st));
+    p->planes_pushed = p->planes;
+    p->pushed_stream = st;
     return 0;
 }
 
@@ -662,7 +675,7 @@ static int encode_impl(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, 
         launches += 2;
     }
     if (phases & (1u << AEAJ_PHASE_TREE)) {
-        rc = launch_hysteresis(h, p->planes_dev, NP, p->ntiles, p->ring_cap, A.flags, A.ring, A.ctrl, io->status, st); if (rc) return rc;
+        rc = launch_hysteresis(h, p->planes_dev, p->planes.data(), NP, p->ntiles, p->ring_cap, A.flags, A.ring, A.ctrl, io->status, st); if (rc) return rc;
         p->mark("hysteresis");
         launches += 1;
         if (any_tap_edge) {
@@ -725,8 +738,7 @@ static int decode_impl(aeaj_plan* p, const aeaj_decode_io* io, void* workspace, 
     p->ev_n = 0; p->ev_stream = st; p->mark("start");
     if (phases & (1u << AEAJ_DPHASE_IDCT)) {
         AEAJ_CUDA(cudaMemsetAsync(A.class_counts, 0, 16 * sizeof(int), st));
-        rc = launch_bucket_leaves(p->planes_dev, p->planes.data(), NP, A.class_lists, A.class_counts, p->class_off_dev, p->lg_min, p->lg_max,
-                                  p->cg.cap, st);
+        rc = launch_bucket_leaves(p->planes_dev, p->planes.data(), NP, A.class_lists, A.class_counts, p->class_off_dev, p->lg_min, p->lg_max, st);
         if (rc) return rc;
         launches++;
         p->mark("bucket_leaves");
@@ -757,6 +769,76 @@ extern "C" int aeaj_decode(aeaj_plan* p, const aeaj_decode_io* io, void* workspa
 extern "C" int aeaj_decode_phase(aeaj_plan* p, const aeaj_decode_io* io, void* workspace, void* stream, int phase, int band0, int band1) {
     AEAJ_REQUIRE(phase >= AEAJ_DPHASE_IDCT && phase <= AEAJ_DPHASE_COLOR, "aeaj_decode_phase: bad phase");
     return decode_impl(p, io, workspace, ST(stream), 1u << phase, band0, band1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// packed coefficient streams (pack.cu)
+// ---------------------------------------------------------------------------------------------
+static int pack_impl(aeaj_plan* p, const int32_t* const* coef3, const int32_t* counts, const aeaj_packed_io* pk, void* workspace, cudaStream_t st, int unpack) {
+    AEAJ_REQUIRE(p && coef3 && pk && pk->counts && workspace && (unpack || counts), "aeaj_(un)pack_coefficients: bad arguments");
+    const int B = p->info.batch;
+    size_t s1 = plan_carve(p, workspace);
+    PlanAux A;
+    plan_carve_aux(p, workspace, s1, A);
+    int64_t max_cap = 1;
+    for (int l = 0; l < 3; l++) {
+        AEAJ_REQUIRE(coef3[l] && pk->mask[l] && pk->vals[l], "aeaj_(un)pack_coefficients: NULL buffer");
+        const int64_t cap = p->info.cap_coef[l];
+        max_cap = std::max(max_cap, cap);
+        const size_t per = aeaj_pack_scratch_ints(cap);
+        for (int i = 0; i < B; i++) {
+            PackPlane& P = p->pack_planes[i * 3 + l];
+            P.coef = coef3[l] + (size_t)i * cap;
+            P.mask = pk->mask[l] + (size_t)i * (cap / 32 + 1);
+            P.vals = pk->vals[l] + (size_t)i * cap;
+            P.pk_counts = pk->counts + ((size_t)i * 3 + l) * 4;
+            P.n_coef = unpack ? P.pk_counts + 1 : counts + ((size_t)i * 3 + l) * 4 + 2;
+            P.chunk_sums = A.pack_sums[l] + per * i;
+            P.cap_coef = cap;
+        }
+    }
+    if (!unpack) AEAJ_CUDA(cudaMemsetAsync(pk->counts, 0, sizeof(int32_t) * 12 * (size_t)B, st));
+    return launch_pack(p->pack_planes.data(), p->pack_planes_dev, p->nplanes, max_cap, unpack, st);
+}
+extern "C" int aeaj_pack_coefficients(aeaj_plan* p, const int32_t* const* coef3, const int32_t* counts, const aeaj_packed_io* out,
+                                      void* workspace, void* stream) {
+    return pack_impl(p, coef3, counts, out, workspace, ST(stream), 0);
+}
+extern "C" int aeaj_unpack_coefficients(aeaj_plan* p, const aeaj_packed_io* in, int32_t* const* coef3, void* workspace, void* stream) {
+    return pack_impl(p, coef3, nullptr, in, workspace, ST(stream), 1);
+}
+extern "C" int aeaj_pack_coefficients_host(const int32_t* coef, int64_t n, uint32_t* mask, int16_t* vals, int64_t* nnz, int* overflow) {
+    AEAJ_REQUIRE(coef && mask && vals && nnz && n >= 0, "aeaj_pack_coefficients_host: bad arguments");
+    int64_t k = 0;
+    int ovf = 0;
+    for (int64_t w = 0; w * 32 < n; w++) {
+        uint32_t m = 0;
+        const int64_t e = std::min<int64_t>(n - w * 32, 32);
+        for (int64_t i = 0; i < e; i++) {
+            const int32_t v = coef[w * 32 + i];
+            if (v != 0) { m |= 1u << i; vals[k++] = (int16_t)v; ovf |= (v > 32767 || v < -32768); }
+        }
+        mask[w] = m;
+    }
+    *nnz = k;
+    if (overflow) *overflow = ovf;
+    return 0;
+}
+extern "C" int aeaj_unpack_coefficients_host(const uint32_t* mask, const int16_t* vals, int64_t n, int64_t nnz, int32_t* coef) {
+    AEAJ_REQUIRE(coef && mask && (vals || nnz == 0) && n >= 0 && nnz >= 0, "aeaj_unpack_coefficients_host: bad arguments");
+    int64_t k = 0;
+    for (int64_t w = 0; w * 32 < n; w++) {
+        const uint32_t m = mask[w];
+        const int64_t e = std::min<int64_t>(n - w * 32, 32);
+        if (m == 0) { for (int64_t i = 0; i < e; i++) coef[w * 32 + i] = 0; continue; }
+        for (int64_t i = 0; i < e; i++) {
+            int32_t v = 0;
+            if ((m >> i) & 1u) { AEAJ_REQUIRE(k < nnz, "packed stream: more mask bits than values"); v = vals[k++]; }
+            coef[w * 32 + i] = v;
+        }
+    }
+    AEAJ_REQUIRE(k == nnz, "packed stream: value count does not match the mask");
+    return 0;
 }
 
 // device pointers of the planes a halo-split caller exchanges between phases (batch 1)

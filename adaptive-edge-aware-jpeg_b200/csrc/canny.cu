@@ -579,19 +579,23 @@ __global__ void __launch_bounds__(256) k_canny_nms(const PlaneDesc* __restrict__
 // Bit-packed frontier propagation without grid-wide barriers.  A tile is 8 words x 32 rows (256 x 32 px), one
 // word per thread; a CTA takes a tile to local convergence in shared memory (word-parallel 3x3 spread + in-word
 // flood), ORs the new bits into the global bitmap and -- if bits on the tile's border changed -- pushes the (up to
-// 8) neighbour tiles that can see them onto a global work queue.  One persistent kernel: every CTA first walks
-// its static share of the tiles (each tile needs one pass anyway), then pulls re-visits from the queue until the
-// outstanding-work counter drops to zero.  The result is the fixed point reach(strong) through weak pixels, which
-// does not depend on the order of the passes (reach(S u T) = reach(S) u reach(T), bits are only ever set, stores
-// are atomic ORs), so asynchronous propagation is bit-identical to the round-synchronous version it replaces.
+// 8) neighbour tiles that can see them onto a global work queue.  One persistent kernel; a CTA that needs work
+// takes a re-visit from the queue if there is one (they sit on the critical path), else the next tile that has not
+// had its first pass, else it exits -- nobody ever waits for anybody: a push is always followed by its own CTA
+// looking at the queue again, so the queue drains, and idle CTAs leave the SMs to whatever else is running.
+// The result is the fixed point reach(strong) through weak pixels, which does not depend on the order of the
+// passes (reach(S u T) = reach(S) u reach(T), bits are only ever set, stores are atomic ORs), so asynchronous
+// propagation is bit-identical to the round-synchronous version it replaces.
 //
-// queue: ring of tile ids (-1 = empty slot), capacity >= 2 x tiles; a tile is in the ring at most once (flags[]);
-// ctrl: [0] head  [1] tail  [2] pending re-visits (queued or running)  [3] first passes finished  [4] abort
+// flags[t] != 0: tile t is queued or has not had its first pass (its next pass will load after any store that
+// precedes a push attempt, so the push can be dropped).  ring: tile ids, -1 = empty slot, capacity >= 2 x tiles.
+// ctrl (one 128-byte line each): [0] head  [32] tail  [64] next first-pass tile  [96] abort
 // ---------------------------------------------------------------------------------------------
 constexpr int HY_WW = 8, HY_TR = 32;
 constexpr int HY_THREADS = HY_WW * HY_TR;
 constexpr int HY_SS = HY_WW + 3;                      // smem row stride (odd: lanes that differ in the row hit different banks)
-constexpr long long HY_SPIN_LIMIT = 4000000;          // x >= 200 ns: a lost wake-up must not hang the GPU
+constexpr int HY_HEAD = 0, HY_TAIL = 32, HY_NEXT = 64, HY_ABORT = 96, HY_CTRL_INTS = 128;
+constexpr long long HY_SPIN_LIMIT = 20000000;         // a slot that is never published must not hang the GPU
 
 struct HystQueue { int* flags; int* ring; int* ctrl; int ring_mask; int ntiles; };
 
@@ -601,21 +605,16 @@ __device__ __forceinline__ unsigned spread3(unsigned L, unsigned Cw, unsigned R)
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
 // one pass over one tile: local convergence, atomic write-back, neighbour pushes
-__device__ __forceinline__ void hyst_process_tile(const PlaneDesc* __restrict__ planes, int nplanes, int tile, const HystQueue& q,
-                                                  unsigned (*sS)[HY_SS], int* sPlane, int* sNbr) {
+__device__ __forceinline__ void hyst_process_tile(const PlaneDesc* __restrict__ planes, const TileMap& tm, int tile, const HystQueue& q,
+                                                  unsigned (*sS)[HY_SS], int* sNbr) {
     const int tid = threadIdx.x, tr = tid & 31, tc = tid >> 5;     // warp = word column, lane = row
-    __syncthreads();
-    if (tid == 0) {
-        int p = 0;
-        while (p + 1 < nplanes && planes[p + 1].hy_base <= tile) p++;
-        *sPlane = p; *sNbr = 0;
-    }
-    __syncthreads();
-    const PlaneDesc& P = planes[*sPlane];
-    const int local = tile - P.hy_base;
+    int plane_i, txi, tyi;
+    tile_decode(tm, tile, plane_i, txi, tyi);
+    const PlaneDesc& P = planes[plane_i];
     const int ntx = aeaj_cdiv(P.wpr, HY_WW);
-    const int tyi = local / ntx, txi = local - tyi * ntx;
     const int gy0 = tyi * HY_TR, gw0 = txi * HY_WW;
+    __syncthreads();                                               // the previous pass is done with sS / sNbr
+    if (tid == 0) *sNbr = 0;
     for (int i = tid; i < (HY_TR + 2) * (HY_WW + 2); i += HY_THREADS) {
         const int ry = i / (HY_WW + 2), rw = i - ry * (HY_WW + 2);
         const int gy = gy0 + ry - 1, gw = gw0 + rw - 1;
@@ -659,67 +658,52 @@ __device__ __forceinline__ void hyst_process_tile(const PlaneDesc* __restrict__ 
         const int dy = tid / 3 - 1, dx = tid % 3 - 1;
         const int nx = txi + dx, ny = tyi + dy;
         if (nx >= 0 && nx < ntx && ny >= 0 && ny * HY_TR < P.h) {
-            const int nt = P.hy_base + ny * ntx + nx;
-            if (atomicExch(&q.flags[nt], 1) == 0) {                            // not queued yet (a queued tile will load after our store)
-                atomicAdd(&q.ctrl[2], 1);
-                const int slot = atomicAdd(&q.ctrl[1], 1) & q.ring_mask;
+            const int nt = tile + dy * ntx + dx;                               // tiles of a plane are consecutive, row-major
+            if (atomicExch(&q.flags[nt], 1) == 0) {                            // processed before and not queued: queue a re-visit
+                const int slot = atomicAdd(&q.ctrl[HY_TAIL], 1) & q.ring_mask;
                 long long spins = 0;
                 while (atomicCAS(&q.ring[slot], -1, nt) != -1)                 // the slot's previous ticket has not been read yet
-                    if (++spins > HY_SPIN_LIMIT) { atomicExch(&q.ctrl[4], 1); break; }
+                    if (++spins > HY_SPIN_LIMIT) { atomicExch(&q.ctrl[HY_ABORT], 1); break; }
             }
         }
     }
-    __syncthreads();
 }
 
-__global__ void __launch_bounds__(HY_THREADS) k_hysteresis(const PlaneDesc* __restrict__ planes, int nplanes, HystQueue q, int* __restrict__ status) {
+__global__ void __launch_bounds__(HY_THREADS) k_hysteresis(const PlaneDesc* __restrict__ planes, const __grid_constant__ TileMap tm, HystQueue q,
+                                                           int* __restrict__ status) {
     __shared__ unsigned sS[HY_TR + 2][HY_SS];
-    __shared__ int sPlane, sNbr, sTile;
+    __shared__ int sNbr, sTile;
     const int tid = threadIdx.x;
-    // first pass: a static share of the tiles
-    for (int tile = blockIdx.x; tile < q.ntiles; tile += gridDim.x) {
-        if (tid == 0) { atomicExch(&q.flags[tile], 0); __threadfence(); }
-        hyst_process_tile(planes, nplanes, tile, q, sS, &sPlane, &sNbr);
-        if (tid == 0) { __threadfence(); atomicAdd(&q.ctrl[3], 1); }
-    }
-    // re-visits from the queue until nothing is queued or running anywhere
     for (;;) {
+        __syncthreads();                                                       // pushes of the previous pass are out; sTile is free
         if (tid == 0) {
-            int t = -2;
-            long long spins = 0;
-            for (;;) {
-                const int hd = ld_volatile(&q.ctrl[0]), tl = ld_volatile(&q.ctrl[1]);
-                if (hd < tl) {
-                    if (atomicCAS(&q.ctrl[0], hd, hd + 1) != hd) continue;
-                    const int slot = hd & q.ring_mask;
-                    int v;
-                    long long sp2 = 0;
-                    while ((v = ld_volatile(&q.ring[slot])) == -1)
-                        if (++sp2 > HY_SPIN_LIMIT) { atomicExch(&q.ctrl[4], 1); break; }
-                    if (v >= 0) atomicExch(&q.ring[slot], -1);
-                    t = v >= 0 ? v : -2;
-                    break;
-                }
-                if (ld_volatile(&q.ctrl[4])) break;
-                if (ld_volatile(&q.ctrl[3]) >= q.ntiles) {                     // every first pass (and its pushes) is counted ...
-                    __threadfence();
-                    if (ld_volatile(&q.ctrl[2]) == 0) break;                   // ... and no re-visit is queued or running
-                }
-                if (++spins > HY_SPIN_LIMIT) { atomicExch(&q.ctrl[4], 1); break; }
-                __nanosleep(200);
+            int t = -1;
+            for (;;) {                                                         // 1. a queued re-visit
+                const int hd = ld_volatile(&q.ctrl[HY_HEAD]), tl = ld_volatile(&q.ctrl[HY_TAIL]);
+                if (hd >= tl) break;
+                if (atomicCAS(&q.ctrl[HY_HEAD], hd, hd + 1) != hd) continue;
+                const int slot = hd & q.ring_mask;
+                long long spins = 0;
+                while ((t = ld_volatile(&q.ring[slot])) == -1)                 // reserved, about to be published by a running CTA
+                    if (++spins > HY_SPIN_LIMIT) { atomicExch(&q.ctrl[HY_ABORT], 1); break; }
+                if (t >= 0) atomicExch(&q.ring[slot], -1);
+                break;
             }
+            if (t < 0 && ld_volatile(&q.ctrl[HY_NEXT]) < q.ntiles) {           // 2. a tile that has not had its first pass
+                const int f = atomicAdd(&q.ctrl[HY_NEXT], 1);
+                if (f < q.ntiles) t = f;
+            }
+            if (t >= 0) { atomicExch(&q.flags[t], 0); __threadfence(); }       // from here on a neighbour's new bits need a new push
             sTile = t;
         }
         __syncthreads();
         const int tile = sTile;
-        if (tile < 0) break;
-        if (tid == 0) { atomicExch(&q.flags[tile], 0); __threadfence(); }
-        hyst_process_tile(planes, nplanes, tile, q, sS, &sPlane, &sNbr);
-        if (tid == 0) { __threadfence(); atomicSub(&q.ctrl[2], 1); }
+        if (tile < 0) break;                                                   // 3. nothing to do: leave (whoever pushes later pops later)
+        hyst_process_tile(planes, tm, tile, q, sS, &sNbr);
     }
-    if (tid == 0 && status) {                                                  // every CTA reports the same final values
-        status[0] = ld_volatile(&q.ctrl[1]);                                   // tile re-visits in total
-        status[1] = ld_volatile(&q.ctrl[4]) ? 0 : 1;                           // converged
+    if (tid == 0 && status) {                                                  // the last CTAs to leave write the final values
+        status[0] = ld_volatile(&q.ctrl[HY_TAIL]);                             // tile re-visits in total
+        status[1] = ld_volatile(&q.ctrl[HY_ABORT]) ? 0 : 1;                    // converged
     }
 }
 
@@ -808,18 +792,16 @@ int launch_canny_nms(const PlaneDesc* planes_dev, const PlaneDesc* P, int nplane
     return 0;
 }
 
-// fills hy_base of every plane; returns the number of hysteresis tiles
+// number of hysteresis tiles of a batch (the tile index space of make_tile_map(.., 256, 32)) and the ring capacity
 int hysteresis_tiles(PlaneDesc* P, int nplanes, int* ring_cap) {
-    int ns = 0;
-    for (int i = 0; i < nplanes; i++) {
-        P[i].hy_base = ns;
-        ns += aeaj_cdiv(P[i].wpr, HY_WW) * aeaj_cdiv(P[i].h, HY_TR);
-    }
+    const TileMap tm = make_tile_map(P, nplanes, HY_WW * 32, HY_TR);
+    const int ns = tile_map_total(tm, nplanes);
     int cap = 64;
     while (cap < 2 * ns) cap *= 2;
     *ring_cap = cap;
     return ns;
 }
+int hysteresis_ctrl_ints() { return HY_CTRL_INTS; }
 
 int aeaj_canny_init(aeaj_handle* h) {
     int rc = aeaj_canny_init_constants(); if (rc) return rc;
@@ -828,16 +810,17 @@ int aeaj_canny_init(aeaj_handle* h) {
     return 0;
 }
 
-// flags: int[ntiles] (set = queued; the first pass counts as queued); ring: int[ring_cap]; ctrl: int[8]
-int launch_hysteresis(aeaj_handle* h, const PlaneDesc* planes_dev, int nplanes, int ntiles, int ring_cap,
+// flags: int[ntiles]; ring: int[ring_cap]; ctrl: int[hysteresis_ctrl_ints()]
+int launch_hysteresis(aeaj_handle* h, const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, int ntiles, int ring_cap,
                       int* flags, int* ring, int* ctrl, int* status, cudaStream_t st) {
     AEAJ_CUDA(cudaMemsetAsync(flags, 1, sizeof(int) * (size_t)ntiles, st));
     AEAJ_CUDA(cudaMemsetAsync(ring, 0xff, sizeof(int) * (size_t)ring_cap, st));
-    AEAJ_CUDA(cudaMemsetAsync(ctrl, 0, sizeof(int) * 8, st));
+    AEAJ_CUDA(cudaMemsetAsync(ctrl, 0, sizeof(int) * HY_CTRL_INTS, st));
     HystQueue q;
     q.flags = flags; q.ring = ring; q.ctrl = ctrl; q.ring_mask = ring_cap - 1; q.ntiles = ntiles;
-    const int grid = std::max(1, std::min(ntiles, std::min(h->hyst_blocks_per_sm, 6) * h->sm_count));
-    k_hysteresis<<<grid, HY_THREADS, 0, st>>>(planes_dev, nplanes, q, status);
+    const TileMap tm = make_tile_map(planes_host, nplanes, HY_WW * 32, HY_TR);
+    const int grid = std::max(1, std::min(ntiles, h->hyst_blocks_per_sm * h->sm_count));
+    k_hysteresis<<<grid, HY_THREADS, 0, st>>>(planes_dev, tm, q, status);
     AEAJ_LAUNCH_CHECK();
     return 0;
 }

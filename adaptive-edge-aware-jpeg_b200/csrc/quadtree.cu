@@ -239,9 +239,10 @@ __global__ void __launch_bounds__(QT_THREADS) k_qt_scan(const PlaneDesc* __restr
 // A leaf list that did not come from aeaj_quadtree / aeaj_states_to_leaves_host is not trusted: leaves whose size is not a
 // power of two inside [2^lg_min, 2^lg_max], whose origin lies outside the layer or whose coefficient block leaves the
 // plane's buffer are skipped and counted in class_counts[15] (reported through aeaj_decode_io.status).
+// class_offsets: [0..8] first slot of every size class in class_lists, [9..17] capacity of the class.
 __global__ void __launch_bounds__(256) k_bucket_leaves(const PlaneDesc* __restrict__ planes, ClassEntry* __restrict__ class_lists,
                                                        int* __restrict__ class_counts, const long long* __restrict__ class_offsets,
-                                                       int lg_min, int lg_max, const ClassCaps caps) {
+                                                       int lg_min, int lg_max) {
     const PlaneDesc& P = planes[blockIdx.y];
     const int nl = (int)min((long long)max(P.counts[0], 0), (long long)P.cap_leaves);
     __shared__ int s_cls[9], s_base[9];
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(256) k_bucket_leaves(const PlaneDesc* __restri
     if (i < nl && lg >= 0) {
         ClassEntry e; e.x = lf.x; e.y = lf.y; e.plane = blockIdx.y; e.coef_off = lf.w;
         const long long slot = (long long)s_base[lg] + rank;
-        if (slot < caps.cap[lg]) class_lists[class_offsets[lg] + slot] = e;      // more leaves of a size than can tile the planes: overlapping leaves
+        if (slot < class_offsets[9 + lg]) class_lists[class_offsets[lg] + slot] = e;      // more leaves of a size than can tile the planes: overlapping leaves
         else atomicAdd(&class_counts[15], 1);
     }
 }
@@ -309,14 +310,11 @@ int launch_quadtree(const PlaneDesc* planes_dev, const PlaneDesc* P, int nplanes
 }
 
 int launch_bucket_leaves(const PlaneDesc* planes_dev, const PlaneDesc* P, int nplanes, ClassEntry* class_lists,
-                         int* class_counts, const long long* class_offsets_dev, int lg_min, int lg_max, const int64_t* class_caps_host,
-                         cudaStream_t st) {
+                         int* class_counts, const long long* class_offsets_dev, int lg_min, int lg_max, cudaStream_t st) {
     int64_t maxl = 1;
     for (int i = 0; i < nplanes; i++) maxl = std::max<int64_t>(maxl, P[i].cap_leaves);
     dim3 grd((unsigned)aeaj_cdiv64(maxl, 256), nplanes);
-    ClassCaps caps;
-    for (int k = 0; k < 9; k++) caps.cap[k] = class_caps_host[k];
-    k_bucket_leaves<<<grd, 256, 0, st>>>(planes_dev, class_lists, class_counts, class_offsets_dev, lg_min, lg_max, caps);
+    k_bucket_leaves<<<grd, 256, 0, st>>>(planes_dev, class_lists, class_counts, class_offsets_dev, lg_min, lg_max);
     AEAJ_LAUNCH_CHECK();
     return 0;
 }

@@ -213,6 +213,30 @@ AEAJ_API int aeaj_states_to_leaves_host(const uint8_t* states_host, int n_states
 /* 2 bits per state, MSB first, zero padded; packed_host holds ceil(n_states/4) bytes */
 AEAJ_API int aeaj_pack_states_host(const uint8_t* states_host, int n_states, uint8_t* packed_host);
 
+/* ---------------------------------------------------------------------------------------------
+ * Packed coefficient streams for the trip to the host-side entropy coder and back (jpeg.py:573-590, 655-672): once the
+ * hot path is on the GPU, two thirds of the PCIe bytes of an encode + decode are int32 coefficients, most of them zero.
+ * Lossless packed form of one plane's stream of n coefficients (either block layout):
+ *     mask: uint32[ceil(n/32)], bit i of word j set <=> coefficient 32 j + i is non-zero;  vals: int16[nnz], the
+ *     non-zero coefficients in stream order (|c| <= 127 * block size <= 32512 for normalised samples).
+ * counts: int32 [batch][3][4] on the device = nnz, n_coef, overflow flag (a value did not fit int16: move that plane as
+ * int32 instead), number of mask words.  aeaj_pack_coefficients reads the n_coef of aeaj_encode's `counts`;
+ * aeaj_unpack_coefficients reads them from in->counts.  Both are asynchronous on `stream` and use the plan workspace.
+ * The *_host functions are the CPU counterparts for the container writer / reader (no device work).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    uint32_t* mask[3];       /* [batch][cap_coef[l] / 32 + 1] */
+    int16_t* vals[3];        /* [batch][cap_coef[l]] */
+    int32_t* counts;         /* [batch][3][4] */
+} aeaj_packed_io;
+AEAJ_API int aeaj_pack_coefficients(aeaj_plan* p, const int32_t* const* coef3, const int32_t* counts, const aeaj_packed_io* out,
+                                    void* workspace, void* stream);
+AEAJ_API int aeaj_unpack_coefficients(aeaj_plan* p, const aeaj_packed_io* in, int32_t* const* coef3, void* workspace, void* stream);
+AEAJ_API int aeaj_pack_coefficients_host(const int32_t* coef_host, int64_t n_coef, uint32_t* mask_host, int16_t* vals_host,
+                                         int64_t* nnz, int* overflow);
+AEAJ_API int aeaj_unpack_coefficients_host(const uint32_t* mask_host, const int16_t* vals_host, int64_t n_coef, int64_t nnz,
+                                           int32_t* coef_host);
+
 /* Stream layout.  zigzag = 0 (default): each block of the coefficient stream is row-major,
  * i.e. the reference's img_quantized blocks.  zigzag = 1: each block is stored in the zigzag order of
  * Jpeg._zigzag_ordering (jpeg.py:726-766), i.e. the stream is byte-for-byte what _entropy_encode hands to zlib

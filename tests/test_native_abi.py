@@ -129,3 +129,20 @@ def test_corrupt_state_streams_are_rejected():
     # a truncated stream yields the leaves seen so far (jpeg.py:784 stops the same way); the caller's length check catches it
     part, _ = native.states_to_leaves(states[: len(states) // 2], root, *shape, (mn, mx))
     assert 0 < len(part) < len(leaves)
+
+
+def test_packed_coefficient_host_helpers():
+    """aeaj_pack_coefficients_host / aeaj_unpack_coefficients_host: the packed PCIe form (bit mask + int16 non-zeros)"""
+    from aeaj import native
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 31, 32, 33, 1000, 100003):
+        c = (rng.integers(-300, 300, n) * (rng.random(n) < 0.2)).astype(np.int32)
+        m, v, ovf = native.pack_coefficients_host(c)
+        assert not ovf and m.size == (n + 31) // 32 and v.size == int((c != 0).sum())
+        assert np.array_equal(native.unpack_coefficients_host(m, v, n), c)
+    assert native.pack_coefficients_host(np.array([0, 40000, -5], np.int32))[2]           # does not fit int16: flagged
+    m, v, _ = native.pack_coefficients_host(np.array([1, 0, 2, 0, 0, 3], np.int32))
+    with pytest.raises(ValueError):
+        native.unpack_coefficients_host(m, v[:2], 6)                                         # fewer values than mask bits
+    with pytest.raises(ValueError):
+        native.unpack_coefficients_host(m[:0], v, 6)                                         # mask too short
