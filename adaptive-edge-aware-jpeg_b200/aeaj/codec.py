@@ -81,7 +81,12 @@ class DeviceCodec:
         self.handle = native.handle(device)
         self._plans: "OrderedDict[tuple, _Plan]" = OrderedDict()
         self.last_launches = 0
-        self.tensor_dct = True         # tcgen05 / TMEM path for the 128x128 DCT and IDCT (False: FP32-FMA kernels)
+        # size classes whose DCT / IDCT run on the tcgen05 / TMEM kernels: bit k = class 16 << k (True = all four, False / 0 =
+        # the FP32-FMA kernels everywhere)
+        self.tensor_dct = 0xf
+
+    def _tensor_mask(self) -> int:
+        return 0xf if self.tensor_dct is True else int(self.tensor_dct) & 0xf
 
     def tensor_dct_timed_out(self) -> bool:
         t = (C.c_int * 32)()
@@ -185,7 +190,7 @@ class DeviceCodec:
         io.counts = o.counts.data_ptr()
         io.status = o.status.data_ptr()
         native.check(self.lib.aeaj_plan_set_stream_layout(p.ptr, int(stream)), "aeaj_plan_set_stream_layout")
-        native.check(self.lib.aeaj_plan_set_tensor_dct(p.ptr, int(self.tensor_dct)), "aeaj_plan_set_tensor_dct")
+        native.check(self.lib.aeaj_plan_set_tensor_dct(p.ptr, self._tensor_mask()), "aeaj_plan_set_tensor_dct")
         o.zigzag = bool(stream)
         if stream:
             if o.packed_states is None:
@@ -213,7 +218,7 @@ class DeviceCodec:
             raise ValueError("out must be 'f32', 'u8' or 'both'")
         p = self._plan(B, H, W, space, brange, qrange, instance)
         native.check(self.lib.aeaj_plan_set_stream_layout(p.ptr, int(zigzag)), "aeaj_plan_set_stream_layout")
-        native.check(self.lib.aeaj_plan_set_tensor_dct(p.ptr, int(self.tensor_dct)), "aeaj_plan_set_tensor_dct")
+        native.check(self.lib.aeaj_plan_set_tensor_dct(p.ptr, self._tensor_mask()), "aeaj_plan_set_tensor_dct")
         io = native.DecodeIO()
         for l in range(3):
             if coef[l].shape[1] != p.info.cap_coef[l] or leaves[l].shape[1] != p.info.cap_leaves[l]:

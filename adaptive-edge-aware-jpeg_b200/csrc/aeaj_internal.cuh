@@ -143,8 +143,9 @@ struct aeaj_handle {
     int32_t* zz_dev[9];           // zigzag tables per log2(size), device
     int32_t* zz_all_dev;
     int32_t* izz256_dev;          // inverse zigzag permutation for 256x256
-    int32_t* tc_izz_dev;          // inverse zigzag permutation for 128x128 (tensor-core IDCT loader)
-    float* dct_tc_tiles_dev;      // [Ch | Cl] tiles of the 128x128 DCT matrix for the tcgen05 path
+    int32_t* tc_izz_dev[4];       // inverse zigzag permutations for 16 .. 128 (tensor-core kernels)
+    int32_t* tc_izz_all_dev;
+    float* dct_tc_tiles_dev;      // [size class 16..128][fwd, inv][Ah | Al]: block-diagonal DCT matrices for the tcgen05 path
     int* tc_err_dev;              // set by the tcgen05 kernel if a barrier wait timed out
     // device scratch for single-plane stage calls
     struct PlaneDesc* stage_plane_dev;
@@ -176,6 +177,7 @@ struct PlaneDesc {
     int* tb_coef;            // per in-bounds top block: n_coef
     int4* tb_base;           // per in-bounds top block: state base, leaf base, coef base, -
     const int32_t* qtab[9];  // per log2(size)
+    const float* qtabf[9];   // the same tables as float (tensor-core epilogue); null in single-plane stage calls
     const int32_t* zz[9];    // zigzag order per log2(size): stream index -> row-major index (jpeg.py:726-766)
     int zigzag;              // 1: coefficient streams are stored zigzag-ordered per block (the .ajpg layout)
     uint8_t* packed_states;  // optional: 2-bit MSB-first packing of `states` (jpeg.py:563-571)
@@ -265,7 +267,7 @@ int launch_dct_quant(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEnt
                      cudaStream_t st, int* launches, void (*mark)(void*, const char*), void* mark_ctx, int tensor_dct, float* scratch256);
 size_t aeaj_dct256_scratch_floats();
 int aeaj_dct_tc_init(aeaj_handle* h);
-int launch_dct_tc128(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* list, const int* count, int64_t cap, int inverse, cudaStream_t st);
+int launch_dct_tc(aeaj_handle* h, int size, const PlaneDesc* planes_dev, const ClassEntry* list, const int* count, int64_t cap, int inverse, cudaStream_t st);
 int launch_dequant_idct(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* class_lists, const int* class_counts,
                         const int64_t* class_offsets_host, const int64_t* class_caps_host, int lg_min, int lg_max,
                         cudaStream_t st, int* launches, void (*mark)(void*, const char*), void* mark_ctx, int tensor_dct, float* scratch256);

@@ -129,7 +129,7 @@ extern "C" int aeaj_create(int device, aeaj_handle** out) {
 extern "C" int aeaj_destroy(aeaj_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    cudaFree(h->srgb_lut_dev); cudaFree(h->dct_all_dev); cudaFree(h->dct_half_all_dev); cudaFree(h->zz_all_dev); cudaFree(h->izz256_dev); cudaFree(h->dct_tc_tiles_dev); cudaFree(h->tc_izz_dev); cudaFree(h->tc_err_dev); cudaFree(h->stage_plane_dev);
+    cudaFree(h->srgb_lut_dev); cudaFree(h->dct_all_dev); cudaFree(h->dct_half_all_dev); cudaFree(h->zz_all_dev); cudaFree(h->izz256_dev); cudaFree(h->dct_tc_tiles_dev); cudaFree(h->tc_izz_all_dev); cudaFree(h->tc_err_dev); cudaFree(h->stage_plane_dev);
     cudaFree(h->stage_class_off_dev); cudaFree(h->stage_tile_base_dev); cudaFree(h->stage_outs_dev);
     free(h);
     return 0;
@@ -378,14 +378,16 @@ struct aeaj_plan {
     long long* class_off_dev;
     ClassGeom cg;
     int32_t* qtab_dev; size_t qtab_entries;
+    float* qtabf_dev;                    // the same entries as float
     const int32_t* qtab_ptr[2][9];       // device pointers per table (0 luma, 1 chroma) and log2 size
+    const float* qtabf_ptr[2][9];
     uint8_t** outs_dev;                  // tap pointers [nplanes]
     std::vector<PackPlane> pack_planes;  // host copy of the packing descriptors
     PackPlane* pack_planes_dev;
     int last_launches;
     bool need_full_chroma;
     int zigzag = 0;
-    int tensor_dct = 1;           // tcgen05 kernels for 128x128 leaves (aeaj_plan_set_tensor_dct)
+    int tensor_dct = 0xe;         // size classes on the tcgen05 kernels: bit k = class 16 << k (aeaj_plan_set_tensor_dct)
     // optional per-stage CUDA-event timing (bench.py roofline leg)
     bool timing_on = false;
     std::vector<cudaEvent_t> ev;
@@ -506,8 +508,9 @@ extern "C" int aeaj_plan_create(aeaj_handle* h, int batch, int height, int width
     AEAJ_CUDA(cudaMalloc(&p->pack_planes_dev, sizeof(PackPlane) * p->nplanes));
     long long off[18]; for (int k = 0; k < 9; k++) { off[k] = p->cg.off[k]; off[9 + k] = p->cg.cap[k]; }
     AEAJ_CUDA(cudaMemcpy(p->class_off_dev, off, sizeof off, cudaMemcpyHostToDevice));
-    p->qtab_dev = nullptr; p->qtab_entries = 0;
+    p->qtab_dev = nullptr; p->qtabf_dev = nullptr; p->qtab_entries = 0;
     memset(p->qtab_ptr, 0, sizeof p->qtab_ptr);
+    memset(p->qtabf_ptr, 0, sizeof p->qtabf_ptr);
     p->last_launches = 0;
     *out = p;
     return 0;
@@ -516,7 +519,7 @@ extern "C" int aeaj_plan_create(aeaj_handle* h, int batch, int height, int width
 extern "C" int aeaj_plan_destroy(aeaj_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->h->device);
-    cudaFree(p->planes_dev); cudaFree(p->class_off_dev); cudaFree(p->outs_dev); cudaFree(p->qtab_dev); cudaFree(p->pack_planes_dev);
+    cudaFree(p->planes_dev); cudaFree(p->class_off_dev); cudaFree(p->outs_dev); cudaFree(p->qtab_dev); cudaFree(p->qtabf_dev); cudaFree(p->pack_planes_dev);
     delete p;
     return 0;
 }
@@ -528,7 +531,7 @@ extern "C" int aeaj_plan_get_info(const aeaj_plan* p, aeaj_plan_info* info) {
 extern "C" int aeaj_plan_last_launches(const aeaj_plan* p) { return p ? p->last_launches : 0; }
 extern "C" int aeaj_plan_set_tensor_dct(aeaj_plan* p, int enable) {
     AEAJ_REQUIRE(p, "aeaj_plan_set_tensor_dct: NULL plan");
-    p->tensor_dct = enable != 0;
+    p->tensor_dct = enable & 0xf;
     return 0;
 }
 extern "C" int aeaj_tensor_dct_status(aeaj_handle* h, int* timed_out) {
@@ -574,14 +577,24 @@ extern "C" int aeaj_plan_set_qtables(aeaj_plan* p, const int32_t* tables, size_t
     for (int k = p->lg_min; k <= p->lg_max; k++) per += (size_t)1 << (2 * k);
     AEAJ_REQUIRE(n_entries == 2 * per, "aeaj_plan_set_qtables: expected [luma sizes...][chroma sizes...] entries");
     AEAJ_CUDA(cudaSetDevice(p->h->device));
-    if (!p->qtab_dev) AEAJ_CUDA(cudaMalloc(&p->qtab_dev, sizeof(int32_t) * n_entries));
+    if (!p->qtab_dev) {
+        AEAJ_CUDA(cudaMalloc(&p->qtab_dev, sizeof(int32_t) * n_entries));
+        AEAJ_CUDA(cudaMalloc(&p->qtabf_dev, sizeof(float) * n_entries));
+    }
     p->qtab_entries = n_entries;
+    std::vector<float> asf(n_entries);
+    for (size_t i = 0; i < n_entries; i++) asf[i] = (float)tables[i];           // entries <= 6050 (quality 1): exact
     AEAJ_CUDA(cudaMemcpyAsync(p->qtab_dev, tables, sizeof(int32_t) * n_entries, cudaMemcpyHostToDevice, ST(stream)));
+    AEAJ_CUDA(cudaMemcpyAsync(p->qtabf_dev, asf.data(), sizeof(float) * n_entries, cudaMemcpyHostToDevice, ST(stream)));
+    AEAJ_CUDA(cudaStreamSynchronize(ST(stream)));                                // `asf` is a temporary
     size_t o = 0;
     for (int t = 0; t < 2; t++)
-        for (int k = p->lg_min; k <= p->lg_max; k++) { p->qtab_ptr[t][k] = p->qtab_dev + o; o += (size_t)1 << (2 * k); }
+        for (int k = p->lg_min; k <= p->lg_max; k++) { p->qtab_ptr[t][k] = p->qtab_dev + o; p->qtabf_ptr[t][k] = p->qtabf_dev + o; o += (size_t)1 << (2 * k); }
     for (int i = 0; i < p->nplanes; i++)
-        for (int k = 0; k < 9; k++) p->planes[i].qtab[k] = p->qtab_ptr[p->planes[i].layer ? 1 : 0][k];
+        for (int k = 0; k < 9; k++) {
+            p->planes[i].qtab[k] = p->qtab_ptr[p->planes[i].layer ? 1 : 0][k];
+            p->planes[i].qtabf[k] = p->qtabf_ptr[p->planes[i].layer ? 1 : 0][k];
+        }
     return 0;
 }
 

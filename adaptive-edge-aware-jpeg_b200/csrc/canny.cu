@@ -643,7 +643,6 @@ __device__ __forceinline__ void hyst_process_tile(const PlaneDesc* __restrict__ 
     unsigned nb = 0;
     if (inb && s != s_init) {
         atomicOr(P.strong + (size_t)gy * P.wpr + gw, s);
-        __threadfence();                                                       // the new bits are visible before any push below
         // which of the 8 neighbours can see the new bits (bit index = (dy+1)*3 + (dx+1))
         const unsigned diff = s ^ s_init;
         const bool L = (tc == 0) && (diff & 1u), R = (tc == HY_WW - 1) && (diff >> 31);
@@ -653,6 +652,11 @@ __device__ __forceinline__ void hyst_process_tile(const PlaneDesc* __restrict__ 
         if (R) nb |= 32u;
     }
     if (nb) atomicOr(sNbr, (int)nb);
+    __syncthreads();
+    if (*sNbr == 0) return;                                                    // nothing a neighbour could see (uniform)
+    // ONE gpu-scope fence per pass that pushes (a fence invalidates the SM's L1, so not one per thread): it orders the
+    // atomic ORs of all threads of the CTA (observed through the barrier above) before the pushes below
+    if (tid == 0) __threadfence();
     __syncthreads();
     if (tid < 9 && tid != 4 && ((*sNbr >> tid) & 1)) {
         const int dy = tid / 3 - 1, dx = tid % 3 - 1;
@@ -693,7 +697,9 @@ __global__ void __launch_bounds__(HY_THREADS) k_hysteresis(const PlaneDesc* __re
                 const int f = atomicAdd(&q.ctrl[HY_NEXT], 1);
                 if (f < q.ntiles) t = f;
             }
-            if (t >= 0) { atomicExch(&q.flags[t], 0); __threadfence(); }       // from here on a neighbour's new bits need a new push
+            // from here on a neighbour's new bits need a new push.  No fence: the loads of the pass read L2 (ld.cg) and are issued
+            // after this atomic has returned (barrier below), so they see every store that preceded a dropped push
+            if (t >= 0 && atomicExch(&q.flags[t], 0) == 0x7fffffff) t = -1;    // (never true: forces the value-returning form)
             sTile = t;
         }
         __syncthreads();

@@ -667,11 +667,15 @@ int launch_all(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* cl
             case 1: rc = launch_rows<2, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
             case 2: rc = launch_rows<4, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
             case 3: rc = launch_rows<8, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
-            case 4: rc = launch_rows<16, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
-            case 5: rc = launch_rows<32, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
-            case 6: rc = launch_cta<64, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
-            case 7: rc = tensor_dct ? launch_dct_tc128(h, planes_dev, list, cnt, caps[lg], INV ? 1 : 0, st)
-                                              : launch_cta<128, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
+            // tensor_dct bit k: size class 16 << k runs on the tcgen05 kernels of dct_tc.cu, else on the FP32 kernels of this file
+            case 4: rc = (tensor_dct & 1) ? launch_dct_tc(h, 16, planes_dev, list, cnt, caps[lg], INV ? 1 : 0, st)
+                                          : launch_rows<16, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
+            case 5: rc = (tensor_dct & 2) ? launch_dct_tc(h, 32, planes_dev, list, cnt, caps[lg], INV ? 1 : 0, st)
+                                          : launch_rows<32, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
+            case 6: rc = (tensor_dct & 4) ? launch_dct_tc(h, 64, planes_dev, list, cnt, caps[lg], INV ? 1 : 0, st)
+                                          : launch_cta<64, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
+            case 7: rc = (tensor_dct & 8) ? launch_dct_tc(h, 128, planes_dev, list, cnt, caps[lg], INV ? 1 : 0, st)
+                                          : launch_cta<128, INV>(h, planes_dev, list, cnt, caps[lg], st); break;
             case 8: rc = launch_256<INV>(h, planes_dev, list, cnt, caps[lg], scratch256, st); break;
             default: aeaj_set_error("block size %d not supported (2..256)", 1 << lg); return AEAJ_EINVAL;
         }

@@ -1,18 +1,26 @@
-// dct_tc.cu -- 128x128 DCT + quantise / dequantise + IDCT on the 5th-generation tensor cores (tcgen05, TMEM),
-// error-compensated 3xTF32:  Out = A.X.A^T  (A = C forward, C^T inverse) with every operand split as v = hi + lo
-// (hi = top 11 mantissa bits, exactly representable in TF32) and  P.Q ~= Ph.Qh + Ph.Ql + Pl.Qh  accumulated in
-// FP32 in tensor memory.
+// dct_tc.cu -- DCT + quantise / dequantise + IDCT for the size classes 16 .. 128 on the 5th-generation tensor cores
+// (tcgen05, TMEM), error-compensated 3xTF32.
 //
-// Default path for 128x128 leaves (aeaj_plan_set_tensor_dct(plan, 0) selects the FP32-FMA kernels of dct.cu): the
-// parity bar for the forward DCT is the quantiser (tie class T-DCT) and for the inverse the <= 1 LSB / 3e-6 bound of
-// the decoded samples; tests/test_gpu_parity.py::test_tensor_core_dct_parity compares both paths against the oracle.
+// One kernel shape for every class: a CTA transforms a 128 x 128 SUPER-TILE that holds (128/S)^2 leaves of size S
+// (S = 128: one leaf) as   Out = A . X . A^T   with A = blockdiag(C_S, .., C_S) forward and blockdiag(C_S^T, ..) inverse:
+// the (p, q) sub-block of Out is C_S . X_pq . C_S^T, i.e. the 2-D DCT of leaf (p, q).  Small leaves therefore run at
+// the same per-sample cost as 128 x 128 ones, on the tensor pipe instead of through shared-memory-bound FP32 loops.
+// Every operand is split as v = hi + lo (both rounded to nearest TF32) and  P.Q ~= Ph.Qh + Ph.Ql + Pl.Qh  accumulates
+// in FP32 in tensor memory: the error is at FP32 rounding level, the parity bar is the exact quantiser (tie class T-DCT)
+// forward and the <= 1 LSB / 3e-6 bound of the decoded samples inverse (tests/test_gpu_parity.py).
 //
-// One CTA (256 threads) per 128x128 leaf, persistent over the size-128 work list:
-//   GEMM1  W = A . X      A tile (smem, K-major, hi/lo)         B = X^T (smem, K-major, hi/lo; four 32-row K chunks)
+// One persistent CTA (256 threads) per SM over the super-tiles of a class:
+//   GEMM1  W = A . X      A tiles (smem, K-major, hi/lo; 128 KB, loaded once)   B = X^T (smem, K-major, hi/lo), streamed
+//                         in four K chunks of 32 super-rows through two buffers guarded by mbarriers (tcgen05.commit)
 //   split  W -> Wh, Wl    TMEM -> registers -> TMEM (tcgen05.ld / tcgen05.st)
-//   GEMM2  Out = W . A^T  A operand = W (TMEM, hi/lo)           B = the same shared-memory tiles as GEMM1's A
-//   epilogue: tcgen05.ld -> smem staging -> exact float32 quantiser -> int32 coefficients   (forward)
-//                                        -> de-normalise, crop -> float32 layer samples    (inverse)
+//   GEMM2  Out = W . A^T  A operand = W (TMEM, hi/lo)   B = the same shared-memory tiles as GEMM1's A; A is block
+//                         diagonal, so every K step only needs the N = S columns of its own block
+//   epilogue: tcgen05.ld -> registers -> exact float32 quantiser -> 256-bit stores of int32 coefficients     (forward)
+//                                     -> de-normalise, crop -> 256-bit stores of float32 layer samples       (inverse)
+// Software pipeline: the loads of a tile's first two chunks are issued while the previous tile is in GEMM1; their
+// conversion / stores and MMAs are issued right after the previous tile's GEMM2 is launched, so the tensor pipe works on
+// GEMM2(i) and the head of GEMM1(i+1) while the CUDA cores run the epilogue of tile i straight out of tensor memory
+// (no shared-memory staging: D2 stays valid because GEMM1 writes D1).
 // Shared-memory operands use the canonical no-swizzle K-major layout: [K/4 chunks][rows][4 floats], i.e. 8x16-byte
 // core matrices, stride-byte-offset 128 B (next 8 rows), leading-byte-offset rows*16 B (next K chunk).
 #include "aeaj_internal.cuh"
@@ -72,44 +80,45 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
                     "r"(v[30]), "r"(v[31])
                  : "memory");
 }
+// 256-bit global stores (sm_100): one full 32-byte sector per instruction and thread
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* v) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 // round to the nearest TF32 value (10 explicit mantissa bits; ties away from zero).  The tensor core truncates the low 13
 // bits of an FP32 operand, so both parts are rounded here: hi = rn(v), lo = rn(v - hi) leaves |v - hi - lo| <= 2^-24 |v|
 // and |lo| <= 2^-12 |v|, i.e. the dropped lo.lo product and the representation error are both at FP32 rounding level.
 __device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) { hi = tf32_rn(v); lo = tf32_rn(__fsub_rn(v, hi)); }
 
-struct LeafGeo {
-    float* base;            // layer + e.y * w + e.x
+// one leaf of the current super-tile (shared memory)
+struct TcLeaf {
+    float* base;            // layer + y * w + x (forward: source, inverse: destination); nullptr: empty slot / leaf of another band
     int* cf;                // coefficient block of this leaf
-    const int* qt;          // quantiser table (128 x 128)
-    const int* zz;          // zigzag order, or nullptr for the row-major stream
-    int w, bh, bw;
+    const float* qf;        // quantiser steps as float, S x S (forward)
+    const int* qi;          // quantiser steps, S x S (inverse)
+    int w, bh, bw, zig;
     float mid, sc;
-    int col[4];             // the four columns (g + 32 q) this thread reads, reflect-padded
-    bool fast;
 };
 
-// c_tiles: [Ch | Cl], each TC_N*TC_N floats in the canonical layout [K/4][128][4] (built on the host)
-//
-// Pipeline of one leaf (all 256 threads unless noted):
-//   GEMM1 runs over K (= rows of X) in four chunks of 32 rows.  A chunk is 32 x 128 samples: thread (warp kc, lane g)
-//   holds rows 4kc..4kc+3 of columns g, g+32, g+64, g+96 in registers (coalesced 128-byte loads, issued two chunks
-//   ahead -- the first two chunks of the NEXT leaf are fetched while this leaf is in GEMM2 / the epilogue), splits them
-//   into hi/lo and stores them into one of two K-major shared-memory buffers (16-byte stores, conflict free); thread 0
-//   then issues the 12 MMAs (N = 128) of that chunk and commits to the buffer's mbarrier, which the stores of chunk c+2
-//   wait for.  split / GEMM2 / epilogue as described in the file header.
-template <bool INV>
-__global__ void __launch_bounds__(256, 1) k_dct_tc128(const PlaneDesc* __restrict__ planes, const ClassEntry* __restrict__ list,
-                                                      const int* __restrict__ count_ptr, const float* __restrict__ c_tiles,
-                                                      const int* __restrict__ izz, int* __restrict__ err) {
+// a_tiles: [Ah | Al], each 128 x 128 floats in the canonical layout [K/4][128][4] (built on the host): blockdiag(C_S) or its transpose
+// izz: inverse zigzag permutation of an S x S block (row-major index -> stream position)
+template <int S, bool INV>
+__global__ void __launch_bounds__(256, 1) k_dct_tc(const PlaneDesc* __restrict__ planes, const ClassEntry* __restrict__ list,
+                                                   const int* __restrict__ count_ptr, const float* __restrict__ a_tiles,
+                                                   const int* __restrict__ izz, int* __restrict__ err) {
+    constexpr int NB = TC_N / S;                                          // leaves per super-tile side
+    constexpr int NL = NB * NB;                                           // leaves per super-tile
+    constexpr int LG = (S == 16) ? 4 : (S == 32) ? 5 : (S == 64) ? 6 : 7;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     float* sCh = reinterpret_cast<float*>(smem_raw);                     // 64 KB
     float* sCl = sCh + TC_N * TC_N;                                      // 64 KB
-    float* sX = sCl + TC_N * TC_N;                                       // 2 buffers x (hi 16 KB + lo 16 KB); the epilogue's staging tile
+    float* sX = sCl + TC_N * TC_N;                                       // 2 buffers x (hi 16 KB + lo 16 KB)
     __shared__ __align__(8) unsigned long long mbar_storage[3];
     __shared__ uint32_t tmem_base_s;
+    __shared__ TcLeaf sLeaf[2][NL];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < 2 * TC_N * TC_N / 4; i += 256) reinterpret_cast<float4*>(sCh)[i] = __ldg(reinterpret_cast<const float4*>(c_tiles) + i);
+    for (int i = tid; i < 2 * TC_N * TC_N / 4; i += 256) reinterpret_cast<float4*>(sCh)[i] = __ldg(reinterpret_cast<const float4*>(a_tiles) + i);
     const uint32_t bar0 = smem_u32(&mbar_storage[0]), bar1 = smem_u32(&mbar_storage[1]), bar2 = smem_u32(&mbar_storage[2]);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar0) : "memory");
@@ -128,65 +137,81 @@ __global__ void __launch_bounds__(256, 1) k_dct_tc128(const PlaneDesc* __restric
     const uint32_t tbase = tmem_base_s;
     const uint32_t D1 = tbase, WH = tbase + 128, WL = tbase + 256, D2 = tbase + 384;
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;          // this warp's 32 TMEM lanes (warps w and w+4 share a quadrant)
-    const int row = (warp & 3) * 32 + lane;                               // the matrix row this thread reads from TMEM
+    const int row = (warp & 3) * 32 + lane;                               // the super-tile row this thread reads from TMEM
     const int cbeg = (warp >> 2) * 2;                                     // ... and its two 32-column chunks
     const uint32_t aCh = smem_u32(sCh), aCl = smem_u32(sCl), aX = smem_u32(sX);
     const int count = *count_ptr;
+    const int ntiles = (count + NL - 1) / NL;
 
-    auto next_valid = [&](int li) {
-        while (li < count) {
-            const ClassEntry e = list[li];
-            const PlaneDesc& P = planes[e.plane];
-            if (e.y >= P.ry0 && e.y < P.ry1) break;
-            li += gridDim.x;
+    // leaf table of one super-tile: slot t = p * NB + q holds list entry tile * NL + t
+    auto fill_table = [&](int buf, int tile) {
+        if (tid < NL) {
+            TcLeaf L;
+            L.base = nullptr; L.cf = nullptr; L.qf = nullptr; L.qi = nullptr; L.w = 0; L.bh = 0; L.bw = 0; L.zig = 0; L.mid = 0.0f; L.sc = 1.0f;
+            const int li = tile * NL + tid;
+            if (li < count) {
+                const ClassEntry e = list[li];
+                const PlaneDesc& P = planes[e.plane];
+                if (e.y >= P.ry0 && e.y < P.ry1) {                        // halo-split: only the leaves of this call's band
+                    L.base = P.layer_f32 + (size_t)e.y * P.w + e.x;
+                    L.cf = P.coef + (size_t)e.coef_off;
+                    L.qf = P.qtabf[LG]; L.qi = P.qtab[LG];
+                    L.w = P.w; L.bh = min(S, P.h - e.y); L.bw = min(S, P.w - e.x);
+                    L.zig = P.zigzag; L.mid = P.mid; L.sc = P.scale;
+                }
+            }
+            sLeaf[buf][tid] = L;
         }
-        return li;
     };
-    auto geo_of = [&](int li) {
-        const ClassEntry e = list[li];
-        const PlaneDesc& P = planes[e.plane];
-        LeafGeo G;
-        G.w = P.w; G.bh = min(TC_N, P.h - e.y); G.bw = min(TC_N, P.w - e.x);
-        G.base = P.layer_f32 + (size_t)e.y * P.w + e.x;
-        G.cf = P.coef + (size_t)e.coef_off;
-        G.qt = P.qtab[7];
-        G.zz = P.zigzag ? P.zz[7] : nullptr;
-        G.mid = P.mid; G.sc = P.scale;
-        G.fast = (G.bh == TC_N && G.bw == TC_N);
+    // registers of two chunks in flight: thread (warp kc, lane g) holds super-rows 32c + 4kc .. +3 of columns g, g+32, g+64, g+96
+    uint32_t xr[2][4][4];
+    int xq[INV ? 2 : 1][4][4];                                            // inverse: the quantiser steps of the same positions
+    auto load_chunk = [&](const TcLeaf* T, int c, int slot) {
+        const int r0 = 32 * c + 4 * warp;                                 // super-row of r = 0; the four rows stay inside one leaf row block
+        const int p = r0 / S, li0 = r0 % S;
 #pragma unroll
-        for (int q = 0; q < 4; q++) G.col[q] = G.fast ? lane + 32 * q : pad_reflect(lane + 32 * q, G.bw);
-        return G;
-    };
-    uint32_t xr[2][4][4];                                                 // two chunks in flight (raw bits): [slot][row r][column q]
-    // quantiser steps kept in registers for the whole run of leaves that share a table (luma <-> chroma changes only):
-    // forward: the 64 positions this thread quantises in the epilogue; inverse: the 64 positions it loads
-    // (packed with the position of the coefficient in the block's stream: row-major, or zigzag through izz: pos << 16 | q)
-    float fq[16][4];
-    uint32_t iq[4][4][4];
-    auto load_chunk = [&](const LeafGeo& G, int c, int slot) {
+        for (int q = 0; q < 4; q++) {
+            const int j = lane + 32 * q;
+            const TcLeaf& L = T[p * NB + j / S];
+            const int lj = j % S;
+            if (L.base == nullptr) {
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int i = 32 * c + 4 * warp + r;
+                for (int r = 0; r < 4; r++) { xr[slot][r][q] = 0u; if (INV) xq[INV ? slot : 0][r][q] = 0; }
+                continue;
+            }
             if (INV) {
 #pragma unroll
-                for (int q = 0; q < 4; q++) xr[slot][r][q] = (uint32_t)__ldg(G.cf + (iq[c][r][q] >> 16));
+                for (int r = 0; r < 4; r++) {
+                    const int nat = (li0 + r) * S + lj;
+                    xr[slot][r][q] = (uint32_t)__ldg(L.cf + (L.zig ? __ldg(izz + nat) : nat));
+                    xq[INV ? slot : 0][r][q] = __ldg(L.qi + nat);
+                }
             } else {
-                const float* rp = G.base + (size_t)(G.fast ? i : pad_reflect(i, G.bh)) * G.w;
+                const bool fast = (L.bh == S && L.bw == S);
+                const int col = fast ? lj : pad_reflect(lj, L.bw);
 #pragma unroll
-                for (int q = 0; q < 4; q++) xr[slot][r][q] = __float_as_uint(__ldg(rp + G.col[q]));
+                for (int r = 0; r < 4; r++) {
+                    const int rr = fast ? li0 + r : pad_reflect(li0 + r, L.bh);
+                    xr[slot][r][q] = __float_as_uint(__ldg(L.base + (size_t)rr * L.w + col));
+                }
             }
         }
     };
-    auto store_chunk = [&](const LeafGeo& G, int c, int slot) {         // registers -> hi/lo K-major tiles of buffer `slot`
+    auto store_chunk = [&](const TcLeaf* T, int c, int slot) {           // registers -> hi/lo K-major tiles of buffer `slot`
         float* xh = sX + slot * 8192;
         float* xl = xh + 4096;
+        const int p = (32 * c + 4 * warp) / S;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
+            const TcLeaf& L = T[p * NB + (lane + 32 * q) / S];
+            const bool live = (L.base != nullptr);
+            const float mid = L.mid, sc = L.sc;
             float hi[4], lo[4];
 #pragma unroll
             for (int r = 0; r < 4; r++) {
-                const float x = INV ? (float)((int)xr[slot][r][q] * (int)(iq[c][r][q] & 0xffffu))      // jpeg.py:524
-                                    : __fmul_rn(__fsub_rn(__uint_as_float(xr[slot][r][q]), G.mid), G.sc);
+                float x = INV ? (float)((int)xr[slot][r][q] * xq[INV ? slot : 0][r][q])          // jpeg.py:524
+                              : __fmul_rn(__fsub_rn(__uint_as_float(xr[slot][r][q]), mid), sc);   // jpeg.py:387-390
+                x = live ? x : 0.0f;
                 tf32_split(x, hi[r], lo[r]);
             }
             const int o = (warp * TC_N + lane + 32 * q) * 4;
@@ -194,77 +219,60 @@ __global__ void __launch_bounds__(256, 1) k_dct_tc128(const PlaneDesc* __restric
             *reinterpret_cast<float4*>(xl + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
     };
+    // thread 0: the 12 MMAs of K chunk c (W += A[:, 32c .. 32c+31] . X[32c .. 32c+31, :]) and the commit that releases buffer c & 1
+    auto issue_gemm1_chunk = [&](int c) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t idesc = TC_IDESC_BASE | ((128u >> 3) << 17);
+        const int b = c & 1;
+        const uint32_t xh = aX + b * 32768, xl = xh + 16384;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const uint32_t ao = (c * 4 + s) * (TC_N * 32);
+            const uint64_t ah = make_desc(aCh + ao, TC_N * 16, 128), al = make_desc(aCl + ao, TC_N * 16, 128);
+            const uint64_t bh_ = make_desc(xh + s * (TC_N * 32), TC_N * 16, 128), bl = make_desc(xl + s * (TC_N * 32), TC_N * 16, 128);
+            mma_ss(D1, ah, bh_, idesc, (c | s) != 0);
+            mma_ss(D1, ah, bl, idesc, 1);
+            mma_ss(D1, al, bh_, idesc, 1);
+        }
+        mma_commit(b == 0 ? bar0 : bar1);
+    };
 
-    const int* cur_qt = nullptr;
-    const int* cur_zz = nullptr;
     uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
     bool alive = true;
-    int li = next_valid(blockIdx.x);
-    LeafGeo cur, nxt;
-    auto load_tables = [&](const LeafGeo& G) {                          // on a change of plane type only
-        cur_qt = G.qt; cur_zz = G.zz;
-        if (INV) {
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-#pragma unroll
-                for (int r = 0; r < 4; r++)
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int nat = (32 * c + 4 * warp + r) * TC_N + lane + 32 * q;
-                        const int pos = G.zz ? __ldg(izz + nat) : nat;
-                        iq[c][r][q] = ((uint32_t)pos << 16) | (uint32_t)__ldg(G.qt + nat);
-                    }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const int4 qv = __ldg(reinterpret_cast<const int4*>(G.qt) + tid + 256 * i);
-                fq[i][0] = (float)qv.x; fq[i][1] = (float)qv.y; fq[i][2] = (float)qv.z; fq[i][3] = (float)qv.w;
-            }
-        }
-    };
-    if (li < count) { cur = geo_of(li); load_tables(cur); load_chunk(cur, 0, 0); load_chunk(cur, 1, 1); }
-    int leaf_no = 0;
-    while (li < count && alive) {
-        const int nli = next_valid(li + gridDim.x);
-        const bool has_next = nli < count;
-        if (has_next) nxt = geo_of(nli);
-        if (cur.qt != cur_qt || cur.zz != cur_zz) load_tables(cur);
-        const bool dbg = (blockIdx.x == 0 && tid == 0 && leaf_no == 2);   // phase clocks of one steady-state leaf -> err[1..]
-        long long t0 = clock64(); int ti = 1;
-#define TC_STAMP() do { if (dbg) { long long t1 = clock64(); err[ti++] = (int)(t1 - t0); t0 = t1; } } while (0)
-        // ---- GEMM1: W = C . X over four K chunks -----------------------------------------------------------
+    int tile = blockIdx.x, it = 0;
+    if (tile < ntiles) {
+        fill_table(0, tile);
+        __syncthreads();
+        load_chunk(sLeaf[0], 0, 0);
+        load_chunk(sLeaf[0], 1, 1);
+    }
+    while (tile < ntiles && alive) {
+        const TcLeaf* Tc = sLeaf[it & 1];
+        const TcLeaf* Tn = sLeaf[(it + 1) & 1];
+        const int ntile = tile + gridDim.x;
+        const bool has_next = ntile < ntiles;
+        __syncthreads();                                                   // the previous tile's epilogue is done with the other table
+        if (has_next) fill_table((it + 1) & 1, ntile);
+        __syncthreads();
+        // ---- GEMM1: W = A . X.  Chunks 0 and 1 of every tile but a CTA's first were stored and issued at the end of the
+        //      previous iteration (behind that tile's GEMM2).
 #pragma unroll
         for (int c = 0; c < 4; c++) {
+            if (c < 2 && it > 0) continue;
             const int b = c & 1;
             if (c >= 2 && alive) {                                         // the MMAs of chunk c-2 have released buffer b
                 if (b == 0) { alive = mbar_wait(bar0, ph0, err); ph0 ^= 1; } else { alive = mbar_wait(bar1, ph1, err); ph1 ^= 1; }
             }
-            store_chunk(cur, c, b);
-            if (c < 2) load_chunk(cur, c + 2, b);
-            else if (has_next) load_chunk(nxt, c - 2, b);              // (stream positions: the layout is the same for all planes of a plan)
+            store_chunk(Tc, c, b);
+            if (c < 2) load_chunk(Tc, c + 2, b);
+            else if (has_next) load_chunk(Tn, c - 2, b);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();
-            if (tid == 0 && alive) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t idesc = TC_IDESC_BASE | ((128u >> 3) << 17);
-                const uint32_t xh = aX + b * 32768, xl = xh + 16384;
-#pragma unroll
-                for (int s = 0; s < 4; s++) {
-                    const uint32_t ao = (c * 4 + s) * (TC_N * 32);
-                    const uint64_t ah = make_desc(aCh + ao, TC_N * 16, 128), al = make_desc(aCl + ao, TC_N * 16, 128);
-                    const uint64_t bh_ = make_desc(xh + s * (TC_N * 32), TC_N * 16, 128), bl = make_desc(xl + s * (TC_N * 32), TC_N * 16, 128);
-                    mma_ss(D1, ah, bh_, idesc, (c | s) != 0);
-                    mma_ss(D1, ah, bl, idesc, 1);
-                    mma_ss(D1, al, bh_, idesc, 1);
-                }
-                mma_commit(b == 0 ? bar0 : bar1);
-            }
-            TC_STAMP();
+            if (tid == 0 && alive) issue_gemm1_chunk(c);
         }
         if (alive) { alive = mbar_wait(bar0, ph0, err); ph0 ^= 1; }
         if (alive) { alive = mbar_wait(bar1, ph1, err); ph1 ^= 1; }
-        TC_STAMP();
         if (!alive) break;
         // ---- split W = Wh + Wl inside tensor memory ------------------------------------------------------
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -285,126 +293,173 @@ __global__ void __launch_bounds__(256, 1) k_dct_tc128(const PlaneDesc* __restric
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        TC_STAMP();
-        // ---- GEMM2: Out = W . C^T -------------------------------------------------------------------------
+        // ---- GEMM2: Out = W . A^T.  A is block diagonal: K step s (columns 8s .. 8s+7 of W) only feeds the S output
+        //      columns of its own block.
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t idesc = TC_IDESC_BASE | ((128u >> 3) << 17);
+            const uint32_t idesc = TC_IDESC_BASE | (((uint32_t)S >> 3) << 17);
+#pragma unroll 4
             for (int s = 0; s < TC_N / 8; s++) {
-                const uint64_t bh_ = make_desc(aCh + s * (TC_N * 32), TC_N * 16, 128), bl = make_desc(aCl + s * (TC_N * 32), TC_N * 16, 128);
-                mma_ts(D2, WH + s * 8, bh_, idesc, s > 0);
-                mma_ts(D2, WH + s * 8, bl, idesc, 1);
-                mma_ts(D2, WL + s * 8, bh_, idesc, 1);
+                const int n0 = (8 * s / S) * S;                            // first output column of the block
+                const uint32_t bo = s * (TC_N * 32) + n0 * 16;             // K chunk pair s, tile rows n0 ..
+                const uint64_t bh_ = make_desc(aCh + bo, TC_N * 16, 128), bl = make_desc(aCl + bo, TC_N * 16, 128);
+                const uint32_t first = (8 * s % S) == 0 ? 0u : 1u;         // first K step of a block overwrites its columns
+                mma_ts(D2 + n0, WH + s * 8, bh_, idesc, first);
+                mma_ts(D2 + n0, WH + s * 8, bl, idesc, 1);
+                mma_ts(D2 + n0, WL + s * 8, bh_, idesc, 1);
             }
             mma_commit(bar2);
         }
-        TC_STAMP();
+        // ---- head of the next tile's GEMM1 behind GEMM2 (both X buffers and D1 are free: all of this tile's GEMM1 MMAs have
+        //      completed and W has been copied out of D1)
+        if (has_next) {
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                store_chunk(Tn, c, c);
+                load_chunk(Tn, c + 2, c);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncthreads();
+                if (tid == 0) issue_gemm1_chunk(c);
+            }
+        }
         alive = mbar_wait(bar2, ph2, err);
         ph2 ^= 1;
-        TC_STAMP();
         if (!alive) break;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- epilogue: TMEM -> shared staging (row-major, 16-byte groups XOR-swizzled by the row so that the
-        //      row-per-thread writes are bank-conflict free) -> coalesced quantise + store by all threads
-        float* stage = sX;                                                 // 128 x 128 floats: the X buffers are free now
+        // ---- epilogue straight from tensor memory: this thread owns super-row `row`, columns 32 cbeg .. 32 cbeg + 63
+        {
+            const int p = row / S, li = row % S;
 #pragma unroll 1
-        for (int c = cbeg; c < cbeg + 2; c++) {
-            uint32_t v[32];
-            tmem_ld32(D2 + lane_sel + c * 32, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int c = cbeg; c < cbeg + 2; c++) {
+                uint32_t v[32];
+                tmem_ld32(D2 + lane_sel + c * 32, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int i = 0; i < 8; i++)
-                *reinterpret_cast<float4*>(stage + row * TC_N + c * 32 + ((i ^ (row & 7)) * 4)) =
-                    make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        TC_STAMP();
-        if (INV) {
-            const bool vec = (cur.w & 3) == 0;
+                for (int g = 0; g < 4; g++) {
+                    const int j = c * 32 + g * 8;                          // 8 consecutive columns: inside one leaf (8 | S)
+                    const TcLeaf& L = Tc[p * NB + j / S];
+                    const int lj = j % S;
+                    if (L.base == nullptr) continue;
+                    if (INV) {
+                        if (li >= L.bh) continue;
+                        float* rp = L.base + (size_t)li * L.w + lj;
+                        uint32_t o[8];
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const int idx = tid + 256 * i, r = idx >> 5, j4 = idx & 31;
-                const float4 z = *reinterpret_cast<const float4*>(stage + r * TC_N + (((j4 & ~7) | ((j4 & 7) ^ (r & 7))) * 4));
-                const float v[4] = {__fadd_rn(__fdiv_rn(z.x, cur.sc), cur.mid), __fadd_rn(__fdiv_rn(z.y, cur.sc), cur.mid),
-                                    __fadd_rn(__fdiv_rn(z.z, cur.sc), cur.mid), __fadd_rn(__fdiv_rn(z.w, cur.sc), cur.mid)};
-                if (r < cur.bh) {
-                    float* rp = cur.base + (size_t)r * cur.w + 4 * j4;
-                    if (vec && 4 * j4 + 3 < cur.bw) *reinterpret_cast<float4*>(rp) = make_float4(v[0], v[1], v[2], v[3]);
-                    else {
+                        for (int k = 0; k < 8; k++) o[k] = __float_as_uint(__fadd_rn(__fdiv_rn(__uint_as_float(v[g * 8 + k]), L.sc), L.mid));   // jpeg.py:452-455
+                        if (lj + 7 < L.bw && (reinterpret_cast<uintptr_t>(rp) & 31) == 0) st_global_v8(rp, o);
+                        else {
 #pragma unroll
-                        for (int k = 0; k < 4; k++) if (4 * j4 + k < cur.bw) rp[k] = v[k];
+                            for (int k = 0; k < 8; k++) if (lj + k < L.bw) rp[k] = __uint_as_float(o[k]);
+                        }
+                    } else {
+                        const int nat = li * S + lj;
+                        const float4 qa = __ldg(reinterpret_cast<const float4*>(L.qf + nat)), qb = __ldg(reinterpret_cast<const float4*>(L.qf + nat) + 1);
+                        const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+                        uint32_t o[8];
+#pragma unroll
+                        for (int k = 0; k < 8; k++) o[k] = (uint32_t)quantize_f(__uint_as_float(v[g * 8 + k]), qv[k]);
+                        if (!L.zig) {
+                            int* dst = L.cf + nat;                             // 32-byte aligned unless 2 x 2 leaves precede the block
+                            if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) st_global_v8(dst, o);
+                            else {
+                                *reinterpret_cast<int4*>(dst) = make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]);
+                                *reinterpret_cast<int4*>(dst + 4) = make_int4((int)o[4], (int)o[5], (int)o[6], (int)o[7]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 8; k++) L.cf[__ldg(izz + nat + k)] = (int)o[k];
+                        }
                     }
                 }
             }
-        } else {
-            const bool zig = cur.zz != nullptr;
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const int idx = tid + 256 * i, r = idx >> 5, j4 = idx & 31;
-                float* sp = stage + r * TC_N + (((j4 & ~7) | ((j4 & 7) ^ (r & 7))) * 4);
-                const float4 z = *reinterpret_cast<const float4*>(sp);
-                const int4 o = make_int4(quantize_f(z.x, fq[i][0]), quantize_f(z.y, fq[i][1]), quantize_f(z.z, fq[i][2]), quantize_f(z.w, fq[i][3]));
-                if (zig) *reinterpret_cast<int4*>(sp) = o;                 // in place; gathered in stream order below
-                else reinterpret_cast<int4*>(cur.cf)[idx] = o;
-            }
-            if (zig) {
-                __syncthreads();
-                const int* si = reinterpret_cast<const int*>(stage);
-#pragma unroll 4
-                for (int i = tid; i < TC_N * TC_N; i += 256) {
-                    const int z = __ldg(cur.zz + i), r = z >> 7, j = z & 127;
-                    cur.cf[i] = si[r * TC_N + ((((j >> 2) & ~7) | (((j >> 2) & 7) ^ (r & 7))) * 4) + (j & 3)];
-                }
-            }
         }
-        TC_STAMP();
-        __syncthreads();                                                   // the staging tile / TMEM are free for the next leaf
-        li = nli; cur = nxt; leaf_no++;
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        tile = ntile; it++;
     }
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tbase) : "memory");
 }
 
+constexpr int tc_slot(int S) { return S == 16 ? 0 : S == 32 ? 1 : S == 64 ? 2 : 3; }
+
+template <int S>
+int set_attrs() {
+    AEAJ_CUDA(cudaFuncSetAttribute(k_dct_tc<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    AEAJ_CUDA(cudaFuncSetAttribute(k_dct_tc<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    return 0;
+}
+
+template <int S>
+int launch_one(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* list, const int* count, int64_t cap, int inverse, cudaStream_t st) {
+    constexpr int NL = (TC_N / S) * (TC_N / S);
+    const int64_t tiles = std::max<int64_t>((cap + NL - 1) / NL, 1);
+    const int blocks = (int)std::min<int64_t>(tiles, (int64_t)h->sm_count);
+    const float* a = h->dct_tc_tiles_dev + (size_t)(tc_slot(S) * 2 + (inverse ? 1 : 0)) * 2 * TC_N * TC_N;
+    const int* izz = h->tc_izz_dev[tc_slot(S)];
+    if (inverse) k_dct_tc<S, true><<<blocks, 256, TC_SMEM_BYTES, st>>>(planes_dev, list, count, a, izz, h->tc_err_dev);
+    else k_dct_tc<S, false><<<blocks, 256, TC_SMEM_BYTES, st>>>(planes_dev, list, count, a, izz, h->tc_err_dev);
+    AEAJ_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace
 
-// tiles [fwd: Ch | Cl][inv: Ch | Cl] in the canonical K-major layout: element (row r, k) at (k/4)*(128*4) + r*4 + (k%4);
-// forward tile element (r, k) = C[r][k], inverse tile element (r, k) = C[k][r]
+// tiles per class S in {16, 32, 64, 128} and direction: [Ah | Al] in the canonical K-major layout, element (row r, k) at
+// (k/4)*(128*4) + r*4 + (k%4); forward A = blockdiag(C_S), inverse A = blockdiag(C_S^T)
 int aeaj_dct_tc_init(aeaj_handle* h) {
     const int N = TC_N;
-    AEAJ_CUDA(cudaFuncSetAttribute(k_dct_tc128<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-    AEAJ_CUDA(cudaFuncSetAttribute(k_dct_tc128<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-    std::vector<float> host(4 * (size_t)N * N);
-    for (int inv = 0; inv < 2; inv++)
-        for (int r = 0; r < N; r++)
-            for (int k = 0; k < N; k++) {
-                const int u = inv ? k : r, x = inv ? r : k;                  // C[u][x] = a(u) cos(pi (2x+1) u / 2N)
-                double v = sqrt(2.0 / N) * cos(M_PI * (2 * x + 1) * u / (2.0 * N));
-                if (u == 0) v *= sqrt(0.5);
-                const float c = (float)v;
-                auto rn = [](float f) { uint32_t b; memcpy(&b, &f, 4); b = (b + 0x1000u) & 0xffffe000u; memcpy(&f, &b, 4); return f; };
-                const float hi = rn(c);
-                const size_t o = (size_t)inv * 2 * N * N + (size_t)(k / 4) * (N * 4) + (size_t)r * 4 + (k % 4);
-                host[o] = hi; host[(size_t)N * N + o] = rn(c - hi);
-            }
+    int rc;
+    if ((rc = set_attrs<16>()) || (rc = set_attrs<32>()) || (rc = set_attrs<64>()) || (rc = set_attrs<128>())) return rc;
+    std::vector<float> host((size_t)4 * 2 * 2 * N * N, 0.0f);
+    auto rn = [](float f) { uint32_t b; memcpy(&b, &f, 4); b = (b + 0x1000u) & 0xffffe000u; memcpy(&f, &b, 4); return f; };
+    for (int slot = 0; slot < 4; slot++) {
+        const int S = 16 << slot;
+        for (int inv = 0; inv < 2; inv++) {
+            float* dst = host.data() + (size_t)(slot * 2 + inv) * 2 * N * N;
+            for (int r = 0; r < N; r++)
+                for (int k = 0; k < N; k++) {
+                    if (r / S != k / S) continue;                            // off-diagonal blocks stay zero
+                    const int rr = r % S, kk = k % S;
+                    const int u = inv ? kk : rr, x = inv ? rr : kk;          // C[u][x] = a(u) cos(pi (2x+1) u / 2S)
+                    double v = sqrt(2.0 / S) * cos(M_PI * (2 * x + 1) * u / (2.0 * S));
+                    if (u == 0) v *= sqrt(0.5);
+                    const float c = (float)v;
+                    const float hi = rn(c);
+                    const size_t o = (size_t)(k / 4) * (N * 4) + (size_t)r * 4 + (k % 4);
+                    dst[o] = hi; dst[(size_t)N * N + o] = rn(c - hi);
+                }
+        }
+    }
     AEAJ_CUDA(cudaMalloc(&h->dct_tc_tiles_dev, host.size() * sizeof(float)));
     AEAJ_CUDA(cudaMemcpy(h->dct_tc_tiles_dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
-    // inverse zigzag permutation for 128x128 (row-major index -> stream position), from the table aeaj_dct_init built
-    std::vector<int32_t> zz((size_t)N * N), izz((size_t)N * N);
-    AEAJ_CUDA(cudaMemcpy(zz.data(), h->zz_dev[7], zz.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < N * N; i++) izz[zz[i]] = i;
-    AEAJ_CUDA(cudaMalloc(&h->tc_izz_dev, izz.size() * sizeof(int32_t)));
-    AEAJ_CUDA(cudaMemcpy(h->tc_izz_dev, izz.data(), izz.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    // inverse zigzag permutations (row-major index -> stream position), from the tables aeaj_dct_init built
+    size_t total = 0;
+    for (int slot = 0; slot < 4; slot++) total += (size_t)(16 << slot) * (16 << slot);
+    AEAJ_CUDA(cudaMalloc(&h->tc_izz_all_dev, total * sizeof(int32_t)));
+    size_t off = 0;
+    for (int slot = 0; slot < 4; slot++) {
+        const int S = 16 << slot, n = S * S;
+        std::vector<int32_t> zz((size_t)n), izz((size_t)n);
+        AEAJ_CUDA(cudaMemcpy(zz.data(), h->zz_dev[4 + slot], zz.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; i++) izz[zz[i]] = i;
+        h->tc_izz_dev[slot] = h->tc_izz_all_dev + off;
+        AEAJ_CUDA(cudaMemcpy(h->tc_izz_dev[slot], izz.data(), izz.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        off += (size_t)n;
+    }
     AEAJ_CUDA(cudaMalloc(&h->tc_err_dev, 32 * sizeof(int)));
     AEAJ_CUDA(cudaMemset(h->tc_err_dev, 0, 32 * sizeof(int)));
     return 0;
 }
 
-int launch_dct_tc128(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* list, const int* count, int64_t cap, int inverse, cudaStream_t st) {
-    const size_t smem = TC_SMEM_BYTES;                  // opted in per device by aeaj_dct_tc_init
-    int blocks = (int)std::min<int64_t>(std::max<int64_t>(cap, 1), (int64_t)h->sm_count);
-    if (inverse) k_dct_tc128<true><<<blocks, 256, smem, st>>>(planes_dev, list, count, h->dct_tc_tiles_dev + 2 * TC_N * TC_N, h->tc_izz_dev, h->tc_err_dev);
-    else k_dct_tc128<false><<<blocks, 256, smem, st>>>(planes_dev, list, count, h->dct_tc_tiles_dev, h->tc_izz_dev, h->tc_err_dev);
-    AEAJ_LAUNCH_CHECK();
-    return 0;
+// size in {16, 32, 64, 128}
+int launch_dct_tc(aeaj_handle* h, int size, const PlaneDesc* planes_dev, const ClassEntry* list, const int* count, int64_t cap, int inverse, cudaStream_t st) {
+    switch (size) {
+        case 16: return launch_one<16>(h, planes_dev, list, count, cap, inverse, st);
+        case 32: return launch_one<32>(h, planes_dev, list, count, cap, inverse, st);
+        case 64: return launch_one<64>(h, planes_dev, list, count, cap, inverse, st);
+        case 128: return launch_one<128>(h, planes_dev, list, count, cap, inverse, st);
+    }
+    aeaj_set_error("tensor-core DCT: unsupported size %d", size);
+    return AEAJ_EINVAL;
 }

@@ -5,7 +5,7 @@ from aeaj.codec import get_codec
 from synth import synth
 c = get_codec(0)
 B = int(sys.argv[1]) if len(sys.argv)>1 else 4
-c.tensor_dct = len(sys.argv)>2 and sys.argv[2]=='1'
+c.tensor_dct = int(sys.argv[2], 0) if len(sys.argv)>2 else 0xf   # mask: bit k = class 16 << k on the tensor cores
 H,W=2160,3840
 rgb = torch.from_numpy(np.stack([synth(H,W,s) for s in range(B)])).cuda()
 sp,q,b='YCbCr',(30,95),(4,128)
