@@ -589,12 +589,14 @@ __global__ void __launch_bounds__(256) k_canny_nms(const PlaneDesc* __restrict__
 //
 // flags[t] != 0: tile t is queued or has not had its first pass (its next pass will load after any store that
 // precedes a push attempt, so the push can be dropped).  ring: tile ids, -1 = empty slot, capacity >= 2 x tiles.
-// ctrl (one 128-byte line each): [0] head  [32] tail  [64] next first-pass tile  [96] abort
+// ctrl (one 128-byte line each): [0] head  [32] tail  [64] next first-pass tile  [96] abort  [128] published entries not yet
+// claimed (a counting semaphore: a pop is one atomicSub + one atomicAdd, never a compare-and-swap retry loop -- with a
+// thousand CTAs looking for work at once, CAS retries on one word were 98 % of the first version's run time)
 // ---------------------------------------------------------------------------------------------
 constexpr int HY_WW = 8, HY_TR = 32;
 constexpr int HY_THREADS = HY_WW * HY_TR;
 constexpr int HY_SS = HY_WW + 3;                      // smem row stride (odd: lanes that differ in the row hit different banks)
-constexpr int HY_HEAD = 0, HY_TAIL = 32, HY_NEXT = 64, HY_ABORT = 96, HY_CTRL_INTS = 128;
+constexpr int HY_HEAD = 0, HY_TAIL = 32, HY_NEXT = 64, HY_ABORT = 96, HY_AVAIL = 128, HY_CTRL_INTS = 160;
 constexpr long long HY_SPIN_LIMIT = 20000000;         // a slot that is never published must not hang the GPU
 
 struct HystQueue { int* flags; int* ring; int* ctrl; int ring_mask; int ntiles; };
@@ -602,7 +604,11 @@ struct HystQueue { int* flags; int* ring; int* ctrl; int ring_mask; int ntiles; 
 __device__ __forceinline__ unsigned spread3(unsigned L, unsigned Cw, unsigned R) {
     return Cw | (Cw << 1) | (Cw >> 1) | (L >> 31) | (R << 31);
 }
-__device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ int ld_gpu(const int* p) {                     // one L2 read, gpu scope (a plain volatile load is system scope)
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // one pass over one tile: local convergence, atomic write-back, neighbour pushes
 __device__ __forceinline__ void hyst_process_tile(const PlaneDesc* __restrict__ planes, const TileMap& tm, int tile, const HystQueue& q,
@@ -668,6 +674,9 @@ __device__ __forceinline__ void hyst_process_tile(const PlaneDesc* __restrict__ 
                 long long spins = 0;
                 while (atomicCAS(&q.ring[slot], -1, nt) != -1)                 // the slot's previous ticket has not been read yet
                     if (++spins > HY_SPIN_LIMIT) { atomicExch(&q.ctrl[HY_ABORT], 1); break; }
+                // published (the CAS above has returned): one more entry may be claimed.  The value-returning form makes the
+                // increment complete before this CTA looks at the counter again after the barrier.
+                if (atomicAdd(&q.ctrl[HY_AVAIL], 1) == 0x7fffffff) atomicExch(&q.ctrl[HY_ABORT], 1);
             }
         }
     }
@@ -682,18 +691,16 @@ __global__ void __launch_bounds__(HY_THREADS) k_hysteresis(const PlaneDesc* __re
         __syncthreads();                                                       // pushes of the previous pass are out; sTile is free
         if (tid == 0) {
             int t = -1;
-            for (;;) {                                                         // 1. a queued re-visit
-                const int hd = ld_volatile(&q.ctrl[HY_HEAD]), tl = ld_volatile(&q.ctrl[HY_TAIL]);
-                if (hd >= tl) break;
-                if (atomicCAS(&q.ctrl[HY_HEAD], hd, hd + 1) != hd) continue;
-                const int slot = hd & q.ring_mask;
-                long long spins = 0;
-                while ((t = ld_volatile(&q.ring[slot])) == -1)                 // reserved, about to be published by a running CTA
-                    if (++spins > HY_SPIN_LIMIT) { atomicExch(&q.ctrl[HY_ABORT], 1); break; }
-                if (t >= 0) atomicExch(&q.ring[slot], -1);
-                break;
+            if (ld_gpu(&q.ctrl[HY_AVAIL]) > 0) {                               // 1. a queued re-visit
+                if (atomicSub(&q.ctrl[HY_AVAIL], 1) > 0) {                     // claimed one published entry: the ticket below exists
+                    const int slot = atomicAdd(&q.ctrl[HY_HEAD], 1) & q.ring_mask;
+                    long long spins = 0;
+                    while ((t = ld_gpu(&q.ring[slot])) == -1)                  // (an earlier ticket whose pusher is between its two atomics)
+                        if (++spins > HY_SPIN_LIMIT) { atomicExch(&q.ctrl[HY_ABORT], 1); break; }
+                    if (t >= 0) atomicExch(&q.ring[slot], -1);
+                } else atomicAdd(&q.ctrl[HY_AVAIL], 1);                        // lost the race for the last entry: give the count back
             }
-            if (t < 0 && ld_volatile(&q.ctrl[HY_NEXT]) < q.ntiles) {           // 2. a tile that has not had its first pass
+            if (t < 0 && ld_gpu(&q.ctrl[HY_NEXT]) < q.ntiles) {           // 2. a tile that has not had its first pass
                 const int f = atomicAdd(&q.ctrl[HY_NEXT], 1);
                 if (f < q.ntiles) t = f;
             }
@@ -708,8 +715,8 @@ __global__ void __launch_bounds__(HY_THREADS) k_hysteresis(const PlaneDesc* __re
         hyst_process_tile(planes, tm, tile, q, sS, &sNbr);
     }
     if (tid == 0 && status) {                                                  // the last CTAs to leave write the final values
-        status[0] = ld_volatile(&q.ctrl[HY_TAIL]);                             // tile re-visits in total
-        status[1] = ld_volatile(&q.ctrl[HY_ABORT]) ? 0 : 1;                    // converged
+        status[0] = ld_gpu(&q.ctrl[HY_TAIL]);                             // tile re-visits in total
+        status[1] = ld_gpu(&q.ctrl[HY_ABORT]) ? 0 : 1;                    // converged
     }
 }
 

@@ -377,8 +377,8 @@ def test_corrupt_streams_raise(codec):
     with pytest.raises(ValueError):
         Jpeg(JpegCompressionSettings()).decompress(bytes(patched))
     # C ABI: a hostile leaf list (sizes 0, 3, 512, negative / far positions, wild offsets) is skipped and counted
-    H, W, space, q, b = 96, 160, "YCbCr", (40, 80), (4, 64)
-    enc = codec.encode(torch.from_numpy(rgb).cuda(), space, q, b)
+    H, W, space, q, b = 192, 320, "YCbCr", (40, 80), (4, 64)
+    enc = codec.encode(torch.from_numpy(synth(H, W, seed=4)).cuda(), space, q, b)
     lv = enc.leaves[0].clone()
     n = int(enc.counts[0, 0, 0])
     evil = torch.tensor([[0, 0, 0, 0], [4, 4, 3, 16], [0, 0, 512, 0], [-8, 0, 8, 0], [100000, 0, 8, 0], [0, 0, 8, 2 ** 30], [0, 0, 128, 0]],
