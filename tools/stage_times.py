@@ -1,4 +1,4 @@
-"""measurement tool: per-stage device times (ms) of the C2 workload; usage: python tools/stage_times.py [B] [tensor]"""
+"""measurement tool: per-stage device times (ms) of the C2 workload; usage: python tools/stage_times.py [B] [tensor mask] [space]"""
 import sys, torch, numpy as np
 sys.path.insert(0,'adaptive-edge-aware-jpeg_b200'); sys.path.insert(0,'tests')
 from aeaj.codec import get_codec
@@ -8,7 +8,7 @@ B = int(sys.argv[1]) if len(sys.argv)>1 else 4
 c.tensor_dct = int(sys.argv[2], 0) if len(sys.argv)>2 else 0xf   # mask: bit k = class 16 << k on the tensor cores
 H,W=2160,3840
 rgb = torch.from_numpy(np.stack([synth(H,W,s) for s in range(B)])).cuda()
-sp,q,b='YCbCr',(30,95),(4,128)
+sp,q,b=(sys.argv[3] if len(sys.argv)>3 else 'YCbCr'),(30,95),(4,128)
 args=(B,H,W,sp,b,q)
 for _ in range(3):
     enc=c.encode(rgb,sp,q,b); c.decode_encoded(enc,sp,q,b)
