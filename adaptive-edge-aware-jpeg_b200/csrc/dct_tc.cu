@@ -9,18 +9,15 @@
 // in FP32 in tensor memory: the error is at FP32 rounding level, the parity bar is the exact quantiser (tie class T-DCT)
 // forward and the <= 1 LSB / 3e-6 bound of the decoded samples inverse (tests/test_gpu_parity.py).
 //
-// One persistent CTA (256 threads) per SM over the super-tiles of a class:
+// One persistent, warp-specialised CTA per SM over the super-tiles of a class (roles and mbarriers: see k_dct_tc):
 //   GEMM1  W = A . X      A tiles (smem, K-major, hi/lo; 128 KB, loaded once)   B = X^T (smem, K-major, hi/lo), streamed
-//                         in four K chunks of 32 super-rows through two buffers guarded by mbarriers (tcgen05.commit)
+//                         in four K chunks of 32 super-rows through two buffers (full / empty mbarriers, tcgen05.commit)
 //   split  W -> Wh, Wl    TMEM -> registers -> TMEM (tcgen05.ld / tcgen05.st)
 //   GEMM2  Out = W . A^T  A operand = W (TMEM, hi/lo)   B = the same shared-memory tiles as GEMM1's A; A is block
 //                         diagonal, so every K step only needs the N = S columns of its own block
 //   epilogue: tcgen05.ld -> registers -> exact float32 quantiser -> 256-bit stores of int32 coefficients     (forward)
 //                                     -> de-normalise, crop -> 256-bit stores of float32 layer samples       (inverse)
-// Software pipeline: the loads of a tile's first two chunks are issued while the previous tile is in GEMM1; their
-// conversion / stores and MMAs are issued right after the previous tile's GEMM2 is launched, so the tensor pipe works on
-// GEMM2(i) and the head of GEMM1(i+1) while the CUDA cores run the epilogue of tile i straight out of tensor memory
-// (no shared-memory staging: D2 stays valid because GEMM1 writes D1).
+// No shared-memory staging of the result: D2 stays valid during the next tile's GEMM1 because that writes D1.
 // Shared-memory operands use the canonical no-swizzle K-major layout: [K/4 chunks][rows][4 floats], i.e. 8x16-byte
 // core matrices, stride-byte-offset 128 B (next 8 rows), leading-byte-offset rows*16 B (next K chunk).
 #include "aeaj_internal.cuh"
@@ -70,16 +67,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
                    "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                  : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
-                 "%25, %26, %27, %28, %29, %30, %31, %32};\n"
-                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-                    "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
-                    "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
-                    "r"(v[30]), "r"(v[31])
-                 : "memory");
-}
 // 256-bit global stores (sm_100): one full 32-byte sector per instruction and thread
 __device__ __forceinline__ void st_global_v8(void* p, const uint32_t* v) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -91,7 +78,7 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t* v) {
 __device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) { hi = tf32_rn(v); lo = tf32_rn(__fsub_rn(v, hi)); }
 
-// one leaf of the current super-tile (shared memory)
+// one leaf of a super-tile (shared memory)
 struct TcLeaf {
     float* base;            // layer + y * w + x (forward: source, inverse: destination); nullptr: empty slot / leaf of another band
     int* cf;                // coefficient block of this leaf
@@ -101,12 +88,43 @@ struct TcLeaf {
     float mid, sc;
 };
 
+__device__ __noinline__ int pad_reflect_slow(int p, int n) { return pad_reflect(p, n); }     // partial leaves only (keeps the hot code small)
+
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+                    "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+                 : "memory");
+}
+
+constexpr int TC_CONSUMERS = 128, TC_PRODUCERS = 256, TC_THREADS = TC_CONSUMERS + TC_PRODUCERS + 32;
+constexpr int TC_TABS = 4;                                                // leaf tables in flight (ring)
+
+// Warp-specialised, persistent: one CTA per SM loops over the super-tiles blockIdx.x, blockIdx.x + gridDim.x, ..
+//   warps 4-11  PRODUCERS  global -> registers (one chunk ahead) -> normalise / dequantise -> hi/lo split -> K-major smem tiles
+//   warp 12     MMA        one thread issues GEMM1 chunk by chunk as buffers fill, then GEMM2 once W is split
+//   warps 0-3   CONSUMERS  (one per TMEM lane quadrant; a thread owns one super-tile row) split W inside tensor memory, then
+//                          the epilogue straight out of tensor memory
+// mbarriers: full[b] (256 producer arrivals) / empty[b] (tcgen05.commit) per X buffer; d1_full (commit: W complete),
+// w_ready (128 consumer arrivals: Wh, Wl written, D1 free), d2_full (commit: Out complete), d2_free (128 arrivals: D2 read).
+// The tensor pipe runs GEMM1 of tile i+1 while the consumers are in the epilogue of tile i and the producers already
+// stage tile i+2.  Every wait is bounded: a protocol error raises the error flag instead of hanging the GPU.
+//
 // a_tiles: [Ah | Al], each 128 x 128 floats in the canonical layout [K/4][128][4] (built on the host): blockdiag(C_S) or its transpose
 // izz: inverse zigzag permutation of an S x S block (row-major index -> stream position)
 template <int S, bool INV>
-__global__ void __launch_bounds__(256, 1) k_dct_tc(const PlaneDesc* __restrict__ planes, const ClassEntry* __restrict__ list,
-                                                   const int* __restrict__ count_ptr, const float* __restrict__ a_tiles,
-                                                   const int* __restrict__ izz, int* __restrict__ err) {
+__global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __restrict__ planes, const ClassEntry* __restrict__ list,
+                                                          const int* __restrict__ count_ptr, const float* __restrict__ a_tiles,
+                                                          const int* __restrict__ izz, int* __restrict__ err) {
     constexpr int NB = TC_N / S;                                          // leaves per super-tile side
     constexpr int NL = NB * NB;                                           // leaves per super-tile
     constexpr int LG = (S == 16) ? 4 : (S == 32) ? 5 : (S == 64) ? 6 : 7;
@@ -114,16 +132,19 @@ __global__ void __launch_bounds__(256, 1) k_dct_tc(const PlaneDesc* __restrict__
     float* sCh = reinterpret_cast<float*>(smem_raw);                     // 64 KB
     float* sCl = sCh + TC_N * TC_N;                                      // 64 KB
     float* sX = sCl + TC_N * TC_N;                                       // 2 buffers x (hi 16 KB + lo 16 KB)
-    __shared__ __align__(8) unsigned long long mbar_storage[3];
+    __shared__ __align__(8) unsigned long long mbar_storage[8];
     __shared__ uint32_t tmem_base_s;
-    __shared__ TcLeaf sLeaf[2][NL];
+    __shared__ TcLeaf sLeaf[TC_TABS][NL];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < 2 * TC_N * TC_N / 4; i += 256) reinterpret_cast<float4*>(sCh)[i] = __ldg(reinterpret_cast<const float4*>(a_tiles) + i);
-    const uint32_t bar0 = smem_u32(&mbar_storage[0]), bar1 = smem_u32(&mbar_storage[1]), bar2 = smem_u32(&mbar_storage[2]);
+    for (int i = tid; i < 2 * TC_N * TC_N / 4; i += TC_THREADS) reinterpret_cast<float4*>(sCh)[i] = __ldg(reinterpret_cast<const float4*>(a_tiles) + i);
+    const uint32_t bar_full[2] = {smem_u32(&mbar_storage[0]), smem_u32(&mbar_storage[1])};
+    const uint32_t bar_empty[2] = {smem_u32(&mbar_storage[2]), smem_u32(&mbar_storage[3])};
+    const uint32_t bar_d1full = smem_u32(&mbar_storage[4]), bar_wready = smem_u32(&mbar_storage[5]);
+    const uint32_t bar_d2full = smem_u32(&mbar_storage[6]), bar_d2free = smem_u32(&mbar_storage[7]);
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar0) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar1) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar2) : "memory");
+        auto init = [](uint32_t b, int n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b), "r"(n) : "memory"); };
+        init(bar_full[0], TC_PRODUCERS); init(bar_full[1], TC_PRODUCERS); init(bar_empty[0], 1); init(bar_empty[1], 1);
+        init(bar_d1full, 1); init(bar_wready, TC_CONSUMERS); init(bar_d2full, 1); init(bar_d2free, TC_CONSUMERS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -136,20 +157,19 @@ __global__ void __launch_bounds__(256, 1) k_dct_tc(const PlaneDesc* __restrict__
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tbase = tmem_base_s;
     const uint32_t D1 = tbase, WH = tbase + 128, WL = tbase + 256, D2 = tbase + 384;
-    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;          // this warp's 32 TMEM lanes (warps w and w+4 share a quadrant)
-    const int row = (warp & 3) * 32 + lane;                               // the super-tile row this thread reads from TMEM
-    const int cbeg = (warp >> 2) * 2;                                     // ... and its two 32-column chunks
     const uint32_t aCh = smem_u32(sCh), aCl = smem_u32(sCl), aX = smem_u32(sX);
     const int count = *count_ptr;
     const int ntiles = (count + NL - 1) / NL;
+    const int my_tiles = (blockIdx.x < ntiles) ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
-    // leaf table of one super-tile: slot t = p * NB + q holds list entry tile * NL + t
-    auto fill_table = [&](int buf, int tile) {
-        if (tid < NL) {
+    if (warp >= 4 && warp < 12) {
+        // =============================================== PRODUCERS ===============================================
+        const int pt = tid - TC_CONSUMERS, pw = pt >> 5;                  // producer thread / warp (0 .. 7)
+        auto make_leaf = [&](int tile) {                                  // list entry tile * NL + pt -> leaf descriptor (registers)
             TcLeaf L;
             L.base = nullptr; L.cf = nullptr; L.qf = nullptr; L.qi = nullptr; L.w = 0; L.bh = 0; L.bw = 0; L.zig = 0; L.mid = 0.0f; L.sc = 1.0f;
-            const int li = tile * NL + tid;
-            if (li < count) {
+            const int li = tile * NL + pt;
+            if (pt < NL && tile < ntiles && li < count) {
                 const ClassEntry e = list[li];
                 const PlaneDesc& P = planes[e.plane];
                 if (e.y >= P.ry0 && e.y < P.ry1) {                        // halo-split: only the leaves of this call's band
@@ -160,184 +180,188 @@ __global__ void __launch_bounds__(256, 1) k_dct_tc(const PlaneDesc* __restrict__
                     L.zig = P.zigzag; L.mid = P.mid; L.sc = P.scale;
                 }
             }
-            sLeaf[buf][tid] = L;
-        }
-    };
-    // registers of two chunks in flight: thread (warp kc, lane g) holds super-rows 32c + 4kc .. +3 of columns g, g+32, g+64, g+96
-    uint32_t xr[2][4][4];
-    int xq[INV ? 2 : 1][4][4];                                            // inverse: the quantiser steps of the same positions
-    auto load_chunk = [&](const TcLeaf* T, int c, int slot) {
-        const int r0 = 32 * c + 4 * warp;                                 // super-row of r = 0; the four rows stay inside one leaf row block
-        const int p = r0 / S, li0 = r0 % S;
+            return L;
+        };
+        auto producers_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+        // registers of two chunks in flight: thread (warp kc, lane g) holds super-rows 32c + 4kc .. +3 of columns g, g+32, g+64, g+96
+        uint32_t xr[2][4][4];
+        int xq[INV ? 2 : 1][4][4];                                        // inverse: the quantiser steps of the same positions
+        auto load_chunk = [&](const TcLeaf* T, int c, int slot) {
+            const int r0 = 32 * c + 4 * pw;                               // super-row of r = 0; the four rows stay inside one leaf row block
+            const int p = r0 / S, li0 = r0 % S;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int j = lane + 32 * q;
-            const TcLeaf& L = T[p * NB + j / S];
-            const int lj = j % S;
-            if (L.base == nullptr) {
+            for (int q = 0; q < 4; q++) {
+                const int j = lane + 32 * q;
+                const TcLeaf& L = T[p * NB + j / S];
+                const int lj = j % S;
+                if (L.base == nullptr) {
 #pragma unroll
-                for (int r = 0; r < 4; r++) { xr[slot][r][q] = 0u; if (INV) xq[INV ? slot : 0][r][q] = 0; }
-                continue;
-            }
-            if (INV) {
-#pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    const int nat = (li0 + r) * S + lj;
-                    xr[slot][r][q] = (uint32_t)__ldg(L.cf + (L.zig ? __ldg(izz + nat) : nat));
-                    xq[INV ? slot : 0][r][q] = __ldg(L.qi + nat);
+                    for (int r = 0; r < 4; r++) { xr[slot][r][q] = 0u; if (INV) xq[INV ? slot : 0][r][q] = 0; }
+                    continue;
                 }
-            } else {
-                const bool fast = (L.bh == S && L.bw == S);
-                const int col = fast ? lj : pad_reflect(lj, L.bw);
+                if (INV) {
 #pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    const int rr = fast ? li0 + r : pad_reflect(li0 + r, L.bh);
-                    xr[slot][r][q] = __float_as_uint(__ldg(L.base + (size_t)rr * L.w + col));
-                }
-            }
-        }
-    };
-    auto store_chunk = [&](const TcLeaf* T, int c, int slot) {           // registers -> hi/lo K-major tiles of buffer `slot`
-        float* xh = sX + slot * 8192;
-        float* xl = xh + 4096;
-        const int p = (32 * c + 4 * warp) / S;
+                    for (int r = 0; r < 4; r++) {
+                        const int nat = (li0 + r) * S + lj;
+                        xr[slot][r][q] = (uint32_t)__ldg(L.cf + (L.zig ? __ldg(izz + nat) : nat));
+                        xq[INV ? slot : 0][r][q] = __ldg(L.qi + nat);
+                    }
+                } else if (L.bh == S && L.bw == S) {
+                    const float* src = L.base + (size_t)li0 * L.w + lj;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const TcLeaf& L = T[p * NB + (lane + 32 * q) / S];
-            const bool live = (L.base != nullptr);
-            const float mid = L.mid, sc = L.sc;
-            float hi[4], lo[4];
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                float x = INV ? (float)((int)xr[slot][r][q] * xq[INV ? slot : 0][r][q])          // jpeg.py:524
-                              : __fmul_rn(__fsub_rn(__uint_as_float(xr[slot][r][q]), mid), sc);   // jpeg.py:387-390
-                x = live ? x : 0.0f;
-                tf32_split(x, hi[r], lo[r]);
-            }
-            const int o = (warp * TC_N + lane + 32 * q) * 4;
-            *reinterpret_cast<float4*>(xh + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4*>(xl + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        }
-    };
-    // thread 0: the 12 MMAs of K chunk c (W += A[:, 32c .. 32c+31] . X[32c .. 32c+31, :]) and the commit that releases buffer c & 1
-    auto issue_gemm1_chunk = [&](int c) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t idesc = TC_IDESC_BASE | ((128u >> 3) << 17);
-        const int b = c & 1;
-        const uint32_t xh = aX + b * 32768, xl = xh + 16384;
-#pragma unroll
-        for (int s = 0; s < 4; s++) {
-            const uint32_t ao = (c * 4 + s) * (TC_N * 32);
-            const uint64_t ah = make_desc(aCh + ao, TC_N * 16, 128), al = make_desc(aCl + ao, TC_N * 16, 128);
-            const uint64_t bh_ = make_desc(xh + s * (TC_N * 32), TC_N * 16, 128), bl = make_desc(xl + s * (TC_N * 32), TC_N * 16, 128);
-            mma_ss(D1, ah, bh_, idesc, (c | s) != 0);
-            mma_ss(D1, ah, bl, idesc, 1);
-            mma_ss(D1, al, bh_, idesc, 1);
-        }
-        mma_commit(b == 0 ? bar0 : bar1);
-    };
-
-    uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
-    bool alive = true;
-    int tile = blockIdx.x, it = 0;
-    if (tile < ntiles) {
-        fill_table(0, tile);
-        __syncthreads();
-        load_chunk(sLeaf[0], 0, 0);
-        load_chunk(sLeaf[0], 1, 1);
-    }
-    while (tile < ntiles && alive) {
-        const TcLeaf* Tc = sLeaf[it & 1];
-        const TcLeaf* Tn = sLeaf[(it + 1) & 1];
-        const int ntile = tile + gridDim.x;
-        const bool has_next = ntile < ntiles;
-        __syncthreads();                                                   // the previous tile's epilogue is done with the other table
-        if (has_next) fill_table((it + 1) & 1, ntile);
-        __syncthreads();
-        // ---- GEMM1: W = A . X.  Chunks 0 and 1 of every tile but a CTA's first were stored and issued at the end of the
-        //      previous iteration (behind that tile's GEMM2).
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            if (c < 2 && it > 0) continue;
-            const int b = c & 1;
-            if (c >= 2 && alive) {                                         // the MMAs of chunk c-2 have released buffer b
-                if (b == 0) { alive = mbar_wait(bar0, ph0, err); ph0 ^= 1; } else { alive = mbar_wait(bar1, ph1, err); ph1 ^= 1; }
-            }
-            store_chunk(Tc, c, b);
-            if (c < 2) load_chunk(Tc, c + 2, b);
-            else if (has_next) load_chunk(Tn, c - 2, b);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncthreads();
-            if (tid == 0 && alive) issue_gemm1_chunk(c);
-        }
-        if (alive) { alive = mbar_wait(bar0, ph0, err); ph0 ^= 1; }
-        if (alive) { alive = mbar_wait(bar1, ph1, err); ph1 ^= 1; }
-        if (!alive) break;
-        // ---- split W = Wh + Wl inside tensor memory ------------------------------------------------------
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (int r = 0; r < 4; r++) xr[slot][r][q] = __float_as_uint(__ldg(src + (size_t)r * L.w));
+                } else {
+                    const int col = pad_reflect_slow(lj, L.bw);
 #pragma unroll 1
-        for (int c = cbeg; c < cbeg + 2; c++) {
-            uint32_t v[32], h[32], l[32];
-            tmem_ld32(D1 + lane_sel + c * 32, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int i = 0; i < 32; i++) {
-                float wh, wl;
-                tf32_split(__uint_as_float(v[i]), wh, wl);
-                h[i] = __float_as_uint(wh); l[i] = __float_as_uint(wl);
+                    for (int r = 0; r < 4; r++) {
+                        const uint32_t v = __float_as_uint(__ldg(L.base + (size_t)pad_reflect_slow(li0 + r, L.bh) * L.w + col));
+                        if (r == 0) xr[slot][0][q] = v; else if (r == 1) xr[slot][1][q] = v; else if (r == 2) xr[slot][2][q] = v; else xr[slot][3][q] = v;
+                    }
+                }
             }
-            tmem_st32(WH + lane_sel + c * 32, h);
-            tmem_st32(WL + lane_sel + c * 32, l);
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        // ---- GEMM2: Out = W . A^T.  A is block diagonal: K step s (columns 8s .. 8s+7 of W) only feeds the S output
-        //      columns of its own block.
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t idesc = TC_IDESC_BASE | (((uint32_t)S >> 3) << 17);
-#pragma unroll 4
-            for (int s = 0; s < TC_N / 8; s++) {
-                const int n0 = (8 * s / S) * S;                            // first output column of the block
-                const uint32_t bo = s * (TC_N * 32) + n0 * 16;             // K chunk pair s, tile rows n0 ..
-                const uint64_t bh_ = make_desc(aCh + bo, TC_N * 16, 128), bl = make_desc(aCl + bo, TC_N * 16, 128);
-                const uint32_t first = (8 * s % S) == 0 ? 0u : 1u;         // first K step of a block overwrites its columns
-                mma_ts(D2 + n0, WH + s * 8, bh_, idesc, first);
-                mma_ts(D2 + n0, WH + s * 8, bl, idesc, 1);
-                mma_ts(D2 + n0, WL + s * 8, bh_, idesc, 1);
-            }
-            mma_commit(bar2);
-        }
-        // ---- head of the next tile's GEMM1 behind GEMM2 (both X buffers and D1 are free: all of this tile's GEMM1 MMAs have
-        //      completed and W has been copied out of D1)
-        if (has_next) {
+        };
+        auto store_chunk = [&](const TcLeaf* T, int c, int slot) {       // registers -> hi/lo K-major tiles of buffer `slot`
+            float* xh = sX + slot * 8192;
+            float* xl = xh + 4096;
+            const int p = (32 * c + 4 * pw) / S;
 #pragma unroll
-            for (int c = 0; c < 2; c++) {
-                store_chunk(Tn, c, c);
-                load_chunk(Tn, c + 2, c);
+            for (int q = 0; q < 4; q++) {
+                const TcLeaf& L = T[p * NB + (lane + 32 * q) / S];
+                const bool live = (L.base != nullptr);
+                const float mid = L.mid, sc = L.sc;
+                float hi[4], lo[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    float x = INV ? (float)((int)xr[slot][r][q] * xq[INV ? slot : 0][r][q])          // jpeg.py:524
+                                  : __fmul_rn(__fsub_rn(__uint_as_float(xr[slot][r][q]), mid), sc);   // jpeg.py:387-390
+                    x = live ? x : 0.0f;
+                    tf32_split(x, hi[r], lo[r]);
+                }
+                const int o = (pw * TC_N + lane + 32 * q) * 4;
+                *reinterpret_cast<float4*>(xh + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(xl + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        };
+        bool alive = true;
+        if (my_tiles > 0) {
+            if (pt < NL) sLeaf[0][pt] = make_leaf(blockIdx.x);
+            producers_sync();
+            load_chunk(sLeaf[0], 0, 0);
+            load_chunk(sLeaf[0], 1, 1);
+        }
+        TcLeaf Lp = make_leaf(blockIdx.x + gridDim.x);                   // the next tile's entry, prefetched into registers
+        uint32_t uses = 0;                                                // chunk stores so far: buffer b has been used (uses + 1 - b) / 2 times
+        for (int it = 0; it < my_tiles && alive; it++) {
+            const TcLeaf* Tc = sLeaf[it & (TC_TABS - 1)];
+            const TcLeaf* Tn = sLeaf[(it + 1) & (TC_TABS - 1)];
+            const bool has_next = it + 1 < my_tiles;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int b = c & 1;
+                if (uses >= 2) alive = alive && mbar_wait(bar_empty[b], ((uses >> 1) - 1) & 1, err);   // the MMAs that read this buffer last are done
+                if (c == 0) {
+                    // the table ring slot of tile it + 1 belonged to tile it - 3, whose epilogue is over (its consumers went on to
+                    // split tile it - 2 before the MMAs just waited for could be issued)
+                    if (pt < NL) sLeaf[(it + 1) & (TC_TABS - 1)][pt] = Lp;
+                    producers_sync();
+                    Lp = make_leaf(blockIdx.x + (it + 2) * gridDim.x);
+                }
+                store_chunk(Tc, c, b);
+                if (c < 2) load_chunk(Tc, c + 2, b);
+                else if (has_next) load_chunk(Tn, c - 2, b);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncthreads();
-                if (tid == 0) issue_gemm1_chunk(c);
+                mbar_arrive(bar_full[b]);
+                uses++;
             }
         }
-        alive = mbar_wait(bar2, ph2, err);
-        ph2 ^= 1;
-        if (!alive) break;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- epilogue straight from tensor memory: this thread owns super-row `row`, columns 32 cbeg .. 32 cbeg + 63
-        {
-            const int p = row / S, li = row % S;
+    } else if (warp == 12) {
+        // =============================================== MMA ISSUER ===============================================
+        if (lane == 0) {
+            bool alive = true;
+            uint32_t nfull = 0;                                           // chunks consumed so far
+            for (int it = 0; it < my_tiles && alive; it++) {
+                const uint32_t idesc1 = TC_IDESC_BASE | ((128u >> 3) << 17);
 #pragma unroll 1
-            for (int c = cbeg; c < cbeg + 2; c++) {
+                for (int c = 0; c < 4 && alive; c++) {
+                    const int b = c & 1;
+                    alive = mbar_wait(bar_full[b], (nfull >> 1) & 1, err);
+                    nfull++;
+                    if (!alive) break;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t xh = aX + b * 32768, xl = xh + 16384;
+#pragma unroll
+                    for (int s = 0; s < 4; s++) {
+                        const uint32_t ao = (c * 4 + s) * (TC_N * 32);
+                        const uint64_t ah = make_desc(aCh + ao, TC_N * 16, 128), al = make_desc(aCl + ao, TC_N * 16, 128);
+                        const uint64_t bh_ = make_desc(xh + s * (TC_N * 32), TC_N * 16, 128), bl = make_desc(xl + s * (TC_N * 32), TC_N * 16, 128);
+                        mma_ss(D1, ah, bh_, idesc1, (c | s) != 0);
+                        mma_ss(D1, ah, bl, idesc1, 1);
+                        mma_ss(D1, al, bh_, idesc1, 1);
+                    }
+                    mma_commit(bar_empty[b]);
+                }
+                if (!alive) break;
+                mma_commit(bar_d1full);                                    // W = A . X complete
+                alive = mbar_wait(bar_wready, it & 1, err);                // Wh / Wl written, D1 free again
+                if (alive && it > 0) alive = mbar_wait(bar_d2free, (it - 1) & 1, err);   // the previous tile's Out has been read
+                if (!alive) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // GEMM2: Out = W . A^T.  A is block diagonal: K step s (columns 8s .. 8s+7 of W) only feeds the S output columns of its block
+                const uint32_t idesc2 = TC_IDESC_BASE | (((uint32_t)S >> 3) << 17);
+#pragma unroll 4
+                for (int s = 0; s < TC_N / 8; s++) {
+                    const int n0 = (8 * s / S) * S;                        // first output column of the block
+                    const uint32_t bo = s * (TC_N * 32) + n0 * 16;         // K chunk pair s, tile rows n0 ..
+                    const uint64_t bh_ = make_desc(aCh + bo, TC_N * 16, 128), bl = make_desc(aCl + bo, TC_N * 16, 128);
+                    const uint32_t first = (8 * s % S) == 0 ? 0u : 1u;     // first K step of a block overwrites its columns
+                    mma_ts(D2 + n0, WH + s * 8, bh_, idesc2, first);
+                    mma_ts(D2 + n0, WH + s * 8, bl, idesc2, 1);
+                    mma_ts(D2 + n0, WL + s * 8, bh_, idesc2, 1);
+                }
+                mma_commit(bar_d2full);
+            }
+        }
+    } else {
+        // =============================================== CONSUMERS ===============================================
+        const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;            // this warp's 32 TMEM lanes
+        const int row = warp * 32 + lane;                                 // the super-tile row this thread owns in tensor memory
+        const int p = row / S, li = row % S;
+        bool alive = true;
+        for (int it = 0; it < my_tiles && alive; it++) {
+            const TcLeaf* Tc = sLeaf[it & (TC_TABS - 1)];
+            alive = mbar_wait(bar_d1full, it & 1, err);
+            if (!alive) break;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // split W = Wh + Wl inside tensor memory (Wh / Wl are free: this thread waited for the previous tile's d2_full)
+#pragma unroll 1
+            for (int c = 0; c < 8; c++) {
+                uint32_t v[16], h[16], l[16];
+                tmem_ld16(D1 + lane_sel + c * 16, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    float wh, wl;
+                    tf32_split(__uint_as_float(v[i]), wh, wl);
+                    h[i] = __float_as_uint(wh); l[i] = __float_as_uint(wl);
+                }
+                tmem_st16(WH + lane_sel + c * 16, h);
+                tmem_st16(WL + lane_sel + c * 16, l);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(bar_wready);
+            alive = mbar_wait(bar_d2full, it & 1, err);
+            if (!alive) break;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // epilogue straight from tensor memory: super-row `row`, 32 columns at a time
+#pragma unroll 1
+            for (int c = 0; c < 4; c++) {
                 uint32_t v[32];
                 tmem_ld32(D2 + lane_sel + c * 32, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
-                    const int j = c * 32 + g * 8;                          // 8 consecutive columns: inside one leaf (8 | S)
+                    const int j = c * 32 + g * 8;                   // 8 consecutive columns: inside one leaf (8 | S)
                     const TcLeaf& L = Tc[p * NB + j / S];
                     const int lj = j % S;
                     if (L.base == nullptr) continue;
@@ -373,9 +397,9 @@ __global__ void __launch_bounds__(256, 1) k_dct_tc(const PlaneDesc* __restrict__
                     }
                 }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(bar_d2free);
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        tile = ntile; it++;
     }
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tbase) : "memory");
@@ -397,8 +421,8 @@ int launch_one(aeaj_handle* h, const PlaneDesc* planes_dev, const ClassEntry* li
     const int blocks = (int)std::min<int64_t>(tiles, (int64_t)h->sm_count);
     const float* a = h->dct_tc_tiles_dev + (size_t)(tc_slot(S) * 2 + (inverse ? 1 : 0)) * 2 * TC_N * TC_N;
     const int* izz = h->tc_izz_dev[tc_slot(S)];
-    if (inverse) k_dct_tc<S, true><<<blocks, 256, TC_SMEM_BYTES, st>>>(planes_dev, list, count, a, izz, h->tc_err_dev);
-    else k_dct_tc<S, false><<<blocks, 256, TC_SMEM_BYTES, st>>>(planes_dev, list, count, a, izz, h->tc_err_dev);
+    if (inverse) k_dct_tc<S, true><<<blocks, TC_THREADS, TC_SMEM_BYTES, st>>>(planes_dev, list, count, a, izz, h->tc_err_dev);
+    else k_dct_tc<S, false><<<blocks, TC_THREADS, TC_SMEM_BYTES, st>>>(planes_dev, list, count, a, izz, h->tc_err_dev);
     AEAJ_LAUNCH_CHECK();
     return 0;
 }
