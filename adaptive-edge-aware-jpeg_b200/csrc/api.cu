@@ -582,8 +582,22 @@ extern "C" int aeaj_plan_set_qtables(aeaj_plan* p, const int32_t* tables, size_t
         AEAJ_CUDA(cudaMalloc(&p->qtabf_dev, sizeof(float) * n_entries));
     }
     p->qtab_entries = n_entries;
+    // float copy for the tensor-core epilogue, per table in the layout [s/8 column groups][s rows][8]: a warp whose lanes own
+    // consecutive rows reads the 8 steps of one column group with one contiguous 256-bit load per lane (entries <= 6050: exact)
     std::vector<float> asf(n_entries);
-    for (size_t i = 0; i < n_entries; i++) asf[i] = (float)tables[i];           // entries <= 6050 (quality 1): exact
+    {
+        size_t o = 0;
+        for (int t = 0; t < 2; t++)
+            for (int k = p->lg_min; k <= p->lg_max; k++) {
+                const int s = 1 << k;
+                for (int r = 0; r < s; r++)
+                    for (int c = 0; c < s; c++) {
+                        const size_t dst = (s >= 8) ? ((size_t)(c >> 3) * s + r) * 8 + (c & 7) : (size_t)r * s + c;
+                        asf[o + dst] = (float)tables[o + (size_t)r * s + c];
+                    }
+                o += (size_t)s * s;
+            }
+    }
     AEAJ_CUDA(cudaMemcpyAsync(p->qtab_dev, tables, sizeof(int32_t) * n_entries, cudaMemcpyHostToDevice, ST(stream)));
     AEAJ_CUDA(cudaMemcpyAsync(p->qtabf_dev, asf.data(), sizeof(float) * n_entries, cudaMemcpyHostToDevice, ST(stream)));
     AEAJ_CUDA(cudaStreamSynchronize(ST(stream)));                                // `asf` is a temporary

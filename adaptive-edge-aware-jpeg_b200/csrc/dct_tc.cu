@@ -67,7 +67,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
                    "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                  : "r"(taddr) : "memory");
 }
-// 256-bit global stores (sm_100): one full 32-byte sector per instruction and thread
+// 256-bit global loads / stores (sm_100): one full 32-byte sector per instruction and thread
+__device__ __forceinline__ void ld_global_v8(const void* p, uint32_t* v) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
 __device__ __forceinline__ void st_global_v8(void* p, const uint32_t* v) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
@@ -82,7 +86,7 @@ __device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) { hi =
 struct TcLeaf {
     float* base;            // layer + y * w + x (forward: source, inverse: destination); nullptr: empty slot / leaf of another band
     int* cf;                // coefficient block of this leaf
-    const float* qf;        // quantiser steps as float, S x S (forward)
+    const float* qf;        // quantiser steps as float in the epilogue layout [S/8 column groups][S rows][8] (forward)
     const int* qi;          // quantiser steps, S x S (inverse)
     int w, bh, bw, zig;
     float mid, sc;
@@ -378,11 +382,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
                         }
                     } else {
                         const int nat = li * S + lj;
-                        const float4 qa = __ldg(reinterpret_cast<const float4*>(L.qf + nat)), qb = __ldg(reinterpret_cast<const float4*>(L.qf + nat) + 1);
-                        const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+                        // the 8 quantiser steps of (li, lj .. lj + 7): the lanes of a warp are consecutive rows, and the table is stored
+                        // [column group][row][8], so a warp reads one contiguous 1 KB run (one request, full sectors)
+                        uint32_t qv[8];
+                        ld_global_v8(L.qf + ((size_t)(lj >> 3) * S + li) * 8, qv);
                         uint32_t o[8];
 #pragma unroll
-                        for (int k = 0; k < 8; k++) o[k] = (uint32_t)quantize_f(__uint_as_float(v[g * 8 + k]), qv[k]);
+                        for (int k = 0; k < 8; k++) o[k] = (uint32_t)quantize_f(__uint_as_float(v[g * 8 + k]), __uint_as_float(qv[k]));
                         if (!L.zig) {
                             int* dst = L.cf + nat;                             // 32-byte aligned unless 2 x 2 leaves precede the block
                             if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) st_global_v8(dst, o);
