@@ -92,8 +92,6 @@ struct TcLeaf {
     float mid, sc;
 };
 
-__device__ __noinline__ int pad_reflect_slow(int p, int n) { return pad_reflect(p, n); }     // partial leaves only (keeps the hot code small)
-
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(mbar) : "memory");
 }
@@ -110,16 +108,16 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
                  : "memory");
 }
 
-constexpr int TC_CONSUMERS = 128, TC_PRODUCERS = 256, TC_THREADS = TC_CONSUMERS + TC_PRODUCERS + 32;
+constexpr int TC_CONSUMERS = 256, TC_PRODUCERS = 256, TC_THREADS = TC_CONSUMERS + TC_PRODUCERS + 32;
 constexpr int TC_TABS = 4;                                                // leaf tables in flight (ring)
 
 // Warp-specialised, persistent: one CTA per SM loops over the super-tiles blockIdx.x, blockIdx.x + gridDim.x, ..
-//   warps 4-11  PRODUCERS  global -> registers (one chunk ahead) -> normalise / dequantise -> hi/lo split -> K-major smem tiles
-//   warp 12     MMA        one thread issues GEMM1 chunk by chunk as buffers fill, then GEMM2 once W is split
-//   warps 0-3   CONSUMERS  (one per TMEM lane quadrant; a thread owns one super-tile row) split W inside tensor memory, then
-//                          the epilogue straight out of tensor memory
+//   warps 8-15  PRODUCERS  global -> registers (one chunk ahead) -> normalise / dequantise -> hi/lo split -> K-major smem tiles
+//   warp 16     MMA        one thread issues GEMM1 chunk by chunk as buffers fill, then GEMM2 once W is split
+//   warps 0-7   CONSUMERS  (two per TMEM lane quadrant; a thread owns 64 columns of one super-tile row) split W inside tensor
+//                          memory, then the epilogue straight out of tensor memory
 // mbarriers: full[b] (256 producer arrivals) / empty[b] (tcgen05.commit) per X buffer; d1_full (commit: W complete),
-// w_ready (128 consumer arrivals: Wh, Wl written, D1 free), d2_full (commit: Out complete), d2_free (128 arrivals: D2 read).
+// w_ready (256 consumer arrivals: Wh, Wl written, D1 free), d2_full (commit: Out complete), d2_free (256 arrivals: D2 read).
 // The tensor pipe runs GEMM1 of tile i+1 while the consumers are in the epilogue of tile i and the producers already
 // stage tile i+2.  Every wait is bounded: a protocol error raises the error flag instead of hanging the GPU.
 //
@@ -166,7 +164,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
     const int ntiles = (count + NL - 1) / NL;
     const int my_tiles = (blockIdx.x < ntiles) ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
-    if (warp >= 4 && warp < 12) {
+    if (warp >= 8 && warp < 16) {
         // =============================================== PRODUCERS ===============================================
         const int pt = tid - TC_CONSUMERS, pw = pt >> 5;                  // producer thread / warp (0 .. 7)
         auto make_leaf = [&](int tile) {                                  // list entry tile * NL + pt -> leaf descriptor (registers)
@@ -189,7 +187,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
         auto producers_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
         // registers of two chunks in flight: thread (warp kc, lane g) holds super-rows 32c + 4kc .. +3 of columns g, g+32, g+64, g+96
         uint32_t xr[2][4][4];
-        int xq[INV ? 2 : 1][4][4];                                        // inverse: the quantiser steps of the same positions
         auto load_chunk = [&](const TcLeaf* T, int c, int slot) {
             const int r0 = 32 * c + 4 * pw;                               // super-row of r = 0; the four rows stay inside one leaf row block
             const int p = r0 / S, li0 = r0 % S;
@@ -200,7 +197,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
                 const int lj = j % S;
                 if (L.base == nullptr) {
 #pragma unroll
-                    for (int r = 0; r < 4; r++) { xr[slot][r][q] = 0u; if (INV) xq[INV ? slot : 0][r][q] = 0; }
+                    for (int r = 0; r < 4; r++) xr[slot][r][q] = 0u;
                     continue;
                 }
                 if (INV) {
@@ -208,18 +205,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
                     for (int r = 0; r < 4; r++) {
                         const int nat = (li0 + r) * S + lj;
                         xr[slot][r][q] = (uint32_t)__ldg(L.cf + (L.zig ? __ldg(izz + nat) : nat));
-                        xq[INV ? slot : 0][r][q] = __ldg(L.qi + nat);
                     }
                 } else if (L.bh == S && L.bw == S) {
                     const float* src = L.base + (size_t)li0 * L.w + lj;
 #pragma unroll
                     for (int r = 0; r < 4; r++) xr[slot][r][q] = __float_as_uint(__ldg(src + (size_t)r * L.w));
                 } else {
-                    const int col = pad_reflect_slow(lj, L.bw);
-#pragma unroll 1
+                    // partial leaf (np.pad 'reflect', jpeg.py:402): one modulo for the column and one for the first row, the other
+                    // three rows follow the triangle wave
+                    const float* src = L.base + pad_reflect(lj, L.bw);
+                    int rr = pad_reflect(li0, L.bh);
+                    int dir = (L.bh > 1 && (li0 % (2 * (L.bh - 1))) >= L.bh) ? -1 : 1;
+#pragma unroll
                     for (int r = 0; r < 4; r++) {
-                        const uint32_t v = __float_as_uint(__ldg(L.base + (size_t)pad_reflect_slow(li0 + r, L.bh) * L.w + col));
-                        if (r == 0) xr[slot][0][q] = v; else if (r == 1) xr[slot][1][q] = v; else if (r == 2) xr[slot][2][q] = v; else xr[slot][3][q] = v;
+                        xr[slot][r][q] = __float_as_uint(__ldg(src + (size_t)rr * L.w));
+                        if (L.bh > 1) {
+                            int nx = rr + dir;
+                            if (nx >= L.bh) { dir = -1; nx = L.bh - 2; } else if (nx < 0) { dir = 1; nx = 1; }
+                            rr = nx;
+                        }
                     }
                 }
             }
@@ -227,16 +231,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
         auto store_chunk = [&](const TcLeaf* T, int c, int slot) {       // registers -> hi/lo K-major tiles of buffer `slot`
             float* xh = sX + slot * 8192;
             float* xl = xh + 4096;
-            const int p = (32 * c + 4 * pw) / S;
+            const int r0 = 32 * c + 4 * pw;
+            const int p = r0 / S, li0 = r0 % S;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                const TcLeaf& L = T[p * NB + (lane + 32 * q) / S];
+                const int j = lane + 32 * q;
+                const TcLeaf& L = T[p * NB + j / S];
                 const bool live = (L.base != nullptr);
                 const float mid = L.mid, sc = L.sc;
+                int qv[4] = {0, 0, 0, 0};
+                if (INV && live) {                                         // quantiser steps of the four positions (coalesced, cache resident)
+#pragma unroll
+                    for (int r = 0; r < 4; r++) qv[r] = __ldg(L.qi + (li0 + r) * S + j % S);
+                }
                 float hi[4], lo[4];
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
-                    float x = INV ? (float)((int)xr[slot][r][q] * xq[INV ? slot : 0][r][q])          // jpeg.py:524
+                    float x = INV ? (float)((int)xr[slot][r][q] * qv[r])                               // jpeg.py:524
                                   : __fmul_rn(__fsub_rn(__uint_as_float(xr[slot][r][q]), mid), sc);   // jpeg.py:387-390
                     x = live ? x : 0.0f;
                     tf32_split(x, hi[r], lo[r]);
@@ -278,7 +289,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
                 uses++;
             }
         }
-    } else if (warp == 12) {
+    } else if (warp == 16) {
         // =============================================== MMA ISSUER ===============================================
         if (lane == 0) {
             bool alive = true;
@@ -327,8 +338,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
         }
     } else {
         // =============================================== CONSUMERS ===============================================
-        const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;            // this warp's 32 TMEM lanes
-        const int row = warp * 32 + lane;                                 // the super-tile row this thread owns in tensor memory
+        const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;      // this warp's 32 TMEM lanes (warps w and w + 4 share a quadrant)
+        const int row = (warp & 3) * 32 + lane;                           // the super-tile row this thread owns in tensor memory
+        const int cbeg = (warp >> 2) * 64;                                // ... and its 64 columns
         const int p = row / S, li = row % S;
         bool alive = true;
         for (int it = 0; it < my_tiles && alive; it++) {
@@ -338,9 +350,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // split W = Wh + Wl inside tensor memory (Wh / Wl are free: this thread waited for the previous tile's d2_full)
 #pragma unroll 1
-            for (int c = 0; c < 8; c++) {
+            for (int c = 0; c < 4; c++) {
                 uint32_t v[16], h[16], l[16];
-                tmem_ld16(D1 + lane_sel + c * 16, v);
+                tmem_ld16(D1 + lane_sel + cbeg + c * 16, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
@@ -348,8 +360,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
                     tf32_split(__uint_as_float(v[i]), wh, wl);
                     h[i] = __float_as_uint(wh); l[i] = __float_as_uint(wl);
                 }
-                tmem_st16(WH + lane_sel + c * 16, h);
-                tmem_st16(WL + lane_sel + c * 16, l);
+                tmem_st16(WH + lane_sel + cbeg + c * 16, h);
+                tmem_st16(WL + lane_sel + cbeg + c * 16, l);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -357,15 +369,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
             alive = mbar_wait(bar_d2full, it & 1, err);
             if (!alive) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // epilogue straight from tensor memory: super-row `row`, 32 columns at a time
+            // epilogue straight from tensor memory: super-row `row`, columns cbeg .. cbeg + 63, 32 at a time
 #pragma unroll 1
-            for (int c = 0; c < 4; c++) {
+            for (int c = 0; c < 2; c++) {
                 uint32_t v[32];
-                tmem_ld32(D2 + lane_sel + c * 32, v);
+                tmem_ld32(D2 + lane_sel + cbeg + c * 32, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
-                    const int j = c * 32 + g * 8;                   // 8 consecutive columns: inside one leaf (8 | S)
+                    const int j = cbeg + c * 32 + g * 8;                   // 8 consecutive columns: inside one leaf (8 | S)
                     const TcLeaf& L = Tc[p * NB + j / S];
                     const int lj = j % S;
                     if (L.base == nullptr) continue;

@@ -1,0 +1,97 @@
+// peer.cu -- one image over several GPUs of one node (BASELINE config C4): shared device memory, a
+// device-side barrier and gathers over NVLink, without NCCL on the data path.
+//
+// Every rank allocates its plan workspace with aeaj_peer_alloc and exports it (CUDA IPC); the ranks open each other's
+// workspaces, so a buffer that lives at offset o of this rank's workspace lives at offset o of every peer's: kernels
+// reach a neighbour's copy of a plane by adding a byte delta to their own pointer.  The stencil kernels read the few
+// halo rows outside their band straight from the neighbour (prefilter 3 rows, Sobel / NMS 2, chroma upsampling 1),
+// the CLAHE / percentile kernels sum the per-rank partial histograms on the fly, and two small gathers copy the other
+// ranks' rows of the strong / weak bitmaps (hysteresis runs replicated) and of the quadtree block totals.  Between the
+// phases the ranks meet at k_peer_barrier: rank r stores the epoch into slot r of every peer's flag array and spins on
+// its own array -- one tiny kernel per rank, a few microseconds over NVLink, ordered with the data by the stream.
+// All waits are bounded (error flag instead of a hang).  Peer data is read with ld.cv: never from a stale cache line.
+#include "aeaj_internal.cuh"
+
+namespace {
+
+struct PeerFlags { int* f[AEAJ_MAX_PEERS]; };
+
+__global__ void k_peer_barrier(PeerFlags F, int rank, int world, int epoch, int* err) {
+    const int t = threadIdx.x;
+    if (t < world && t != rank) {
+        __threadfence_system();                                            // everything this GPU wrote before is visible to the peers
+        *reinterpret_cast<volatile int*>(F.f[t] + rank) = epoch;           // "rank has reached `epoch`", into rank t's array
+        const volatile int* mine = F.f[rank] + t;
+        long long spins = 0;
+        while (*mine < epoch)
+            if (++spins > 2000000000ll) { if (err) atomicExch(err, 2); break; }
+        __threadfence_system();
+    }
+}
+
+// copies `nseg` byte ranges (all multiples of 4 bytes, 4-byte aligned) from peer memory into local memory; grid: (blocks, nseg)
+__global__ void __launch_bounds__(256) k_peer_gather(const PeerSeg* __restrict__ segs) {
+    const PeerSeg s = segs[blockIdx.y];
+    const long long n4 = s.bytes >> 2;
+    const unsigned* src = reinterpret_cast<const unsigned*>(s.src);
+    unsigned* dst = reinterpret_cast<unsigned*>(s.dst);
+    if ((((uintptr_t)s.src | (uintptr_t)s.dst) & 15) == 0) {
+        const long long n16 = n4 >> 2;
+        for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n16; i += (long long)gridDim.x * 256)
+            reinterpret_cast<uint4*>(dst)[i] = __ldcv(reinterpret_cast<const uint4*>(src) + i);
+        for (long long i = n16 * 4 + (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) dst[i] = __ldcv(src + i);
+    } else {
+        for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) dst[i] = __ldcv(src + i);
+    }
+}
+
+}  // namespace
+
+int launch_peer_barrier(int* const* flags_host, int rank, int world, int epoch, int* err_dev, cudaStream_t st) {
+    PeerFlags F;
+    for (int i = 0; i < AEAJ_MAX_PEERS; i++) F.f[i] = i < world ? flags_host[i] : nullptr;
+    k_peer_barrier<<<1, 32, 0, st>>>(F, rank, world, epoch, err_dev);
+    AEAJ_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_peer_gather(const PeerSeg* segs_dev, int nseg, long long max_bytes, cudaStream_t st) {
+    if (nseg <= 0) return 0;
+    const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>((max_bytes / 16 + 255) / 256, 64));
+    k_peer_gather<<<dim3(blocks, nseg), 256, 0, st>>>(segs_dev);
+    AEAJ_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared allocations (CUDA IPC)
+// ---------------------------------------------------------------------------------------------
+extern "C" int aeaj_peer_alloc(size_t bytes, void** ptr) {
+    AEAJ_REQUIRE(ptr && bytes > 0, "aeaj_peer_alloc: bad arguments");
+    AEAJ_CUDA(cudaMalloc(ptr, bytes));                                     // a plain cudaMalloc block: exportable with cudaIpcGetMemHandle
+    AEAJ_CUDA(cudaMemset(*ptr, 0, bytes));
+    return 0;
+}
+extern "C" int aeaj_peer_free(void* ptr) {
+    if (ptr) AEAJ_CUDA(cudaFree(ptr));
+    return 0;
+}
+extern "C" int aeaj_peer_export(void* ptr, void* handle64_host) {
+    AEAJ_REQUIRE(ptr && handle64_host, "aeaj_peer_export: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    AEAJ_CUDA(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle64_host, &h, 64);
+    return 0;
+}
+extern "C" int aeaj_peer_open(const void* handle64_host, void** ptr) {
+    AEAJ_REQUIRE(ptr && handle64_host, "aeaj_peer_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64_host, 64);
+    AEAJ_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int aeaj_peer_close(void* ptr) {
+    if (ptr) AEAJ_CUDA(cudaIpcCloseMemHandle(ptr));
+    return 0;
+}
