@@ -47,6 +47,12 @@ struct ColorConsts {          // per colour space, device-resident copy inside t
     float mid[3], scale[3];   // normalisation (MIDPOINTS / SCALE_FACTORS)
 };
 
+// one image over several GPUs (peer.cu): ranks share their plan workspaces; a buffer of rank r is reached by adding
+// delta[r] (bytes) to the address of this rank's copy
+#define AEAJ_MAX_PEERS 8
+struct PeerSeg { const void* src; void* dst; long long bytes; };
+struct PeerSet { int world, rank; long long delta[AEAJ_MAX_PEERS]; };
+
 // one "plane" = one layer of one image
 struct PlaneGeom {
     int h, w;          // layer size
@@ -158,6 +164,7 @@ struct aeaj_handle {
 struct PlaneDesc {
     int h, w, wpr, root, top, ntx, nty, layer;
     int ry0, ry1;                     // rows of this plane the current call works on (halo-split bands); default [0, h)
+    long long peer_up, peer_dn;       // byte deltas to the workspaces of the ranks that own the rows above ry0 / from ry1 on (0: this GPU)
     float mid, scale;
     float* layer_f32;        // downsampled un-normalised layer
     uint8_t* u8a;            // cast / stage ping
@@ -239,13 +246,15 @@ int launch_area(const float* src, int H, int W, float* dst, int dh, int dw, uint
 int launch_resize_linear(const float* src, int sh, int sw, float* dst, int H, int W, cudaStream_t st);
 int launch_upsample_color_inverse(aeaj_handle* h, int space, const PlaneDesc* planes_host, int B, int H, int W,
                                   float* rgb, uint8_t* rgb_u8, cudaStream_t st, int band0 = 0, int band1 = -1);
+int launch_peer_barrier(int* const* flags_host, int rank, int world, int epoch, int* err_dev, cudaStream_t st);
+int launch_peer_gather(const PeerSeg* segs_dev, int nseg, long long max_bytes, cudaStream_t st);
 int launch_cast_u8(const float* in, uint8_t* out, size_t n, cudaStream_t st);
 
 int launch_clahe_hist(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, cudaStream_t st);
-int launch_clahe_lut(const PlaneDesc* planes_dev, int nplanes, cudaStream_t st);
+int launch_clahe_lut(const PlaneDesc* planes_dev, int nplanes, const PeerSet& peers, cudaStream_t st);
 int launch_prefilter(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, int stages, int do_hist, cudaStream_t st);
 int launch_hist_u8(const uint8_t* src, size_t n, unsigned int* hist, cudaStream_t st);
-int launch_thresholds(const PlaneDesc* planes_dev, int nplanes, cudaStream_t st);
+int launch_thresholds(const PlaneDesc* planes_dev, int nplanes, const PeerSet& peers, cudaStream_t st);
 int launch_thresholds_from_double(const double* thr_d, int* thr, cudaStream_t st);
 int launch_canny_nms(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, cudaStream_t st);
 int hysteresis_tiles(PlaneDesc* planes_host, int nplanes, int* ring_cap);
@@ -258,7 +267,7 @@ int launch_u8_to_bitmap(const uint8_t* edge, int h, int w, uint32_t* bits, cudaS
 
 int launch_quadtree(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, int min_size, int max_size,
                     ClassEntry* class_lists, int* class_counts, const long long* class_offsets_dev, cudaStream_t st,
-                    int* launches);
+                    int* launches, int parts = 7);      // parts: 1 count per top block, 2 scan, 4 emit
 int launch_pack_states(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, cudaStream_t st);
 int launch_bucket_leaves(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, ClassEntry* class_lists,
                          int* class_counts, const long long* class_offsets_dev, int lg_min, int lg_max, cudaStream_t st);

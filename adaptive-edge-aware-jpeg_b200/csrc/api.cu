@@ -237,7 +237,7 @@ static int push_stage_plane(aeaj_handle* h, const PlaneDesc& P, cudaStream_t st)
 static int run_clahe(aeaj_handle* hd, StageWs& S, cudaStream_t st) {
     AEAJ_CUDA(cudaMemsetAsync(S.P.clahe_hist, 0, 16 * 256 * sizeof(uint32_t), st));
     int rc = launch_clahe_hist(hd->stage_plane_dev, &S.P, 1, st); if (rc) return rc;
-    return launch_clahe_lut(hd->stage_plane_dev, 1, st);
+    return launch_clahe_lut(hd->stage_plane_dev, 1, PeerSet{1, 0, {0}}, st);
 }
 
 extern "C" int aeaj_clahe(aeaj_handle* hd, const uint8_t* src, int h, int w, uint8_t* dst, void* ws, void* stream) {
@@ -270,7 +270,7 @@ extern "C" int aeaj_percentile_thresholds(aeaj_handle* hd, const uint8_t* src, i
     AEAJ_CUDA(cudaMemsetAsync(S.P.hist, 0, 256 * sizeof(uint32_t), st));
     int rc = push_stage_plane(hd, S.P, st); if (rc) return rc;
     rc = launch_hist_u8(src, (size_t)h * w, S.P.hist, st); if (rc) return rc;
-    return launch_thresholds(hd->stage_plane_dev, 1, st);
+    return launch_thresholds(hd->stage_plane_dev, 1, PeerSet{1, 0, {0}}, st);
 }
 
 static int run_nms_hysteresis(aeaj_handle* hd, StageWs& S, uint8_t* edge, cudaStream_t st) {
@@ -302,7 +302,7 @@ extern "C" int aeaj_canny(aeaj_handle* hd, const float* layer, int h, int w, uin
     rc = run_clahe(hd, S, st); if (rc) return rc;
     AEAJ_CUDA(cudaMemsetAsync(S.P.hist, 0, 256 * sizeof(uint32_t), st));
     rc = launch_prefilter(hd->stage_plane_dev, &S.P, 1, 7, 1, st); if (rc) return rc;
-    rc = launch_thresholds(hd->stage_plane_dev, 1, st); if (rc) return rc;
+    rc = launch_thresholds(hd->stage_plane_dev, 1, PeerSet{1, 0, {0}}, st); if (rc) return rc;
     return run_nms_hysteresis(hd, S, edge, st);
 }
 
@@ -384,10 +384,16 @@ struct aeaj_plan {
     uint8_t** outs_dev;                  // tap pointers [nplanes]
     std::vector<PackPlane> pack_planes;  // host copy of the packing descriptors
     PackPlane* pack_planes_dev;
+    // one image over several GPUs (peer.cu): the other ranks' workspaces / barrier flags, opened through CUDA IPC by the caller
+    PeerSet peers = {1, 0, {0}};
+    void* peer_ws[AEAJ_MAX_PEERS] = {nullptr};
+    int* peer_flags[AEAJ_MAX_PEERS] = {nullptr};
+    int peer_epoch = 0;
+    PeerSeg* peer_segs_dev = nullptr;
     int last_launches;
     bool need_full_chroma;
     int zigzag = 0;
-    int tensor_dct = 0xe;         // size classes on the tcgen05 kernels: bit k = class 16 << k (aeaj_plan_set_tensor_dct)
+    int tensor_dct = 0x8;         // size classes on the tcgen05 kernels: bit k = class 16 << k (aeaj_plan_set_tensor_dct)
     // optional per-stage CUDA-event timing (bench.py roofline leg)
     bool timing_on = false;
     std::vector<cudaEvent_t> ev;
@@ -519,7 +525,7 @@ extern "C" int aeaj_plan_create(aeaj_handle* h, int batch, int height, int width
 extern "C" int aeaj_plan_destroy(aeaj_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->h->device);
-    cudaFree(p->planes_dev); cudaFree(p->class_off_dev); cudaFree(p->outs_dev); cudaFree(p->qtab_dev); cudaFree(p->qtabf_dev); cudaFree(p->pack_planes_dev);
+    cudaFree(p->planes_dev); cudaFree(p->class_off_dev); cudaFree(p->outs_dev); cudaFree(p->qtab_dev); cudaFree(p->qtabf_dev); cudaFree(p->pack_planes_dev); cudaFree(p->peer_segs_dev);
     delete p;
     return 0;
 }
@@ -577,33 +583,37 @@ extern "C" int aeaj_plan_set_qtables(aeaj_plan* p, const int32_t* tables, size_t
     for (int k = p->lg_min; k <= p->lg_max; k++) per += (size_t)1 << (2 * k);
     AEAJ_REQUIRE(n_entries == 2 * per, "aeaj_plan_set_qtables: expected [luma sizes...][chroma sizes...] entries");
     AEAJ_CUDA(cudaSetDevice(p->h->device));
+    const size_t nf = n_entries + 8 * 2 * 9;                                     // float copy: every table padded to a 32-byte boundary
     if (!p->qtab_dev) {
         AEAJ_CUDA(cudaMalloc(&p->qtab_dev, sizeof(int32_t) * n_entries));
-        AEAJ_CUDA(cudaMalloc(&p->qtabf_dev, sizeof(float) * n_entries));
+        AEAJ_CUDA(cudaMalloc(&p->qtabf_dev, sizeof(float) * nf));
     }
     p->qtab_entries = n_entries;
     // float copy for the tensor-core epilogue, per table in the layout [s/8 column groups][s rows][8]: a warp whose lanes own
     // consecutive rows reads the 8 steps of one column group with one contiguous 256-bit load per lane (entries <= 6050: exact)
-    std::vector<float> asf(n_entries);
+    std::vector<float> asf(nf, 0.0f);
+    size_t foff[2][9] = {{0}};
     {
-        size_t o = 0;
+        size_t o = 0, of = 0;
         for (int t = 0; t < 2; t++)
             for (int k = p->lg_min; k <= p->lg_max; k++) {
                 const int s = 1 << k;
+                of = (of + 7) & ~(size_t)7;
+                foff[t][k] = of;
                 for (int r = 0; r < s; r++)
                     for (int c = 0; c < s; c++) {
                         const size_t dst = (s >= 8) ? ((size_t)(c >> 3) * s + r) * 8 + (c & 7) : (size_t)r * s + c;
-                        asf[o + dst] = (float)tables[o + (size_t)r * s + c];
+                        asf[of + dst] = (float)tables[o + (size_t)r * s + c];
                     }
-                o += (size_t)s * s;
+                o += (size_t)s * s; of += (size_t)s * s;
             }
     }
     AEAJ_CUDA(cudaMemcpyAsync(p->qtab_dev, tables, sizeof(int32_t) * n_entries, cudaMemcpyHostToDevice, ST(stream)));
-    AEAJ_CUDA(cudaMemcpyAsync(p->qtabf_dev, asf.data(), sizeof(float) * n_entries, cudaMemcpyHostToDevice, ST(stream)));
+    AEAJ_CUDA(cudaMemcpyAsync(p->qtabf_dev, asf.data(), sizeof(float) * nf, cudaMemcpyHostToDevice, ST(stream)));
     AEAJ_CUDA(cudaStreamSynchronize(ST(stream)));                                // `asf` is a temporary
     size_t o = 0;
     for (int t = 0; t < 2; t++)
-        for (int k = p->lg_min; k <= p->lg_max; k++) { p->qtab_ptr[t][k] = p->qtab_dev + o; p->qtabf_ptr[t][k] = p->qtabf_dev + o; o += (size_t)1 << (2 * k); }
+        for (int k = p->lg_min; k <= p->lg_max; k++) { p->qtab_ptr[t][k] = p->qtab_dev + o; p->qtabf_ptr[t][k] = p->qtabf_dev + foff[t][k]; o += (size_t)1 << (2 * k); }
     for (int i = 0; i < p->nplanes; i++)
         for (int k = 0; k < 9; k++) {
             p->planes[i].qtab[k] = p->qtab_ptr[p->planes[i].layer ? 1 : 0][k];
@@ -641,6 +651,12 @@ static int set_band(aeaj_plan* p, int band0, int band1) {
                          "band boundaries must be multiples of max(128, block_max) rows in every layer");
         }
         P.ry0 = band0 / rh; P.ry1 = (band1 == H) ? P.h : band1 / rh;
+        // rows above / below the band: the neighbour rank's workspace if this plan is one rank of a multi-GPU halo-split
+        P.peer_up = P.peer_dn = 0;
+        if (p->peers.world > 1 && !full) {
+            if (band0 > 0 && p->peers.rank > 0) P.peer_up = p->peers.delta[p->peers.rank - 1];
+            if (band1 < H && p->peers.rank + 1 < p->peers.world) P.peer_dn = p->peers.delta[p->peers.rank + 1];
+        }
     }
     return 0;
 }
@@ -688,20 +704,21 @@ static int encode_impl(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, 
         p->mark("clahe_hist");
     }
     if (phases & (1u << AEAJ_PHASE_PREFILTER)) {
-        rc = launch_clahe_lut(p->planes_dev, NP, st); if (rc) return rc;
+        rc = launch_clahe_lut(p->planes_dev, NP, p->peers, st); if (rc) return rc;
         p->mark("clahe_lut");
         rc = launch_prefilter(p->planes_dev, p->planes.data(), NP, 7, 1, st); if (rc) return rc;
         p->mark("prefilter");
         launches += 2;
     }
     if (phases & (1u << AEAJ_PHASE_NMS)) {
-        rc = launch_thresholds(p->planes_dev, NP, st); if (rc) return rc;
+        rc = launch_thresholds(p->planes_dev, NP, p->peers, st); if (rc) return rc;
         p->mark("thresholds");
         rc = launch_canny_nms(p->planes_dev, p->planes.data(), NP, st); if (rc) return rc;
         p->mark("canny_nms");
         launches += 2;
     }
-    if (phases & (1u << AEAJ_PHASE_TREE)) {
+    const bool tree_all = (phases & (1u << AEAJ_PHASE_TREE)) != 0;
+    if (tree_all || (phases & (1u << AEAJ_PHASE_HYST))) {
         rc = launch_hysteresis(h, p->planes_dev, p->planes.data(), NP, p->ntiles, p->ring_cap, A.flags, A.ring, A.ctrl, io->status, st); if (rc) return rc;
         p->mark("hysteresis");
         launches += 1;
@@ -714,10 +731,14 @@ static int encode_impl(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, 
             if (io->tap_layers[l])
                 AEAJ_CUDA(cudaMemcpyAsync(io->tap_layers[l], p->planes[l].layer_f32, sizeof(float) * (size_t)B * p->info.layer_h[l] * p->info.layer_w[l],
                                           cudaMemcpyDeviceToDevice, st));
+    }
+    // quadtree: per-top-block counts (band), scan over all top blocks (needs every band's counts), emit (band)
+    const int qt_parts = (tree_all ? 7 : 0) | ((phases & (1u << AEAJ_PHASE_QT_COUNT)) ? 1 : 0) | ((phases & (1u << AEAJ_PHASE_QT_EMIT)) ? 6 : 0);
+    if (qt_parts) {
         rc = launch_quadtree(p->planes_dev, p->planes.data(), NP, p->info.block_min, p->info.block_max, A.class_lists, A.class_counts,
-                             p->class_off_dev, st, &launches);
+                             p->class_off_dev, st, &launches, qt_parts);
         if (rc) return rc;
-        if (io->packed_states[0] || io->packed_states[1] || io->packed_states[2]) {
+        if ((qt_parts & 4) && (io->packed_states[0] || io->packed_states[1] || io->packed_states[2])) {
             rc = launch_pack_states(p->planes_dev, p->planes.data(), NP, st); if (rc) return rc;
             launches++;
         }
@@ -737,7 +758,7 @@ extern "C" int aeaj_encode(aeaj_plan* p, const aeaj_encode_io* io, void* workspa
     return encode_impl(p, io, workspace, ST(stream), 0x3fu, 0, -1);
 }
 extern "C" int aeaj_encode_phase(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, void* stream, int phase, int band0, int band1) {
-    AEAJ_REQUIRE(phase >= AEAJ_PHASE_COLOR && phase <= AEAJ_PHASE_DCT, "aeaj_encode_phase: bad phase");
+    AEAJ_REQUIRE(phase >= AEAJ_PHASE_COLOR && phase <= AEAJ_PHASE_QT_EMIT, "aeaj_encode_phase: bad phase");
     return encode_impl(p, io, workspace, ST(stream), 1u << phase, band0, band1);
 }
 
@@ -866,6 +887,80 @@ extern "C" int aeaj_unpack_coefficients_host(const uint32_t* mask, const int16_t
     }
     AEAJ_REQUIRE(k == nnz, "packed stream: value count does not match the mask");
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one image over several GPUs: peers (peer.cu)
+// ---------------------------------------------------------------------------------------------
+extern "C" int aeaj_plan_set_peers(aeaj_plan* p, int rank, int world, void* const* peer_workspaces_host, void* const* peer_flags_host) {
+    AEAJ_REQUIRE(p && world >= 1 && world <= AEAJ_MAX_PEERS && rank >= 0 && rank < world, "aeaj_plan_set_peers: bad arguments");
+    AEAJ_REQUIRE(p->info.batch == 1, "a multi-GPU halo-split plan holds one image");
+    AEAJ_REQUIRE(world == 1 || (peer_workspaces_host && peer_flags_host), "aeaj_plan_set_peers: NULL peer tables");
+    p->peers.world = world; p->peers.rank = rank;
+    for (int r = 0; r < AEAJ_MAX_PEERS; r++) {
+        p->peer_ws[r] = r < world && peer_workspaces_host ? peer_workspaces_host[r] : nullptr;
+        p->peer_flags[r] = r < world && peer_flags_host ? (int*)peer_flags_host[r] : nullptr;
+        p->peers.delta[r] = 0;
+    }
+    for (int r = 0; r < world && world > 1; r++) {
+        AEAJ_REQUIRE(p->peer_ws[r] && p->peer_flags[r], "aeaj_plan_set_peers: NULL peer pointer");
+        p->peers.delta[r] = (long long)((const char*)p->peer_ws[r] - (const char*)p->peer_ws[rank]);
+    }
+    p->planes_pushed.clear();
+    if (world > 1 && !p->peer_segs_dev) {
+        AEAJ_CUDA(cudaSetDevice(p->h->device));
+        AEAJ_CUDA(cudaMalloc(&p->peer_segs_dev, sizeof(PeerSeg) * 64 * 2));
+    }
+    return 0;
+}
+
+// all ranks meet: everything the ranks enqueued before the barrier is complete and visible before anything enqueued after it runs
+extern "C" int aeaj_plan_peer_barrier(aeaj_plan* p, void* stream) {
+    AEAJ_REQUIRE(p, "aeaj_plan_peer_barrier: NULL plan");
+    if (p->peers.world <= 1) return 0;
+    p->peer_epoch++;
+    return launch_peer_barrier(p->peer_flags, p->peers.rank, p->peers.world, p->peer_epoch, p->h->tc_err_dev + 1, ST(stream));
+}
+
+// copy the other ranks' rows into this rank's buffers.  what = 0: the strong / weak candidate bitmaps (before the replicated
+// hysteresis); what = 1: the per-top-block quadtree totals (before the scan).  Bands are the equal split used by aeaj/tiled.py.
+extern "C" int aeaj_plan_peer_gather(aeaj_plan* p, int what, void* workspace, void* stream) {
+    AEAJ_REQUIRE(p && workspace && (what == 0 || what == 1), "aeaj_plan_peer_gather: bad arguments");
+    const int world = p->peers.world, rank = p->peers.rank;
+    if (world <= 1) return 0;
+    AEAJ_REQUIRE(workspace == p->peer_ws[rank], "aeaj_plan_peer_gather: the workspace must be the shared allocation registered with aeaj_plan_set_peers");
+    plan_carve(p, workspace);
+    const int H = p->info.height;
+    AEAJ_REQUIRE(H % world == 0, "halo-split bands: the height must be a multiple of the number of ranks");
+    std::vector<PeerSeg> segs;
+    long long maxb = 0;
+    auto add = [&](const void* mine, long long off, long long bytes, int r) {
+        if (bytes <= 0) return;
+        PeerSeg s;
+        s.dst = (char*)mine + off; s.src = (const char*)mine + p->peers.delta[r] + off; s.bytes = bytes;
+        segs.push_back(s); maxb = std::max(maxb, bytes);
+    };
+    for (int r = 0; r < world; r++) {
+        if (r == rank) continue;
+        const int b0 = (H / world) * r, b1 = (H / world) * (r + 1);
+        for (int l = 0; l < 3; l++) {
+            const PlaneDesc& P = p->planes[l];
+            const int rh = H / P.h;
+            const int y0 = b0 / rh, y1 = (b1 == H) ? P.h : b1 / rh;
+            if (what == 0) {
+                add(P.strong, (long long)y0 * P.wpr * 4, (long long)(y1 - y0) * P.wpr * 4, r);
+                add(P.weak, (long long)y0 * P.wpr * 4, (long long)(y1 - y0) * P.wpr * 4, r);
+            } else {
+                const int t0 = y0 / P.top, t1 = aeaj_cdiv(y1, P.top);      // top-block rows of that band
+                add(P.tb_tot, (long long)t0 * P.ntx * sizeof(int2), (long long)(t1 - t0) * P.ntx * sizeof(int2), r);
+                add(P.tb_coef, (long long)t0 * P.ntx * sizeof(int), (long long)(t1 - t0) * P.ntx * sizeof(int), r);
+            }
+        }
+    }
+    AEAJ_REQUIRE(segs.size() <= 64, "too many gather segments");
+    PeerSeg* dev = p->peer_segs_dev + (what ? 64 : 0);
+    AEAJ_CUDA(cudaMemcpyAsync(dev, segs.data(), sizeof(PeerSeg) * segs.size(), cudaMemcpyHostToDevice, ST(stream)));
+    return launch_peer_gather(dev, (int)segs.size(), maxb, ST(stream));
 }
 
 // device pointers of the planes a halo-split caller exchanges between phases (batch 1)

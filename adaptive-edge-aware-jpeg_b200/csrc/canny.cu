@@ -92,12 +92,20 @@ __global__ void __launch_bounds__(256) k_clahe_hist(const PlaneDesc* __restrict_
 }
 
 // grid: (16 tiles, planes), 256 threads = bins
-__global__ void __launch_bounds__(256) k_clahe_lut(const PlaneDesc* __restrict__ planes) {
+// sum over the ranks of a halo-split (world == 1: just this GPU's counters); peer counters are read uncached
+__device__ __forceinline__ unsigned peer_sum(const unsigned int* mine, const PeerSet& peers) {
+    unsigned s = 0;
+    for (int r = 0; r < peers.world; r++)
+        s += (r == peers.rank) ? *mine : __ldcv(reinterpret_cast<const unsigned int*>(reinterpret_cast<const char*>(mine) + peers.delta[r]));
+    return s;
+}
+
+__global__ void __launch_bounds__(256) k_clahe_lut(const PlaneDesc* __restrict__ planes, const __grid_constant__ PeerSet peers) {
     const PlaneDesc& P = planes[blockIdx.y];
     ClaheGeom g = clahe_geom(P.h, P.w);
     const int tile = blockIdx.x, i = threadIdx.x;
     __shared__ int red[256];
-    int hv = (int)P.clahe_hist[tile * 256 + i];
+    int hv = (int)peer_sum(&P.clahe_hist[tile * 256 + i], peers);
     int excess = hv > g.clip ? hv - g.clip : 0;
     hv = hv > g.clip ? g.clip : hv;
     red[i] = excess;
@@ -231,14 +239,23 @@ __global__ void __launch_bounds__(256, 4) k_prefilter(const PlaneDesc* __restric
         __syncthreads();
     }
     const uint8_t* src = P.u8a;
+    // halo-split: the (at most 3) source rows outside this call's band live in the neighbour rank's copy of the plane
+    auto src_row = [&](int y, bool& remote) -> const uint8_t* {
+        const long long d = (y < P.ry0) ? P.peer_up : ((y >= P.ry1) ? P.peer_dn : 0ll);
+        remote = d != 0;
+        return src + d + (size_t)y * P.w;
+    };
     // stage A: source (folded coordinates) -> CLAHE; the staging region is PF_TH + 6 rows x 72 columns (2 spare
     // columns keep the index arithmetic to shifts; they hold valid folded pixels and are never read)
     if (!clahe || uniform) {
         for (int it = tid; it < (PF_TH + 6) * PF_AG; it += 256) {
             const int ry = it / PF_AG, gx = (it - ry * PF_AG) * 4;
-            const uint8_t* srow = src + (size_t)sFy[ry] * P.w;
+            bool remote;
+            const uint8_t* srow = src_row(sFy[ry], remote);
             const int4 fx = *reinterpret_cast<const int4*>(&sFx[gx]);
-            const int v[4] = {srow[fx.x], srow[fx.y], srow[fx.z], srow[fx.w]};
+            int v[4];
+            if (!remote) { v[0] = srow[fx.x]; v[1] = srow[fx.y]; v[2] = srow[fx.z]; v[3] = srow[fx.w]; }
+            else { v[0] = __ldcv(srow + fx.x); v[1] = __ldcv(srow + fx.y); v[2] = __ldcv(srow + fx.z); v[3] = __ldcv(srow + fx.w); }
             uint32_t packed = 0;
             if (clahe) {
                 const float4 xa4 = *reinterpret_cast<const float4*>(&sXa[gx]);
@@ -265,7 +282,9 @@ __global__ void __launch_bounds__(256, 4) k_prefilter(const PlaneDesc* __restric
     } else {
         for (int i = tid; i < (PF_TH + 6) * PF_AS; i += 256) {
             const int ry = i / PF_AS, rx = i - ry * PF_AS;
-            const int v = src[(size_t)sFy[ry] * P.w + sFx[rx]];
+            bool remote;
+            const uint8_t* srow = src_row(sFy[ry], remote);
+            const int v = remote ? __ldcv(srow + sFx[rx]) : srow[sFx[rx]];
             const float xa = sXa[rx], xa1 = __fsub_rn(1.0f, xa), ya = sYa[ry], ya1 = __fsub_rn(1.0f, ya);
             const uint8_t* l0 = &sLut[sTy[ry][0]][v];
             const uint8_t* l1 = &sLut[sTy[ry][1]][v];
@@ -422,14 +441,14 @@ __device__ __forceinline__ double percentile_warp(const unsigned long long* cum8
     const double d = (double)(b - a);
     return gfrac < 0.5 ? (double)a + d * gfrac : (double)b - d * (1.0 - gfrac);
 }
-__global__ void __launch_bounds__(128) k_thresholds(const PlaneDesc* __restrict__ planes, int nplanes) {
+__global__ void __launch_bounds__(128) k_thresholds(const PlaneDesc* __restrict__ planes, int nplanes, const __grid_constant__ PeerSet peers) {
     const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (p >= nplanes) return;
     const PlaneDesc& P = planes[p];
     unsigned long long cum8[8];
     unsigned long long run = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { run += P.hist[8 * lane + k]; cum8[k] = run; }
+    for (int k = 0; k < 8; k++) { run += peer_sum(&P.hist[8 * lane + k], peers); cum8[k] = run; }
     unsigned long long inc = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
@@ -471,18 +490,26 @@ __global__ void __launch_bounds__(256) k_canny_nms(const PlaneDesc* __restrict__
     __shared__ __align__(16) int sD[NM_TH + 2][NM_MS];           // dx | dy << 16
     const int tid = threadIdx.x;
     const uint8_t* src = P.u8b;
+    // halo-split: the (at most 2) source rows outside this call's band live in the neighbour rank's copy of the plane
+    auto src_row = [&](int y, bool& remote) -> const uint8_t* {
+        const long long d = (y < P.ry0) ? P.peer_up : ((y >= P.ry1) ? P.peer_dn : 0ll);
+        remote = d != 0;
+        return src + d + (size_t)y * P.w;
+    };
     // stage 1: source tile.  Interior tiles of 4-aligned planes use 32-bit loads.
     if (X0 >= 4 && X0 + NM_SS - 4 <= P.w && (P.w & 3) == 0) {
         for (int i = tid; i < (NM_TH + 4) * (NM_SS / 4); i += 256) {
             const int ry = i / (NM_SS / 4), rw = i - ry * (NM_SS / 4);
-            const int y = clampi(Y0 + ry - 2, 0, P.h - 1);
-            reinterpret_cast<uint32_t*>(&sS[ry][0])[rw] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)y * P.w + X0 - 4) + rw);
+            bool remote;
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(src_row(clampi(Y0 + ry - 2, 0, P.h - 1), remote) + X0 - 4) + rw;
+            reinterpret_cast<uint32_t*>(&sS[ry][0])[rw] = remote ? __ldcv(p) : __ldg(p);
         }
     } else {
         for (int i = tid; i < (NM_TH + 4) * NM_SS; i += 256) {
             const int ry = i / NM_SS, rx = i - ry * NM_SS;
-            const int y = clampi(Y0 + ry - 2, 0, P.h - 1), x = clampi(X0 + rx - 4, 0, P.w - 1);
-            sS[ry][rx] = src[(size_t)y * P.w + x];
+            bool remote;
+            const uint8_t* p = src_row(clampi(Y0 + ry - 2, 0, P.h - 1), remote) + clampi(X0 + rx - 4, 0, P.w - 1);
+            sS[ry][rx] = remote ? __ldcv(p) : *p;
         }
     }
     __syncthreads();
@@ -771,8 +798,8 @@ int launch_clahe_hist(const PlaneDesc* planes_dev, const PlaneDesc* P, int nplan
     AEAJ_LAUNCH_CHECK();
     return 0;
 }
-int launch_clahe_lut(const PlaneDesc* planes_dev, int nplanes, cudaStream_t st) {
-    k_clahe_lut<<<dim3(16, nplanes), 256, 0, st>>>(planes_dev);
+int launch_clahe_lut(const PlaneDesc* planes_dev, int nplanes, const PeerSet& peers, cudaStream_t st) {
+    k_clahe_lut<<<dim3(16, nplanes), 256, 0, st>>>(planes_dev, peers);
     AEAJ_LAUNCH_CHECK();
     return 0;
 }
@@ -788,8 +815,8 @@ int launch_hist_u8(const uint8_t* src, size_t n, unsigned int* hist, cudaStream_
     AEAJ_LAUNCH_CHECK();
     return 0;
 }
-int launch_thresholds(const PlaneDesc* planes_dev, int nplanes, cudaStream_t st) {
-    k_thresholds<<<aeaj_cdiv(nplanes, 4), 128, 0, st>>>(planes_dev, nplanes);
+int launch_thresholds(const PlaneDesc* planes_dev, int nplanes, const PeerSet& peers, cudaStream_t st) {
+    k_thresholds<<<aeaj_cdiv(nplanes, 4), 128, 0, st>>>(planes_dev, nplanes, peers);
     AEAJ_LAUNCH_CHECK();
     return 0;
 }

@@ -434,13 +434,15 @@ __device__ __forceinline__ void lin_coord(int d, double scale, int ssize, int& s
     if (s >= ssize - 1) { fx = 0.0f; s = ssize - 1; }
     s0 = s; s1 = min(s + 1, ssize - 1); f = fx;
 }
-__device__ __forceinline__ float lin_sample(const float* __restrict__ p, int sw, int x0, int x1, float fx, int y0, int y1, float fy) {
-    const float* r0 = p + (size_t)y0 * sw;
-    const float* r1 = p + (size_t)y1 * sw;
+__device__ __forceinline__ float ldf(const float* p, bool remote) { return remote ? __ldcv(p) : __ldg(p); }   // remote: a peer GPU's row
+__device__ __forceinline__ float lin_sample_rows(const float* r0, const float* r1, bool rem0, bool rem1, int x0, int x1, float fx, float fy) {
     float a0 = __fsub_rn(1.0f, fx), b0 = __fsub_rn(1.0f, fy);
-    float t0 = __fadd_rn(__fmul_rn(__ldg(r0 + x0), a0), __fmul_rn(__ldg(r0 + x1), fx));
-    float t1 = __fadd_rn(__fmul_rn(__ldg(r1 + x0), a0), __fmul_rn(__ldg(r1 + x1), fx));
+    float t0 = __fadd_rn(__fmul_rn(ldf(r0 + x0, rem0), a0), __fmul_rn(ldf(r0 + x1, rem0), fx));
+    float t1 = __fadd_rn(__fmul_rn(ldf(r1 + x0, rem1), a0), __fmul_rn(ldf(r1 + x1, rem1), fx));
     return __fadd_rn(__fmul_rn(t0, b0), __fmul_rn(t1, fy));
+}
+__device__ __forceinline__ float lin_sample(const float* __restrict__ p, int sw, int x0, int x1, float fx, int y0, int y1, float fy) {
+    return lin_sample_rows(p + (size_t)y0 * sw, p + (size_t)y1 * sw, false, false, x0, x1, fx, fy);
 }
 __global__ void __launch_bounds__(256) k_resize_linear(const float* __restrict__ src, int sh, int sw, float* __restrict__ dst, int H, int W) {
     int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y * blockDim.y + threadIdx.y;
@@ -454,7 +456,18 @@ __global__ void __launch_bounds__(256) k_resize_linear(const float* __restrict__
 
 // fused decode tail: per-layer INTER_LINEAR upsample (jpeg.py:340-354) + stack + inverse colour
 // (jpeg.py:290-297) -> RGB HWC
-struct UpIn { const float* p[3]; int h[3], w[3]; size_t stride[3]; };
+struct UpIn {
+    const float* p[3]; int h[3], w[3]; size_t stride[3];
+    int lo[3], hi[3];                  // halo-split: rows of every layer held by this GPU ...
+    long long peer_up, peer_dn;        // ... the row above / below comes from the neighbour rank's copy (byte deltas; 0: local)
+};
+// row `y` of layer l (batch image b): this GPU's copy or the neighbour's
+__device__ __forceinline__ const float* up_row(const UpIn& in, int l, int b, int y, bool& remote) {
+    const long long d = (y < in.lo[l]) ? in.peer_up : ((y >= in.hi[l]) ? in.peer_dn : 0ll);
+    remote = d != 0;
+    return reinterpret_cast<const float*>(reinterpret_cast<const char*>(in.p[l] + (size_t)b * in.stride[l]) + d) + (size_t)y * in.w[l];
+}
+
 template <int SPACE>
 __global__ void __launch_bounds__(256) k_upsample_color_inverse(const __grid_constant__ ColorConsts C, UpIn in, int H, int W, float* __restrict__ rgb,
                                                                 uint8_t* __restrict__ rgb8, int y_lo, int y_hi) {
@@ -473,7 +486,10 @@ __global__ void __launch_bounds__(256) k_upsample_color_inverse(const __grid_con
             int x0, x1, y0, y1; float fx, fy;
             lin_coord(dx, (double)in.w[l] / W, in.w[l], x0, x1, fx);
             lin_coord(dy, (double)in.h[l] / H, in.h[l], y0, y1, fy);
-            v[l] = lin_sample(p, in.w[l], x0, x1, fx, y0, y1, fy);
+            bool rem0, rem1;
+            const float* r0 = up_row(in, l, b, y0, rem0);
+            const float* r1 = up_row(in, l, b, y1, rem1);
+            v[l] = lin_sample_rows(r0, r1, rem0, rem1, x0, x1, fx, fy);
         }
     }
     float r, g, bl;
@@ -519,13 +535,13 @@ __global__ void __launch_bounds__(256) k_upsample2x_color_inverse(const __grid_c
     float cv[2][4];
 #pragma unroll
     for (int l = 1; l <= 2; l++) {
-        const float* p = in.p[l] + (size_t)b * in.stride[l];
         float t[2][4];
 #pragma unroll
         for (int r = 0; r < 2; r++) {
-            const float* row = p + (size_t)(r ? y1 : y0) * cw;
-            const float2 mid = __ldg(reinterpret_cast<const float2*>(row + m2));
-            const float vm = __ldg(row + max(m2 - 1, 0)), vp = __ldg(row + min(m2 + 2, cw - 1));
+            bool rem;
+            const float* row = up_row(in, l, b, r ? y1 : y0, rem);
+            const float2 mid = rem ? __ldcv(reinterpret_cast<const float2*>(row + m2)) : __ldg(reinterpret_cast<const float2*>(row + m2));
+            const float vm = ldf(row + max(m2 - 1, 0), rem), vp = ldf(row + min(m2 + 2, cw - 1), rem);
             const float p0a = first ? mid.x : vm, p0b = first ? mid.y : mid.x;        // (x0, x1) of px0
             const float p3b = last ? mid.y : vp;                                       // x1 of px3 (x0 = 2m+1)
             t[r][0] = __fadd_rn(__fmul_rn(p0a, a0), __fmul_rn(p0b, f0));
@@ -693,7 +709,11 @@ int launch_upsample_color_inverse(aeaj_handle* h, int space, const PlaneDesc* P,
     if (band1 < 0) band1 = H;
     const int Hb = band1 - band0;
     UpIn in;
-    for (int l = 0; l < 3; l++) { in.p[l] = P[l].layer_f32; in.h[l] = P[l].h; in.w[l] = P[l].w; in.stride[l] = (size_t)P[l].h * P[l].w; }
+    for (int l = 0; l < 3; l++) {
+        in.p[l] = P[l].layer_f32; in.h[l] = P[l].h; in.w[l] = P[l].w; in.stride[l] = (size_t)P[l].h * P[l].w;
+        in.lo[l] = P[l].ry0; in.hi[l] = P[l].ry1;
+    }
+    in.peer_up = P[0].peer_up; in.peer_dn = P[0].peer_dn;
     const bool fast2x = (in.h[1] * 2 == H && in.w[1] * 2 == W && in.h[2] == in.h[1] && in.w[2] == in.w[1] && (W % 4) == 0 &&
                          in.h[0] == H && in.w[0] == W);
     return dispatch_space(space, [&](auto S) {

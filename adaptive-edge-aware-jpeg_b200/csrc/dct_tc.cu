@@ -69,7 +69,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 }
 // 256-bit global loads / stores (sm_100): one full 32-byte sector per instruction and thread
 __device__ __forceinline__ void ld_global_v8(const void* p, uint32_t* v) {
-    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+    // volatile: stays where it is written relative to the other volatile statements, i.e. ABOVE the tensor-memory load that
+    // follows it in the epilogue (a plain asm is sunk to its first use and its L2 latency exposed once per group)
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
 }
 __device__ __forceinline__ void st_global_v8(void* p, const uint32_t* v) {
@@ -108,16 +110,25 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
                  : "memory");
 }
 
-constexpr int TC_CONSUMERS = 256, TC_PRODUCERS = 256, TC_THREADS = TC_CONSUMERS + TC_PRODUCERS + 32;
+#ifdef AEAJ_TC_STAMPS
+#define TC_STAMP(slot) do { if (blockIdx.x == 0 && it == 3 && lane == 0) err[(slot)] = (int)(clock64() & 0x7fffffff); } while (0)
+#else
+#define TC_STAMP(slot) do { } while (0)
+#endif
+constexpr int TC_CONSUMERS = 128, TC_PRODUCERS = 256, TC_THREADS = TC_CONSUMERS + TC_PRODUCERS + 32;
 constexpr int TC_TABS = 4;                                                // leaf tables in flight (ring)
 
 // Warp-specialised, persistent: one CTA per SM loops over the super-tiles blockIdx.x, blockIdx.x + gridDim.x, ..
-//   warps 8-15  PRODUCERS  global -> registers (one chunk ahead) -> normalise / dequantise -> hi/lo split -> K-major smem tiles
-//   warp 16     MMA        one thread issues GEMM1 chunk by chunk as buffers fill, then GEMM2 once W is split
-//   warps 0-7   CONSUMERS  (two per TMEM lane quadrant; a thread owns 64 columns of one super-tile row) split W inside tensor
-//                          memory, then the epilogue straight out of tensor memory
-// mbarriers: full[b] (256 producer arrivals) / empty[b] (tcgen05.commit) per X buffer; d1_full (commit: W complete),
-// w_ready (256 consumer arrivals: Wh, Wl written, D1 free), d2_full (commit: Out complete), d2_free (256 arrivals: D2 read).
+//   warps 4-11  PRODUCERS  global -> registers (one chunk ahead) -> normalise / dequantise -> hi/lo split -> K-major smem tiles
+//   warp 12     MMA        one thread issues GEMM1 chunk by chunk as buffers fill, then GEMM2 once W is split
+//   warps 0-3   CONSUMERS  (one per TMEM lane quadrant; a thread owns one super-tile row) split W inside tensor memory, then
+//                          the epilogue straight out of tensor memory
+// mbarriers: full[b] (one arrival per producer warp) / empty[b] (tcgen05.commit) per X buffer; d1_full (commit: W complete),
+// w_ready (one arrival per consumer warp: Wh, Wl written, D1 free), d2_full (commit: Out complete), d2_free (D2 read).
+// Measured alternatives (profiles/r2_tc_variants.md): eight consumer warps halve the epilogue (12 k -> 6.5 k cycles per tile)
+// but need 17 warps = 96 registers per thread, which spills the inverse producers and loses what the epilogue gains;
+// setmaxnreg rebalancing (MMA warpgroup 40, producers 120) starves the MMA-issuing thread.  This 13-warp layout is the
+// fastest of the variants tried.
 // The tensor pipe runs GEMM1 of tile i+1 while the consumers are in the epilogue of tile i and the producers already
 // stage tile i+2.  Every wait is bounded: a protocol error raises the error flag instead of hanging the GPU.
 //
@@ -145,8 +156,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
     const uint32_t bar_d2full = smem_u32(&mbar_storage[6]), bar_d2free = smem_u32(&mbar_storage[7]);
     if (tid == 0) {
         auto init = [](uint32_t b, int n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b), "r"(n) : "memory"); };
-        init(bar_full[0], TC_PRODUCERS); init(bar_full[1], TC_PRODUCERS); init(bar_empty[0], 1); init(bar_empty[1], 1);
-        init(bar_d1full, 1); init(bar_wready, TC_CONSUMERS); init(bar_d2full, 1); init(bar_d2free, TC_CONSUMERS);
+        // producer / consumer warps arrive once per warp (lane 0, after __syncwarp): 8 and 4 arrivals instead of 256 and 128
+        init(bar_full[0], TC_PRODUCERS / 32); init(bar_full[1], TC_PRODUCERS / 32); init(bar_empty[0], 1); init(bar_empty[1], 1);
+        init(bar_d1full, 1); init(bar_wready, TC_CONSUMERS / 32); init(bar_d2full, 1); init(bar_d2free, TC_CONSUMERS / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -164,7 +176,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
     const int ntiles = (count + NL - 1) / NL;
     const int my_tiles = (blockIdx.x < ntiles) ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
-    if (warp >= 8 && warp < 16) {
+    if (warp >= 4 && warp < 12) {
         // =============================================== PRODUCERS ===============================================
         const int pt = tid - TC_CONSUMERS, pw = pt >> 5;                  // producer thread / warp (0 .. 7)
         auto make_leaf = [&](int tile) {                                  // list entry tile * NL + pt -> leaf descriptor (registers)
@@ -187,6 +199,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
         auto producers_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
         // registers of two chunks in flight: thread (warp kc, lane g) holds super-rows 32c + 4kc .. +3 of columns g, g+32, g+64, g+96
         uint32_t xr[2][4][4];
+        int xq[INV ? 2 : 1][4][4];                                        // inverse: the quantiser steps of the same positions
         auto load_chunk = [&](const TcLeaf* T, int c, int slot) {
             const int r0 = 32 * c + 4 * pw;                               // super-row of r = 0; the four rows stay inside one leaf row block
             const int p = r0 / S, li0 = r0 % S;
@@ -197,7 +210,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
                 const int lj = j % S;
                 if (L.base == nullptr) {
 #pragma unroll
-                    for (int r = 0; r < 4; r++) xr[slot][r][q] = 0u;
+                    for (int r = 0; r < 4; r++) { xr[slot][r][q] = 0u; if (INV) xq[INV ? slot : 0][r][q] = 0; }
                     continue;
                 }
                 if (INV) {
@@ -205,6 +218,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
                     for (int r = 0; r < 4; r++) {
                         const int nat = (li0 + r) * S + lj;
                         xr[slot][r][q] = (uint32_t)__ldg(L.cf + (L.zig ? __ldg(izz + nat) : nat));
+                        xq[INV ? slot : 0][r][q] = __ldg(L.qi + nat);
                     }
                 } else if (L.bh == S && L.bw == S) {
                     const float* src = L.base + (size_t)li0 * L.w + lj;
@@ -231,23 +245,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
         auto store_chunk = [&](const TcLeaf* T, int c, int slot) {       // registers -> hi/lo K-major tiles of buffer `slot`
             float* xh = sX + slot * 8192;
             float* xl = xh + 4096;
-            const int r0 = 32 * c + 4 * pw;
-            const int p = r0 / S, li0 = r0 % S;
+            const int p = (32 * c + 4 * pw) / S;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                const int j = lane + 32 * q;
-                const TcLeaf& L = T[p * NB + j / S];
+                const TcLeaf& L = T[p * NB + (lane + 32 * q) / S];
                 const bool live = (L.base != nullptr);
                 const float mid = L.mid, sc = L.sc;
-                int qv[4] = {0, 0, 0, 0};
-                if (INV && live) {                                         // quantiser steps of the four positions (coalesced, cache resident)
-#pragma unroll
-                    for (int r = 0; r < 4; r++) qv[r] = __ldg(L.qi + (li0 + r) * S + j % S);
-                }
                 float hi[4], lo[4];
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
-                    float x = INV ? (float)((int)xr[slot][r][q] * qv[r])                               // jpeg.py:524
+                    float x = INV ? (float)((int)xr[slot][r][q] * xq[INV ? slot : 0][r][q])          // jpeg.py:524
                                   : __fmul_rn(__fsub_rn(__uint_as_float(xr[slot][r][q]), mid), sc);   // jpeg.py:387-390
                     x = live ? x : 0.0f;
                     tf32_split(x, hi[r], lo[r]);
@@ -274,6 +281,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
             for (int c = 0; c < 4; c++) {
                 const int b = c & 1;
                 if (uses >= 2) alive = alive && mbar_wait(bar_empty[b], ((uses >> 1) - 1) & 1, err);   // the MMAs that read this buffer last are done
+                if (warp == 4) TC_STAMP(2 + 2 * c);
                 if (c == 0) {
                     // the table ring slot of tile it + 1 belonged to tile it - 3, whose epilogue is over (its consumers went on to
                     // split tile it - 2 before the MMAs just waited for could be issued)
@@ -285,11 +293,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
                 if (c < 2) load_chunk(Tc, c + 2, b);
                 else if (has_next) load_chunk(Tn, c - 2, b);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(bar_full[b]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full[b]);
+                if (warp == 4) TC_STAMP(3 + 2 * c);
                 uses++;
             }
         }
-    } else if (warp == 16) {
+    } else if (warp == 12) {
         // =============================================== MMA ISSUER ===============================================
         if (lane == 0) {
             bool alive = true;
@@ -300,6 +310,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
                 for (int c = 0; c < 4 && alive; c++) {
                     const int b = c & 1;
                     alive = mbar_wait(bar_full[b], (nfull >> 1) & 1, err);
+                    TC_STAMP(10 + c);
                     nfull++;
                     if (!alive) break;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -317,13 +328,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
                 }
                 if (!alive) break;
                 mma_commit(bar_d1full);                                    // W = A . X complete
+                TC_STAMP(14);
                 alive = mbar_wait(bar_wready, it & 1, err);                // Wh / Wl written, D1 free again
+                TC_STAMP(15);
                 if (alive && it > 0) alive = mbar_wait(bar_d2free, (it - 1) & 1, err);   // the previous tile's Out has been read
                 if (!alive) break;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // GEMM2: Out = W . A^T.  A is block diagonal: K step s (columns 8s .. 8s+7 of W) only feeds the S output columns of its block
                 const uint32_t idesc2 = TC_IDESC_BASE | (((uint32_t)S >> 3) << 17);
-#pragma unroll 4
+#pragma unroll
                 for (int s = 0; s < TC_N / 8; s++) {
                     const int n0 = (8 * s / S) * S;                        // first output column of the block
                     const uint32_t bo = s * (TC_N * 32) + n0 * 16;         // K chunk pair s, tile rows n0 ..
@@ -334,23 +347,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
                     mma_ts(D2 + n0, WL + s * 8, bh_, idesc2, 1);
                 }
                 mma_commit(bar_d2full);
+                TC_STAMP(16);
             }
         }
     } else {
         // =============================================== CONSUMERS ===============================================
-        const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;      // this warp's 32 TMEM lanes (warps w and w + 4 share a quadrant)
-        const int row = (warp & 3) * 32 + lane;                           // the super-tile row this thread owns in tensor memory
-        const int cbeg = (warp >> 2) * 64;                                // ... and its 64 columns
+        const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;            // this warp's 32 TMEM lanes
+        const int row = warp * 32 + lane;                                 // the super-tile row this thread owns in tensor memory
+        constexpr int cbeg = 0;
         const int p = row / S, li = row % S;
         bool alive = true;
         for (int it = 0; it < my_tiles && alive; it++) {
             const TcLeaf* Tc = sLeaf[it & (TC_TABS - 1)];
+            if (warp == 0) TC_STAMP(20);
             alive = mbar_wait(bar_d1full, it & 1, err);
+            if (warp == 0) TC_STAMP(21);
             if (!alive) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // split W = Wh + Wl inside tensor memory (Wh / Wl are free: this thread waited for the previous tile's d2_full)
 #pragma unroll 1
-            for (int c = 0; c < 4; c++) {
+            for (int c = 0; c < 8; c++) {
                 uint32_t v[16], h[16], l[16];
                 tmem_ld16(D1 + lane_sel + cbeg + c * 16, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -365,13 +381,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(bar_wready);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_wready);
+            if (warp == 0) TC_STAMP(22);
             alive = mbar_wait(bar_d2full, it & 1, err);
+            if (warp == 0) TC_STAMP(23);
             if (!alive) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // epilogue straight from tensor memory: super-row `row`, columns cbeg .. cbeg + 63, 32 at a time
+            // epilogue straight from tensor memory: super-row `row`, 32 columns at a time
 #pragma unroll 1
-            for (int c = 0; c < 2; c++) {
+            for (int c = 0; c < 4; c++) {
+                // forward: the quantiser steps of this thread's 32 positions first -- they do not depend on tensor memory, and their
+                // L2 latency would otherwise be paid once per group of 8, serially (table layout [column group][row][8]: a warp reads
+                // one contiguous 1 KB run per group)
+                uint32_t qv[INV ? 1 : 4][8];
+                if (!INV) {
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        const int j = cbeg + c * 32 + g * 8;
+                        const TcLeaf& L = Tc[p * NB + j / S];
+                        if (L.base != nullptr) ld_global_v8(L.qf + ((size_t)((j % S) >> 3) * S + li) * 8, qv[INV ? 0 : g]);
+                    }
+                }
                 uint32_t v[32];
                 tmem_ld32(D2 + lane_sel + cbeg + c * 32, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -394,13 +425,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
                         }
                     } else {
                         const int nat = li * S + lj;
-                        // the 8 quantiser steps of (li, lj .. lj + 7): the lanes of a warp are consecutive rows, and the table is stored
-                        // [column group][row][8], so a warp reads one contiguous 1 KB run (one request, full sectors)
-                        uint32_t qv[8];
-                        ld_global_v8(L.qf + ((size_t)(lj >> 3) * S + li) * 8, qv);
                         uint32_t o[8];
 #pragma unroll
-                        for (int k = 0; k < 8; k++) o[k] = (uint32_t)quantize_f(__uint_as_float(v[g * 8 + k]), __uint_as_float(qv[k]));
+                        for (int k = 0; k < 8; k++) o[k] = (uint32_t)quantize_f(__uint_as_float(v[g * 8 + k]), __uint_as_float(qv[INV ? 0 : g][k]));
                         if (!L.zig) {
                             int* dst = L.cf + nat;                             // 32-byte aligned unless 2 x 2 leaves precede the block
                             if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) st_global_v8(dst, o);
@@ -416,7 +443,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(bar_d2free);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_d2free);
+            if (warp == 0) TC_STAMP(24);
         }
     }
     __syncthreads();

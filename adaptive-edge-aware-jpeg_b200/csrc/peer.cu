@@ -22,9 +22,9 @@ __global__ void k_peer_barrier(PeerFlags F, int rank, int world, int epoch, int*
         __threadfence_system();                                            // everything this GPU wrote before is visible to the peers
         *reinterpret_cast<volatile int*>(F.f[t] + rank) = epoch;           // "rank has reached `epoch`", into rank t's array
         const volatile int* mine = F.f[rank] + t;
-        long long spins = 0;
+        const long long t0 = clock64();
         while (*mine < epoch)
-            if (++spins > 2000000000ll) { if (err) atomicExch(err, 2); break; }
+            if (clock64() - t0 > 6000000000ll) { if (err) atomicExch(err, 2); break; }    // ~3 s: a missing rank must not hang the GPU
         __threadfence_system();
     }
 }

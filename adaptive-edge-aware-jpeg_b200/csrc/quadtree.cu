@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_qt_blocks(const PlaneDesc* __res
     const PlaneDesc& P = planes[plane_i];
     const int tb = by * P.ntx + bx;
     const int T = P.top, c = q.min_size;
+    if (by * T < P.ry0 || by * T >= P.ry1) return;     // halo-split: only the top blocks of this call's band (bands are multiples of T rows)
     const int n = T / c;                               // cells per side (power of two, >= 1)
     int L = 0; while ((1 << L) < n) L++;
     const int X0 = bx * T, Y0 = by * T;
@@ -295,17 +296,25 @@ int launch_pack_states(const PlaneDesc* planes_dev, const PlaneDesc* P, int npla
 }
 
 int launch_quadtree(const PlaneDesc* planes_dev, const PlaneDesc* P, int nplanes, int min_size, int max_size,
-                    ClassEntry* class_lists, int* class_counts, const long long* class_offsets_dev, cudaStream_t st, int* launches) {
+                    ClassEntry* class_lists, int* class_counts, const long long* class_offsets_dev, cudaStream_t st, int* launches, int parts) {
     QtParams q; q.min_size = min_size; q.lg_min = ilog2i(min_size); q.max_size = max_size;
     const TileMap tm = make_tile_map(P, nplanes, 0, 0, true);
     const int grd = tile_map_total(tm, nplanes);
-    k_qt_blocks<<<grd, QT_THREADS, 0, st>>>(planes_dev, tm, q, 0, class_lists, class_counts, class_offsets_dev);
-    AEAJ_LAUNCH_CHECK();
-    k_qt_scan<<<nplanes, QT_THREADS, 0, st>>>(planes_dev);
-    AEAJ_LAUNCH_CHECK();
-    k_qt_blocks<<<grd, QT_THREADS, 0, st>>>(planes_dev, tm, q, 1, class_lists, class_counts, class_offsets_dev);
-    AEAJ_LAUNCH_CHECK();
-    if (launches) *launches += 3;
+    if (parts & 1) {
+        k_qt_blocks<<<grd, QT_THREADS, 0, st>>>(planes_dev, tm, q, 0, class_lists, class_counts, class_offsets_dev);
+        AEAJ_LAUNCH_CHECK();
+        if (launches) (*launches)++;
+    }
+    if (parts & 2) {
+        k_qt_scan<<<nplanes, QT_THREADS, 0, st>>>(planes_dev);
+        AEAJ_LAUNCH_CHECK();
+        if (launches) (*launches)++;
+    }
+    if (parts & 4) {
+        k_qt_blocks<<<grd, QT_THREADS, 0, st>>>(planes_dev, tm, q, 1, class_lists, class_counts, class_offsets_dev);
+        AEAJ_LAUNCH_CHECK();
+        if (launches) (*launches)++;
+    }
     return 0;
 }
 

@@ -188,7 +188,11 @@ enum { AEAJ_PHASE_COLOR = 0,      /* clears accumulators; colour + subsample + u
        AEAJ_PHASE_PREFILTER = 2,  /* needs all-gathered u8a; LUTs + CLAHE/Gauss/bilateral of the band         */
        AEAJ_PHASE_NMS = 3,        /* needs all-gathered u8b, all-reduced hist; thresholds + NMS of the band   */
        AEAJ_PHASE_TREE = 4,       /* needs all-gathered strong/weak; hysteresis + quadtree, whole image       */
-       AEAJ_PHASE_DCT = 5 };      /* DCT + quantise of the band's leaves (coefficients at global offsets)     */
+       AEAJ_PHASE_DCT = 5,        /* DCT + quantise of the band's leaves (coefficients at global offsets)     */
+       /* AEAJ_PHASE_TREE in three steps, for ranks that shard the quadtree as well:                           */
+       AEAJ_PHASE_HYST = 6,       /* hysteresis, whole image (needs every band's strong / weak rows)          */
+       AEAJ_PHASE_QT_COUNT = 7,   /* quadtree: node counts of the band's top blocks                           */
+       AEAJ_PHASE_QT_EMIT = 8 };  /* needs every band's counts; scan + states / leaves / work lists of the band */
 enum { AEAJ_DPHASE_IDCT = 0,      /* dequantise + IDCT + merge of the band's leaves                           */
        AEAJ_DPHASE_COLOR = 1 };   /* needs the neighbouring chroma rows; upsample + inverse colour of the band */
 typedef struct {
@@ -200,6 +204,26 @@ typedef struct {
 AEAJ_API int aeaj_encode_phase(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, void* stream, int phase, int band0, int band1);
 AEAJ_API int aeaj_decode_phase(aeaj_plan* p, const aeaj_decode_io* io, void* workspace, void* stream, int phase, int band0, int band1);
 AEAJ_API int aeaj_plan_buffers(aeaj_plan* p, void* workspace, aeaj_plan_buffers_t* out);
+
+/* The same split WITHOUT collectives on the data path: the ranks (one process per GPU of one node) share their plan
+ * workspaces through CUDA IPC and the kernels read the few rows they need from the neighbour GPU directly over NVLink.
+ *   aeaj_peer_alloc / aeaj_peer_export: allocate the workspace (and a 64-byte-per-rank flag array) as exportable device
+ *   memory and produce its 64-byte IPC handle; aeaj_peer_open / aeaj_peer_close: map / unmap another rank's allocation.
+ *   aeaj_plan_set_peers: rank, world (<= 8) and, per rank, the address of its workspace and of its flag array as mapped in
+ *   THIS process (own entries: the local allocations).  Afterwards aeaj_encode_phase / aeaj_decode_phase with a band read
+ *   the halo rows outside the band from the neighbour's workspace, and the CLAHE / percentile kernels sum the per-rank
+ *   partial histograms.  aeaj_plan_peer_barrier: a device-side barrier of all ranks on `stream` (one small kernel; it
+ *   orders the ranks' earlier work before their later reads).  aeaj_plan_peer_gather: copies the other ranks' rows of the
+ *   strong / weak bitmaps (what = 0) or of the quadtree block totals (what = 1) into this rank's workspace.
+ * Sequence: aeaj/tiled.py.  Every rank must issue the same sequence of barriers. */
+AEAJ_API int aeaj_peer_alloc(size_t bytes, void** ptr);
+AEAJ_API int aeaj_peer_free(void* ptr);
+AEAJ_API int aeaj_peer_export(void* ptr, void* handle64_host);
+AEAJ_API int aeaj_peer_open(const void* handle64_host, void** ptr);
+AEAJ_API int aeaj_peer_close(void* ptr);
+AEAJ_API int aeaj_plan_set_peers(aeaj_plan* p, int rank, int world, void* const* peer_workspaces_host, void* const* peer_flags_host);
+AEAJ_API int aeaj_plan_peer_barrier(aeaj_plan* p, void* stream);
+AEAJ_API int aeaj_plan_peer_gather(aeaj_plan* p, int what, void* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * host-side helpers for the entropy-coding side (plain CPU code, no device work):
@@ -246,7 +270,7 @@ AEAJ_API int aeaj_plan_set_stream_layout(aeaj_plan* p, int zigzag);
 /* Tensor-core path for the DCT (cv.dct, jpeg.py:471) and IDCT (cv.idct, jpeg.py:483) of the size classes 16 .. 128: tcgen05
  * kind::tf32, error-compensated 3xTF32, FP32 accumulation in tensor memory; (128/S)^2 leaves of size S form one 128 x 128 tile
  * that is transformed with block-diagonal DCT matrices.  `mask` bit k selects the tensor-core kernel for class 16 << k (default
- * 0xe: 32, 64 and 128; 0 = the FP32-FMA kernels everywhere -- same parity class, the quantiser is exact in both).
+ * 0x8: 128 only, the class where it is faster; 0 = the FP32-FMA kernels everywhere -- same parity class, the quantiser is exact in both).
  * aeaj_tensor_dct_status: timed_out must point to int[32]; [0] is set if a tensor-core kernel ever gave up on a barrier
  * wait (also reported in the status words of aeaj_encode / aeaj_decode).  Synchronises the device. */
 AEAJ_API int aeaj_plan_set_tensor_dct(aeaj_plan* p, int mask);
