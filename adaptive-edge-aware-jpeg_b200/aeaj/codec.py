@@ -156,6 +156,8 @@ class DeviceCodec:
         s = status[:4].cpu().numpy()
         if what == "encode" and int(s[1]) != 1:
             raise native.AeajError("hysteresis did not converge")
+        if int(s[2]) == 2:
+            raise native.AeajError("a rank did not reach a peer barrier of the multi-GPU halo-split within its time limit; the results are invalid")
         if int(s[2]) != 0:
             raise native.AeajError("the tensor-core DCT kernel timed out on a barrier wait; its coefficients are invalid")
         if what == "decode" and int(s[3]) != 0:

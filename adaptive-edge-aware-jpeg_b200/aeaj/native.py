@@ -24,6 +24,8 @@ EXPORTS = [
     "aeaj_plan_set_stream_layout", "aeaj_plan_set_tensor_dct", "aeaj_tensor_dct_status",
     "aeaj_states_to_leaves_host", "aeaj_pack_states_host",
     "aeaj_pack_coefficients", "aeaj_unpack_coefficients", "aeaj_pack_coefficients_host", "aeaj_unpack_coefficients_host",
+    "aeaj_peer_alloc", "aeaj_peer_free", "aeaj_peer_export", "aeaj_peer_open", "aeaj_peer_close",
+    "aeaj_plan_set_peers", "aeaj_plan_peer_barrier", "aeaj_plan_peer_gather",
 ]
 
 
@@ -117,6 +119,14 @@ def load():
         lib.aeaj_plan_read_timing.argtypes = [vp, C.c_char_p, sz, vp, i, C.POINTER(i)]
         lib.aeaj_states_to_leaves_host.argtypes = [vp, i, i, i, i, i, i, vp, C.POINTER(i), C.POINTER(C.c_int64)]
         lib.aeaj_pack_states_host.argtypes = [vp, i, vp]
+        lib.aeaj_peer_alloc.argtypes = [sz, C.POINTER(vp)]
+        lib.aeaj_peer_free.argtypes = [vp]
+        lib.aeaj_peer_export.argtypes = [vp, vp]
+        lib.aeaj_peer_open.argtypes = [vp, C.POINTER(vp)]
+        lib.aeaj_peer_close.argtypes = [vp]
+        lib.aeaj_plan_set_peers.argtypes = [vp, i, i, C.POINTER(vp), C.POINTER(vp)]
+        lib.aeaj_plan_peer_barrier.argtypes = [vp, vp]
+        lib.aeaj_plan_peer_gather.argtypes = [vp, i, vp, vp]
         lib.aeaj_pack_coefficients.argtypes = [vp, C.POINTER(vp), vp, C.POINTER(PackedIO), vp, vp]
         lib.aeaj_unpack_coefficients.argtypes = [vp, C.POINTER(PackedIO), C.POINTER(vp), vp, vp]
         lib.aeaj_pack_coefficients_host.argtypes = [vp, C.c_int64, vp, vp, C.POINTER(C.c_int64), C.POINTER(i)]

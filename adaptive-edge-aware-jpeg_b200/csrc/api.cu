@@ -687,10 +687,16 @@ static int encode_impl(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, 
     int rc = set_band(p, band0, band1); if (rc) return rc;
     rc = plan_push_planes(p, st); if (rc) return rc;
     p->ev_n = 0; p->ev_stream = st; p->mark("start");
+    // a whole-image call on a plan that is one rank of a halo-split is a plain single-GPU call: no partial histograms to sum
+    const bool whole = band0 == 0 && (band1 < 0 || band1 == p->info.height);
+    const PeerSet solo = {1, 0, {0}};
+    const PeerSet& peers = whole ? solo : p->peers;
     if (phases & (1u << AEAJ_PHASE_COLOR)) {
         AEAJ_CUDA(cudaMemsetAsync(p->planes[0].clahe_hist, 0, (size_t)NP * 16 * 256 * sizeof(uint32_t), st));
         AEAJ_CUDA(cudaMemsetAsync(p->planes[0].hist, 0, (size_t)NP * 256 * sizeof(uint32_t), st));
         AEAJ_CUDA(cudaMemsetAsync(A.class_counts, 0, 16 * sizeof(int), st));
+        if (peers.world > 1)                               // sharded quadtree: this rank fills only its band's leaf slots; the others read as absent
+            for (int l = 0; l < 3; l++) AEAJ_CUDA(cudaMemsetAsync(io->leaves[l], 0, sizeof(int32_t) * 4 * (size_t)p->info.cap_leaves[l], st));
         // colour + chroma subsampling + u8 cast
         rc = launch_color_forward_planar(h, p->info.space, io->rgb, io->rgb ? nullptr : io->rgb_u8, B, p->info.height, p->info.width, p->planes_dev, p->planes.data(),
                                          A.full_c1, A.full_c2, st, &launches, band0, band1);
@@ -704,14 +710,14 @@ static int encode_impl(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, 
         p->mark("clahe_hist");
     }
     if (phases & (1u << AEAJ_PHASE_PREFILTER)) {
-        rc = launch_clahe_lut(p->planes_dev, NP, p->peers, st); if (rc) return rc;
+        rc = launch_clahe_lut(p->planes_dev, NP, peers, st); if (rc) return rc;
         p->mark("clahe_lut");
         rc = launch_prefilter(p->planes_dev, p->planes.data(), NP, 7, 1, st); if (rc) return rc;
         p->mark("prefilter");
         launches += 2;
     }
     if (phases & (1u << AEAJ_PHASE_NMS)) {
-        rc = launch_thresholds(p->planes_dev, NP, p->peers, st); if (rc) return rc;
+        rc = launch_thresholds(p->planes_dev, NP, peers, st); if (rc) return rc;
         p->mark("thresholds");
         rc = launch_canny_nms(p->planes_dev, p->planes.data(), NP, st); if (rc) return rc;
         p->mark("canny_nms");
@@ -919,7 +925,7 @@ extern "C" int aeaj_plan_peer_barrier(aeaj_plan* p, void* stream) {
     AEAJ_REQUIRE(p, "aeaj_plan_peer_barrier: NULL plan");
     if (p->peers.world <= 1) return 0;
     p->peer_epoch++;
-    return launch_peer_barrier(p->peer_flags, p->peers.rank, p->peers.world, p->peer_epoch, p->h->tc_err_dev + 1, ST(stream));
+    return launch_peer_barrier(p->peer_flags, p->peers.rank, p->peers.world, p->peer_epoch, p->h->tc_err_dev, ST(stream));
 }
 
 // copy the other ranks' rows into this rank's buffers.  what = 0: the strong / weak candidate bitmaps (before the replicated

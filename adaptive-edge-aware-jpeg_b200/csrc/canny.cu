@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(256, 4) k_prefilter(const PlaneDesc* __restric
             else { v[0] = __ldcv(srow + fx.x); v[1] = __ldcv(srow + fx.y); v[2] = __ldcv(srow + fx.z); v[3] = __ldcv(srow + fx.w); }
             uint32_t packed = 0;
             if (clahe) {
+                int o[4];
                 const float4 xa4 = *reinterpret_cast<const float4*>(&sXa[gx]);
                 const float xav[4] = {xa4.x, xa4.y, xa4.z, xa4.w};
                 const float ya = sYa[ry], ya1 = __fsub_rn(1.0f, ya);
@@ -271,9 +272,10 @@ __global__ void __launch_bounds__(256, 4) k_prefilter(const PlaneDesc* __restric
                     const float xa = xav[k], xa1 = __fsub_rn(1.0f, xa);
                     const float a = __fmul_rn((float)(q & 0xffu), xa1), b = __fmul_rn((float)((q >> 8) & 0xffu), xa);
                     const float c = __fmul_rn((float)((q >> 16) & 0xffu), xa1), d = __fmul_rn((float)(q >> 24), xa);
-                    const float r = __fadd_rn(__fmul_rn(__fadd_rn(a, b), ya1), __fmul_rn(__fadd_rn(c, d), ya));
-                    packed |= (uint32_t)min(max(__float2int_rn(r), 0), 255) << (8 * k);
+                    // a convex combination of bytes: within rounding noise of [0, 255], so cvRound needs no saturation
+                    o[k] = __float2int_rn(__fadd_rn(__fmul_rn(__fadd_rn(a, b), ya1), __fmul_rn(__fadd_rn(c, d), ya)));
                 }
+                packed = __byte_perm(__byte_perm(o[0], o[1], 0x0040), __byte_perm(o[2], o[3], 0x0040), 0x5410);
             } else {
                 packed = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
             }
@@ -344,29 +346,45 @@ __global__ void __launch_bounds__(256, 4) k_prefilter(const PlaneDesc* __restric
         if (stages & 4) {
             const float w_c = sW[0][0];
             const char* wbase = reinterpret_cast<const char*>(&sW[0][0]);
-#pragma unroll
-            for (int rr = 0; rr < 2; rr++)
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int v0 = wi[rr + 2][k + 2];
-                    float sum = 0.0f, wsum = 0.0f;
 #define BIL_ONE(idx, dy, dx, cls) { const int v = wi[rr + 2 + (dy)][k + 2 + (dx)]; \
                                     const float wgt = *reinterpret_cast<const float*>(wbase + (cls) * 1024 + __sad(v, v0, 0u)); \
                                     sum = __fmaf_rn((float)v, wgt, sum); wsum = __fadd_rn(wsum, wgt); }
-                    BIL_TAPS_UP(BIL_ONE)
-                    sum = __fmaf_rn((float)v0, w_c, sum); wsum = __fadd_rn(wsum, w_c);
-                    BIL_TAPS_DN(BIL_ONE)
-#undef BIL_ONE
-                    // cvRound(sum / wsum): an approximate quotient decides unless it is within 1e-3 of a .5 tie (its error is
-                    // < 1e-4 on values <= 255), where the correctly rounded division is taken
-                    float rw;
+#define BIL_PIXEL { const int v0 = wi[rr + 2][k + 2]; \
+                    sum = 0.0f; wsum = 0.0f; \
+                    BIL_TAPS_UP(BIL_ONE) \
+                    sum = __fmaf_rn((float)v0, w_c, sum); wsum = __fadd_rn(wsum, w_c); \
+                    BIL_TAPS_DN(BIL_ONE) }
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                // cvRound(sum / wsum): an approximate quotient decides unless it is within 1e-3 of a .5 tie (its error is
+                // < 1e-4 on values <= 255).  The test is made once per 4 px; the rare row that fails it (< 1 %) is redone
+                // with the correctly rounded division, so the common case carries neither a branch per pixel nor the sums.
+                // A weighted mean of bytes needs no saturation.
+                constexpr unsigned ins[4] = {0x3214u, 0x3240u, 0x3410u, 0x4210u};      // byte k of the word <- low byte of the result
+                uint32_t word = 0;
+                float worst = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    float sum, wsum, rw;
+                    BIL_PIXEL
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rw) : "f"(wsum));
                     const float q0 = __fmul_rn(__fmul_rn(sum, rw), 0.25f);
                     const float kf = rintf(q0);
-                    int res = (int)kf;
-                    if (fabsf(__fsub_rn(q0, kf)) > 0.499f) res = __float2int_rn(__fmul_rn(__fdiv_rn(sum, wsum), 0.25f));
-                    outw[rr] |= (uint32_t)min(max(res, 0), 255) << (8 * k);
+                    word = __byte_perm(word, (uint32_t)(int)kf, ins[k]);
+                    worst = fmaxf(worst, fabsf(__fsub_rn(q0, kf)));
                 }
+                if (worst > 0.499f) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        float sum, wsum;
+                        BIL_PIXEL
+                        word = __byte_perm(word, (uint32_t)__float2int_rn(__fmul_rn(__fdiv_rn(sum, wsum), 0.25f)), ins[k]);
+                    }
+                }
+                outw[rr] = word;
+            }
+#undef BIL_PIXEL
+#undef BIL_ONE
         } else {
 #pragma unroll
             for (int rr = 0; rr < 2; rr++)
@@ -479,6 +497,13 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
     return d;
 }
 
+// c != 0 ? a : b as one SEL (written as a ?: chain the compiler builds branches that every warp then walks through entirely)
+__device__ __forceinline__ int selnz(int a, int b, int c) {
+    int r;
+    asm("{.reg .pred p; setp.ne.s32 p, %3, 0; selp.s32 %0, %1, %2, p;}" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
 __global__ void __launch_bounds__(256) k_canny_nms(const PlaneDesc* __restrict__ planes, const __grid_constant__ TileMap tm) {
     int plane_i, txi, tyi;
     tile_decode(tm, blockIdx.x, plane_i, txi, tyi);
@@ -486,8 +511,10 @@ __global__ void __launch_bounds__(256) k_canny_nms(const PlaneDesc* __restrict__
     const int X0 = txi * NM_TW, Y0 = tyi * NM_TH;
     if (Y0 < P.ry0 || Y0 >= P.ry1) return;
     __shared__ __align__(16) uint8_t sS[NM_TH + 4][NM_SS];       // rows Y0-2.., cols X0-4.. (BORDER_REPLICATE)
-    __shared__ __align__(16) int sM[NM_TH + 2][NM_MS];           // magnitude, rows Y0-1.., cols X0-1.. (0 outside the image)
-    __shared__ __align__(16) int sD[NM_TH + 2][NM_MS];           // dx | dy << 16
+    // 4 x squared magnitude + direction class of the gradient (0 horizontal, 1 vertical, 2 / 3 the diagonals); rows Y0-1..,
+    // cols X0-1.. (magnitude 0 outside the image).  One word per cell: with c = 4 m + d,  m > m'  <=>  (c & ~3) > c'  and
+    // m >= m'  <=>  (c | 3) >= c', so the neighbours are compared as loaded and the direction never has to be recomputed.
+    __shared__ __align__(16) int sM[NM_TH + 2][NM_MS];
     const int tid = threadIdx.x;
     const uint8_t* src = P.u8b;
     // halo-split: the (at most 2) source rows outside this call's band live in the neighbour rank's copy of the plane
@@ -513,81 +540,82 @@ __global__ void __launch_bounds__(256) k_canny_nms(const PlaneDesc* __restrict__
         }
     }
     __syncthreads();
-    // stage 2: Sobel + L2 magnitude for 4 cells per task; cell (ry, c) <-> pixel (Y0-1+ry, X0-1+c),
-    // its 3x3 window starts at source tile row ry, column c+2
-    for (int i = tid; i < (NM_TH + 2) * (NM_MS / 4); i += 256) {
-        const int ry = i / (NM_MS / 4), c0 = (i - ry * (NM_MS / 4)) * 4;
-        // columns c0 .. c0+7 of the three source rows as two aligned words each; cell k reads bytes k+2 .. k+4.  The Sobel
-        // sums are byte dot products (dp4a, unsigned pixels x signed taps): gx = rows (1,2,1) x (-1,0,1), gy = (bottom - top) x (1,2,1)
-        uint32_t wa[3], wb[3];
+    // stage 2: Sobel + L2 magnitude + direction class for 4 cells per task; cell (ry, c) <-> pixel (Y0-1+ry, X0-1+c),
+    // its 3x3 window starts at source tile row ry, column c+2.  Tiles whose cells all lie inside the image (all but the
+    // border tiles) skip the per-cell bounds selects.
+    auto sobel = [&](auto interior_tag) {
+        constexpr bool INTERIOR = decltype(interior_tag)::value;
+        for (int i = tid; i < (NM_TH + 2) * (NM_MS / 4); i += 256) {
+            const int ry = i / (NM_MS / 4), c0 = (i - ry * (NM_MS / 4)) * 4;
+            // columns c0 .. c0+7 of the three source rows as two aligned words each; cell k reads bytes k+2 .. k+4.  The Sobel
+            // sums are byte dot products (dp4a, unsigned pixels x signed taps): gx = rows (1,2,1) x (-1,0,1), gy = (bottom - top) x (1,2,1)
+            uint32_t wa[3], wb[3];
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            wa[k] = *reinterpret_cast<const uint32_t*>(&sS[ry + k][c0]);
-            wb[k] = *reinterpret_cast<const uint32_t*>(&sS[ry + k][c0 + 4]);
-        }
-        int m[4], d[4];
-        const int y = Y0 - 1 + ry;
-        const bool yin = (y >= 0 && y < P.h);
+            for (int k = 0; k < 3; k++) {
+                wa[k] = *reinterpret_cast<const uint32_t*>(&sS[ry + k][c0]);
+                wb[k] = *reinterpret_cast<const uint32_t*>(&sS[ry + k][c0 + 4]);
+            }
+            int m[4];
+            const int y = Y0 - 1 + ry;
+            const bool yin = (y >= 0 && y < P.h);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            constexpr unsigned sel[4] = {0x5432u, 0x6543u, 0x7654u, 0x7765u};
-            const uint32_t t = __byte_perm(wa[0], wb[0], sel[k]), c = __byte_perm(wa[1], wb[1], sel[k]), b = __byte_perm(wa[2], wb[2], sel[k]);
-            int gx = dp4a_us(b, 0x000100ffu, dp4a_us(c, 0x000200feu, dp4a_us(t, 0x000100ffu, 0)));
-            int gy = dp4a_us(b, 0x00010201u, dp4a_us(t, 0x00fffeffu, 0));
-            const int x = X0 - 1 + c0 + k;
-            const bool in = yin && x >= 0 && x < P.w;
-            gx = in ? gx : 0; gy = in ? gy : 0;
-            m[k] = gx * gx + gy * gy;
-            d[k] = (int)((unsigned)(gx & 0xffff) | ((unsigned)gy << 16));
+            for (int k = 0; k < 4; k++) {
+                constexpr unsigned sel[4] = {0x5432u, 0x6543u, 0x7654u, 0x7765u};
+                const uint32_t t = __byte_perm(wa[0], wb[0], sel[k]), c = __byte_perm(wa[1], wb[1], sel[k]), b = __byte_perm(wa[2], wb[2], sel[k]);
+                const int gx = dp4a_us(b, 0x000100ffu, dp4a_us(c, 0x000200feu, dp4a_us(t, 0x000100ffu, 0)));
+                const int gy = dp4a_us(b, 0x00010201u, dp4a_us(t, 0x00fffeffu, 0));
+                // direction (cv.Canny, L2gradient: tan 22.5 = 13573 / 2^15): |gy| < |gx| tan 22.5 -> horizontal neighbours,
+                // |gy| > |gx| tan 67.5 -> vertical, else the diagonal on which gx and gy have the same / opposite sign
+                const int ax = abs(gx), ay = abs(gy) << 15;
+                const int tg22x = ax * 13573, tg67x = tg22x + (ax << 16);
+                const int nh = ay >= tg22x, dg = nh && !(ay > tg67x), pos = dg && ((gx ^ gy) >= 0);
+                int v = ((gx * gx + gy * gy) << 2) + nh + dg + pos;
+                if (!INTERIOR) {
+                    const int x = X0 - 1 + c0 + k;
+                    v = (yin && x >= 0 && x < P.w) ? v : 0;
+                }
+                m[k] = v;
+            }
+            *reinterpret_cast<int4*>(&sM[ry][c0]) = make_int4(m[0], m[1], m[2], m[3]);
         }
-        *reinterpret_cast<int4*>(&sM[ry][c0]) = make_int4(m[0], m[1], m[2], m[3]);
-        *reinterpret_cast<int4*>(&sD[ry][c0]) = make_int4(d[0], d[1], d[2], d[3]);
-    }
+    };
+    if (X0 >= 1 && X0 + NM_MS - 1 <= P.w && Y0 >= 1 && Y0 + NM_TH + 1 <= P.h) sobel(std::true_type{});
+    else sobel(std::false_type{});
     __syncthreads();
-    // stage 3: NMS + double threshold, 4 px per thread; a warp covers 2 rows x 64 px = 4 bitmap words
-    const int low = P.thr[0], high = P.thr[1];
+    // stage 3: NMS + double threshold, 4 px per thread; a warp covers 2 rows x 64 px = 4 bitmap words.  Branch-free: the two
+    // neighbours along the gradient are picked with selects on the direction class.  m < 2^21, so thresholds above 2^22 are
+    // equivalent to 2^22 and 4 thr + 3 cannot overflow; c > 4 thr + 3  <=>  m > thr.
+    const int low4 = min(P.thr[0], 1 << 22) * 4 + 3, high4 = min(P.thr[1], 1 << 22) * 4 + 3;
     const int lane = tid & 31;
     const int gx4 = (tid & 15) * 4;                                // first of the 4 px inside the tile row
 #pragma unroll 2
     for (int half = 0; half < NM_TH / 16; half++) {
         const int ty = (tid >> 4) + half * 16;
         const int y = Y0 + ty;
-        // magnitude rows ty, ty+1, ty+2 of sM (pixel rows y-1, y, y+1), columns gx4 .. gx4+5 (pixel x-1 .. x+4)
+        // rows ty, ty+1, ty+2 of sM (pixel rows y-1, y, y+1), columns gx4 .. gx4+5 (pixel x-1 .. x+4)
         int mg[3][6];
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             const int4 a = *reinterpret_cast<const int4*>(&sM[ty + k][gx4]);
-            mg[k][0] = a.x; mg[k][1] = a.y; mg[k][2] = a.z; mg[k][3] = a.w;
-            mg[k][4] = sM[ty + k][gx4 + 4]; mg[k][5] = sM[ty + k][gx4 + 5];
+            const int2 b = *reinterpret_cast<const int2*>(&sM[ty + k][gx4 + 4]);
+            mg[k][0] = a.x; mg[k][1] = a.y; mg[k][2] = a.z; mg[k][3] = a.w; mg[k][4] = b.x; mg[k][5] = b.y;
         }
-        const int4 dq = *reinterpret_cast<const int4*>(&sD[ty + 1][gx4]);   // cells gx4..gx4+3 = pixels x-1..x+2
-        const int dd[5] = {dq.x, dq.y, dq.z, dq.w, sD[ty + 1][gx4 + 4]};
         unsigned sb = 0, wb = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int x = X0 + gx4 + k;
-            const int mm = mg[1][k + 1];
-            int cls = 0;
-            if (y < P.h && x < P.w && mm > low) {
-                const int dv = dd[k + 1];
-                const int xs = (int)(short)(dv & 0xffff), ys = dv >> 16;
-                const int ax = abs(xs), ay = abs(ys) << 15;
-                const int tg22x = ax * 13573;
-                bool keep;
-                if (ay < tg22x) keep = (mm > mg[1][k]) && (mm >= mg[1][k + 2]);
-                else {
-                    const int tg67x = tg22x + (ax << 16);
-                    if (ay > tg67x) keep = (mm > mg[0][k + 1]) && (mm >= mg[2][k + 1]);
-                    else {
-                        const bool neg = (xs ^ ys) < 0;                      // s = -1: up-right / down-left
-                        const int up = neg ? mg[0][k + 2] : mg[0][k], dn = neg ? mg[2][k] : mg[2][k + 2];
-                        keep = (mm > up) && (mm > dn);
-                    }
-                }
-                if (keep) cls = (mm > high) ? 2 : 1;
-            }
-            sb |= (unsigned)(cls == 2) << k;
-            wb |= (unsigned)(cls == 1) << k;
+            const int c = mg[1][k + 1];
+            const int d = c & 3;
+            // d = 0: left / right, 1: up / down, 2: up-right / down-left (gx, gy of opposite sign), 3: up-left / down-right
+            const int d1 = d & 1, d2 = d & 2;
+            const int n1 = selnz(selnz(mg[0][k], mg[0][k + 2], d1), selnz(mg[0][k + 1], mg[1][k], d1), d2);
+            const int n2 = selnz(selnz(mg[2][k + 2], mg[2][k], d1), selnz(mg[2][k + 1], mg[1][k + 2], d1), d2);
+            // m > m(n1), and m >= m(n2) along the axes / m > m(n2) on the diagonals (the asymmetry of cv.Canny's NMS)
+            const int c_gt = c & ~3;
+            const int c2 = selnz(c_gt - 1, c | 3, d2);
+            const int keep = (c > low4) & (c_gt > n1) & (c2 >= n2);
+            const int strong = keep & (c > high4);
+            sb |= (unsigned)strong << k;
+            wb |= (unsigned)(keep ^ strong) << k;
         }
         // OR the nibbles of 8 neighbouring lanes into one 32-bit word
         sb <<= 4 * (lane & 7); wb <<= 4 * (lane & 7);

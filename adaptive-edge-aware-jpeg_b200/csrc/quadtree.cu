@@ -257,8 +257,10 @@ __global__ void __launch_bounds__(256) k_bucket_leaves(const PlaneDesc* __restri
         lg = lf.z > 0 ? 31 - __clz(lf.z) : -1;
         const bool ok = lg >= lg_min && lg <= lg_max && lf.z == (1 << lg) && lf.x >= 0 && lf.y >= 0 && lf.x < P.w && lf.y < P.h &&
                         lf.w >= 0 && (long long)lf.w + (long long)lf.z * lf.z <= (long long)P.cap_coef;
+        // multi-GPU halo-split: the leaf slots other ranks own are zero-filled on this rank (api.cu, AEAJ_PHASE_COLOR): not an error
+        const bool absent = lf.z == 0 && (P.ry0 > 0 || P.ry1 < P.h);
         if (ok) rank = atomicAdd(&s_cls[lg], 1);
-        else { lg = -1; atomicAdd(&class_counts[15], 1); }
+        else { lg = -1; if (!absent) atomicAdd(&class_counts[15], 1); }
     }
     __syncthreads();
     if (threadIdx.x < 9 && s_cls[threadIdx.x] > 0) s_base[threadIdx.x] = atomicAdd(&class_counts[threadIdx.x], s_cls[threadIdx.x]);
