@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(256, 4) k_prefilter(const PlaneDesc* __restric
     __shared__ float sYa[PF_TH + 6];
     __shared__ uint8_t sTx[PF_AS][2], sTy[PF_TH + 6][2];       // CLAHE tile indices per tile column / row
     __shared__ __align__(16) int sFx[PF_AS];                   // REFLECT_101-folded source coordinates
-    __shared__ int sFy[PF_TH + 6];
+    __shared__ long long sRow[PF_TH + 6];                      // byte offset of the (folded) source row from P.u8a; rows outside this
+                                                               // call's band (multi-GPU halo-split) point into the neighbour rank's copy
     __shared__ __align__(16) int sCo[PF_AS];                   // byte offset of the column's regime table inside sQuad (0 / 1024)
     __shared__ int sRo[PF_TH + 6];                             // same for the row regime (0 / 2048)
     const int tid = threadIdx.x;
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(256, 4) k_prefilter(const PlaneDesc* __restric
     } else if (tid >= PF_AS && tid < PF_AS + PF_TH + 6) {
         const int r = tid - PF_AS;
         const int y = reflect101(Y0 + r - 3, P.h);
-        sFy[r] = y;
+        sRow[r] = ((y < P.ry0) ? P.peer_up : ((y >= P.ry1) ? P.peer_dn : 0ll)) + (long long)y * P.w;
         float fr, fr0; int lo, hi, lo0, hi0, loL, hiL;
         tile_of(y, g.inv_th, fr, lo, hi);
         tile_of(reflect101(Y0 - 3, P.h), g.inv_th, fr0, lo0, hi0);
@@ -239,64 +240,80 @@ __global__ void __launch_bounds__(256, 4) k_prefilter(const PlaneDesc* __restric
         __syncthreads();
     }
     const uint8_t* src = P.u8a;
-    // halo-split: the (at most 3) source rows outside this call's band live in the neighbour rank's copy of the plane
-    auto src_row = [&](int y, bool& remote) -> const uint8_t* {
-        const long long d = (y < P.ry0) ? P.peer_up : ((y >= P.ry1) ? P.peer_dn : 0ll);
-        remote = d != 0;
-        return src + d + (size_t)y * P.w;
-    };
+    // tiles that touch rows of a neighbour rank read the source with ld.cv (never a stale line); everybody else plain loads
+    const bool tile_remote = (Y0 - 3 < P.ry0 && P.peer_up != 0) || (Y0 + PF_TH + 3 > P.ry1 && P.peer_dn != 0);
     // stage A: source (folded coordinates) -> CLAHE; the staging region is PF_TH + 6 rows x 72 columns (2 spare
     // columns keep the index arithmetic to shifts; they hold valid folded pixels and are never read)
-    if (!clahe || uniform) {
-        for (int it = tid; it < (PF_TH + 6) * PF_AG; it += 256) {
-            const int ry = it / PF_AG, gx = (it - ry * PF_AG) * 4;
-            bool remote;
-            const uint8_t* srow = src_row(sFy[ry], remote);
-            const int4 fx = *reinterpret_cast<const int4*>(&sFx[gx]);
-            int v[4];
-            if (!remote) { v[0] = srow[fx.x]; v[1] = srow[fx.y]; v[2] = srow[fx.z]; v[3] = srow[fx.w]; }
-            else { v[0] = __ldcv(srow + fx.x); v[1] = __ldcv(srow + fx.y); v[2] = __ldcv(srow + fx.z); v[3] = __ldcv(srow + fx.w); }
-            uint32_t packed = 0;
-            if (clahe) {
-                int o[4];
+    auto stage_a = [&](auto remote_tag) {
+        constexpr bool REMOTE = decltype(remote_tag)::value;
+        auto ld8 = [](const uint8_t* p) -> int { return REMOTE ? (int)__ldcv(p) : (int)*p; };
+        if (!clahe || uniform) {
+            // a thread keeps its 4-column group and walks down the rows (7 x 34 = 238 threads busy, 10 rows each): no index
+            // division, and everything that depends on the column only -- folded coordinates, interpolation weights, regime
+            // table offsets -- is loaded once.  Groups whose 8 surrounding bytes lie inside the row fetch two aligned words
+            // instead of four bytes.
+            static_assert((PF_TH + 6) % (256 / PF_AG) == 0, "stage A row walk");
+            constexpr int RSTEP = 256 / PF_AG;
+            if (tid < RSTEP * PF_AG) {
+                const int gx = (tid % PF_AG) * 4;
+                const int4 fx = *reinterpret_cast<const int4*>(&sFx[gx]);
                 const float4 xa4 = *reinterpret_cast<const float4*>(&sXa[gx]);
                 const float xav[4] = {xa4.x, xa4.y, xa4.z, xa4.w};
-                const float ya = sYa[ry], ya1 = __fsub_rn(1.0f, ya);
+                const float xa1v[4] = {__fsub_rn(1.0f, xa4.x), __fsub_rn(1.0f, xa4.y), __fsub_rn(1.0f, xa4.z), __fsub_rn(1.0f, xa4.w)};
                 const int4 co4 = *reinterpret_cast<const int4*>(&sCo[gx]);
-                const int ro = sRo[ry];
-                const int cov[4] = {co4.x + ro, co4.y + ro, co4.z + ro, co4.w + ro};
                 const char* qbase = reinterpret_cast<const char*>(&sQuad[0][0]);
+                const int xw = X0 - 4 + gx;                                  // the aligned word that holds column X0 - 3 + gx in byte 1
+                const bool words = xw >= 0 && xw + 8 <= P.w && (P.w & 3) == 0 && fx.x == xw + 1 && fx.w == xw + 4;
+#pragma unroll 2
+                for (int ry = tid / PF_AG; ry < PF_TH + 6; ry += RSTEP) {
+                    const uint8_t* srow = src + sRow[ry];
+                    int v[4];
+                    if (words) {
+                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(srow + xw);
+                        const uint32_t w0 = REMOTE ? __ldcv(wp) : __ldg(wp), w1 = REMOTE ? __ldcv(wp + 1) : __ldg(wp + 1);
+                        v[0] = (w0 >> 8) & 0xff; v[1] = (w0 >> 16) & 0xff; v[2] = w0 >> 24; v[3] = w1 & 0xff;
+                    } else {
+                        v[0] = ld8(srow + fx.x); v[1] = ld8(srow + fx.y); v[2] = ld8(srow + fx.z); v[3] = ld8(srow + fx.w);
+                    }
+                    uint32_t packed;
+                    if (clahe) {
+                        int o[4];
+                        const float ya = sYa[ry], ya1 = __fsub_rn(1.0f, ya);
+                        const int ro = sRo[ry];
+                        const int cov[4] = {co4.x + ro, co4.y + ro, co4.z + ro, co4.w + ro};
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t q = *reinterpret_cast<const uint32_t*>(qbase + cov[k] + v[k] * 4);
-                    const float xa = xav[k], xa1 = __fsub_rn(1.0f, xa);
-                    const float a = __fmul_rn((float)(q & 0xffu), xa1), b = __fmul_rn((float)((q >> 8) & 0xffu), xa);
-                    const float c = __fmul_rn((float)((q >> 16) & 0xffu), xa1), d = __fmul_rn((float)(q >> 24), xa);
-                    // a convex combination of bytes: within rounding noise of [0, 255], so cvRound needs no saturation
-                    o[k] = __float2int_rn(__fadd_rn(__fmul_rn(__fadd_rn(a, b), ya1), __fmul_rn(__fadd_rn(c, d), ya)));
+                        for (int k = 0; k < 4; k++) {
+                            const uint32_t q = *reinterpret_cast<const uint32_t*>(qbase + cov[k] + v[k] * 4);
+                            const float xa = xav[k], xa1 = xa1v[k];
+                            const float a = __fmul_rn((float)(q & 0xffu), xa1), b = __fmul_rn((float)((q >> 8) & 0xffu), xa);
+                            const float c = __fmul_rn((float)((q >> 16) & 0xffu), xa1), d = __fmul_rn((float)(q >> 24), xa);
+                            // a convex combination of bytes: within rounding noise of [0, 255], so cvRound needs no saturation
+                            o[k] = __float2int_rn(__fadd_rn(__fmul_rn(__fadd_rn(a, b), ya1), __fmul_rn(__fadd_rn(c, d), ya)));
+                        }
+                        packed = __byte_perm(__byte_perm(o[0], o[1], 0x0040), __byte_perm(o[2], o[3], 0x0040), 0x5410);
+                    } else {
+                        packed = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+                    }
+                    *reinterpret_cast<uint32_t*>(&sA[ry][gx]) = packed;
                 }
-                packed = __byte_perm(__byte_perm(o[0], o[1], 0x0040), __byte_perm(o[2], o[3], 0x0040), 0x5410);
-            } else {
-                packed = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
             }
-            *reinterpret_cast<uint32_t*>(&sA[ry][gx]) = packed;
+        } else {
+            for (int i = tid; i < (PF_TH + 6) * PF_AS; i += 256) {
+                const int ry = i / PF_AS, rx = i - ry * PF_AS;
+                const int v = ld8(src + sRow[ry] + sFx[rx]);
+                const float xa = sXa[rx], xa1 = __fsub_rn(1.0f, xa), ya = sYa[ry], ya1 = __fsub_rn(1.0f, ya);
+                const uint8_t* l0 = &sLut[sTy[ry][0]][v];
+                const uint8_t* l1 = &sLut[sTy[ry][1]][v];
+                const int c0 = sTx[rx][0] * 256, c1 = sTx[rx][1] * 256;
+                const float a = __fmul_rn((float)l0[c0], xa1), b = __fmul_rn((float)l0[c1], xa);
+                const float c = __fmul_rn((float)l1[c0], xa1), d = __fmul_rn((float)l1[c1], xa);
+                const float r = __fadd_rn(__fmul_rn(__fadd_rn(a, b), ya1), __fmul_rn(__fadd_rn(c, d), ya));
+                sA[ry][rx] = (uint8_t)min(max(__float2int_rn(r), 0), 255);
+            }
         }
-    } else {
-        for (int i = tid; i < (PF_TH + 6) * PF_AS; i += 256) {
-            const int ry = i / PF_AS, rx = i - ry * PF_AS;
-            bool remote;
-            const uint8_t* srow = src_row(sFy[ry], remote);
-            const int v = remote ? __ldcv(srow + sFx[rx]) : srow[sFx[rx]];
-            const float xa = sXa[rx], xa1 = __fsub_rn(1.0f, xa), ya = sYa[ry], ya1 = __fsub_rn(1.0f, ya);
-            const uint8_t* l0 = &sLut[sTy[ry][0]][v];
-            const uint8_t* l1 = &sLut[sTy[ry][1]][v];
-            const int c0 = sTx[rx][0] * 256, c1 = sTx[rx][1] * 256;
-            const float a = __fmul_rn((float)l0[c0], xa1), b = __fmul_rn((float)l0[c1], xa);
-            const float c = __fmul_rn((float)l1[c0], xa1), d = __fmul_rn((float)l1[c1], xa);
-            const float r = __fadd_rn(__fmul_rn(__fadd_rn(a, b), ya1), __fmul_rn(__fadd_rn(c, d), ya));
-            sA[ry][rx] = (uint8_t)min(max(__float2int_rn(r), 0), 255);
-        }
-    }
+    };
+    if (tile_remote) stage_a(std::true_type{});
+    else stage_a(std::false_type{});
     __syncthreads();
     // stage B: Gaussian [1 2 1]x[1 2 1], 4 outputs per thread sharing the 6 column sums; stored as 4 * value (u16)
     for (int i = tid; i < (PF_TH + 4) * (PF_CG + 1); i += 256) {
@@ -517,26 +534,33 @@ __global__ void __launch_bounds__(256) k_canny_nms(const PlaneDesc* __restrict__
     __shared__ __align__(16) int sM[NM_TH + 2][NM_MS];
     const int tid = threadIdx.x;
     const uint8_t* src = P.u8b;
-    // halo-split: the (at most 2) source rows outside this call's band live in the neighbour rank's copy of the plane
-    auto src_row = [&](int y, bool& remote) -> const uint8_t* {
-        const long long d = (y < P.ry0) ? P.peer_up : ((y >= P.ry1) ? P.peer_dn : 0ll);
-        remote = d != 0;
-        return src + d + (size_t)y * P.w;
+    // halo-split: the (at most 2) source rows outside this call's band live in the neighbour rank's copy of the plane; tiles
+    // that touch them read with ld.cv (never a stale line)
+    const int ph = P.h, pw = P.w, ry0 = P.ry0, ry1 = P.ry1;
+    const long long up = P.peer_up, dn = P.peer_dn;
+    const bool tile_remote = (Y0 - 2 < ry0 && up != 0) || (Y0 + NM_TH + 2 > ry1 && dn != 0);
+    auto src_row = [&](int y) -> const uint8_t* {
+        return src + ((y < ry0) ? up : ((y >= ry1) ? dn : 0ll)) + (size_t)y * pw;
     };
     // stage 1: source tile.  Interior tiles of 4-aligned planes use 32-bit loads.
-    if (X0 >= 4 && X0 + NM_SS - 4 <= P.w && (P.w & 3) == 0) {
-        for (int i = tid; i < (NM_TH + 4) * (NM_SS / 4); i += 256) {
-            const int ry = i / (NM_SS / 4), rw = i - ry * (NM_SS / 4);
-            bool remote;
-            const uint32_t* p = reinterpret_cast<const uint32_t*>(src_row(clampi(Y0 + ry - 2, 0, P.h - 1), remote) + X0 - 4) + rw;
-            reinterpret_cast<uint32_t*>(&sS[ry][0])[rw] = remote ? __ldcv(p) : __ldg(p);
+    if (X0 >= 4 && X0 + NM_SS - 4 <= pw && (pw & 3) == 0) {
+        if (!tile_remote) {
+            for (int i = tid; i < (NM_TH + 4) * (NM_SS / 4); i += 256) {
+                const int ry = i / (NM_SS / 4), rw = i - ry * (NM_SS / 4);
+                reinterpret_cast<uint32_t*>(&sS[ry][0])[rw] =
+                    __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)clampi(Y0 + ry - 2, 0, ph - 1) * pw + X0 - 4) + rw);
+            }
+        } else {
+            for (int i = tid; i < (NM_TH + 4) * (NM_SS / 4); i += 256) {
+                const int ry = i / (NM_SS / 4), rw = i - ry * (NM_SS / 4);
+                reinterpret_cast<uint32_t*>(&sS[ry][0])[rw] = __ldcv(reinterpret_cast<const uint32_t*>(src_row(clampi(Y0 + ry - 2, 0, ph - 1)) + X0 - 4) + rw);
+            }
         }
     } else {
         for (int i = tid; i < (NM_TH + 4) * NM_SS; i += 256) {
             const int ry = i / NM_SS, rx = i - ry * NM_SS;
-            bool remote;
-            const uint8_t* p = src_row(clampi(Y0 + ry - 2, 0, P.h - 1), remote) + clampi(X0 + rx - 4, 0, P.w - 1);
-            sS[ry][rx] = remote ? __ldcv(p) : *p;
+            const uint8_t* p = src_row(clampi(Y0 + ry - 2, 0, ph - 1)) + clampi(X0 + rx - 4, 0, pw - 1);
+            sS[ry][rx] = tile_remote ? __ldcv(p) : *p;
         }
     }
     __syncthreads();

@@ -461,8 +461,12 @@ struct UpIn {
     int lo[3], hi[3];                  // halo-split: rows of every layer held by this GPU ...
     long long peer_up, peer_dn;        // ... the row above / below comes from the neighbour rank's copy (byte deltas; 0: local)
 };
-// row `y` of layer l (batch image b): this GPU's copy or the neighbour's
+// row `y` of layer l (batch image b): this GPU's copy or the neighbour's.  PEER = false (every launch but those of a
+// multi-GPU halo-split rank) compiles to the plain address: no band tests, no second load flavour.
+template <bool PEER>
 __device__ __forceinline__ const float* up_row(const UpIn& in, int l, int b, int y, bool& remote) {
+    remote = false;
+    if (!PEER) return in.p[l] + (size_t)b * in.stride[l] + (size_t)y * in.w[l];
     const long long d = (y < in.lo[l]) ? in.peer_up : ((y >= in.hi[l]) ? in.peer_dn : 0ll);
     remote = d != 0;
     return reinterpret_cast<const float*>(reinterpret_cast<const char*>(in.p[l] + (size_t)b * in.stride[l]) + d) + (size_t)y * in.w[l];
@@ -487,8 +491,8 @@ __global__ void __launch_bounds__(256) k_upsample_color_inverse(const __grid_con
             lin_coord(dx, (double)in.w[l] / W, in.w[l], x0, x1, fx);
             lin_coord(dy, (double)in.h[l] / H, in.h[l], y0, y1, fy);
             bool rem0, rem1;
-            const float* r0 = up_row(in, l, b, y0, rem0);
-            const float* r1 = up_row(in, l, b, y1, rem1);
+            const float* r0 = up_row<true>(in, l, b, y0, rem0);
+            const float* r1 = up_row<true>(in, l, b, y1, rem1);
             v[l] = lin_sample_rows(r0, r1, rem0, rem1, x0, x1, fx, fy);
         }
     }
@@ -510,7 +514,7 @@ __device__ __forceinline__ void up2_coord(int d, int ssize, int& s0, int& s1, fl
     if (s >= ssize - 1) { fx = 0.0f; s = ssize - 1; }
     s0 = s; s1 = min(s + 1, ssize - 1); f = fx;
 }
-template <int SPACE>
+template <int SPACE, bool PEER>
 __global__ void __launch_bounds__(256) k_upsample2x_color_inverse(const __grid_constant__ ColorConsts C, UpIn in, int H, int W, float* __restrict__ rgb,
                                                                   uint8_t* __restrict__ rgb8, int y_lo, int y_hi) {
     __shared__ double pow_s[SPACE > AEAJ_YCOCG_R ? POW_TAB_DOUBLES : 1];
@@ -539,9 +543,9 @@ __global__ void __launch_bounds__(256) k_upsample2x_color_inverse(const __grid_c
 #pragma unroll
         for (int r = 0; r < 2; r++) {
             bool rem;
-            const float* row = up_row(in, l, b, r ? y1 : y0, rem);
-            const float2 mid = rem ? __ldcv(reinterpret_cast<const float2*>(row + m2)) : __ldg(reinterpret_cast<const float2*>(row + m2));
-            const float vm = ldf(row + max(m2 - 1, 0), rem), vp = ldf(row + min(m2 + 2, cw - 1), rem);
+            const float* row = up_row<PEER>(in, l, b, r ? y1 : y0, rem);
+            const float2 mid = (PEER && rem) ? __ldcv(reinterpret_cast<const float2*>(row + m2)) : __ldg(reinterpret_cast<const float2*>(row + m2));
+            const float vm = ldf(row + max(m2 - 1, 0), PEER && rem), vp = ldf(row + min(m2 + 2, cw - 1), PEER && rem);
             const float p0a = first ? mid.x : vm, p0b = first ? mid.y : mid.x;        // (x0, x1) of px0
             const float p3b = last ? mid.y : vp;                                       // x1 of px3 (x0 = 2m+1)
             t[r][0] = __fadd_rn(__fmul_rn(p0a, a0), __fmul_rn(p0b, f0));
@@ -720,7 +724,8 @@ int launch_upsample_color_inverse(aeaj_handle* h, int space, const PlaneDesc* P,
         constexpr int SP = decltype(S)::value;
         if (fast2x) {
             dim3 blk(32, 8), grd(aeaj_cdiv(W / 4, 32), aeaj_cdiv(Hb, 8), B);
-            k_upsample2x_color_inverse<SP><<<grd, blk, 0, st>>>(C, in, H, W, rgb, rgb8, band0, band1);
+            if (in.peer_up != 0 || in.peer_dn != 0) k_upsample2x_color_inverse<SP, true><<<grd, blk, 0, st>>>(C, in, H, W, rgb, rgb8, band0, band1);
+            else k_upsample2x_color_inverse<SP, false><<<grd, blk, 0, st>>>(C, in, H, W, rgb, rgb8, band0, band1);
         } else {
             dim3 blk(32, 8), grd(aeaj_cdiv(W, 32), aeaj_cdiv(Hb, 8), B);
             k_upsample_color_inverse<SP><<<grd, blk, 0, st>>>(C, in, H, W, rgb, rgb8, band0, band1);

@@ -15,10 +15,19 @@ timeout 600 python tests/golden/pin_expected_parity.py --gpu --out $O/expected_p
 # ncu only after the same commands exited cleanly above
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $O/${T}_launches_raw.csv \
     python bench.py --steps 2 --warmup 1 --no-extra > $O/${T}_ncu_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -f -o $O/${T}_full --launch-skip 48 --launch-count 24 \
+# the full report stays on the box unless it is small (gpurun_out/ is capped at 64 MiB): bring back the raw page and the
+# SASS pages of the stencil kernels as CSV
+timeout 900 ncu --set full --clock-control none --import-source on -f -o /tmp/${T}_full --launch-skip 48 --launch-count 24 \
     python tools/prof_step.py 8 0x8 > $O/${T}_ncu_full.log 2>&1
+ncu -i /tmp/${T}_full.ncu-rep --page raw --csv > $O/${T}_full_raw.csv 2>/dev/null
+for k in k_prefilter k_canny_nms k_upsample2x_color_inverse k_color_forward_planar k_qt_blocks k_hysteresis; do
+  ncu -i /tmp/${T}_full.ncu-rep --page source --csv --kernel-name regex:$k 2>/dev/null | gzip -9 > $O/${T}_sass_$k.csv.gz
+done
+sz=$(stat -c %s /tmp/${T}_full.ncu-rep 2>/dev/null || echo 0)
+if [ "$sz" -gt 0 ] && [ "$sz" -lt 40000000 ]; then cp /tmp/${T}_full.ncu-rep $O/; fi
+du -sh $O
 cat $O/${T}_pytest.log | tail -6
 cat $O/${T}_stage_0x8.txt
 grep -E "dct|idct|step" $O/${T}_stage_0x0.txt $O/${T}_stage_0xf.txt
 cat $O/${T}_bench_n1.json | cut -c1-1500
-tail -2 $O/${T}_bench_n1.err $O/${T}_pin.log $O/${T}_ncu_bench.log $O/${T}_ncu_full.log
+for f in $O/${T}_bench_n1.err $O/${T}_pin.log $O/${T}_ncu_bench.log $O/${T}_ncu_full.log; do tail -n 2 $f; done
