@@ -1,9 +1,10 @@
 """Turn the ncu artefacts brought back in gpurun_out/ into the tracked summaries under profiles/.
 
-    python profiles/make_summary.py <launches.csv> <full.ncu-rep> <tag>
+    python profiles/make_summary.py <launches.csv> <full.ncu-rep> <tag> [frames per launch of the full capture, default 8]
 
 <launches.csv>: `ncu --metrics gpu__time_duration.sum --clock-control none --csv` launch list of bench.py
-<full.ncu-rep>: `ncu --set full --clock-control none --import-source on` capture of the top kernels
+<full.ncu-rep>: `ncu --set full --clock-control none --import-source on` capture of the top kernels, or the CSV of its
+                raw page (`ncu -i REP --page raw --csv`; the report itself can exceed what travels back from the GPU box)
 Writes profiles/<tag>_launches.md, profiles/<tag>_kernels.md and profiles/<tag>_traffic.json
 (per-launch DRAM traffic of each captured kernel; bench.py reads it for roofline.traffic).
 """
@@ -52,11 +53,17 @@ KEYS = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "dram r
         ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma pipe %"),
         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe %"),
         ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
-        ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts")]
+        ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts"),
+        ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "LSU data-pipe wavefronts %"),
+        ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU pipe %"),
+        ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe (inst) %"),
+        ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "FP64 pipe %"),
+        ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU pipe %"),
+        ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe (inst) %")]
 
 
-def kernels(rep, tag):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+def kernels(rep, tag, frames=8):
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(raw.splitlines()))
     hdr, units = r[0], r[1]
     out = [f"# {tag}: `ncu --set full --clock-control none` of the top kernels (one launch each)\n"]
@@ -86,16 +93,20 @@ def kernels(rep, tag):
         for k, label in (("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
                          ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct_of_peak"),
                          ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_pct"),
-                         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct")):
+                         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"),
+                         ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu_pipe_pct"),
+                         ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64_pipe_pct"),
+                         ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "lsu_wavefronts_pct")):
             if k in hdr and row[hdr.index(k)] not in ("", "n/a"):
                 st[label] = float(row[hdr.index(k)])
         stats[name] = st
         out.append("")
     open(os.path.join(HERE, f"{tag}_kernels.md"), "w").write("\n".join(out) + "\n")
+    traffic["_frames_per_launch"] = frames
     json.dump(traffic, open(os.path.join(HERE, f"{tag}_traffic.json"), "w"), indent=1, sort_keys=True)
     json.dump(stats, open(os.path.join(HERE, f"{tag}_kernel_stats.json"), "w"), indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":
     launches(sys.argv[1], sys.argv[3])
-    kernels(sys.argv[2], sys.argv[3])
+    kernels(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 8)

@@ -18,7 +18,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --
 # the full report stays on the box unless it is small (gpurun_out/ is capped at 64 MiB): bring back the raw page and the
 # SASS pages of the stencil kernels as CSV
 timeout 900 ncu --set full --clock-control none --import-source on -f -o /tmp/${T}_full --launch-skip 48 --launch-count 24 \
-    python tools/prof_step.py 8 0x8 > $O/${T}_ncu_full.log 2>&1
+    python tools/prof_step.py 16 0x8 > $O/${T}_ncu_full.log 2>&1
 ncu -i /tmp/${T}_full.ncu-rep --page raw --csv > $O/${T}_full_raw.csv 2>/dev/null
 for k in k_prefilter k_canny_nms k_upsample2x_color_inverse k_color_forward_planar k_qt_blocks k_hysteresis; do
   ncu -i /tmp/${T}_full.ncu-rep --page source --csv --kernel-name regex:$k 2>/dev/null | gzip -9 > $O/${T}_sass_$k.csv.gz
