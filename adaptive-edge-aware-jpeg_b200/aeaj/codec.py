@@ -371,6 +371,26 @@ class DeviceCodec:
             st["rgb_out"] = torch.empty((p.info.batch, p.info.height, p.info.width, 3), dtype=torch.float32).pin_memory()
         return st
 
+    def _arena(self, p: _Plan, st: dict):
+        """one contiguous device + pinned-host buffer that holds a whole frame's packed streams (mask words, int16 values,
+        leaves, states of the three layers), so that a frame travels in ONE copy per direction (aeaj_copy_segments)"""
+        if "arena_dev" not in st:
+            n = 0
+            for l in range(3):
+                cc = int(p.info.cap_coef[l])
+                n += (cc // 32 + 1) * 4 + cc * 2 + int(p.info.cap_leaves[l]) * 16 + int(p.info.cap_states[l]) + 4 * 32
+            n = p.info.batch * n
+            st["arena_dev"] = torch.empty(n, dtype=torch.uint8, device=p.rgb_out.device)
+            st["arena_host"] = torch.empty(n, dtype=torch.uint8).pin_memory()
+            st["seg_table"] = torch.empty(64 * 24, dtype=torch.uint8, device=p.rgb_out.device)
+        return st["arena_dev"], st["arena_host"], st["seg_table"]
+
+    def _copy_segments(self, segs, table: torch.Tensor):
+        arr = (native.Segment * len(segs))()
+        for k, (src, dst, nb) in enumerate(segs):
+            arr[k].src, arr[k].dst, arr[k].bytes = src, dst, nb
+        native.check(self.lib.aeaj_copy_segments(arr, len(segs), table.data_ptr(), _stream()), "aeaj_copy_segments")
+
     def host_staging(self, B, H, W, space, brange, qrange):
         return self._host_staging(self._plan(B, H, W, space, brange, qrange))
 
@@ -474,6 +494,38 @@ class DeviceCodec:
         H, W = p.info.height, p.info.width
         pk = p.packed if job.get("packed") else None
         pkc = st["pk_counts"].numpy() if pk is not None else None
+        if pk is not None and not any(pkc[0, l, 2] != 0 for l in range(3)):
+            # the normal case (no int16 overflow): gather the frame's streams into one arena, ONE copy each way, scatter back
+            arena_dev, arena_host, table = self._arena(p, st)
+            base = arena_dev.data_ptr()
+            off = 0
+            there, back = [], []
+            for l in range(3):
+                nl, ns = int(counts[0, l, 0]), int(counts[0, l, 1])
+                nnz, nw = int(pkc[0, l, 0]), int(pkc[0, l, 3])
+                for t, nb, needed_back in ((pk.mask[l], nw * 4, True), (pk.vals[l], nnz * 2, True), (enc.leaves[l], nl * 16, True),
+                                           (enc.states[l], ns, False)):
+                    nb4 = (nb + 3) & ~3
+                    there.append((t.data_ptr(), base + off, nb4))
+                    if needed_back:
+                        back.append((base + off, t.data_ptr(), nb4))
+                    off = (off + nb4 + 15) & ~15
+            with torch.cuda.stream(stream):
+                self._copy_segments(there, table)
+                arena_host[:off].copy_(arena_dev[:off], non_blocking=True)          # -> the host-side entropy coder
+                arena_dev[:off].copy_(arena_host[:off], non_blocking=True)          # <- what the entropy decoder hands back
+                self._copy_segments(back, table)
+                enc.counts.copy_(st["counts"], non_blocking=True)
+                pk.counts.copy_(st["pk_counts"], non_blocking=True)
+                self.unpack(pk, 1, H, W, space, qrange, brange, instance=slot)
+                rgb = self.decode(enc.coef, enc.leaves, enc.counts, 1, H, W, space, qrange, brange, instance=slot,
+                                  out="u8" if host_out.dtype == torch.uint8 else "f32")
+                host_out[job["f"]:job["f"] + 1].copy_(rgb, non_blocking=True)
+                job["ev2"] = torch.cuda.Event()
+                job["ev2"].record(stream)
+            job["phase_b"] = True
+            nb_rgb = rgb.numel() * rgb.element_size()
+            return h2d + off + 2 * st["counts"].numel() * 4, d2h + off + nb_rgb
         with torch.cuda.stream(stream):
             for l in range(3):
                 nl, ns, nc = (int(counts[0, l, k]) for k in range(3))

@@ -25,7 +25,7 @@ EXPORTS = [
     "aeaj_states_to_leaves_host", "aeaj_pack_states_host",
     "aeaj_pack_coefficients", "aeaj_unpack_coefficients", "aeaj_pack_coefficients_host", "aeaj_unpack_coefficients_host",
     "aeaj_peer_alloc", "aeaj_peer_free", "aeaj_peer_export", "aeaj_peer_open", "aeaj_peer_close",
-    "aeaj_plan_set_peers", "aeaj_plan_peer_barrier", "aeaj_plan_peer_gather",
+    "aeaj_plan_set_peers", "aeaj_plan_peer_barrier", "aeaj_plan_peer_gather", "aeaj_copy_segments",
 ]
 
 
@@ -54,6 +54,10 @@ class DecodeIO(C.Structure):
 
 class PackedIO(C.Structure):
     _fields_ = [("mask", C.c_void_p * 3), ("vals", C.c_void_p * 3), ("counts", C.c_void_p)]
+
+
+class Segment(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("bytes", C.c_int64)]
 
 
 class PlanBuffers(C.Structure):
@@ -119,6 +123,7 @@ def load():
         lib.aeaj_plan_read_timing.argtypes = [vp, C.c_char_p, sz, vp, i, C.POINTER(i)]
         lib.aeaj_states_to_leaves_host.argtypes = [vp, i, i, i, i, i, i, vp, C.POINTER(i), C.POINTER(C.c_int64)]
         lib.aeaj_pack_states_host.argtypes = [vp, i, vp]
+        lib.aeaj_copy_segments.argtypes = [C.POINTER(Segment), i, vp, vp]
         lib.aeaj_peer_alloc.argtypes = [sz, C.POINTER(vp)]
         lib.aeaj_peer_free.argtypes = [vp]
         lib.aeaj_peer_export.argtypes = [vp, vp]

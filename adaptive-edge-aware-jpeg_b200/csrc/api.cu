@@ -895,6 +895,27 @@ extern "C" int aeaj_unpack_coefficients_host(const uint32_t* mask, const int16_t
     return 0;
 }
 
+// gather / scatter of one frame's variable-length streams into / out of one contiguous arena (include/aeaj.h)
+extern "C" int aeaj_copy_segments(const aeaj_segment* segs_host, int n, void* table_dev, void* stream) {
+    AEAJ_REQUIRE(n >= 0 && (n == 0 || (segs_host && table_dev)), "aeaj_copy_segments: bad arguments");
+    static_assert(sizeof(aeaj_segment) == sizeof(PeerSeg), "segment layout");
+    long long maxb = 0;
+    int m = 0;
+    std::vector<PeerSeg> segs((size_t)n);
+    for (int i = 0; i < n; i++) {
+        const aeaj_segment& s = segs_host[i];
+        AEAJ_REQUIRE(s.bytes >= 0 && (s.bytes & 3) == 0 && (((uintptr_t)s.src | (uintptr_t)s.dst) & 3) == 0,
+                     "aeaj_copy_segments: ranges must be 4-byte aligned multiples of 4 bytes");
+        if (s.bytes == 0) continue;
+        AEAJ_REQUIRE(s.src && s.dst, "aeaj_copy_segments: NULL range");
+        segs[m].src = s.src; segs[m].dst = s.dst; segs[m].bytes = s.bytes; m++;
+        maxb = std::max<long long>(maxb, s.bytes);
+    }
+    if (m == 0) return 0;
+    AEAJ_CUDA(cudaMemcpyAsync(table_dev, segs.data(), sizeof(PeerSeg) * m, cudaMemcpyHostToDevice, ST(stream)));   // pageable: staged before return
+    return launch_peer_gather((const PeerSeg*)table_dev, m, maxb, ST(stream));
+}
+
 // ---------------------------------------------------------------------------------------------
 // one image over several GPUs: peers (peer.cu)
 // ---------------------------------------------------------------------------------------------

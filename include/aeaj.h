@@ -261,6 +261,15 @@ AEAJ_API int aeaj_pack_coefficients_host(const int32_t* coef_host, int64_t n_coe
 AEAJ_API int aeaj_unpack_coefficients_host(const uint32_t* mask_host, const int16_t* vals_host, int64_t n_coef, int64_t nnz,
                                            int32_t* coef_host);
 
+/* One frame's worth of variable-length streams (packed coefficients, leaves, states of the three layers) in ONE transfer:
+ * copies n byte ranges device -> device in a single launch, so that the caller can gather everything the host-side entropy
+ * coder needs (jpeg.py:531-597) into one contiguous arena, move it with one cudaMemcpy, and scatter what comes back
+ * (jpeg.py:599-674) the same way -- instead of ~27 small copies per frame, each paying its own DMA set-up.
+ * Every range must be 4-byte aligned and a multiple of 4 bytes; 16-byte aligned ranges are moved with 128-bit accesses.
+ * `table_dev`: caller-owned device scratch of at least n * sizeof(aeaj_segment) bytes (the table is staged through it). */
+typedef struct { const void* src; void* dst; int64_t bytes; } aeaj_segment;
+AEAJ_API int aeaj_copy_segments(const aeaj_segment* segs_host, int n, void* table_dev, void* stream);
+
 /* Stream layout.  zigzag = 0 (default): each block of the coefficient stream is row-major,
  * i.e. the reference's img_quantized blocks.  zigzag = 1: each block is stored in the zigzag order of
  * Jpeg._zigzag_ordering (jpeg.py:726-766), i.e. the stream is byte-for-byte what _entropy_encode hands to zlib
