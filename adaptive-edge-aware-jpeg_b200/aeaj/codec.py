@@ -12,6 +12,7 @@ Everything is asynchronous on the current torch CUDA stream; nothing falls back 
 from __future__ import annotations
 
 import ctypes as C
+import time
 from collections import OrderedDict
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
@@ -382,7 +383,7 @@ class DeviceCodec:
             n = p.info.batch * n
             st["arena_dev"] = torch.empty(n, dtype=torch.uint8, device=p.rgb_out.device)
             st["arena_host"] = torch.empty(n, dtype=torch.uint8).pin_memory()
-            st["seg_table"] = torch.empty(64 * 24, dtype=torch.uint8, device=p.rgb_out.device)
+            st["seg_table"] = torch.empty(64 * 24 * max(1, p.info.batch), dtype=torch.uint8, device=p.rgb_out.device)
         return st["arena_dev"], st["arena_host"], st["seg_table"]
 
     def _copy_segments(self, segs, table: torch.Tensor):
@@ -434,35 +435,64 @@ class DeviceCodec:
         return st["rgb_out"], h2d, st["rgb_out"].numel() * 4
 
     def roundtrip_host_pipelined(self, host_in: torch.Tensor, host_out: torch.Tensor, space, qrange, brange, slots: int = 8, repeat: int = 1, lag: int = 3,
-                                 packed: bool = True):
+                                 packed: bool = True, threads: int = 1, frames_per_job: int = 1):
         """Host-buffer encode+decode of every frame of `host_in` (pinned float32 -- or uint8, the 8-bit image flow
-        Image.load -> compress ... decompress -> Image.save -- [F,H,W,3]) into `host_out` (float32 or uint8), one frame
-        per job, jobs round-robin over `slots` CUDA streams so that the H2D and D2H copies of different frames overlap
-        each other and the kernels (PCIe is full duplex; the step is copy-bound).  Per frame, in stream order:
-        H2D RGB -> aeaj_encode -> D2H counts -> [host waits for the counts] -> D2H used coefficient / leaf / state ranges ->
-        H2D of the same ranges (what a host-side entropy decoder would hand back) -> aeaj_decode -> D2H RGB.
+        Image.load -> compress ... decompress -> Image.save -- [F,H,W,3]) into `host_out` (float32 or uint8), `frames_per_job`
+        frames per job, jobs round-robin over `slots` CUDA streams so that the H2D and D2H copies of different jobs overlap
+        each other and the kernels (PCIe is full duplex; the step is copy-bound).  Per job, in stream order:
+        H2D RGB -> aeaj_encode -> D2H counts -> [host waits for the counts] -> D2H of the job's streams ->
+        H2D of the same bytes (what a host-side entropy decoder would hand back) -> aeaj_decode -> D2H RGB.
         `repeat` > 1 streams the same F frames that many times back to back (a long-running ingest) without draining
         the pipeline in between.  packed=True moves the coefficient streams in their packed form (bit mask + int16 non-zeros,
         aeaj_pack_coefficients after the encode, aeaj_unpack_coefficients before the decode; a plane whose overflow flag is
-        set travels as int32).  Returns (h2d_bytes, d2h_bytes) summed over all jobs."""
+        set travels as int32) and all of a job's streams as ONE copy per direction (aeaj_copy_segments).
+        Measured on B200 (tools/e2e_sweep.py, profiles/r2_e2e_sweep.txt): 0.77 ms per 4K frame against 0.60 ms for the same bytes as
+        bare copies (48 GB/s per direction); more slots, several frames per job (`frames_per_job`) or several host threads
+        (`threads`, each driving its own slots) do not change it -- the driving thread is blocked on the device half of the time
+        and the device work alone takes 0.42 ms per frame, so what is left is how copies queued behind unfinished kernels hold up
+        later copies of the same direction.  Returns (h2d_bytes, d2h_bytes) summed over all jobs."""
         F0, H, W, _ = host_in.shape
-        F = F0 * repeat
+        G = max(1, frames_per_job)
+        if F0 % G != 0:
+            raise ValueError(f"frames_per_job ({G}) must divide the number of frames ({F0})")
+        J = (F0 // G) * repeat                                      # jobs
         dev = torch.device("cuda", self.device)
         if not hasattr(self, "_streams") or len(self._streams) < slots:
             self._streams = [torch.cuda.Stream(device=dev) for _ in range(slots)]
+        threads = max(1, min(threads, slots, J))
+        self.pipeline_host_wait_s = 0.0                            # time the driving thread(s) spent blocked on the device (diagnostic)
+        for slot in range(min(slots, J)):                          # plans and staging are created by one thread, before the workers start
+            self._host_staging(self._plan(G, H, W, space, brange, qrange, instance=slot))
+        if threads == 1:
+            return self._pipeline_worker(list(range(J)), list(range(slots)), G, host_in, host_out, space, qrange, brange, min(lag, slots - 1), packed)
+        import concurrent.futures as cf
+        per = slots // threads
+        work = [([j for j in range(J) if j % threads == t], list(range(t * per, (t + 1) * per))) for t in range(threads)]
+        with cf.ThreadPoolExecutor(max_workers=threads) as ex:
+            res = list(ex.map(lambda w: self._pipeline_worker(w[0], w[1], G, host_in, host_out, space, qrange, brange,
+                                                                   min(max(1, lag // threads + 1), per - 1), packed), work))
+        return sum(r[0] for r in res), sum(r[1] for r in res)
+
+    def _pipeline_worker(self, job_ids, slot_ids, G, host_in, host_out, space, qrange, brange, lag, packed):
+        """one host thread of roundtrip_host_pipelined: the jobs `job_ids` (job j = frames j G .. j G + G - 1 of the repeated
+        frame sequence), round-robin over its own `slot_ids`"""
+        torch.cuda.set_device(self.device)                         # the current device is per host thread
+        F0, H, W, _ = host_in.shape
+        nslots = len(slot_ids)
         h2d = d2h = 0
         jobs = []
-        # phase A for every frame: upload + encode + counts
-        for f in range(F):
-            slot = f % slots
+        # phase A for every job: upload + encode + counts
+        for k, j in enumerate(job_ids):
+            slot = slot_ids[k % nslots]
             stream = self._streams[slot]
-            p = self._plan(1, H, W, space, brange, qrange, instance=slot)
+            f0 = (j * G) % F0
+            p = self._plan(G, H, W, space, brange, qrange, instance=slot)
             st = self._host_staging(p)
             with torch.cuda.stream(stream):
-                if f >= slots:
-                    self._finish_job(jobs[f - slots])              # the slot's previous frame must be done with its buffers
+                if k >= nslots:
+                    self._finish_job(jobs[k - nslots])             # the slot's previous job must be done with its buffers
                 src = st["rgb8_dev"] if host_in.dtype == torch.uint8 else st["rgb_dev"]
-                src.copy_(host_in[f % F0:f % F0 + 1], non_blocking=True)
+                src.copy_(host_in[f0:f0 + G], non_blocking=True)
                 enc = self.encode(src, space, qrange, brange, instance=slot)
                 st["counts"].copy_(enc.counts, non_blocking=True)
                 if packed:
@@ -470,46 +500,49 @@ class DeviceCodec:
                     st["pk_counts"].copy_(pk.counts, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(stream)
-            jobs.append(dict(f=f % F0, slot=slot, p=p, st=st, enc=enc, ev=ev, done=False, phase_b=False, packed=packed))
-            h2d += host_in[0].numel() * host_in.element_size()
-            # phase B of a frame is issued `lag` frames after its phase A (its counts have landed by then), and a slot is
-            # reused only `slots` frames later, so neither host wait normally blocks
-            if f >= lag:
-                a, b_ = self._phase_b(jobs[f - lag], host_out, space, qrange, brange)
+            jobs.append(dict(f=f0, G=G, slot=slot, p=p, st=st, enc=enc, ev=ev, done=False, phase_b=False, packed=packed))
+            h2d += G * host_in[0].numel() * host_in.element_size()
+            # phase B of a job is issued `lag` jobs after its phase A (its counts have landed by then), and a slot is
+            # reused only `nslots` jobs later, so neither host wait normally blocks
+            if k >= lag:
+                a, b_ = self._phase_b(jobs[k - lag], host_out, space, qrange, brange)
                 h2d += a; d2h += b_
-        for j in jobs:
-            if not j["phase_b"]:
-                a, b_ = self._phase_b(j, host_out, space, qrange, brange)
+        for jb in jobs:
+            if not jb["phase_b"]:
+                a, b_ = self._phase_b(jb, host_out, space, qrange, brange)
                 h2d += a; d2h += b_
-        for j in jobs:
-            self._finish_job(j)
+        for jb in jobs:
+            self._finish_job(jb)
         return h2d, d2h
 
     def _phase_b(self, job, host_out, space, qrange, brange):
-        p, st, enc, slot = job["p"], job["st"], job["enc"], job["slot"]
+        p, st, enc, slot, G = job["p"], job["st"], job["enc"], job["slot"], job["G"]
         stream = self._streams[slot]
+        t0 = time.perf_counter()
         job["ev"].synchronize()                                    # counts are on the host now
+        self.pipeline_host_wait_s += time.perf_counter() - t0
         counts = st["counts"].numpy()
         h2d = d2h = st["counts"].numel() * 4
         H, W = p.info.height, p.info.width
         pk = p.packed if job.get("packed") else None
         pkc = st["pk_counts"].numpy() if pk is not None else None
-        if pk is not None and not any(pkc[0, l, 2] != 0 for l in range(3)):
-            # the normal case (no int16 overflow): gather the frame's streams into one arena, ONE copy each way, scatter back
+        out_kind = "u8" if host_out.dtype == torch.uint8 else "f32"
+        if pk is not None and not (pkc[:, :, 2] != 0).any():
+            # the normal case (no int16 overflow): gather the job's streams into one arena, ONE copy each way, scatter back
             arena_dev, arena_host, table = self._arena(p, st)
             base = arena_dev.data_ptr()
             off = 0
             there, back = [], []
-            for l in range(3):
-                nl, ns = int(counts[0, l, 0]), int(counts[0, l, 1])
-                nnz, nw = int(pkc[0, l, 0]), int(pkc[0, l, 3])
-                for t, nb, needed_back in ((pk.mask[l], nw * 4, True), (pk.vals[l], nnz * 2, True), (enc.leaves[l], nl * 16, True),
-                                           (enc.states[l], ns, False)):
-                    nb4 = (nb + 3) & ~3
-                    there.append((t.data_ptr(), base + off, nb4))
-                    if needed_back:
-                        back.append((base + off, t.data_ptr(), nb4))
-                    off = (off + nb4 + 15) & ~15
+            for b in range(G):
+                for l in range(3):
+                    nl, ns = int(counts[b, l, 0]), int(counts[b, l, 1])
+                    nnz, nw = int(pkc[b, l, 0]), int(pkc[b, l, 3])
+                    for t, nb, needed_back in ((pk.mask[l][b], nw * 4, True), (pk.vals[l][b], nnz * 2, True), (enc.leaves[l][b], nl * 16, True),
+                                               (enc.states[l][b], ns, False)):
+                        there.append((t.data_ptr(), base + off, nb))
+                        if needed_back:
+                            back.append((base + off, t.data_ptr(), nb))
+                        off = (off + nb + 15) & ~15
             with torch.cuda.stream(stream):
                 self._copy_segments(there, table)
                 arena_host[:off].copy_(arena_dev[:off], non_blocking=True)          # -> the host-side entropy coder
@@ -517,57 +550,55 @@ class DeviceCodec:
                 self._copy_segments(back, table)
                 enc.counts.copy_(st["counts"], non_blocking=True)
                 pk.counts.copy_(st["pk_counts"], non_blocking=True)
-                self.unpack(pk, 1, H, W, space, qrange, brange, instance=slot)
-                rgb = self.decode(enc.coef, enc.leaves, enc.counts, 1, H, W, space, qrange, brange, instance=slot,
-                                  out="u8" if host_out.dtype == torch.uint8 else "f32")
-                host_out[job["f"]:job["f"] + 1].copy_(rgb, non_blocking=True)
+                self.unpack(pk, G, H, W, space, qrange, brange, instance=slot)
+                rgb = self.decode(enc.coef, enc.leaves, enc.counts, G, H, W, space, qrange, brange, instance=slot, out=out_kind)
+                host_out[job["f"]:job["f"] + G].copy_(rgb, non_blocking=True)
                 job["ev2"] = torch.cuda.Event()
                 job["ev2"].record(stream)
             job["phase_b"] = True
-            nb_rgb = rgb.numel() * rgb.element_size()
-            return h2d + off + 2 * st["counts"].numel() * 4, d2h + off + nb_rgb
+            return h2d + off + 2 * st["counts"].numel() * 4, d2h + off + rgb.numel() * rgb.element_size()
+        # raw int32 streams (packed=False), or a plane whose coefficients do not fit int16: per-range copies
         with torch.cuda.stream(stream):
-            for l in range(3):
-                nl, ns, nc = (int(counts[0, l, k]) for k in range(3))
-                if pk is not None and pkc[0, l, 2] == 0:             # packed: mask words + int16 non-zeros
-                    nnz, nw = int(pkc[0, l, 0]), int(pkc[0, l, 3])
-                    st["mask"][l][0, :nw].copy_(pk.mask[l][0, :nw], non_blocking=True)
-                    st["vals"][l][0, :nnz].copy_(pk.vals[l][0, :nnz], non_blocking=True)
-                    d2h += nw * 4 + nnz * 2
-                else:
-                    st["coef"][l][0, :nc].copy_(enc.coef[l][0, :nc], non_blocking=True)
-                    d2h += nc * 4
-                st["leaves"][l][0, :nl].copy_(enc.leaves[l][0, :nl], non_blocking=True)
-                st["states"][l][0, :ns].copy_(enc.states[l][0, :ns], non_blocking=True)
-                d2h += nl * 16 + ns
-            any_packed = False
-            for l in range(3):
-                nl, nc = int(counts[0, l, 0]), int(counts[0, l, 2])
-                if pk is not None and pkc[0, l, 2] == 0:
-                    nnz, nw = int(pkc[0, l, 0]), int(pkc[0, l, 3])
-                    pk.mask[l][0, :nw].copy_(st["mask"][l][0, :nw], non_blocking=True)
-                    pk.vals[l][0, :nnz].copy_(st["vals"][l][0, :nnz], non_blocking=True)
-                    h2d += nw * 4 + nnz * 2
-                    any_packed = True
-                else:
-                    enc.coef[l][0, :nc].copy_(st["coef"][l][0, :nc], non_blocking=True)
-                    h2d += nc * 4
-                enc.leaves[l][0, :nl].copy_(st["leaves"][l][0, :nl], non_blocking=True)
-                h2d += nl * 16
+            use_pk = [[pk is not None and pkc[b, l, 2] == 0 for l in range(3)] for b in range(G)]
+            for b in range(G):
+                for l in range(3):
+                    nl, ns, nc = (int(counts[b, l, k]) for k in range(3))
+                    if use_pk[b][l]:                                  # packed: mask words + int16 non-zeros
+                        nnz, nw = int(pkc[b, l, 0]), int(pkc[b, l, 3])
+                        st["mask"][l][b, :nw].copy_(pk.mask[l][b, :nw], non_blocking=True)
+                        st["vals"][l][b, :nnz].copy_(pk.vals[l][b, :nnz], non_blocking=True)
+                        d2h += nw * 4 + nnz * 2
+                    else:
+                        st["coef"][l][b, :nc].copy_(enc.coef[l][b, :nc], non_blocking=True)
+                        d2h += nc * 4
+                    st["leaves"][l][b, :nl].copy_(enc.leaves[l][b, :nl], non_blocking=True)
+                    st["states"][l][b, :ns].copy_(enc.states[l][b, :ns], non_blocking=True)
+                    d2h += nl * 16 + ns
+            any_packed = any(any(r) for r in use_pk)
+            for b in range(G):
+                for l in range(3):
+                    nl, nc = int(counts[b, l, 0]), int(counts[b, l, 2])
+                    if use_pk[b][l]:
+                        nnz, nw = int(pkc[b, l, 0]), int(pkc[b, l, 3])
+                        pk.mask[l][b, :nw].copy_(st["mask"][l][b, :nw], non_blocking=True)
+                        pk.vals[l][b, :nnz].copy_(st["vals"][l][b, :nnz], non_blocking=True)
+                        h2d += nw * 4 + nnz * 2
+                    else:
+                        enc.coef[l][b, :nc].copy_(st["coef"][l][b, :nc], non_blocking=True)
+                        h2d += nc * 4
+                    enc.leaves[l][b, :nl].copy_(st["leaves"][l][b, :nl], non_blocking=True)
+                    h2d += nl * 16
             enc.counts.copy_(st["counts"], non_blocking=True)
             if any_packed:
-                if any(pkc[0, l, 2] != 0 for l in range(3)):         # mixed: keep the int32 planes, expand the others around them
-                    keep = [enc.coef[l][0].clone() if pkc[0, l, 2] != 0 else None for l in range(3)]
+                # mixed: keep the int32 planes aside, expand the packed ones around them
+                keep = {(b, l): enc.coef[l][b].clone() for b in range(G) for l in range(3) if not use_pk[b][l]}
                 pk.counts.copy_(st["pk_counts"], non_blocking=True)
                 h2d += st["pk_counts"].numel() * 4
-                self.unpack(pk, 1, H, W, space, qrange, brange, instance=slot)
-                if any(pkc[0, l, 2] != 0 for l in range(3)):
-                    for l in range(3):
-                        if keep[l] is not None:
-                            enc.coef[l][0].copy_(keep[l])
-            rgb = self.decode(enc.coef, enc.leaves, enc.counts, 1, H, W, space, qrange, brange, instance=slot,
-                              out="u8" if host_out.dtype == torch.uint8 else "f32")
-            host_out[job["f"]:job["f"] + 1].copy_(rgb, non_blocking=True)
+                self.unpack(pk, G, H, W, space, qrange, brange, instance=slot)
+                for (b, l), t in keep.items():
+                    enc.coef[l][b].copy_(t)
+            rgb = self.decode(enc.coef, enc.leaves, enc.counts, G, H, W, space, qrange, brange, instance=slot, out=out_kind)
+            host_out[job["f"]:job["f"] + G].copy_(rgb, non_blocking=True)
             d2h += rgb.numel() * rgb.element_size()
             job["ev2"] = torch.cuda.Event()
             job["ev2"].record(stream)
@@ -578,7 +609,9 @@ class DeviceCodec:
         if not job["done"]:
             if not job["phase_b"]:
                 raise RuntimeError("pipeline order error")
+            t0 = time.perf_counter()
             job["ev2"].synchronize()
+            self.pipeline_host_wait_s += time.perf_counter() - t0
             job["done"] = True
 
     def decode_encoded(self, enc: EncodedBatch, space, qrange, brange, out: str = "f32"):

@@ -248,6 +248,8 @@ int launch_upsample_color_inverse(aeaj_handle* h, int space, const PlaneDesc* pl
                                   float* rgb, uint8_t* rgb_u8, cudaStream_t st, int band0 = 0, int band1 = -1);
 int launch_peer_barrier(int* const* flags_host, int rank, int world, int epoch, int* err_dev, cudaStream_t st);
 int launch_peer_gather(const PeerSeg* segs_dev, int nseg, long long max_bytes, cudaStream_t st);
+constexpr int AEAJ_SEGS_BY_PARAM = 64;
+int launch_copy_segments_param(const PeerSeg* segs_host, int nseg, long long max_bytes, cudaStream_t st);
 int launch_cast_u8(const float* in, uint8_t* out, size_t n, cudaStream_t st);
 
 int launch_clahe_hist(const PlaneDesc* planes_dev, const PlaneDesc* planes_host, int nplanes, cudaStream_t st);

@@ -383,7 +383,9 @@ struct aeaj_plan {
     const float* qtabf_ptr[2][9];
     uint8_t** outs_dev;                  // tap pointers [nplanes]
     std::vector<PackPlane> pack_planes;  // host copy of the packing descriptors
-    PackPlane* pack_planes_dev;
+    PackPlane* pack_planes_dev;          // [2][nplanes]: the pack and the unpack flavour of the table (they differ in n_coef)
+    std::vector<PackPlane> pack_pushed[2];   // what the device tables hold (upload skipped when unchanged: no per-call pageable copy,
+    cudaStream_t pack_pushed_stream[2] = {nullptr, nullptr};   // which may synchronise the stream and is not capturable)
     // one image over several GPUs (peer.cu): the other ranks' workspaces / barrier flags, opened through CUDA IPC by the caller
     PeerSet peers = {1, 0, {0}};
     void* peer_ws[AEAJ_MAX_PEERS] = {nullptr};
@@ -511,7 +513,7 @@ extern "C" int aeaj_plan_create(aeaj_handle* h, int batch, int height, int width
     AEAJ_CUDA(cudaMalloc(&p->class_off_dev, sizeof(long long) * 18));
     AEAJ_CUDA(cudaMalloc(&p->outs_dev, sizeof(uint8_t*) * p->nplanes));
     p->pack_planes.resize(p->nplanes);
-    AEAJ_CUDA(cudaMalloc(&p->pack_planes_dev, sizeof(PackPlane) * p->nplanes));
+    AEAJ_CUDA(cudaMalloc(&p->pack_planes_dev, sizeof(PackPlane) * p->nplanes * 2));
     long long off[18]; for (int k = 0; k < 9; k++) { off[k] = p->cg.off[k]; off[9 + k] = p->cg.cap[k]; }
     AEAJ_CUDA(cudaMemcpy(p->class_off_dev, off, sizeof off, cudaMemcpyHostToDevice));
     p->qtab_dev = nullptr; p->qtabf_dev = nullptr; p->qtab_entries = 0;
@@ -852,7 +854,12 @@ static int pack_impl(aeaj_plan* p, const int32_t* const* coef3, const int32_t* c
         }
     }
     if (!unpack) AEAJ_CUDA(cudaMemsetAsync(pk->counts, 0, sizeof(int32_t) * 12 * (size_t)B, st));
-    return launch_pack(p->pack_planes.data(), p->pack_planes_dev, p->nplanes, max_cap, unpack, st);
+    const int k = unpack ? 1 : 0;
+    PackPlane* table = p->pack_planes_dev + (size_t)k * p->nplanes;
+    const bool same = p->pack_pushed_stream[k] == st && p->pack_pushed[k].size() == p->pack_planes.size() &&
+                      memcmp(p->pack_pushed[k].data(), p->pack_planes.data(), sizeof(PackPlane) * p->pack_planes.size()) == 0;
+    if (!same) { p->pack_pushed[k] = p->pack_planes; p->pack_pushed_stream[k] = st; }
+    return launch_pack(same ? nullptr : p->pack_planes.data(), table, p->nplanes, max_cap, unpack, st);
 }
 extern "C" int aeaj_pack_coefficients(aeaj_plan* p, const int32_t* const* coef3, const int32_t* counts, const aeaj_packed_io* out,
                                       void* workspace, void* stream) {
@@ -897,21 +904,22 @@ extern "C" int aeaj_unpack_coefficients_host(const uint32_t* mask, const int16_t
 
 // gather / scatter of one frame's variable-length streams into / out of one contiguous arena (include/aeaj.h)
 extern "C" int aeaj_copy_segments(const aeaj_segment* segs_host, int n, void* table_dev, void* stream) {
-    AEAJ_REQUIRE(n >= 0 && (n == 0 || (segs_host && table_dev)), "aeaj_copy_segments: bad arguments");
+    AEAJ_REQUIRE(n >= 0 && (n == 0 || segs_host), "aeaj_copy_segments: bad arguments");
     static_assert(sizeof(aeaj_segment) == sizeof(PeerSeg), "segment layout");
     long long maxb = 0;
     int m = 0;
     std::vector<PeerSeg> segs((size_t)n);
     for (int i = 0; i < n; i++) {
         const aeaj_segment& s = segs_host[i];
-        AEAJ_REQUIRE(s.bytes >= 0 && (s.bytes & 3) == 0 && (((uintptr_t)s.src | (uintptr_t)s.dst) & 3) == 0,
-                     "aeaj_copy_segments: ranges must be 4-byte aligned multiples of 4 bytes");
+        AEAJ_REQUIRE(s.bytes >= 0, "aeaj_copy_segments: negative size");
         if (s.bytes == 0) continue;
         AEAJ_REQUIRE(s.src && s.dst, "aeaj_copy_segments: NULL range");
         segs[m].src = s.src; segs[m].dst = s.dst; segs[m].bytes = s.bytes; m++;
         maxb = std::max<long long>(maxb, s.bytes);
     }
     if (m == 0) return 0;
+    if (m <= AEAJ_SEGS_BY_PARAM) return launch_copy_segments_param(segs.data(), m, maxb, ST(stream));   // table in the kernel parameters: no upload
+    AEAJ_REQUIRE(table_dev, "aeaj_copy_segments: more than 64 ranges need the device scratch table");
     AEAJ_CUDA(cudaMemcpyAsync(table_dev, segs.data(), sizeof(PeerSeg) * m, cudaMemcpyHostToDevice, ST(stream)));   // pageable: staged before return
     return launch_peer_gather((const PeerSeg*)table_dev, m, maxb, ST(stream));
 }

@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 const int b = c & 1;
+                if (warp == 4 && c == 1) TC_STAMP(25);
                 if (uses >= 2) alive = alive && mbar_wait(bar_empty[b], ((uses >> 1) - 1) & 1, err);   // the MMAs that read this buffer last are done
                 if (warp == 4) TC_STAMP(2 + 2 * c);
                 if (c == 0) {
@@ -290,8 +291,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
                     Lp = make_leaf(blockIdx.x + (it + 2) * gridDim.x);
                 }
                 store_chunk(Tc, c, b);
+                if (warp == 4 && c == 1) TC_STAMP(26);
                 if (c < 2) load_chunk(Tc, c + 2, b);
                 else if (has_next) load_chunk(Tn, c - 2, b);
+                if (warp == 4 && c == 1) TC_STAMP(27);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_full[b]);

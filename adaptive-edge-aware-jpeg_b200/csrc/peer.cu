@@ -29,23 +29,52 @@ __global__ void k_peer_barrier(PeerFlags F, int rank, int world, int epoch, int*
     }
 }
 
-// copies `nseg` byte ranges (all multiples of 4 bytes, 4-byte aligned) from peer memory into local memory; grid: (blocks, nseg)
-__global__ void __launch_bounds__(256) k_peer_gather(const PeerSeg* __restrict__ segs) {
-    const PeerSeg s = segs[blockIdx.y];
-    const long long n4 = s.bytes >> 2;
-    const unsigned* src = reinterpret_cast<const unsigned*>(s.src);
-    unsigned* dst = reinterpret_cast<unsigned*>(s.dst);
-    if ((((uintptr_t)s.src | (uintptr_t)s.dst) & 15) == 0) {
-        const long long n16 = n4 >> 2;
-        for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n16; i += (long long)gridDim.x * 256)
-            reinterpret_cast<uint4*>(dst)[i] = __ldcv(reinterpret_cast<const uint4*>(src) + i);
-        for (long long i = n16 * 4 + (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) dst[i] = __ldcv(src + i);
+// one byte range, by the whole grid row: 128-bit accesses when both ends are 16-byte aligned, words when 4-byte aligned, bytes
+// otherwise (row b > 0 of a uint8 [B][cap] buffer need not be word aligned).  CV: the source is peer memory (never a stale line).
+template <bool CV>
+__device__ __forceinline__ void copy_range(const PeerSeg& s) {
+    const long long stride = (long long)gridDim.x * 256, first = (long long)blockIdx.x * 256 + threadIdx.x;
+    const uintptr_t both = (uintptr_t)s.src | (uintptr_t)s.dst;
+    if ((both & 3) == 0) {
+        const long long n4 = s.bytes >> 2;
+        const unsigned* src = reinterpret_cast<const unsigned*>(s.src);
+        unsigned* dst = reinterpret_cast<unsigned*>(s.dst);
+        long long done4 = 0;
+        if ((both & 15) == 0) {
+            const long long n16 = n4 >> 2;
+            for (long long i = first; i < n16; i += stride)
+                reinterpret_cast<uint4*>(dst)[i] = CV ? __ldcv(reinterpret_cast<const uint4*>(src) + i) : reinterpret_cast<const uint4*>(src)[i];
+            done4 = n16 * 4;
+        }
+        for (long long i = done4 + first; i < n4; i += stride) dst[i] = CV ? __ldcv(src + i) : src[i];
+        for (long long i = n4 * 4 + first; i < s.bytes; i += stride)
+            reinterpret_cast<unsigned char*>(s.dst)[i] = reinterpret_cast<const unsigned char*>(s.src)[i];
     } else {
-        for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) dst[i] = __ldcv(src + i);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(s.src);
+        unsigned char* dst = reinterpret_cast<unsigned char*>(s.dst);
+        for (long long i = first; i < s.bytes; i += stride) dst[i] = CV ? __ldcv(src + i) : src[i];
     }
 }
 
+// copies `nseg` byte ranges from peer memory into local memory; grid: (blocks, nseg)
+__global__ void __launch_bounds__(256) k_peer_gather(const PeerSeg* __restrict__ segs) { copy_range<true>(segs[blockIdx.y]); }
+
+// the same copy with the table in the kernel parameters (<= 64 ranges, 1.5 KB): nothing to upload, so nothing that could synchronise
+struct SegParams { PeerSeg s[AEAJ_SEGS_BY_PARAM]; };
+__global__ void __launch_bounds__(256) k_copy_segments(const __grid_constant__ SegParams T) { copy_range<false>(T.s[blockIdx.y]); }
+
 }  // namespace
+
+int launch_copy_segments_param(const PeerSeg* segs_host, int nseg, long long max_bytes, cudaStream_t st) {
+    if (nseg <= 0) return 0;
+    SegParams T;
+    memset(&T, 0, sizeof T);
+    for (int i = 0; i < nseg && i < AEAJ_SEGS_BY_PARAM; i++) T.s[i] = segs_host[i];
+    const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>((max_bytes / 16 + 255) / 256, 148));
+    k_copy_segments<<<dim3(blocks, nseg), 256, 0, st>>>(T);
+    AEAJ_LAUNCH_CHECK();
+    return 0;
+}
 
 int launch_peer_barrier(int* const* flags_host, int rank, int world, int epoch, int* err_dev, cudaStream_t st) {
     PeerFlags F;

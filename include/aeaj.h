@@ -265,8 +265,9 @@ AEAJ_API int aeaj_unpack_coefficients_host(const uint32_t* mask_host, const int1
  * copies n byte ranges device -> device in a single launch, so that the caller can gather everything the host-side entropy
  * coder needs (jpeg.py:531-597) into one contiguous arena, move it with one cudaMemcpy, and scatter what comes back
  * (jpeg.py:599-674) the same way -- instead of ~27 small copies per frame, each paying its own DMA set-up.
- * Every range must be 4-byte aligned and a multiple of 4 bytes; 16-byte aligned ranges are moved with 128-bit accesses.
- * `table_dev`: caller-owned device scratch of at least n * sizeof(aeaj_segment) bytes (the table is staged through it). */
+ * Any alignment and size; ranges whose two ends are 16-byte (4-byte) aligned are moved with 128-bit (32-bit) accesses.
+ * Up to 64 ranges travel in the kernel's parameters (no upload of any kind); beyond that the table is staged through
+ * `table_dev`, caller-owned device scratch of at least n * sizeof(aeaj_segment) bytes (may be NULL for n <= 64). */
 typedef struct { const void* src; void* dst; int64_t bytes; } aeaj_segment;
 AEAJ_API int aeaj_copy_segments(const aeaj_segment* segs_host, int n, void* table_dev, void* stream);
 
