@@ -83,9 +83,9 @@ class DeviceCodec:
         self._plans: "OrderedDict[tuple, _Plan]" = OrderedDict()
         self.last_launches = 0
         # size classes whose DCT / IDCT run on the tcgen05 / TMEM kernels: bit k = class 16 << k (True = all four, False / 0 =
-        # the FP32-FMA kernels everywhere).  Default: 128 x 128 only -- measured on B200 (profiles/r2_tc_variants.md) the FP32
-        # kernels are as fast or faster for the smaller classes (0.09-0.1 ms vs 0.09-0.11 ms per 8 4K frames for 32 / 64)
-        self.tensor_dct = 0x8
+        # the FP32-FMA kernels everywhere).  Default: 32 x 32 and 128 x 128 -- measured on B200 (profiles/r2_tc_variants.md) the
+        # FP32 kernels are as fast for 64 and faster for 16
+        self.tensor_dct = 0xa
 
     def _tensor_mask(self) -> int:
         return 0xf if self.tensor_dct is True else int(self.tensor_dct) & 0xf

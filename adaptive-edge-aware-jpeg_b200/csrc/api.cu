@@ -395,7 +395,7 @@ struct aeaj_plan {
     int last_launches;
     bool need_full_chroma;
     int zigzag = 0;
-    int tensor_dct = 0x8;         // size classes on the tcgen05 kernels: bit k = class 16 << k (aeaj_plan_set_tensor_dct)
+    int tensor_dct = 0xa;         // size classes on the tcgen05 kernels: bit k = class 16 << k (aeaj_plan_set_tensor_dct)
     // optional per-stage CUDA-event timing (bench.py roofline leg)
     bool timing_on = false;
     std::vector<cudaEvent_t> ev;

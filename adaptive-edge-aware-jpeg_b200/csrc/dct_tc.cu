@@ -33,6 +33,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
 }
+// the same descriptor `units` 16-byte units further on: only the 14-bit address field in the low word changes (no carry out of
+// it: shared memory is < 256 KB), so stepping through a tile costs one 32-bit add per operand instead of rebuilding 64 bits
+__device__ __forceinline__ uint64_t desc_at(uint64_t base, uint32_t units) {
+    return (base & 0xffffffff00000000ull) | (uint64_t)((uint32_t)base + units);
+}
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
@@ -115,22 +120,31 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
 #else
 #define TC_STAMP(slot) do { } while (0)
 #endif
-constexpr int TC_CONSUMERS = 128, TC_PRODUCERS = 256, TC_THREADS = TC_CONSUMERS + TC_PRODUCERS + 32;
-constexpr int TC_TABS = 4;                                                // leaf tables in flight (ring)
+constexpr int TC_CONSUMERS = 256, TC_PRODUCERS = 256, TC_THREADS = TC_CONSUMERS + TC_PRODUCERS + 128;
+constexpr int TC_CW = TC_CONSUMERS / 32, TC_PW = TC_PRODUCERS / 32;       // consumer / producer warps; the MMA warp is warp TC_CW + TC_PW
+// Registers: 20 warps = 5 per SM sub-partition, whose register file holds 512 per thread slot.  The kernel is compiled for 96
+// (launch bound); the role branches then trade with setmaxnreg: the MMA warpgroup (one issuing thread, three idle warps)
+// shrinks to 40 and the consumer / producer warpgroups grow to 112 / 104.  The trade happens inside the CTA's own allocation
+// (20 x 32 x 96 registers): 256 x 112 + 256 x 104 + 128 x 40 = 60416 <= 61440 -- asking for more than the pool holds never returns.
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(N)); }
+constexpr int TC_TABS = 8;                                                // leaf tables in flight (ring): the producers run up to 4 tiles ahead of the epilogue
 
 // Warp-specialised, persistent: one CTA per SM loops over the super-tiles blockIdx.x, blockIdx.x + gridDim.x, ..
-//   warps 4-11  PRODUCERS  global -> registers (one chunk ahead) -> normalise / dequantise -> hi/lo split -> K-major smem tiles
-//   warp 12     MMA        one thread issues GEMM1 chunk by chunk as buffers fill, then GEMM2 once W is split
-//   warps 0-3   CONSUMERS  (one per TMEM lane quadrant; a thread owns one super-tile row) split W inside tensor memory, then
-//                          the epilogue straight out of tensor memory
+//   warps 0-7    CONSUMERS  (two per TMEM lane quadrant: a thread owns one super-tile row and half of its columns) split W in
+//                           place inside tensor memory, then the epilogue straight out of tensor memory
+//   warps 8-15   PRODUCERS  global -> registers (one chunk ahead) -> normalise / dequantise -> hi/lo split -> K-major smem tiles
+//   warp 16      MMA        one thread issues G1(0), then per tile G2(i), G1(i+1) -- GEMM1 chunk by chunk as the X buffers fill
+//   warps 17-19  idle       (setmaxnreg works on whole warpgroups; they give their registers away and wait for the end)
 // mbarriers: full[b] (one arrival per producer warp) / empty[b] (tcgen05.commit) per X buffer; d1_full (commit: W complete),
-// w_ready (one arrival per consumer warp: Wh, Wl written, D1 free), d2_full (commit: Out complete), d2_free (D2 read).
-// Measured alternatives (profiles/r2_tc_variants.md): eight consumer warps halve the epilogue (12 k -> 6.5 k cycles per tile)
-// but need 17 warps = 96 registers per thread, which spills the inverse producers and loses what the epilogue gains;
-// setmaxnreg rebalancing (MMA warpgroup 40, producers 120) starves the MMA-issuing thread.  This 13-warp layout is the
-// fastest of the variants tried.
-// The tensor pipe runs GEMM1 of tile i+1 while the consumers are in the epilogue of tile i and the producers already
-// stage tile i+2.  Every wait is bounded: a protocol error raises the error flag instead of hanging the GPU.
+// w_ready (one arrival per consumer warp: Wh, Wl written), d2_full[k] (commit: Out buffer k complete), d2_free[k] (Out buffer k read).
+// Two Out buffers: the consumers split W(i+1) BEFORE the epilogue of tile i, so that G2(i+1) and G1(i+2) run on the tensor pipe
+// during that epilogue.  Measured history (profiles/r2_tc_variants.md): 13 warps with 4 consumer warps 0.215 / 0.203 ms (128 class,
+// forward / inverse, 8 4K frames); 17 warps capped every thread at 96 registers (5 warps on one SM sub-partition) and spilled;
+// this layout with the setmaxnreg trade 0.20 / 0.166 ms.  What bounds it now is the tensor side itself: an MMA of K = 8 reads
+// 8 KB of operands from shared memory and issues at ~100 cycles, 96 of them per tile, and the two X buffers (all the shared
+// memory that is left next to the 128 KB of C tiles) let the producers run only half a tile ahead of GEMM1.
+// Every wait is bounded: a protocol error raises the error flag instead of hanging the GPU.
 //
 // a_tiles: [Ah | Al], each 128 x 128 floats in the canonical layout [K/4][128][4] (built on the host): blockdiag(C_S) or its transpose
 // izz: inverse zigzag permutation of an S x S block (row-major index -> stream position)
@@ -145,7 +159,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
     float* sCh = reinterpret_cast<float*>(smem_raw);                     // 64 KB
     float* sCl = sCh + TC_N * TC_N;                                      // 64 KB
     float* sX = sCl + TC_N * TC_N;                                       // 2 buffers x (hi 16 KB + lo 16 KB)
-    __shared__ __align__(8) unsigned long long mbar_storage[8];
+    __shared__ __align__(8) unsigned long long mbar_storage[10];
     __shared__ uint32_t tmem_base_s;
     __shared__ TcLeaf sLeaf[TC_TABS][NL];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -153,12 +167,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
     const uint32_t bar_full[2] = {smem_u32(&mbar_storage[0]), smem_u32(&mbar_storage[1])};
     const uint32_t bar_empty[2] = {smem_u32(&mbar_storage[2]), smem_u32(&mbar_storage[3])};
     const uint32_t bar_d1full = smem_u32(&mbar_storage[4]), bar_wready = smem_u32(&mbar_storage[5]);
-    const uint32_t bar_d2full = smem_u32(&mbar_storage[6]), bar_d2free = smem_u32(&mbar_storage[7]);
+    const uint32_t bar_d2full[2] = {smem_u32(&mbar_storage[6]), smem_u32(&mbar_storage[7])};      // per Out buffer
+    const uint32_t bar_d2free[2] = {smem_u32(&mbar_storage[8]), smem_u32(&mbar_storage[9])};
     if (tid == 0) {
         auto init = [](uint32_t b, int n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b), "r"(n) : "memory"); };
         // producer / consumer warps arrive once per warp (lane 0, after __syncwarp): 8 and 4 arrivals instead of 256 and 128
         init(bar_full[0], TC_PRODUCERS / 32); init(bar_full[1], TC_PRODUCERS / 32); init(bar_empty[0], 1); init(bar_empty[1], 1);
-        init(bar_d1full, 1); init(bar_wready, TC_CONSUMERS / 32); init(bar_d2full, 1); init(bar_d2free, TC_CONSUMERS / 32);
+        init(bar_d1full, 1); init(bar_wready, TC_CONSUMERS / 32);
+        init(bar_d2full[0], 1); init(bar_d2full[1], 1); init(bar_d2free[0], TC_CONSUMERS / 32); init(bar_d2free[1], TC_CONSUMERS / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -170,14 +186,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tbase = tmem_base_s;
-    const uint32_t D1 = tbase, WH = tbase + 128, WL = tbase + 256, D2 = tbase + 384;
+    // tensor memory, 512 columns: W = A.X is split into hi + lo IN PLACE (hi over D1, lo next to it), which leaves room for two
+    // Out buffers -- GEMM2 of tile i+1 runs while the consumers still read tile i
+    const uint32_t D1 = tbase, WH = tbase, WL = tbase + 128, D2A = tbase + 256;
     const uint32_t aCh = smem_u32(sCh), aCl = smem_u32(sCl), aX = smem_u32(sX);
     const int count = *count_ptr;
     const int ntiles = (count + NL - 1) / NL;
     const int my_tiles = (blockIdx.x < ntiles) ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
-    if (warp >= 4 && warp < 12) {
+    if (warp >= TC_CW && warp < TC_CW + TC_PW) {
         // =============================================== PRODUCERS ===============================================
+        reg_inc<104>();
         const int pt = tid - TC_CONSUMERS, pw = pt >> 5;                  // producer thread / warp (0 .. 7)
         auto make_leaf = [&](int tile) {                                  // list entry tile * NL + pt -> leaf descriptor (registers)
             TcLeaf L;
@@ -280,9 +299,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 const int b = c & 1;
-                if (warp == 4 && c == 1) TC_STAMP(25);
+                if (warp == TC_CW && c == 1) TC_STAMP(25);
                 if (uses >= 2) alive = alive && mbar_wait(bar_empty[b], ((uses >> 1) - 1) & 1, err);   // the MMAs that read this buffer last are done
-                if (warp == 4) TC_STAMP(2 + 2 * c);
+                if (warp == TC_CW) TC_STAMP(2 + 2 * c);
                 if (c == 0) {
                     // the table ring slot of tile it + 1 belonged to tile it - 3, whose epilogue is over (its consumers went on to
                     // split tile it - 2 before the MMAs just waited for could be issued)
@@ -291,24 +310,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
                     Lp = make_leaf(blockIdx.x + (it + 2) * gridDim.x);
                 }
                 store_chunk(Tc, c, b);
-                if (warp == 4 && c == 1) TC_STAMP(26);
-                if (c < 2) load_chunk(Tc, c + 2, b);
-                else if (has_next) load_chunk(Tn, c - 2, b);
-                if (warp == 4 && c == 1) TC_STAMP(27);
+                if (warp == TC_CW && c == 1) TC_STAMP(26);
+                // publish the chunk BEFORE issuing the next global loads: the proxy fence waits for every memory operation of the
+                // thread that is still in flight, so behind the loads it exposed their whole latency (~1.4 k cycles per chunk, half of
+                // the producers' time, measured with the cycle stamps)
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_full[b]);
-                if (warp == 4) TC_STAMP(3 + 2 * c);
+                if (warp == TC_CW) TC_STAMP(3 + 2 * c);
+                if (c < 2) load_chunk(Tc, c + 2, b);
+                else if (has_next) load_chunk(Tn, c - 2, b);
+                if (warp == TC_CW && c == 1) TC_STAMP(27);
                 uses++;
             }
         }
-    } else if (warp == 12) {
+    } else if (warp >= TC_CW + TC_PW) {
         // =============================================== MMA ISSUER ===============================================
-        if (lane == 0) {
+        reg_dec<40>();
+        if (warp == TC_CW + TC_PW && lane == 0) {
             bool alive = true;
             uint32_t nfull = 0;                                           // chunks consumed so far
-            for (int it = 0; it < my_tiles && alive; it++) {
-                const uint32_t idesc1 = TC_IDESC_BASE | ((128u >> 3) << 17);
+            const uint32_t idesc1 = TC_IDESC_BASE | ((128u >> 3) << 17);
+            const uint32_t idesc2 = TC_IDESC_BASE | (((uint32_t)S >> 3) << 17);
+            const uint64_t dCh = make_desc(aCh, TC_N * 16, 128), dCl = make_desc(aCl, TC_N * 16, 128), dX = make_desc(aX, TC_N * 16, 128);
+            // GEMM1 of one tile: chunk by chunk as the producers fill the X buffers
+            auto gemm1 = [&](int it) {
 #pragma unroll 1
                 for (int c = 0; c < 4 && alive; c++) {
                     const int b = c & 1;
@@ -317,59 +343,64 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
                     nfull++;
                     if (!alive) break;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t xh = aX + b * 32768, xl = xh + 16384;
+                    // K step s of chunk c: A tile 256 units (TC_N * 32 bytes) per step, X buffer b = 2048 units, lo half 1024 units in
+                    const uint32_t au = (uint32_t)c * 1024u, xu = (uint32_t)b * 2048u;
 #pragma unroll
                     for (int s = 0; s < 4; s++) {
-                        const uint32_t ao = (c * 4 + s) * (TC_N * 32);
-                        const uint64_t ah = make_desc(aCh + ao, TC_N * 16, 128), al = make_desc(aCl + ao, TC_N * 16, 128);
-                        const uint64_t bh_ = make_desc(xh + s * (TC_N * 32), TC_N * 16, 128), bl = make_desc(xl + s * (TC_N * 32), TC_N * 16, 128);
+                        const uint64_t ah = desc_at(dCh, au + s * 256u), al = desc_at(dCl, au + s * 256u);
+                        const uint64_t bh_ = desc_at(dX, xu + s * 256u), bl = desc_at(dX, xu + 1024u + s * 256u);
                         mma_ss(D1, ah, bh_, idesc1, (c | s) != 0);
                         mma_ss(D1, ah, bl, idesc1, 1);
                         mma_ss(D1, al, bh_, idesc1, 1);
                     }
                     mma_commit(bar_empty[b]);
                 }
-                if (!alive) break;
-                mma_commit(bar_d1full);                                    // W = A . X complete
+                if (alive) mma_commit(bar_d1full);                         // W = A . X complete (and every MMA issued before it)
                 TC_STAMP(14);
-                alive = mbar_wait(bar_wready, it & 1, err);                // Wh / Wl written, D1 free again
+            };
+            // Order of issue = order of execution: G1(0), then per tile G2(i), G1(i+1).  G1(i+1) overwrites D1 = Wh(i), which G2(i)
+            // -- issued just before it -- still reads: the tensor pipe executes a thread's MMAs in order.  The consumers split
+            // W(i+1) only after d1_full(i+1), a commit that also covers G2(i).
+            if (my_tiles > 0) gemm1(0);
+            for (int it = 0; it < my_tiles && alive; it++) {
+                alive = mbar_wait(bar_wready, it & 1, err);                // Wh / Wl of this tile written
                 TC_STAMP(15);
-                if (alive && it > 0) alive = mbar_wait(bar_d2free, (it - 1) & 1, err);   // the previous tile's Out has been read
+                if (alive && it >= 2) alive = mbar_wait(bar_d2free[it & 1], ((it >> 1) - 1) & 1, err);   // Out buffer read by tile it - 2
                 if (!alive) break;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // GEMM2: Out = W . A^T.  A is block diagonal: K step s (columns 8s .. 8s+7 of W) only feeds the S output columns of its block
-                const uint32_t idesc2 = TC_IDESC_BASE | (((uint32_t)S >> 3) << 17);
-#pragma unroll
+                const uint32_t D2 = D2A + (it & 1) * 128;
+#pragma unroll 4
                 for (int s = 0; s < TC_N / 8; s++) {
                     const int n0 = (8 * s / S) * S;                        // first output column of the block
-                    const uint32_t bo = s * (TC_N * 32) + n0 * 16;         // K chunk pair s, tile rows n0 ..
-                    const uint64_t bh_ = make_desc(aCh + bo, TC_N * 16, 128), bl = make_desc(aCl + bo, TC_N * 16, 128);
+                    const uint32_t bu = (uint32_t)s * 256u + (uint32_t)n0; // K chunk pair s, tile rows n0 .. (16-byte units)
+                    const uint64_t bh_ = desc_at(dCh, bu), bl = desc_at(dCl, bu);
                     const uint32_t first = (8 * s % S) == 0 ? 0u : 1u;     // first K step of a block overwrites its columns
                     mma_ts(D2 + n0, WH + s * 8, bh_, idesc2, first);
                     mma_ts(D2 + n0, WH + s * 8, bl, idesc2, 1);
                     mma_ts(D2 + n0, WL + s * 8, bh_, idesc2, 1);
                 }
-                mma_commit(bar_d2full);
+                mma_commit(bar_d2full[it & 1]);
                 TC_STAMP(16);
+                if (it + 1 < my_tiles) gemm1(it + 1);
             }
         }
     } else {
         // =============================================== CONSUMERS ===============================================
-        const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;            // this warp's 32 TMEM lanes
-        const int row = warp * 32 + lane;                                 // the super-tile row this thread owns in tensor memory
-        constexpr int cbeg = 0;
+        reg_inc<112>();
+        const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;      // this warp's 32 TMEM lanes (hardware: quadrant warp % 4)
+        const int row = (warp & 3) * 32 + lane;                           // the super-tile row this thread owns in tensor memory
+        const int cbeg = (warp >> 2) * (TC_N / 2);                        // ... and the half of its columns: two warps share a row
         const int p = row / S, li = row % S;
         bool alive = true;
-        for (int it = 0; it < my_tiles && alive; it++) {
-            const TcLeaf* Tc = sLeaf[it & (TC_TABS - 1)];
-            if (warp == 0) TC_STAMP(20);
-            alive = mbar_wait(bar_d1full, it & 1, err);
+        // W = Wh + Wl of tile `t`, in place inside tensor memory (hi over D1, lo in WL); then tell the MMA thread
+        auto split_w = [&](int it) {
+            alive = mbar_wait(bar_d1full, it & 1, err);                    // GEMM1(t) complete -- and GEMM2(t - 1), the last reader of Wh / Wl
             if (warp == 0) TC_STAMP(21);
-            if (!alive) break;
+            if (!alive) return;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // split W = Wh + Wl inside tensor memory (Wh / Wl are free: this thread waited for the previous tile's d2_full)
 #pragma unroll 1
-            for (int c = 0; c < 8; c++) {
+            for (int c = 0; c < 4; c++) {
                 uint32_t v[16], h[16], l[16];
                 tmem_ld16(D1 + lane_sel + cbeg + c * 16, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -386,14 +417,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_wready);
+        };
+        if (my_tiles > 0) split_w(0);
+        for (int it = 0; it < my_tiles && alive; it++) {
+            const TcLeaf* Tc = sLeaf[it & (TC_TABS - 1)];
+            if (warp == 0) TC_STAMP(20);
+            // the next tile's split comes BEFORE this tile's epilogue: GEMM2(it + 1) and GEMM1(it + 2) then run on the tensor pipe
+            // while the consumers are busy with the epilogue, instead of the two sides waiting for each other in turn
+            if (it + 1 < my_tiles) split_w(it + 1);
+            if (!alive) break;
             if (warp == 0) TC_STAMP(22);
-            alive = mbar_wait(bar_d2full, it & 1, err);
+            alive = mbar_wait(bar_d2full[it & 1], (it >> 1) & 1, err);
             if (warp == 0) TC_STAMP(23);
             if (!alive) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t D2 = D2A + (it & 1) * 128;
             // epilogue straight from tensor memory: super-row `row`, 32 columns at a time
 #pragma unroll 1
-            for (int c = 0; c < 4; c++) {
+            for (int c = 0; c < 2; c++) {
                 // forward: the quantiser steps of this thread's 32 positions first -- they do not depend on tensor memory, and their
                 // L2 latency would otherwise be paid once per group of 8, serially (table layout [column group][row][8]: a warp reads
                 // one contiguous 1 KB run per group)
@@ -447,7 +488,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dct_tc(const PlaneDesc* __res
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_d2free);
+            if (lane == 0) mbar_arrive(bar_d2free[it & 1]);
             if (warp == 0) TC_STAMP(24);
         }
     }

@@ -280,7 +280,7 @@ AEAJ_API int aeaj_plan_set_stream_layout(aeaj_plan* p, int zigzag);
 /* Tensor-core path for the DCT (cv.dct, jpeg.py:471) and IDCT (cv.idct, jpeg.py:483) of the size classes 16 .. 128: tcgen05
  * kind::tf32, error-compensated 3xTF32, FP32 accumulation in tensor memory; (128/S)^2 leaves of size S form one 128 x 128 tile
  * that is transformed with block-diagonal DCT matrices.  `mask` bit k selects the tensor-core kernel for class 16 << k (default
- * 0x8: 128 only, the class where it is faster; 0 = the FP32-FMA kernels everywhere -- same parity class, the quantiser is exact in both).
+ * 0xa: 32 and 128, the classes where it is faster; 0 = the FP32-FMA kernels everywhere -- same parity class, the quantiser is exact in both).
  * aeaj_tensor_dct_status: timed_out must point to int[32]; [0] is set if a tensor-core kernel ever gave up on a barrier
  * wait (also reported in the status words of aeaj_encode / aeaj_decode).  Synchronises the device. */
 AEAJ_API int aeaj_plan_set_tensor_dct(aeaj_plan* p, int mask);
