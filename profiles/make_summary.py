@@ -66,7 +66,7 @@ def kernels(rep, tag, frames=8):
     raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(raw.splitlines()))
     hdr, units = r[0], r[1]
-    out = [f"# {tag}: `ncu --set full --clock-control none` of the top kernels (one launch each)\n"]
+    out = [f"# {tag}: `ncu --set full --clock-control none` of the top kernels (one launch each, {frames} 4K frames per launch: `tools/prof_step.py {frames}`)\n"]
     traffic = {}
     stats = {}
     seen = set()
