@@ -62,6 +62,7 @@ class _Peers:
     def __init__(self, lib, plan, rank, world, group):
         import torch.distributed as dist
         self.lib, self.world = lib, world
+        self.plan_ptr = plan.ptr.value
         nbytes = int(plan.info.workspace_bytes)
         self.ws, self.flags = C.c_void_p(), C.c_void_p()
         native.check(lib.aeaj_peer_alloc(nbytes, C.byref(self.ws)), "aeaj_peer_alloc")
@@ -108,9 +109,13 @@ class TiledCodec:
         if self.transport != "peer":
             return p.workspace.data_ptr()
         key = id(p)
-        if key not in self._peers:
-            self._peers[key] = _Peers(self.lib, p, self.rank, self.world, self.group)
-        return self._peers[key].ws.value
+        pe = self._peers.get(key)
+        if pe is not None and pe.plan_ptr != p.ptr.value:          # the codec evicted / rebuilt that plan: the mapping is stale
+            pe.close()
+            pe = None
+        if pe is None:
+            pe = self._peers[key] = _Peers(self.lib, p, self.rank, self.world, self.group)
+        return pe.ws.value
 
     def close(self):
         torch.cuda.synchronize()
@@ -229,10 +234,12 @@ class TiledCodec:
             each(PH_QT_EMIT)
             each(PH_DCT)
         if multi and exchange_coef:
+            import torch.distributed as dist
             for l in range(3):
-                if self.transport == "peer":  # sharded quadtree: every rank wrote only its band's leaves / states (the all-split
-                    self._reduce(o.leaves[l])  # upper levels and absent nodes are written by every rank: take the maximum)
-                    import torch.distributed as dist
+                if self.transport == "peer":
+                    # sharded quadtree: every rank wrote only its band's leaves / states (zero elsewhere: sum); the all-split levels
+                    # above the top blocks and the absent nodes are written by every rank with the same value: maximum
+                    self._reduce(o.leaves[l])
                     dist.all_reduce(o.states[l], op=dist.ReduceOp.MAX, group=self.group)
                 self._reduce(o.coef[l])
         return o

@@ -745,3 +745,24 @@ def test_two_stream_roundtrip_equals_single_stream(codec):
     ref8 = codec.decode_encoded(codec.encode((batch * 255).to(torch.uint8), space, q, b), space, q, b, out="u8")
     torch.cuda.synchronize()
     assert torch.equal(torch.cat(parts8), ref8)
+
+
+def test_halo_split_two_gpus_over_peer_memory():
+    """SURVEY 8e on real hardware: two ranks (torchrun), each with a band of one image, halo rows / partial histograms read from
+    the neighbour's workspace over NVLink, device-side barriers -- streams and decoded rows identical to the single-GPU run.
+    Needs two GPUs in one box (skipped otherwise; tests/multi_gpu_halo.py is the script, bench.py --gpus N repeats it at 8192^2)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29541", os.path.join(root, "tests", "multi_gpu_halo.py"), "1024", "1280"],
+                         capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    line = [l for l in out.stdout.splitlines() if l.startswith('{"halo_split"')][-1]
+    res = json.loads(line)["halo_split"]
+    assert res["transport"] == "peer" and all(v["identical_to_single_gpu"] for v in res["results"].values())
