@@ -217,6 +217,11 @@ class TiledCodec:
             io.rgb = rgb.data_ptr() - lo * W * 12
             native.check(self.lib.aeaj_encode_phase(p.ptr, C.byref(io), ws, _stream(), PH_TREE, 0, H), "aeaj_encode_phase(tree)")
             each(PH_DCT)
+        elif self.transport == "peer":
+            # one foreign call runs the whole schedule below for this rank (the phase calls are what emulation uses)
+            lo, hi = band_of(self.rank, G, H, brange[1])
+            io.rgb = rgb.data_ptr() - lo * W * 12
+            native.check(self.lib.aeaj_encode_halo(p.ptr, C.byref(io), ws, _stream(), lo, hi), "aeaj_encode_halo")
         else:
             self._barrier(p)                  # the previous call's neighbours are done reading this rank's planes
             each(PH_COLOR)                    # also clears the histogram accumulators (before any histogram work)
@@ -261,6 +266,10 @@ class TiledCodec:
             lo, hi = band_of(r, G, H, brange[1])
             native.check(self.lib.aeaj_decode_phase(p.ptr, C.byref(io), ws, _stream(), phase, lo, hi), f"aeaj_decode_phase({phase})")
 
+        if self.transport == "peer":
+            lo, hi = band_of(self.rank, G, H, brange[1])
+            native.check(self.lib.aeaj_decode_halo(p.ptr, C.byref(io), ws, _stream(), lo, hi), "aeaj_decode_halo")
+            return p.rgb_out[0]
         for r in ranks:
             run(DPH_IDCT, r)
         if self.transport == "nccl":

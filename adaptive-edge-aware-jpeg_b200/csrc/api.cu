@@ -998,6 +998,36 @@ extern "C" int aeaj_plan_peer_gather(aeaj_plan* p, int what, void* workspace, vo
     return launch_peer_gather(dev, (int)segs.size(), maxb, ST(stream));
 }
 
+// The whole schedule of one rank of a multi-GPU halo-split in ONE call (aeaj/tiled.py documents it; the phase-wise entry
+// points stay for callers that bring their own exchange): ~45 launches behind a single foreign call instead of twenty.
+extern "C" int aeaj_encode_halo(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, void* stream, int band0, int band1) {
+    AEAJ_REQUIRE(p && p->peers.world > 1, "aeaj_encode_halo: the plan has no peers (aeaj_plan_set_peers)");
+    AEAJ_REQUIRE(workspace == p->peer_ws[p->peers.rank], "aeaj_encode_halo: the workspace must be the shared allocation registered with aeaj_plan_set_peers");
+    const cudaStream_t st = ST(stream);
+    auto ph = [](int k) { return 1u << k; };
+    int rc;
+    if ((rc = aeaj_plan_peer_barrier(p, stream))) return rc;          // the previous call's neighbours are done reading this rank's planes
+    if ((rc = encode_impl(p, io, workspace, st, ph(AEAJ_PHASE_COLOR) | ph(AEAJ_PHASE_CLAHE_HIST), band0, band1))) return rc;
+    if ((rc = aeaj_plan_peer_barrier(p, stream))) return rc;
+    if ((rc = encode_impl(p, io, workspace, st, ph(AEAJ_PHASE_PREFILTER), band0, band1))) return rc;
+    if ((rc = aeaj_plan_peer_barrier(p, stream))) return rc;
+    if ((rc = encode_impl(p, io, workspace, st, ph(AEAJ_PHASE_NMS), band0, band1))) return rc;
+    if ((rc = aeaj_plan_peer_barrier(p, stream))) return rc;
+    if ((rc = aeaj_plan_peer_gather(p, 0, workspace, stream))) return rc;
+    if ((rc = encode_impl(p, io, workspace, st, ph(AEAJ_PHASE_HYST) | ph(AEAJ_PHASE_QT_COUNT), band0, band1))) return rc;
+    if ((rc = aeaj_plan_peer_barrier(p, stream))) return rc;
+    if ((rc = aeaj_plan_peer_gather(p, 1, workspace, stream))) return rc;
+    return encode_impl(p, io, workspace, st, ph(AEAJ_PHASE_QT_EMIT) | ph(AEAJ_PHASE_DCT), band0, band1);
+}
+extern "C" int aeaj_decode_halo(aeaj_plan* p, const aeaj_decode_io* io, void* workspace, void* stream, int band0, int band1) {
+    AEAJ_REQUIRE(p && p->peers.world > 1, "aeaj_decode_halo: the plan has no peers (aeaj_plan_set_peers)");
+    AEAJ_REQUIRE(workspace == p->peer_ws[p->peers.rank], "aeaj_decode_halo: the workspace must be the shared allocation registered with aeaj_plan_set_peers");
+    int rc;
+    if ((rc = decode_impl(p, io, workspace, ST(stream), 1u << AEAJ_DPHASE_IDCT, band0, band1))) return rc;
+    if ((rc = aeaj_plan_peer_barrier(p, stream))) return rc;
+    return decode_impl(p, io, workspace, ST(stream), 1u << AEAJ_DPHASE_COLOR, band0, band1);
+}
+
 // device pointers of the planes a halo-split caller exchanges between phases (batch 1)
 extern "C" int aeaj_plan_buffers(aeaj_plan* p, void* workspace, aeaj_plan_buffers_t* out) {
     AEAJ_REQUIRE(p && workspace && out, "aeaj_plan_buffers: bad arguments");

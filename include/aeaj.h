@@ -224,6 +224,10 @@ AEAJ_API int aeaj_peer_close(void* ptr);
 AEAJ_API int aeaj_plan_set_peers(aeaj_plan* p, int rank, int world, void* const* peer_workspaces_host, void* const* peer_flags_host);
 AEAJ_API int aeaj_plan_peer_barrier(aeaj_plan* p, void* stream);
 AEAJ_API int aeaj_plan_peer_gather(aeaj_plan* p, int what, void* workspace, void* stream);
+/* One rank's whole halo-split schedule in a single call: barriers, the band-restricted phases (reading halo rows / partial
+ * histograms from the neighbours), the two gathers -- what aeaj/tiled.py otherwise issues as twenty calls. */
+AEAJ_API int aeaj_encode_halo(aeaj_plan* p, const aeaj_encode_io* io, void* workspace, void* stream, int band0, int band1);
+AEAJ_API int aeaj_decode_halo(aeaj_plan* p, const aeaj_decode_io* io, void* workspace, void* stream, int band0, int band1);
 
 /* ---------------------------------------------------------------------------------------------
  * host-side helpers for the entropy-coding side (plain CPU code, no device work):
