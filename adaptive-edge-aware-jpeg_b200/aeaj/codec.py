@@ -435,7 +435,7 @@ class DeviceCodec:
         return st["rgb_out"], h2d, st["rgb_out"].numel() * 4
 
     def roundtrip_host_pipelined(self, host_in: torch.Tensor, host_out: torch.Tensor, space, qrange, brange, slots: int = 8, repeat: int = 1, lag: int = 3,
-                                 packed: bool = True, threads: int = 1, frames_per_job: int = 1):
+                                 packed: bool = True, threads: int = 1, frames_per_job: int = 1, zero_copy: bool = False):
         """Host-buffer encode+decode of every frame of `host_in` (pinned float32 -- or uint8, the 8-bit image flow
         Image.load -> compress ... decompress -> Image.save -- [F,H,W,3]) into `host_out` (float32 or uint8), `frames_per_job`
         frames per job, jobs round-robin over `slots` CUDA streams so that the H2D and D2H copies of different jobs overlap
@@ -446,6 +446,11 @@ class DeviceCodec:
         the pipeline in between.  packed=True moves the coefficient streams in their packed form (bit mask + int16 non-zeros,
         aeaj_pack_coefficients after the encode, aeaj_unpack_coefficients before the decode; a plane whose overflow flag is
         set travels as int32) and all of a job's streams as ONE copy per direction (aeaj_copy_segments).
+        zero_copy=True (packed only): the small transfers -- the counts and the arena of packed streams, ~4 MB per 4K frame -- are
+        written to / read from the pinned host buffers by the gather / scatter kernels themselves (pinned memory is mapped
+        into the device's address space), so the copy engines carry nothing but the two pixel transfers of every frame and
+        a copy that is ready is never queued behind one that still waits for a kernel.  Measured: no faster (0.85 vs 0.82 ms per
+        frame), so it is off by default -- the copy queues are not what keeps copies and kernels from overlapping fully.
         Measured on B200 (tools/e2e_sweep.py, profiles/r2_e2e_sweep.txt): 0.77 ms per 4K frame against 0.60 ms for the same bytes as
         bare copies (48 GB/s per direction); more slots, several frames per job (`frames_per_job`) or several host threads
         (`threads`, each driving its own slots) do not change it -- the driving thread is blocked on the device half of the time
@@ -464,16 +469,17 @@ class DeviceCodec:
         for slot in range(min(slots, J)):                          # plans and staging are created by one thread, before the workers start
             self._host_staging(self._plan(G, H, W, space, brange, qrange, instance=slot))
         if threads == 1:
-            return self._pipeline_worker(list(range(J)), list(range(slots)), G, host_in, host_out, space, qrange, brange, min(lag, slots - 1), packed)
+            return self._pipeline_worker(list(range(J)), list(range(slots)), G, host_in, host_out, space, qrange, brange, min(lag, slots - 1), packed,
+                                         zero_copy)
         import concurrent.futures as cf
         per = slots // threads
         work = [([j for j in range(J) if j % threads == t], list(range(t * per, (t + 1) * per))) for t in range(threads)]
         with cf.ThreadPoolExecutor(max_workers=threads) as ex:
             res = list(ex.map(lambda w: self._pipeline_worker(w[0], w[1], G, host_in, host_out, space, qrange, brange,
-                                                                   min(max(1, lag // threads + 1), per - 1), packed), work))
+                                                                   min(max(1, lag // threads + 1), per - 1), packed, zero_copy), work))
         return sum(r[0] for r in res), sum(r[1] for r in res)
 
-    def _pipeline_worker(self, job_ids, slot_ids, G, host_in, host_out, space, qrange, brange, lag, packed):
+    def _pipeline_worker(self, job_ids, slot_ids, G, host_in, host_out, space, qrange, brange, lag, packed, zero_copy=False):
         """one host thread of roundtrip_host_pipelined: the jobs `job_ids` (job j = frames j G .. j G + G - 1 of the repeated
         frame sequence), round-robin over its own `slot_ids`"""
         torch.cuda.set_device(self.device)                         # the current device is per host thread
@@ -494,13 +500,19 @@ class DeviceCodec:
                 src = st["rgb8_dev"] if host_in.dtype == torch.uint8 else st["rgb_dev"]
                 src.copy_(host_in[f0:f0 + G], non_blocking=True)
                 enc = self.encode(src, space, qrange, brange, instance=slot)
-                st["counts"].copy_(enc.counts, non_blocking=True)
-                if packed:
+                if packed and zero_copy:
                     pk = self.pack(enc, space, qrange, brange, instance=slot)
-                    st["pk_counts"].copy_(pk.counts, non_blocking=True)
+                    _, _, table = self._arena(p, st)
+                    self._copy_segments([(enc.counts.data_ptr(), st["counts"].data_ptr(), st["counts"].numel() * 4),
+                                         (pk.counts.data_ptr(), st["pk_counts"].data_ptr(), st["pk_counts"].numel() * 4)], table)
+                else:
+                    st["counts"].copy_(enc.counts, non_blocking=True)
+                    if packed:
+                        pk = self.pack(enc, space, qrange, brange, instance=slot)
+                        st["pk_counts"].copy_(pk.counts, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(stream)
-            jobs.append(dict(f=f0, G=G, slot=slot, p=p, st=st, enc=enc, ev=ev, done=False, phase_b=False, packed=packed))
+            jobs.append(dict(f=f0, G=G, slot=slot, p=p, st=st, enc=enc, ev=ev, done=False, phase_b=False, packed=packed, zero_copy=packed and zero_copy))
             h2d += G * host_in[0].numel() * host_in.element_size()
             # phase B of a job is issued `lag` jobs after its phase A (its counts have landed by then), and a slot is
             # reused only `nslots` jobs later, so neither host wait normally blocks
@@ -530,7 +542,8 @@ class DeviceCodec:
         if pk is not None and not (pkc[:, :, 2] != 0).any():
             # the normal case (no int16 overflow): gather the job's streams into one arena, ONE copy each way, scatter back
             arena_dev, arena_host, table = self._arena(p, st)
-            base = arena_dev.data_ptr()
+            zc = job.get("zero_copy", False)
+            base = arena_host.data_ptr() if zc else arena_dev.data_ptr()
             off = 0
             there, back = [], []
             for b in range(G):
@@ -544,12 +557,19 @@ class DeviceCodec:
                             back.append((base + off, t.data_ptr(), nb))
                         off = (off + nb + 15) & ~15
             with torch.cuda.stream(stream):
-                self._copy_segments(there, table)
-                arena_host[:off].copy_(arena_dev[:off], non_blocking=True)          # -> the host-side entropy coder
-                arena_dev[:off].copy_(arena_host[:off], non_blocking=True)          # <- what the entropy decoder hands back
-                self._copy_segments(back, table)
-                enc.counts.copy_(st["counts"], non_blocking=True)
-                pk.counts.copy_(st["pk_counts"], non_blocking=True)
+                if zc:
+                    # the gather kernel writes the host arena itself, the scatter kernel reads it back (and the counts with it)
+                    back += [(st["counts"].data_ptr(), enc.counts.data_ptr(), st["counts"].numel() * 4),
+                             (st["pk_counts"].data_ptr(), pk.counts.data_ptr(), st["pk_counts"].numel() * 4)]
+                    self._copy_segments(there, table)                                   # -> the host-side entropy coder
+                    self._copy_segments(back, table)                                    # <- what the entropy decoder hands back
+                else:
+                    self._copy_segments(there, table)
+                    arena_host[:off].copy_(arena_dev[:off], non_blocking=True)          # -> the host-side entropy coder
+                    arena_dev[:off].copy_(arena_host[:off], non_blocking=True)          # <- what the entropy decoder hands back
+                    self._copy_segments(back, table)
+                    enc.counts.copy_(st["counts"], non_blocking=True)
+                    pk.counts.copy_(st["pk_counts"], non_blocking=True)
                 self.unpack(pk, G, H, W, space, qrange, brange, instance=slot)
                 rgb = self.decode(enc.coef, enc.leaves, enc.counts, G, H, W, space, qrange, brange, instance=slot, out=out_kind)
                 host_out[job["f"]:job["f"] + G].copy_(rgb, non_blocking=True)

@@ -574,8 +574,9 @@ def test_tensor_core_dct_parity(codec):
     assert err[False] <= 3e-6 and err[True] <= 3e-6
 
 
+@pytest.mark.parametrize("zero_copy", [False, True])
 @pytest.mark.parametrize("slots,threads,lag,G", [(3, 1, 2, 1), (3, 2, 2, 1), (8, 2, 3, 2), (4, 4, 3, 1), (3, 1, 2, 3), (2, 1, 1, 6)])
-def test_host_pipelined_roundtrip_matches_device_path(codec, slots, threads, lag, G):
+def test_host_pipelined_roundtrip_matches_device_path(codec, slots, threads, lag, G, zero_copy):
     """the host-buffer API (bench.py's e2e leg) returns the same pixels as the device-resident path, whatever the number of
     stream slots and of host threads driving them"""
     import torch
@@ -584,7 +585,8 @@ def test_host_pipelined_roundtrip_matches_device_path(codec, slots, threads, lag
     space, q, b = "YCbCr", (30, 95), (4, 64)
     host_in = torch.from_numpy(frames).pin_memory()
     host_out = torch.zeros_like(host_in).pin_memory()
-    h2d, d2h = codec.roundtrip_host_pipelined(host_in, host_out, space, q, b, slots=slots, repeat=2, lag=lag, threads=threads, frames_per_job=G)
+    h2d, d2h = codec.roundtrip_host_pipelined(host_in, host_out, space, q, b, slots=slots, repeat=2, lag=lag, threads=threads, frames_per_job=G,
+                                                  zero_copy=zero_copy)
     dev = codec.decode_encoded(codec.encode(host_in.cuda(), space, q, b), space, q, b).cpu()
     assert torch.equal(dev, host_out)
     assert h2d > 2 * frames.nbytes and d2h > 2 * frames.nbytes

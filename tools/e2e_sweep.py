@@ -23,9 +23,9 @@ def run(**kw):
     print(f"{kw}: {dt * 1e3 / F:.3f} ms/frame  {mp / dt:.0f} MP/s  {h2d / 4 / dt / 1e9:.1f} + {d2h / 4 / dt / 1e9:.1f} GB/s;  host blocked on the device "
           f"{c.pipeline_host_wait_s / 4 * 1e3 / F:.3f} ms/frame", flush=True)
 
-for kw in (dict(slots=8, lag=3, frames_per_job=1), dict(slots=8, lag=3, frames_per_job=2), dict(slots=8, lag=3, frames_per_job=4),
-           dict(slots=4, lag=2, frames_per_job=4), dict(slots=6, lag=2, frames_per_job=4), dict(slots=4, lag=1, frames_per_job=8),
-           dict(slots=8, lag=3, frames_per_job=4, threads=2)):
+for kw in (dict(slots=8, lag=3, zero_copy=False), dict(slots=8, lag=3, zero_copy=True), dict(slots=12, lag=4, zero_copy=True),
+           dict(slots=6, lag=2, zero_copy=True), dict(slots=8, lag=3, zero_copy=True, threads=2), dict(slots=8, lag=3, zero_copy=False, frames_per_job=2),
+           dict(slots=8, lag=3, zero_copy=True, frames_per_job=2)):
     run(**kw)
 
 # pure copies of the same byte counts, both directions at once, 8 streams
