@@ -454,8 +454,8 @@ class DeviceCodec:
         Measured on B200 (tools/e2e_sweep.py, profiles/r2_e2e_sweep.txt): 0.77 ms per 4K frame against 0.60 ms for the same bytes as
         bare copies (48 GB/s per direction); more slots, several frames per job (`frames_per_job`) or several host threads
         (`threads`, each driving its own slots) do not change it -- the driving thread is blocked on the device half of the time
-        and the device work alone takes 0.42 ms per frame, so what is left is how copies queued behind unfinished kernels hold up
-        later copies of the same direction.  Returns (h2d_bytes, d2h_bytes) summed over all jobs."""
+        and the device work alone takes 0.42 ms per frame: copies and kernels do not overlap fully on this box (a bare
+        H2D -> idle kernel -> D2H chain on 8 streams shows the same loss).  Returns (h2d_bytes, d2h_bytes) summed over all jobs."""
         F0, H, W, _ = host_in.shape
         G = max(1, frames_per_job)
         if F0 % G != 0:
