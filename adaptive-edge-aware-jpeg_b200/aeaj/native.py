@@ -26,7 +26,7 @@ EXPORTS = [
     "aeaj_pack_coefficients", "aeaj_unpack_coefficients", "aeaj_pack_coefficients_host", "aeaj_unpack_coefficients_host",
     "aeaj_peer_alloc", "aeaj_peer_free", "aeaj_peer_export", "aeaj_peer_open", "aeaj_peer_close",
     "aeaj_plan_set_peers", "aeaj_plan_peer_barrier", "aeaj_plan_peer_gather", "aeaj_copy_segments",
-    "aeaj_encode_halo", "aeaj_decode_halo",
+    "aeaj_encode_halo", "aeaj_decode_halo", "aeaj_set_fast_transfer",
 ]
 
 
@@ -124,6 +124,7 @@ def load():
         lib.aeaj_plan_read_timing.argtypes = [vp, C.c_char_p, sz, vp, i, C.POINTER(i)]
         lib.aeaj_states_to_leaves_host.argtypes = [vp, i, i, i, i, i, i, vp, C.POINTER(i), C.POINTER(C.c_int64)]
         lib.aeaj_pack_states_host.argtypes = [vp, i, vp]
+        lib.aeaj_set_fast_transfer.argtypes = [vp, i]
         lib.aeaj_encode_halo.argtypes = [vp, C.POINTER(EncodeIO), vp, vp, i, i]
         lib.aeaj_decode_halo.argtypes = [vp, C.POINTER(DecodeIO), vp, vp, i, i]
         lib.aeaj_copy_segments.argtypes = [C.POINTER(Segment), i, vp, vp]

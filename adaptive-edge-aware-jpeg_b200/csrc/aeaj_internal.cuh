@@ -1,6 +1,7 @@
 // aeaj_internal.cuh -- shared declarations for libaeaj.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include "pqfast.h"
 #include <stdint.h>
 #include <stdio.h>
 #include <algorithm>
@@ -41,10 +42,12 @@ void aeaj_set_error(const char* fmt, ...);
 // ---------------------------------------------------------------------------------------------
 // geometry shared by host and device
 // ---------------------------------------------------------------------------------------------
-struct ColorConsts {          // per colour space, device-resident copy inside the handle
+struct ColorConsts {          // per colour space; passed to the kernels by value (kernel parameters)
     float fwd1[9], fwd2[9];   // forward: XYZ->LMS, LMS'->space   (linear spaces: fwd1 = the 3x3)
     float inv1[9], inv2[9];   // inverse: space->LMS', LMS->XYZ   (linear spaces: inv1 = the 3x3)
     float mid[3], scale[3];   // normalisation (MIDPOINTS / SCALE_FACTORS)
+    int fast;                 // 1: try the table-driven transfer functions first (pqfast.h), 0: exact float64 path only
+    PqTabs pq;                // views over the handle's device tables
 };
 
 // one image over several GPUs (peer.cu): ranks share their plan workspaces; a buffer of rank r is reached by adding
@@ -140,6 +143,8 @@ struct aeaj_handle {
     int hyst_blocks_per_sm;       // occupancy of k_hysteresis on this device (aeaj_canny_init)
     ColorConsts colors_host[8];
     ColorConsts* colors_dev;      // [8]
+    double* pq_tabs_dev;          // the fixed-exponent power tables of pqfast.h (one allocation; colors_host[*].pq points into it)
+    double pq_worst_eps;          // largest error bound among them (diagnostic)
     float* srgb_lut_dev;          // 256 floats, 0 until aeaj_set_srgb_lut
     int has_srgb_lut;
     float* dct_dev[9];            // DCT-II matrices C (s x s, row-major) for s = 2^k, k = 1..8
@@ -247,6 +252,7 @@ int launch_resize_linear(const float* src, int sh, int sw, float* dst, int H, in
 int launch_upsample_color_inverse(aeaj_handle* h, int space, const PlaneDesc* planes_host, int B, int H, int W,
                                   float* rgb, uint8_t* rgb_u8, cudaStream_t st, int band0 = 0, int band1 = -1);
 int launch_peer_barrier(int* const* flags_host, int rank, int world, int epoch, int* err_dev, cudaStream_t st);
+int aeaj_color_init(aeaj_handle* h);
 int launch_peer_gather(const PeerSeg* segs_dev, int nseg, long long max_bytes, cudaStream_t st);
 constexpr int AEAJ_SEGS_BY_PARAM = 64;
 int launch_copy_segments_param(const PeerSeg* segs_host, int nseg, long long max_bytes, cudaStream_t st);

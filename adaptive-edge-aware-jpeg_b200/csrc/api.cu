@@ -116,6 +116,8 @@ extern "C" int aeaj_create(int device, aeaj_handle** out) {
     if (rc) { free(h); return rc; }
     rc = aeaj_dct_tc_init(h);
     if (rc) { free(h); return rc; }
+    rc = aeaj_color_init(h);
+    if (rc) { free(h); return rc; }
     AEAJ_CUDA(cudaMalloc(&h->srgb_lut_dev, 256 * sizeof(float)));
     AEAJ_CUDA(cudaMalloc(&h->stage_plane_dev, sizeof(PlaneDesc)));
     AEAJ_CUDA(cudaMalloc(&h->stage_class_off_dev, 18 * sizeof(long long)));
@@ -129,7 +131,7 @@ extern "C" int aeaj_create(int device, aeaj_handle** out) {
 extern "C" int aeaj_destroy(aeaj_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    cudaFree(h->srgb_lut_dev); cudaFree(h->dct_all_dev); cudaFree(h->dct_half_all_dev); cudaFree(h->zz_all_dev); cudaFree(h->izz256_dev); cudaFree(h->dct_tc_tiles_dev); cudaFree(h->tc_izz_all_dev); cudaFree(h->tc_err_dev); cudaFree(h->stage_plane_dev);
+    cudaFree(h->pq_tabs_dev); cudaFree(h->srgb_lut_dev); cudaFree(h->dct_all_dev); cudaFree(h->dct_half_all_dev); cudaFree(h->zz_all_dev); cudaFree(h->izz256_dev); cudaFree(h->dct_tc_tiles_dev); cudaFree(h->tc_izz_all_dev); cudaFree(h->tc_err_dev); cudaFree(h->stage_plane_dev);
     cudaFree(h->stage_class_off_dev); cudaFree(h->stage_tile_base_dev); cudaFree(h->stage_outs_dev);
     free(h);
     return 0;
@@ -145,6 +147,15 @@ extern "C" int aeaj_set_color_tables(aeaj_handle* h, int space, const float* f1,
     if (i2) memcpy(C.inv2, i2, sizeof C.inv2);
     if (mid) memcpy(C.mid, mid, sizeof C.mid);
     if (scale) memcpy(C.scale, scale, sizeof C.scale);
+    return 0;
+}
+
+// 1 (default): the PQ / sRGB / OKLAB transfer functions try the table-driven evaluation first and fall back to the exact float64
+// path for the pixels whose float32 rounding it cannot guarantee; 0: exact path for every pixel.  Same results either way.
+extern "C" int aeaj_set_fast_transfer(aeaj_handle* h, int on) {
+    AEAJ_REQUIRE(h, "aeaj_set_fast_transfer: NULL handle");
+    for (int sp = 0; sp < 8; sp++)
+        h->colors_host[sp].fast = (on && (sp == AEAJ_OKLAB || sp == AEAJ_ICACB || sp == AEAJ_ICTCP || sp == AEAJ_JZAZBZ)) ? 1 : 0;
     return 0;
 }
 

@@ -9,6 +9,7 @@
 //   * INTER_LINEAR: half-pixel centres, edge clamp, horizontal then vertical, a*(1-t)+b*t, no fma
 // The file is compiled with -fmad=false; every fused multiply-add below is explicit.
 #include "aeaj_internal.cuh"
+#include "pqtabs_build.h"
 
 namespace {
 
@@ -153,6 +154,166 @@ __device__ __forceinline__ double mul3add(double a0, double b0, double a1, doubl
     return __dadd_rn(__dadd_rn(__dmul_rn(a0, b0), __dmul_rn(a1, b1)), __dmul_rn(a2, b2));
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fast transfer functions (powtab.h / pqfast.h): fixed-exponent powers by table + polynomial (~12 FP64 instructions instead of
+// ~70) with a bound on the distance to the exact float64 path carried to every float32 rounding.  Each helper returns true
+// only if ALL of its float32 results are provably the exact path's (every double within the bound rounds to the same
+// float); otherwise the caller recomputes the pixel with the exact code below it.  Bit-identical by construction; the tables
+// only decide how often the slow path runs (a few pixels in 10^5; more around the PQ decoder's clamp at black).
+// ---------------------------------------------------------------------------------------------
+#ifdef AEAJ_FAST_STATS
+__device__ unsigned long long g_fast_stats[8];       // [0] forward pixels, [1] forward fallbacks, [2] inverse pixels, [3] inverse XYZ fallbacks, [4] sRGB fallbacks
+#define FAST_STAT(i) atomicAdd(&g_fast_stats[i], 1ull)
+#define FAST_STAT_INV(i) (void)atomicAdd(&g_fast_stats[i], 1ull)
+extern "C" AEAJ_API int aeaj_debug_fast_stats(unsigned long long* out8, int reset) {
+    if (out8) cudaMemcpyFromSymbol(out8, g_fast_stats, sizeof g_fast_stats);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_fast_stats, z, sizeof z); }
+    return 0;
+}
+#else
+#define FAST_STAT(i) do { } while (0)
+#define FAST_STAT_INV(i) (void)0
+#endif
+__device__ __forceinline__ bool row3_fast(const float* q, double p0, double p1, double p2, double r0, double r1, double r2, double& o, double& E) {
+    const double a0 = fabs((double)q[0]) * p0, a1 = fabs((double)q[1]) * p1, a2 = fabs((double)q[2]) * p2;   // p >= 0
+    o = __dadd_rn(__dadd_rn(__dmul_rn((double)q[0], p0), __dmul_rn((double)q[1], p1)), __dmul_rn((double)q[2], p2));   // = mul3add
+    E = a0 * r0 + a1 * r1 + a2 * r2 + 8.0 * PQF_U * (a0 + a1 + a2);
+    return round_is_safe(o, E);
+}
+
+template <int SPACE>
+__device__ __forceinline__ bool color_fwd_fast(const ColorConsts& C, float X, float Y, float Z, float& o0, float& o1, float& o2) {
+    const PqTabs& Q = C.pq;
+    bool ok = true;
+    if (SPACE == AEAJ_OKLAB) {                                   // (float) l^((double)(float)(1/3)), oklab.py:71-75
+        float v[3], w[3];
+        dot3(C.fwd1, X, Y, Z, v[0], v[1], v[2]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (v[k] == 0.0f) { w[k] = 0.0f; continue; }
+            const double p = powtab_eval<8>(Q.cbrt32, (double)v[k], ok);
+            if (!ok || !round_is_safe(p, p * (Q.cbrt32.eps + 2.0 * PQF_U))) return false;
+            w[k] = (float)p;
+        }
+        dot3(C.fwd2, w[0], w[1], w[2], o0, o1, o2);
+        return true;
+    }
+    double p[3], r[3];
+    if (SPACE == AEAJ_ICACB || SPACE == AEAJ_ICTCP) {
+        float l, m, s;
+        dot3(C.fwd1, X, Y, Z, l, m, s);
+        p[0] = pqf_inv_eotf(Q, 0, PQ_M2, (double)l, r[0], ok);
+        p[1] = pqf_inv_eotf(Q, 0, PQ_M2, (double)m, r[1], ok);
+        p[2] = pqf_inv_eotf(Q, 0, PQ_M2, (double)s, r[2], ok);
+        if (!ok) return false;
+        double o, E;
+        if (!row3_fast(C.fwd2, p[0], p[1], p[2], r[0], r[1], r[2], o, E)) return false;
+        o0 = (float)o;
+        if (!row3_fast(C.fwd2 + 3, p[0], p[1], p[2], r[0], r[1], r[2], o, E)) return false;
+        o1 = (float)o;
+        if (!row3_fast(C.fwd2 + 6, p[0], p[1], p[2], r[0], r[1], r[2], o, E)) return false;
+        o2 = (float)o;
+        return true;
+    }
+    // JzAzBz (jzazbz.py:57-97): the operations before and after the three PQ encodes are the exact path's own
+    const double Xd = (double)X, Yd = (double)Y;
+    const double Xp = __dsub_rn(__dmul_rn(JZ_B, Xd), __dmul_rn(JZ_B - 1.0, (double)Z));
+    const double Yp = __dsub_rn(__dmul_rn(JZ_G, Yd), __dmul_rn(JZ_G - 1.0, Xd));
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float* m = C.fwd1 + 3 * k;
+        const float mz = __fmul_rn(m[2], Z);
+        const double L = __dadd_rn(__dadd_rn(__dmul_rn((double)m[0], Xp), __dmul_rn((double)m[1], Yp)), (double)mz);
+        p[k] = pqf_inv_eotf(Q, 1, JZ_P, L, r[k], ok);
+    }
+    if (!ok) return false;
+    double Iz, Ei, o, E;
+    row3_fast(C.fwd2, p[0], p[1], p[2], r[0], r[1], r[2], Iz, Ei);          // Iz stays a double: judged after the Jz formula
+    if (!row3_fast(C.fwd2 + 3, p[0], p[1], p[2], r[0], r[1], r[2], o, E)) return false;
+    o1 = (float)o;
+    if (!row3_fast(C.fwd2 + 6, p[0], p[1], p[2], r[0], r[1], r[2], o, E)) return false;
+    o2 = (float)o;
+    const double den = __dadd_rn(1.0, __dmul_rn(JZ_D, Iz));
+    const double Jz = __dsub_rn(__ddiv_rn(__dmul_rn(1.0 + JZ_D, Iz), den), JZ_D0);
+    const double rd = pqf_rcp(den);
+    const double Ej = Ei * ((1.0 + JZ_D) * rd * rd) * 1.001 + 8.0 * PQF_U * (fabs(Jz) + JZ_D0);      // d/dIz of (1 + d) Iz / (1 + d Iz)
+    if (!(den > 0.25) || !round_is_safe(Jz, Ej)) return false;
+    o0 = (float)Jz;
+    return true;
+}
+
+// space -> XYZ (the part of color_inv before the sRGB encode)
+template <int SPACE>
+__device__ __forceinline__ bool color_inv_xyz_fast(const ColorConsts& C, float a, float b, float c, float& X, float& Y, float& Z) {
+    const PqTabs& Q = C.pq;
+    bool ok = true;
+    if (SPACE == AEAJ_OKLAB) {                                   // (float) l'^3, oklab.py:93-96
+        float v[3], w[3];
+        dot3(C.inv1, a, b, c, v[0], v[1], v[2]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (v[k] == 0.0f) { w[k] = v[k]; continue; }
+            const double p = powtab_eval<8>(Q.cube, fabs((double)v[k]), ok);
+            if (!ok || !round_is_safe(p, p * (Q.cube.eps + 2.0 * PQF_U))) return false;
+            w[k] = v[k] < 0.0f ? -(float)p : (float)p;
+        }
+        dot3(C.inv2, w[0], w[1], w[2], X, Y, Z);
+        return true;
+    }
+    double p[3], r[3], o, E;
+    if (SPACE == AEAJ_ICACB || SPACE == AEAJ_ICTCP) {
+        float lp, mp, sp;
+        dot3(C.inv1, a, b, c, lp, mp, sp);
+        p[0] = pqf_eotf(Q, 0, (double)lp, r[0], ok);
+        p[1] = pqf_eotf(Q, 0, (double)mp, r[1], ok);
+        p[2] = pqf_eotf(Q, 0, (double)sp, r[2], ok);
+        if (!ok) return false;
+        if (!row3_fast(C.inv2, p[0], p[1], p[2], r[0], r[1], r[2], o, E)) return false;
+        X = (float)o;
+        if (!row3_fast(C.inv2 + 3, p[0], p[1], p[2], r[0], r[1], r[2], o, E)) return false;
+        Y = (float)o;
+        if (!row3_fast(C.inv2 + 6, p[0], p[1], p[2], r[0], r[1], r[2], o, E)) return false;
+        Z = (float)o;
+        return true;
+    }
+    // JzAzBz (jzazbz.py:131-171)
+    const double jd = __dadd_rn((double)a, JZ_D0);
+    const double Iz = __ddiv_rn(jd, __dsub_rn(1.0 + JZ_D, __dmul_rn(JZ_D, jd)));
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float* m = C.inv1 + 3 * k;
+        const float ta = __fmul_rn(m[1], b), tb = __fmul_rn(m[2], c);
+        const double lp = __dadd_rn(__dadd_rn(__dmul_rn((double)m[0], Iz), (double)ta), (double)tb);
+        p[k] = pqf_eotf(Q, 1, lp, r[k], ok);
+    }
+    if (!ok) return false;
+    double Xp, Yp, Zp, Ex, Ey, Ez;
+    row3_fast(C.inv2, p[0], p[1], p[2], r[0], r[1], r[2], Xp, Ex);
+    row3_fast(C.inv2 + 3, p[0], p[1], p[2], r[0], r[1], r[2], Yp, Ey);
+    if (!row3_fast(C.inv2 + 6, p[0], p[1], p[2], r[0], r[1], r[2], Zp, Ez)) return false;
+    const double Xd = __ddiv_rn(__dadd_rn(Xp, __dmul_rn(JZ_B - 1.0, Zp)), JZ_B);
+    const double Exd = (Ex + (JZ_B - 1.0) * Ez) / JZ_B + 8.0 * PQF_U * (fabs(Xp) + fabs(Zp));
+    const double Yd = __ddiv_rn(__dadd_rn(Yp, __dmul_rn(JZ_G - 1.0, Xd)), JZ_G);
+    const double Eyd = (Ey + (1.0 - JZ_G) * Exd) / JZ_G + 8.0 * PQF_U * (fabs(Yp) + fabs(Xd)) / JZ_G;
+    if (!round_is_safe(Xd, Exd) || !round_is_safe(Yd, Eyd)) return false;
+    X = (float)Xd; Y = (float)Yd; Z = (float)Zp;
+    return true;
+}
+
+// common.py:62-92 on one channel, clamp included
+__device__ __forceinline__ bool linear_to_srgb_fast(const ColorConsts& C, float v, float& out) {
+    bool ok = true;
+    double E;
+    const double r = pqf_linear_to_srgb(C.pq, (double)v, E, ok);
+    if (!ok || !round_is_safe(r, E)) return false;
+    float f = (float)r;
+    f = (f < 1.0f) ? f : 1.0f;
+    f = (f > 0.0f) ? f : 0.0f;
+    out = f;
+    return true;
+}
+
 template <int SPACE>
 __device__ __forceinline__ void color_fwd(const ColorConsts& C, const PowTabs& T, const float* lut, float r, float g, float b,
                                           float& o0, float& o1, float& o2) {
@@ -161,6 +322,10 @@ __device__ __forceinline__ void color_fwd(const ColorConsts& C, const PowTabs& T
     float X, Y, Z;
     dot3(c_rgb2xyz, lr, lg, lb, X, Y, Z);
     if (SPACE == AEAJ_XYZ) { o0 = X; o1 = Y; o2 = Z; return; }
+    if (C.fast) { FAST_STAT(0); if (color_fwd_fast<SPACE>(C, X, Y, Z, o0, o1, o2)) return; FAST_STAT(1); }
+#ifdef AEAJ_FAST_ONLY                                   /* timing experiment only: wrong results for the pixels that need the exact path */
+    if (C.fast) { o0 = o1 = o2 = 0.0f; return; }
+#endif
     if (SPACE == AEAJ_OKLAB) {                                   // oklab.py:71-75
         float l, m, s;
         dot3(C.fwd1, X, Y, Z, l, m, s);
@@ -206,7 +371,8 @@ __device__ __forceinline__ void color_inv(const ColorConsts& C, const PowTabs& T
     }
     float X, Y, Z;
     if (SPACE == AEAJ_XYZ) { X = a; Y = b; Z = c; }
-    else if (SPACE == AEAJ_OKLAB) {                              // oklab.py:93-96
+    else if (C.fast && (FAST_STAT_INV(2), color_inv_xyz_fast<SPACE>(C, a, b, c, X, Y, Z))) { }
+    else if ((FAST_STAT_INV(3), SPACE == AEAJ_OKLAB)) {          // oklab.py:93-96
         float lp, mp, sp;
         dot3(C.inv1, a, b, c, lp, mp, sp);
         float l = (float)fpow(T, (double)lp, 3.0), m = (float)fpow(T, (double)mp, 3.0), s = (float)fpow(T, (double)sp, 3.0);
@@ -240,7 +406,9 @@ __device__ __forceinline__ void color_inv(const ColorConsts& C, const PowTabs& T
     }
     float lr, lg, lb;
     dot3(c_xyz2rgb, X, Y, Z, lr, lg, lb);
-    r = linear_to_srgb(T, lr); g = linear_to_srgb(T, lg); bl = linear_to_srgb(T, lb);
+    if (!(C.fast && linear_to_srgb_fast(C, lr, r))) { if (C.fast) FAST_STAT(4); r = linear_to_srgb(T, lr); }
+    if (!(C.fast && linear_to_srgb_fast(C, lg, g))) g = linear_to_srgb(T, lg);
+    if (!(C.fast && linear_to_srgb_fast(C, lb, bl))) bl = linear_to_srgb(T, lb);
 }
 
 __device__ __forceinline__ uint8_t cast_u8(float v) {            // (img*255).astype(np.uint8)
@@ -599,6 +767,37 @@ int dispatch_space(int space, F&& f) {
 }
 
 }  // namespace
+
+// builds the power tables on the host (long double), uploads them once and hands every colour space a view (pqtabs_build.h)
+int aeaj_color_init(aeaj_handle* h) {
+    PqTabsHost H;
+    pqtabs_build(H);
+    const PowTabHost* tabs[9] = {&H.m1, &H.m2[0], &H.m2[1], &H.im2[0], &H.im2[1], &H.im1, &H.isrgb, &H.cbrt32, &H.cube};
+    PowTabView* views[9] = {&H.view.m1, &H.view.m2[0], &H.view.m2[1], &H.view.im2[0], &H.view.im2[1], &H.view.im1, &H.view.isrgb, &H.view.cbrt32, &H.view.cube};
+    size_t total = 0;
+    double worst = 0.0;
+    for (int i = 0; i < 9; i++) { total += tabs[i]->te.size() + tabs[i]->coef.size(); worst = std::max(worst, tabs[i]->v.eps); }
+    AEAJ_REQUIRE(worst < 4e-15, "power tables: the fitted polynomials miss their accuracy target (host long double too short?)");
+    std::vector<double> flat;
+    flat.reserve(total + 18);
+    size_t off_te[9], off_coef[9];
+    for (int i = 0; i < 9; i++) {
+        off_te[i] = flat.size();
+        flat.insert(flat.end(), tabs[i]->te.begin(), tabs[i]->te.end());
+        if (flat.size() & 1) flat.push_back(0.0);                  // coefficient pairs are fetched with 16-byte loads
+        off_coef[i] = flat.size();
+        flat.insert(flat.end(), tabs[i]->coef.begin(), tabs[i]->coef.end());
+    }
+    AEAJ_CUDA(cudaMalloc(&h->pq_tabs_dev, flat.size() * sizeof(double)));
+    for (int i = 0; i < 9; i++) { views[i]->te = h->pq_tabs_dev + off_te[i]; views[i]->coef = h->pq_tabs_dev + off_coef[i]; }
+    AEAJ_CUDA(cudaMemcpy(h->pq_tabs_dev, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice));
+    h->pq_worst_eps = worst;
+    for (int sp = 0; sp < 8; sp++) {
+        h->colors_host[sp].pq = H.view;
+        h->colors_host[sp].fast = (sp == AEAJ_OKLAB || sp == AEAJ_ICACB || sp == AEAJ_ICTCP || sp == AEAJ_JZAZBZ) ? 1 : 0;
+    }
+    return 0;
+}
 
 int launch_color_pixels(aeaj_handle* h, int space, int inverse, const float* in, float* out, size_t n, cudaStream_t st) {
     if (n == 0) return 0;

@@ -67,6 +67,11 @@ AEAJ_API int aeaj_destroy(aeaj_handle* h);
 AEAJ_API int aeaj_set_color_tables(aeaj_handle* h, int space, const float* fwd1_host, const float* fwd2_host,
                           const float* inv1_host, const float* inv2_host, const float* mid_host,
                           const float* scale_host);
+/* The transfer functions of the non-linear spaces (PQ: common.py:94-159, sRGB: common.py:62-92, OKLAB: oklab.py:73,94) raise to
+ * fixed powers in float64.  on = 1 (default): table + polynomial evaluation with a carried error bound, and the exact float64
+ * path for every pixel whose float32 rounding the bound cannot guarantee -- bit-identical results, several times faster.
+ * on = 0: the exact path for every pixel (what the tests compare the fast path with). */
+AEAJ_API int aeaj_set_fast_transfer(aeaj_handle* h, int on);
 AEAJ_API int aeaj_set_srgb_lut(aeaj_handle* h, const float* lut256_host);
 
 /* ---------------------------------------------------------------------------------------------

@@ -768,3 +768,44 @@ def test_halo_split_two_gpus_over_peer_memory():
     line = [l for l in out.stdout.splitlines() if l.startswith('{"halo_split"')][-1]
     res = json.loads(line)["halo_split"]
     assert res["transport"] == "peer" and all(v["identical_to_single_gpu"] for v in res["results"].values())
+
+
+@pytest.mark.parametrize("space", ["OKLAB", "ICaCb", "ICtCp", "JzAzBz"])
+def test_fast_transfer_functions_equal_exact_path(st, codec, space):
+    """The table-driven transfer functions (csrc/powtab.h, pqfast.h) must give, bit for bit, what the exact float64 path gives:
+    8-bit colours (random, the grey ramp, the dark corner of the cube where the PQ decoder clamps), then the inverse on those
+    results perturbed the way quantisation perturbs them -- forward and inverse, pixel kernels and the fused 4K-style kernels."""
+    import torch
+    from aeaj import native
+    rng = np.random.default_rng(5)
+    n = 3_000_000
+    rgb8 = np.concatenate([rng.integers(0, 256, (n, 3)), np.repeat(np.arange(256)[:, None], 3, 1),
+                           rng.integers(0, 6, (200_000, 3)), np.zeros((1000, 3), dtype=np.int64)]).astype(np.float32) / np.float32(255.0)
+
+    def both(x, inverse):
+        out = []
+        for on in (1, 0):
+            native.check(st.lib.aeaj_set_fast_transfer(st.handle, on), "aeaj_set_fast_transfer")
+            out.append(st.color(space, x, inverse))
+        return out
+    try:
+        fwd_fast, fwd_exact = both(rgb8, False)
+        assert np.array_equal(fwd_fast.view(np.uint32), fwd_exact.view(np.uint32)), space
+        noisy = fwd_exact + (rng.standard_normal(fwd_exact.shape) * np.abs(fwd_exact).mean(0) * 0.02).astype(np.float32)
+        noisy[::7] = fwd_exact[::7]
+        inv_fast, inv_exact = both(noisy, True)
+        assert np.array_equal(inv_fast.view(np.uint32), inv_exact.view(np.uint32)), space     # NaN -> 1.0 (T-NAN) included
+        # the fused kernels (planar forward with chroma subsampling, upsampling inverse) on an image
+        img = torch.from_numpy(np.stack([synth(270, 480, seed=s) for s in (1, 2)])).cuda()
+        res = []
+        for on in (1, 0):
+            native.check(st.lib.aeaj_set_fast_transfer(codec.handle, on), "aeaj_set_fast_transfer")
+            enc = codec.encode(img, space, (30, 95), (4, 64), taps=True)
+            dec = codec.decode_encoded(enc, space, (30, 95), (4, 64))
+            res.append(([t.clone() for t in enc.layers], [t.clone() for t in enc.coef], dec.clone()))
+        for l in range(3):
+            assert torch.equal(res[0][0][l], res[1][0][l]) and torch.equal(res[0][1][l], res[1][1][l])
+        assert torch.equal(res[0][2].view(torch.int32), res[1][2].view(torch.int32))
+    finally:                                                       # back to the library default
+        native.check(st.lib.aeaj_set_fast_transfer(st.handle, 1), "aeaj_set_fast_transfer")
+        native.check(st.lib.aeaj_set_fast_transfer(codec.handle, 1), "aeaj_set_fast_transfer")

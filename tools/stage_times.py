@@ -9,6 +9,7 @@ c.tensor_dct = int(sys.argv[2], 0) if len(sys.argv)>2 else 0xf   # mask: bit k =
 H,W=2160,3840
 rgb = torch.from_numpy(np.stack([synth(H,W,s) for s in range(B)])).cuda()
 sp,q,b=(sys.argv[3] if len(sys.argv)>3 else 'YCbCr'),(30,95),(4,128)
+if len(sys.argv)>4: c.lib.aeaj_set_fast_transfer(c.handle, int(sys.argv[4]))   # 1: table-driven transfer functions (opt-in)
 args=(B,H,W,sp,b,q)
 for _ in range(3):
     enc=c.encode(rgb,sp,q,b); c.decode_encoded(enc,sp,q,b)
