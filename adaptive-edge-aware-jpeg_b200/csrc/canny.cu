@@ -6,7 +6,8 @@
 //   -> hysteresis by bitmap frontier propagation (persistent CTAs, tile-local convergence in shared
 //   memory, dirty neighbour tiles re-queued through a global work queue; no grid-wide barriers).
 //
-// All of it is integer / u8 work bounded by HBM (or L2) bandwidth and launch latency, not by math.
+// Integer / u8 work.  Measured, the stencil kernels are bound by instruction issue and the shared-memory pipe, not by HBM
+// (DESIGN.md 4); the layout (bit-packed maps, u8 planes, one pass per stage) keeps the traffic at its algorithmic minimum.
 // Arithmetic follows SURVEY.md App. A3 as validated by the CPU oracle against the reference.
 #include "aeaj_internal.cuh"
 

@@ -12,12 +12,13 @@
 // One persistent, warp-specialised CTA per SM over the super-tiles of a class (roles and mbarriers: see k_dct_tc):
 //   GEMM1  W = A . X      A tiles (smem, K-major, hi/lo; 128 KB, loaded once)   B = X^T (smem, K-major, hi/lo), streamed
 //                         in four K chunks of 32 super-rows through two buffers (full / empty mbarriers, tcgen05.commit)
-//   split  W -> Wh, Wl    TMEM -> registers -> TMEM (tcgen05.ld / tcgen05.st)
+//   split  W -> Wh, Wl    TMEM -> registers -> TMEM (tcgen05.ld / tcgen05.st), in place: Wh over D1, Wl next to it
 //   GEMM2  Out = W . A^T  A operand = W (TMEM, hi/lo)   B = the same shared-memory tiles as GEMM1's A; A is block
 //                         diagonal, so every K step only needs the N = S columns of its own block
 //   epilogue: tcgen05.ld -> registers -> exact float32 quantiser -> 256-bit stores of int32 coefficients     (forward)
 //                                     -> de-normalise, crop -> 256-bit stores of float32 layer samples       (inverse)
-// No shared-memory staging of the result: D2 stays valid during the next tile's GEMM1 because that writes D1.
+// No shared-memory staging of the result, and two Out buffers in tensor memory: the epilogue of tile i reads one while GEMM2 of
+// tile i+1 fills the other.
 // Shared-memory operands use the canonical no-swizzle K-major layout: [K/4 chunks][rows][4 floats], i.e. 8x16-byte
 // core matrices, stride-byte-offset 128 B (next 8 rows), leading-byte-offset rows*16 B (next K chunk).
 #include "aeaj_internal.cuh"
