@@ -788,8 +788,19 @@ int aeaj_color_init(aeaj_handle* h) {
         off_coef[i] = flat.size();
         flat.insert(flat.end(), tabs[i]->coef.begin(), tabs[i]->coef.end());
     }
+    FnTabHost* curves[4] = {&H.enc[0], &H.enc[1], &H.dec[0], &H.dec[1]};
+    FnTabView* cviews[4] = {&H.view.enc[0], &H.view.enc[1], &H.view.dec[0], &H.view.dec[1]};
+    size_t off_curve[4];
+    for (int i = 0; i < 4; i++) {
+        if (flat.size() & 1) flat.push_back(0.0);
+        off_curve[i] = flat.size();
+        flat.insert(flat.end(), curves[i]->coef.begin(), curves[i]->coef.end());
+        worst = std::max(worst, curves[i]->v.eps);
+    }
+    AEAJ_REQUIRE(worst < 4e-15, "transfer-curve tables: the fitted polynomials miss their accuracy target");
     AEAJ_CUDA(cudaMalloc(&h->pq_tabs_dev, flat.size() * sizeof(double)));
     for (int i = 0; i < 9; i++) { views[i]->te = h->pq_tabs_dev + off_te[i]; views[i]->coef = h->pq_tabs_dev + off_coef[i]; }
+    for (int i = 0; i < 4; i++) cviews[i]->coef = h->pq_tabs_dev + off_curve[i];
     AEAJ_CUDA(cudaMemcpy(h->pq_tabs_dev, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice));
     h->pq_worst_eps = worst;
     for (int sp = 0; sp < 8; sp++) {

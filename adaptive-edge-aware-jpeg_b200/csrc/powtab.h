@@ -90,3 +90,35 @@ AEAJ_HD double powtab_eval(const PowTabView& T, double x, bool& ok) {
     for (int d = 1; d <= DEG; d++) p = powtab_fma(p, s, cc[d]);
     return p * powtab_ld(T.te + k);
 }
+
+// A whole transfer curve f(x) (not a pure power) tabulated the same way: one degree-8 polynomial per (binade, segment), no 2^(e m)
+// factor.  One evaluation then replaces two powers, a division and the error arithmetic between them.
+struct FnTabView {
+    const double* coef;    // [nexp << lg_nseg][10]  (9 coefficients, highest degree first, padded to 16-byte pairs)
+    double eps;            // bound on |approx - f| / |f| inside the domain
+    int emin, nexp, lg_nseg;
+};
+AEAJ_HD double fntab_eval(const FnTabView& T, double x, bool& ok) {
+    const uint64_t u = powtab_bits(x);
+    const int k = (int)((u >> 52) & 0x7ff) - 1023 - T.emin;
+    ok = ok && ((u >> 63) == 0) && k >= 0 && k < T.nexp;
+    if (!ok) return 0.0;
+    const int j = (int)((u >> (52 - T.lg_nseg)) & ((1u << T.lg_nseg) - 1u));
+    const uint64_t low = (u << T.lg_nseg) & 0x000fffffffffffffull;
+    const double s = (powtab_from_bits(0x3ff0000000000000ull | low) - 1.5) * 2.0;          // exact, in [-1, 1)
+    const double* c = T.coef + ((size_t)((k << T.lg_nseg) + j)) * 10;
+    double cc[10];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int d = 0; d < 5; d++) {
+        const double2 v = __ldg(reinterpret_cast<const double2*>(c) + d);
+        cc[2 * d] = v.x; cc[2 * d + 1] = v.y;
+    }
+#else
+    for (int d = 0; d < 9; d++) cc[d] = c[d];
+#endif
+    double p = cc[0];
+#pragma unroll
+    for (int d = 1; d <= 8; d++) p = powtab_fma(p, s, cc[d]);
+    return p;
+}

@@ -18,6 +18,10 @@ struct PqTabs {
     PowTabView isrgb;       // d^(1/2.4)
     PowTabView cbrt32;      // l^((double)(float)(1/3))   (oklab.py:73: numpy casts the exponent to float32)
     PowTabView cube;        // |l'|^3
+    // the whole PQ curves, one evaluation each (outside their domains the two-stage evaluation above is used, then the exact path)
+    FnTabView enc[2];       // c -> ((c1 + c2 t) / (1 + c3 t))^m2, t = (c / 10000)^m1
+    FnTabView dec[2];       // y -> 10000 ((t - c1) / (c2 - c3 t))^(1/m1), t = y^(1/m2)
+    double enc_rel[2], dec_rel[2];   // table bound + the exact path's own rounding noise over the domain (constants, pqtabs_build.h)
 };
 
 AEAJ_HD double pqf_abs(double x) { return x < 0.0 ? -x : x; }
@@ -43,6 +47,11 @@ AEAJ_HD bool round_is_safe(double v, double E) { return (float)(v + E) == (float
 // common.py:131-159 -- ((c1 + c2 t) / (1 + c3 t))^m2,  t = (c / 10000)^m1
 AEAJ_HD double pqf_inv_eotf(const PqTabs& Q, int which, double m2, double c, double& rel, bool& ok) {
     const double c1 = 3424.0 / 4096.0, c2 = 2413.0 / 128.0, c3 = 2392.0 / 128.0;
+    {
+        bool okc = ok;
+        const double f = fntab_eval(Q.enc[which], c, okc);
+        if (okc) { rel = Q.enc_rel[which]; return f; }
+    }
     const double x = c * 1e-4;                                        // 1 ulp from the exact path's c / 10000: covered by the bound below
     const bool zero = (c == 0.0);                                     // black: 0^m1 = 0 exactly in both paths
     bool okt = ok;
@@ -64,6 +73,11 @@ AEAJ_HD double pqf_inv_eotf(const PqTabs& Q, int which, double m2, double c, dou
 // common.py:94-129 -- 10000 ((t - c1) / (c2 - c3 t))^(1/m1),  t = y^(1/m2);  negative numerator -> 0, non-positive denominator -> 1e-12
 AEAJ_HD double pqf_eotf(const PqTabs& Q, int which, double y, double& rel, bool& ok) {
     const double c1 = 3424.0 / 4096.0, c2 = 2413.0 / 128.0, c3 = 2392.0 / 128.0, m1 = 2610.0 / 16384.0;
+    {
+        bool okc = ok;
+        const double f = fntab_eval(Q.dec[which], y, okc);
+        if (okc) { rel = Q.dec_rel[which]; return f; }
+    }
     const double t = powtab_eval<8>(Q.im2[which], y, ok);
     const double et = (Q.im2[which].eps + PQF_U) * t;                // absolute
     const double num = t - c1, den = c2 - c3 * t;

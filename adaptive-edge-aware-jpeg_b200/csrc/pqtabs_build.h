@@ -70,8 +70,66 @@ inline void powtab_build(PowTabHost& H, double m, int emin, int nexp, int lg_nse
 }
 
 
+struct FnTabHost {
+    std::vector<double> coef;
+    FnTabView v;
+    double measured;
+};
+// f fitted per (binade, segment) at 9 Chebyshev nodes (long double), validated on random points like powtab_build
+template <class F>
+inline void fntab_build(FnTabHost& H, F f, int emin, int nexp, int lg_nseg) {
+    const int n = 9, nseg = 1 << lg_nseg;
+    std::vector<long double> node(n), y(n), a(n);
+    for (int i = 0; i < n; i++) node[i] = cosl(3.14159265358979323846264338327950288L * (2 * i + 1) / (2.0L * n));
+    H.coef.assign((size_t)nexp * nseg * 10, 0.0);
+    for (int k = 0; k < nexp; k++)
+        for (int j = 0; j < nseg; j++) {
+            std::vector<long double> M((size_t)n * n), b(n);
+            for (int i = 0; i < n; i++) {
+                b[i] = f(ldexpl(1.0L + ((long double)j + (1.0L + node[i]) / 2.0L) / nseg, emin + k));
+                long double pw = 1.0L;
+                for (int d = 0; d < n; d++) { M[(size_t)i * n + d] = pw; pw *= node[i]; }
+            }
+            for (int c = 0; c < n; c++) {
+                int piv = c;
+                for (int r = c + 1; r < n; r++) if (fabsl(M[(size_t)r * n + c]) > fabsl(M[(size_t)piv * n + c])) piv = r;
+                for (int d = 0; d < n; d++) std::swap(M[(size_t)c * n + d], M[(size_t)piv * n + d]);
+                std::swap(b[c], b[piv]);
+                for (int r = c + 1; r < n; r++) {
+                    const long double q = M[(size_t)r * n + c] / M[(size_t)c * n + c];
+                    for (int d = c; d < n; d++) M[(size_t)r * n + d] -= q * M[(size_t)c * n + d];
+                    b[r] -= q * b[c];
+                }
+            }
+            for (int c = n - 1; c >= 0; c--) {
+                long double t = b[c];
+                for (int d = c + 1; d < n; d++) t -= M[(size_t)c * n + d] * a[d];
+                a[c] = t / M[(size_t)c * n + c];
+            }
+            for (int d = 0; d < n; d++) H.coef[((size_t)k * nseg + j) * 10 + d] = (double)a[8 - d];
+        }
+    H.v.coef = H.coef.data(); H.v.emin = emin; H.v.nexp = nexp; H.v.lg_nseg = lg_nseg; H.v.eps = 0.0;
+    double worst = 0.0;
+    uint64_t rng = 0x2545f4914f6cdd1dull;
+    for (int k = 0; k < nexp; k++)
+        for (int j = 0; j < nseg; j++)
+            for (int t = 0; t < 6; t++) {
+                rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                const long double pos = (t == 0) ? 0.0L : (t == 1) ? 0.99999999L : (long double)((rng >> 11) & 0xfffffffffffffull) / 4503599627370496.0L;
+                const double x = ldexp(1.0 + (double)(((long double)j + pos) / nseg), emin + k);
+                bool ok = true;
+                const double got = fntab_eval(H.v, x, ok);
+                const long double want = f((long double)x);
+                const double rel = (double)fabsl(((long double)got - want) / want);
+                if (ok && rel > worst) worst = rel;
+            }
+    H.measured = worst;
+    H.v.eps = 2.0 * worst + 4.0 * 1.1102230246251565e-16;
+}
+
 struct PqTabsHost {
     PowTabHost m1, m2[2], im2[2], im1, isrgb, cbrt32, cube;
+    FnTabHost enc[2], dec[2];
     PqTabs view;                                      // views over the host vectors
 };
 
@@ -95,6 +153,20 @@ inline void pqtabs_build(PqTabsHost& H) {
     powtab_build(H.isrgb, 1.0 / 2.4, -9, 11, 5, 8);
     powtab_build(H.cbrt32, (double)(float)(1.0 / 3.0), -24, 26, 5, 8);
     powtab_build(H.cube, 3.0, -10, 12, 5, 8);
+    // the whole curves.  Their constant bounds add the exact path's own rounding noise (u = 2^-52 per operation, pow <= 1 ulp):
+    //   encode: t carries 1.1 u, r = num / den 3.9 u at most, amplified by m2;   decode over the tabulated domain: w = num / den carries
+    //   at most 31 u (cancellation in t - c1 at the low end of the domain), amplified by 1 / m1 = 6.28
+    const long double c1 = 3424.0L / 4096.0L, c2 = 2413.0L / 128.0L, c3 = 2392.0L / 128.0L, m1 = 2610.0L / 16384.0L;
+    for (int w = 0; w < 2; w++) {
+        const long double m2 = w ? 1.7L * 2523.0L / 32.0L : 2523.0L / 32.0L;
+        fntab_build(H.enc[w], [=](long double c) { const long double t = powl(c / 10000.0L, m1); return powl((c1 + c2 * t) / (1.0L + c3 * t), m2); },
+                    -24, 26, 5);
+        fntab_build(H.dec[w], [=](long double y) { const long double t = powl(y, 1.0L / m2); return 10000.0L * powl((t - c1) / (c2 - c3 * t), 1.0L / m1); },
+                    w ? -24 : -12, w ? 24 : 12, 6);          // y < 1: the curve has a pole at y = (c2 / c3)^m2 > 1
+        H.view.enc[w] = H.enc[w].v; H.view.dec[w] = H.dec[w].v;
+        H.view.enc_rel[w] = H.enc[w].v.eps + (3.9 * (double)m2 + 1.0) * PQF_U;
+        H.view.dec_rel[w] = H.dec[w].v.eps + (46.0 / (double)m1 + 2.0) * PQF_U;     // 31 u by the analysis, 1.5 x margin
+    }
     H.view.m1 = H.m1.v; H.view.m2[0] = H.m2[0].v; H.view.m2[1] = H.m2[1].v; H.view.im2[0] = H.im2[0].v; H.view.im2[1] = H.im2[1].v;
     H.view.im1 = H.im1.v; H.view.isrgb = H.isrgb.v; H.view.cbrt32 = H.cbrt32.v; H.view.cube = H.cube.v;
 }

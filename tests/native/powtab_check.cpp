@@ -58,6 +58,10 @@ int main(int argc, char** argv) {
                okb ? "ok" : "VIOLATED");
         bad += !okb;
     }
+    for (int w = 0; w < 2; w++)
+        printf("curve enc[%d] %6.1f KB measured %.2e bound %.2e (+ exact-path noise -> %.2e);  dec[%d] %6.1f KB measured %.2e bound %.2e (-> %.2e)\n", w,
+               H.enc[w].coef.size() * 8 / 1024.0, H.enc[w].measured, H.enc[w].v.eps, Q.enc_rel[w], w, H.dec[w].coef.size() * 8 / 1024.0, H.dec[w].measured,
+               H.dec[w].v.eps, Q.dec_rel[w]);
     // forward chain, float inputs (ICtCp / ICaCb: l is a float32) and double inputs (JzAzBz)
     for (int which = 0; which < 2; which++) {
         const double m2 = which ? 1.7 * 2523.0 / 32.0 : 2523.0 / 32.0;
